@@ -1,0 +1,94 @@
+// hex_inst.cu -- instantiates the hexahedral kernels for one polynomial order (NM = HEX_NM modes per
+// direction, NQ = NM+1 and NM+2 quadrature points) and provides their launchers.  Compiled once per order so the
+// orders build in parallel.
+#include "hex_kernels.cuh"
+#include "op_internal.h"
+#include <string.h>
+
+#ifndef HEX_NM
+#error "compile with -DHEX_NM=<modes per direction>"
+#endif
+#define HEX_CAT2(a, b) a##b
+#define HEX_CAT(a, b) HEX_CAT2(a, b)
+
+namespace nekmf
+{
+
+template <int OP, int NM, int NQ, bool DEF> static int hex_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
+{
+    using Cfg = HexCfg<OP, NM, NQ, DEF>;
+    static int blocks_per_sm = 0;
+    auto kern                = hex_op_kernel<OP, NM, NQ, DEF>;
+    if (blocks_per_sm == 0)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        int nb = 0;
+        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
+        if (nb < 1)
+        {
+            set_error("hex kernel <%d,%d,%d,%d> does not fit on an SM (smem %zu)", OP, NM, NQ, (int)DEF, (size_t)Cfg::SMEM);
+            return NEKMF_ERR_CUDA;
+        }
+        blocks_per_sm = nb;
+    }
+    HexArgs a;
+    a.in0 = in[0]; a.in1 = in[1]; a.in2 = in[2];
+    a.out0 = out[0]; a.out1 = out[1]; a.out2 = out[2];
+    a.jac = op->d_jac; a.df = op->d_df;
+    a.nElmt  = op->nElmt;
+    a.lambda = op->lambda;
+    a.in_aligned = (((uintptr_t)in[0] | (uintptr_t)in[1] | (uintptr_t)in[2]) & 15) == 0;
+    const int nBatches = (op->nElmt + Cfg::E - 1) / Cfg::E;
+    int grid           = blocks_per_sm * NUM_SMS;
+    if (grid > nBatches) grid = nBatches;
+    if (grid < 1) return NEKMF_OK;
+    const HexTab<NM, NQ> *tab = static_cast<const HexTab<NM, NQ> *>(op->kstate);
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->stream>>>(*tab, a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+
+template <int NM, int NQ> static bool hex_install(nekmf_op_s *op)
+{
+    auto *tab = new HexTab<NM, NQ>;
+    memcpy(tab->B, op->b[0].data(), sizeof(tab->B));
+    memcpy(tab->D, op->D[0].data(), sizeof(tab->D));
+    memcpy(tab->w, op->ws[0].data(), sizeof(tab->w));
+    op->kstate      = tab;
+    op->geo_pitch   = round_up(NQ * NQ * NQ, 2);
+    op->kstate_free = [](void *p) { delete static_cast<HexTab<NM, NQ> *>(p); };
+    char name[96];
+    const char *opn[5] = {"bwd", "helm", "iprod", "ipwdb", "physderiv"};
+    snprintf(name, sizeof(name), "hex_op_kernel<%s,nm=%d,nq=%d,%s>", opn[op->optype], NM, NQ, op->deformed ? "deformed" : "regular");
+    op->kname = name;
+#define HEX_CASE(OPC)                                                                     \
+    case OPC:                                                                             \
+        op->launch = op->deformed ? hex_launch<OPC, NM, NQ, true> : hex_launch<OPC, NM, NQ, false>; \
+        return true;
+    switch (op->optype)
+    {
+        HEX_CASE(HEX_BWD)
+        HEX_CASE(HEX_HELM)
+        HEX_CASE(HEX_IPROD)
+        HEX_CASE(HEX_IPWDB)
+        HEX_CASE(HEX_PD)
+    }
+#undef HEX_CASE
+    delete tab;
+    op->kstate    = nullptr;
+    op->geo_pitch = op->nqTot;
+    return false;
+}
+
+bool HEX_CAT(hex_try_nm, HEX_NM)(nekmf_op_s *op)
+{
+    if (op->nm[0] != HEX_NM) return false;
+    if (op->nq[0] == HEX_NM + 1) return hex_install<HEX_NM, HEX_NM + 1>(op);
+#ifdef HEX_WITH_NQ2
+    if (op->nq[0] == HEX_NM + 2) return hex_install<HEX_NM, HEX_NM + 2>(op);
+#endif
+    return false;
+}
+
+} // namespace nekmf

@@ -1,0 +1,51 @@
+// op_internal.h -- the operator object behind nekmf_op_t and the launcher registry.
+#pragma once
+#include "../../include/nekmf_b200.h"
+#include "common.cuh"
+#include <string>
+#include <vector>
+
+struct nekmf_op_s
+{
+    int shape = 0, optype = 0, dim = 0;
+    int nm[3] = {1, 1, 1}, nq[3] = {1, 1, 1}, btype[3] = {0, 0, 0}, ptype[3] = {0, 0, 0}, rows[3] = {0, 0, 0};
+    int nmTot = 0, nqTot = 0, nElmt = 0, deformed = 0, ndf = 0;
+    double lambda       = 0.0;
+    bool lambda_set     = false;
+    bool has_jac        = false;
+    bool has_df         = false;
+    // host copies of the 1-D tables; ws = weights with the collapsed-coordinate factor folded in
+    std::vector<double> b[3], db[3], D[3], Z[3], W[3], ws[3];
+    // device copies for the runtime-sized kernels: packed [b0 db0 D0 Z0 ws0 | b1 ... | b2 ...]
+    double *d_tab = nullptr;
+    int tab_off[3][5] = {{0}};
+    int tab_len       = 0;
+    // device geometry.  regular: jac[nElmt], df[ndf][nElmt].  deformed: jac[nElmt][geo_pitch],
+    // df[ndf][nElmt][geo_pitch] with geo_pitch >= nqTot chosen by the selected kernel (the TMA-fed
+    // kernels need every element block 16-byte aligned; the runtime-sized kernels use nqTot)
+    double *d_jac     = nullptr;
+    double *d_df      = nullptr;
+    int geo_pitch     = 0;
+    cudaStream_t stream = nullptr;
+    // staging for NEKMF_HOST applies
+    double *d_stage_in = nullptr, *d_stage_out = nullptr;
+    size_t stage_in_sz = 0, stage_out_sz = 0;
+    // launcher: device pointers only
+    int (*launch)(nekmf_op_s *, const double *const in[3], double *const out[3]) = nullptr;
+    std::string kname;
+    void *kstate = nullptr; // launcher-private (constant tables etc.)
+    void (*kstate_free)(void *) = nullptr;
+    bool timing      = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed_once = false;
+};
+
+namespace nekmf
+{
+// each returns true if it installed a launcher for this operator
+bool select_hex_fast(nekmf_op_s *op);
+bool select_quad_fast(nekmf_op_s *op);
+bool select_generic(nekmf_op_s *op);
+// called after set_geom / set_lambda so launchers can precompute (e.g. detect diagonal metrics)
+void notify_geom_changed(nekmf_op_s *op);
+} // namespace nekmf
