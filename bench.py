@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- GDOF/s of the FP64 Helmholtz operator apply on a synthetic 64^3 hex mesh at P=4
+(nm=5 modes, nq=6 Gauss-Lobatto-Legendre points per direction; BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one Helmholtz apply over every element of the rank's mesh (262 144 elements,
+32.768 M local DOF, 262 MB in + 262 MB out: larger than the 126 MB L2, so no flush is needed).
+Under torchrun each rank owns its own 64^3 mesh (weak scaling, no data-path collective: the
+elemental operator has no inter-element coupling).  Prints ONE JSON line (see the repo prompt for
+the contract).  `--impl reference` times the reference's own CPU kernels (oracle/_ref, compiled
+from /root/reference/library/MatrixFreeOps in place) on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+NM, NQ = 5, 6
+NX = 64
+LAMBDA = 1.0
+SEED = 1234
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                d = json.load(f)
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded(name, default=None):
+    """numbers taken from committed ncu captures (profiles/recorded.json), never measured here"""
+    p = os.path.join(ROOT, "profiles", "recorded.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return json.load(f).get(name, default)
+        except Exception:
+            pass
+    return default
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled through NVML DURING the timed region (the same counters
+    as the nvidia-smi clocks line of B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.002)
+        except Exception as ex:  # pragma: no cover
+            self.error = repr(ex)
+
+    def start(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=5)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(self.samples)}
+        if self.samples:
+            s = sorted(self.samples)
+            out["sm_mhz"] = s[len(s) // 2]
+        return out
+
+
+def hex_mesh_geometry(torch, dev, nx, deformed):
+    """Geometric factors of a structured nx^3 hex mesh on [0,1]^3 in the reference layout.
+    regular : jac[nElmt], df[9][nElmt]  (df = diag(2/h), jac = (h/2)^3)
+    deformed: same mesh warped by x += 0.05 sin(pi X) sin(pi Y) sin(pi Z) in every component,
+              factors per quadrature point (SpatialDomains/GeomFactors.cpp:399-474 formulas:
+              df[c*3+d] = d xi_d / d x_c, jac = det(d x / d xi))."""
+    nel = nx ** 3
+    h = 1.0 / nx
+    if not deformed:
+        jac = torch.full((nel,), (h / 2) ** 3, dtype=torch.float64, device=dev)
+        df = torch.zeros((9, nel), dtype=torch.float64, device=dev)
+        df[0] = df[4] = df[8] = 2.0 / h
+        return jac, df.reshape(-1)
+    from _util import nekmf
+    nk = nekmf()
+    z, _, _ = nk.points(nk.eGaussLobattoLegendre, NQ)
+    zt = torch.tensor(z, dtype=torch.float64, device=dev)
+    idx = torch.arange(nx, dtype=torch.float64, device=dev)
+    # 1-D physical coordinates of every (element, point): [nx, NQ]
+    X1 = (idx[:, None] + 0.5 * (zt[None, :] + 1.0)) * h
+    import math
+    s, c = torch.sin(math.pi * X1), math.pi * torch.cos(math.pi * X1)
+    # element index e = ex + nx*(ey + nx*ez); point index q = i + NQ*(j + NQ*k)
+    def bc(a, axis):  # broadcast a [nx,NQ] table to [ez,ey,ex,k,j,i]
+        shape = [1] * 6
+        shape[2 - axis] = nx
+        shape[5 - axis] = NQ
+        return a.reshape(shape)
+    sx, sy, sz = bc(s, 0), bc(s, 1), bc(s, 2)
+    cx, cy, cz = bc(c, 0), bc(c, 1), bc(c, 2)
+    a = 0.05
+    g = [a * cx * sy * sz, a * sx * cy * sz, a * sx * sy * cz]  # d disp / d X_d (same for every component)
+    full = (nx, nx, nx, NQ, NQ, NQ)
+    # F[c][d] = d x_c / d xi_d = (h/2) (delta_cd + g_d)
+    F = [[(h / 2) * ((1.0 if cc == d else 0.0) + g[d]).expand(full) for d in range(3)] for cc in range(3)]
+    det = (F[0][0] * (F[1][1] * F[2][2] - F[1][2] * F[2][1]) - F[0][1] * (F[1][0] * F[2][2] - F[1][2] * F[2][0]) +
+           F[0][2] * (F[1][0] * F[2][1] - F[1][1] * F[2][0]))
+    inv = [[None] * 3 for _ in range(3)]  # inv[d][c] = d xi_d / d x_c
+    for d in range(3):
+        for cc in range(3):
+            r0, r1 = [r for r in range(3) if r != cc], [r for r in range(3) if r != d]
+            minor = F[r0[0]][r1[0]] * F[r0[1]][r1[1]] - F[r0[0]][r1[1]] * F[r0[1]][r1[0]]
+            inv[d][cc] = ((-1.0) ** (d + cc)) * minor / det
+    df = torch.stack([inv[d][cc].reshape(-1) for cc in range(3) for d in range(3)])  # row c*3+d
+    return det.reshape(-1).contiguous(), df.reshape(-1).contiguous()
+
+
+def algorithmic_bytes_per_element(deformed):
+    # 8*(2*nmTot + ndf + 1) regular, 8*(2*nmTot + (ndf+1)*nqTot) deformed
+    return 8 * (2 * NM ** 3 + (10 * NQ ** 3 if deformed else 10))
+
+
+def cpu_reference_leg(seconds_target=12.0, max_threads=None):
+    """The reference's own MatrixFree Helmholtz kernels (AVX2 build, width 4) on the host cores,
+    elements split over all threads, on a bounded sample of the same workload."""
+    import numpy as np
+    import pyoracle as po
+    try:
+        ref = po.Ref("avx2")
+        kind, variant = "reference", "oracle/_ref libnekref_avx2.so (reference MatrixFreeOps kernels, AVX2 width 4)"
+    except Exception:
+        ref = None
+        kind, variant = "port", "oracle/libmforacle.so (plain-C restatement)"
+    threads = max_threads or (os.cpu_count() or 1)
+    nel = 16384  # 1/16 of the 64^3 mesh
+    el = po.Elem(po.HEX, NM, NQ)
+    rng = np.random.default_rng(SEED)
+    x = rng.uniform(-1, 1, nel * el.nmTot)
+    h = 1.0 / NX
+    jac = np.full(nel, (h / 2) ** 3)
+    df = np.zeros((9, nel))
+    df[0] = df[4] = df[8] = 2.0 / h
+    df = df.reshape(-1).copy()
+    if ref is not None:
+        op = ref.operator(po.OP_HELM, el, nel, False, jac, df)
+        out = [np.zeros(nel * el.nmTot)]
+        run = lambda: op(x, lam=LAMBDA, nthreads=threads, outs=out)
+    else:
+        po.set_threads(threads)
+        run = lambda: el.helmholtz(nel, False, jac, df, LAMBDA, x)
+    run()
+    t0 = time.perf_counter()
+    run()
+    t1 = time.perf_counter() - t0
+    reps = max(3, min(200, int(seconds_target / max(t1, 1e-4))))
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        run()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    tmed = ts[len(ts) // 2]
+    return {"value": nel * el.nmTot / tmed / 1e9, "unit": "GDOF/s", "cores": threads, "kind": kind,
+            "sample": "%d of %d elements (regular geometry), median of %d applies, %s" % (nel, NX ** 3, reps, variant),
+            "ms_per_sample": tmed * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=NX, help="elements per direction (default 64)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+    config = {"workload": "3D Helmholtz operator apply, synthetic %d^3 hex mesh per GPU, P=4 (nm=5, nq=6), FP64, "
+                          "regular (affine) geometry, lambda=1" % args.nx,
+              "elements_per_gpu": args.nx ** 3, "nm": NM, "nq": NQ,
+              "l2": "inputs larger than L2 (in+out 524 MB per apply), no flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference_leg(seconds_target=max(10.0, min(60.0, 0.5 * (K + W))))
+        line = {"impl": "reference", "metric": "GDOF/s FP64 Helmholtz apply (hex P=4)", "value": cb["value"],
+                "unit": "GDOF/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": cb["ms_per_sample"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    from _util import nekmf
+    nk = nekmf()
+    if not torch.cuda.is_available() or nk.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nel = args.nx ** 3
+    ndof = nel * NM ** 3
+    stdexp = nk.StdExpansion(nk.eHexahedron, NM, NQ)
+    gen = torch.Generator(device="cpu").manual_seed(SEED + rank)
+    x_host = (torch.rand(ndof, dtype=torch.float64, generator=gen) * 2 - 1).pin_memory()
+    y_host = torch.empty(ndof, dtype=torch.float64).pin_memory()
+    x = x_host.to(dev)
+    y = torch.empty_like(x)
+
+    results = {}
+    for variant in ("regular", "deformed"):
+        deformed = variant == "deformed"
+        jac, df = hex_mesh_geometry(torch, dev, args.nx, deformed)
+        coll = nk.Collection(stdexp, nel, nk.CoalescedGeomData(jac, df, deformed))
+        coll.Initialise(nk.eHelmholtz)
+        op = coll.m_ops[nk.eHelmholtz]
+        del jac, df
+        torch.cuda.empty_cache()
+        op.SetLambda(LAMBDA)
+        for _ in range(W):
+            op.apply([x], [y])
+        sampler = ClockSampler(local_rank)
+        if variant == "regular":
+            sampler.start()
+        barrier()
+        l0 = nk.launch_count()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        ev[0].record()
+        for i in range(K):
+            op.apply([x], [y])  # enqueued on the current (default) stream
+            ev[i + 1].record()
+        barrier()
+        launches = nk.launch_count() - l0
+        clocks = sampler.stop() if variant == "regular" else None
+        total_ms = ev[0].elapsed_time(ev[K])
+        per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(K))
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms_max = float(t.item())
+        results[variant] = {"total_ms": total_ms_max, "ms_per_step": total_ms_max / K, "kernel_ms_avg": total_ms / K,
+                            "kernel_ms_median": per[len(per) // 2], "launches": launches, "clocks": clocks,
+                            "kernel": op.kernel_name}
+        if variant == "regular":
+            # ---- end-to-end through the public host-array call: pinned host in, pinned host out
+            Ke = max(3, min(K, 10))
+            for _ in range(2):
+                op.apply([x_host], [y_host])
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                op.apply([x_host], [y_host])  # synchronous: H2D + kernel + D2H
+            torch.cuda.synchronize()
+            te = (time.perf_counter() - t0) / Ke
+            tt = torch.tensor([te], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            results["e2e_s"] = float(tt.item())
+            chk = float(torch.linalg.vector_norm(y).item())
+            chk_host = float(torch.linalg.vector_norm(y_host).item())
+            results["checksum"] = (chk, chk_host)
+        del coll, op
+        torch.cuda.empty_cache()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    reg, dfm = results["regular"], results["deformed"]
+
+    def roof(r, deformed):
+        bytes_launch = algorithmic_bytes_per_element(deformed) * nel
+        ach = bytes_launch / (r["kernel_ms_avg"] * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": recorded("traffic_bytes_deformed" if deformed else "traffic_bytes_regular"),
+                "peak_source": peak_src, "algorithmic_bytes_per_element": algorithmic_bytes_per_element(deformed),
+                "kernel": r["kernel"], "kernel_ms": r["kernel_ms_avg"]}
+
+    value = world * ndof / (reg["ms_per_step"] * 1e-3) / 1e9
+    line = {
+        "metric": "GDOF/s FP64 Helmholtz apply (hex P=4)", "value": value, "unit": "GDOF/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": reg["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        "roofline": roof(reg, False),
+        "e2e": {"value": world * ndof / results["e2e_s"] / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": ndof * 8,
+                "d2h_bytes_per_step": ndof * 8, "ms_per_step": results["e2e_s"] * 1e3,
+                "note": "nekmf_op_apply(NEKMF_HOST) on pinned host arrays: H2D + kernel + D2H per step"},
+        "gpu_launches": reg["launches"],
+        "clocks": {k: reg["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if reg["clocks"] else None,
+        "variants": {"deformed": {"value": world * ndof / (dfm["ms_per_step"] * 1e-3) / 1e9, "unit": "GDOF/s",
+                                  "ms_per_step": dfm["ms_per_step"], "roofline": roof(dfm, True),
+                                  "workload": "same mesh warped by 0.05 sin(pi x) sin(pi y) sin(pi z): geometric "
+                                              "factors per quadrature point"}},
+        "checksum_l2": results["checksum"][0],
+    }
+    fp64_peak = recorded("fp64_tflops_measured")
+    flops_elt = recorded("helm_flops_per_element_regular", 2 * 14700)
+    if fp64_peak:
+        ach = flops_elt * nel / (reg["kernel_ms_avg"] * 1e-3) / 1e12
+        line["roofline_fp64"] = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                                 "frac": ach / fp64_peak, "flops_per_element": flops_elt}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_reference_leg()
+        except Exception as ex:  # the baseline must never take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": "GDOF/s", "cores": 0, "kind": "reference",
+                                    "sample": "failed: %r" % (ex,)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

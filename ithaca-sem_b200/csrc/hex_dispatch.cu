@@ -15,22 +15,25 @@ bool select_hex_fast(nekmf_op_s *op)
         if (op->nm[d] != op->nm[0] || op->nq[d] != op->nq[0] || op->b[d] != op->b[0] || op->D[d] != op->D[0] ||
             op->ws[d] != op->ws[0])
             return false;
+    bool ok = false;
     switch (op->nm[0])
     {
-        case 2: return hex_try_nm2(op);
-        case 3: return hex_try_nm3(op);
-        case 4: return hex_try_nm4(op);
-        case 5: return hex_try_nm5(op);
-        case 6: return hex_try_nm6(op);
-        case 7: return hex_try_nm7(op);
-        case 8: return hex_try_nm8(op);
-        case 9: return hex_try_nm9(op);
-        case 10: return hex_try_nm10(op);
-        case 11: return hex_try_nm11(op);
+        case 2: ok = hex_try_nm2(op); break;
+        case 3: ok = hex_try_nm3(op); break;
+        case 4: ok = hex_try_nm4(op); break;
+        case 5: ok = hex_try_nm5(op); break;
+        case 6: ok = hex_try_nm6(op); break;
+        case 7: ok = hex_try_nm7(op); break;
+        case 8: ok = hex_try_nm8(op); break;
+        case 9: ok = hex_try_nm9(op); break;
+        case 10: ok = hex_try_nm10(op); break;
+        case 11: ok = hex_try_nm11(op); break;
     }
-    return false;
+    // regular Helmholtz: add the coefficient-space kernel (used when the metric is diagonal)
+    if (ok) kron_maybe_wrap(op);
+    return ok;
 }
 
 bool select_quad_fast(nekmf_op_s *) { return false; }
-void notify_geom_changed(nekmf_op_s *) {}
+void notify_geom_changed(nekmf_op_s *op) { kron_geom_changed(op); }
 } // namespace nekmf

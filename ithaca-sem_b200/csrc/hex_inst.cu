@@ -22,6 +22,7 @@ template <int OP, int NM, int NQ, bool DEF> static int hex_launch(nekmf_op_s *op
     if (blocks_per_sm == 0)
     {
         NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int nb = 0;
         NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
         if (nb < 1)

@@ -35,6 +35,7 @@ struct nekmf_op_s
     std::string kname;
     void *kstate = nullptr; // launcher-private (constant tables etc.)
     void (*kstate_free)(void *) = nullptr;
+    bool kron        = false; // Helmholtz/hex/regular: coefficient-space kernel available (hex_kron.cu)
     bool timing      = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed_once = false;
@@ -48,4 +49,6 @@ bool select_quad_fast(nekmf_op_s *op);
 bool select_generic(nekmf_op_s *op);
 // called after set_geom / set_lambda so launchers can precompute (e.g. detect diagonal metrics)
 void notify_geom_changed(nekmf_op_s *op);
+void kron_maybe_wrap(nekmf_op_s *op);
+int kron_geom_changed(nekmf_op_s *op);
 } // namespace nekmf

@@ -1,0 +1,279 @@
+"""GPU suite: the CUDA path, called through the C ABI (ctypes -> libnekmf_b200.so), against the CPU
+oracle on the same seeded inputs and against the reference-generated golden vectors.
+
+Tolerance: relative L2 and Linf <= 1e-12 (BASELINE.json north_star) for every operator.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import pyoracle as po
+from _util import ROOT, nekmf, random_geometry, rel_errs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+SHAPES = {"Quad": po.QUAD, "Tri": po.TRI, "Hex": po.HEX, "Prism": po.PRISM, "Tet": po.TET}
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"))
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def check(got, want, what=""):
+    l2, li = rel_errs(got, want)
+    assert l2 < TOL and li < TOL, "%s: relL2=%.3e relLinf=%.3e" % (what, l2, li)
+
+
+def run_all_ops(nk, shape, nm, nq0, nel, deformed, rng, lam=1.3, geometry=None):
+    el = po.Elem(shape, nm, nq0)
+    std = nk.StdExpansion(shape, nm, nq0)
+    jac, df = geometry if geometry is not None else random_geometry(rng, el.dim, nel, el.nqTot, deformed)
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, deformed))
+    x = rng.uniform(-1, 1, nel * el.nmTot)
+    f = [rng.uniform(-1, 1, nel * el.nqTot) for _ in range(el.dim)]
+    out = np.zeros(nel * el.nqTot)
+    coll.ApplyOperator(nk.eBwdTrans, x, out)
+    check(out, el.bwdtrans(nel, x), "BwdTrans")
+    out = np.zeros(nel * el.nmTot)
+    coll.ApplyOperator(nk.eIProductWRTBase, f[0], out)
+    check(out, el.iproduct(nel, deformed, jac, f[0]), "IProductWRTBase")
+    outs = [np.zeros(nel * el.nqTot) for _ in range(el.dim)]
+    coll.ApplyOperator(nk.ePhysDeriv, f[0], *outs)
+    check(np.concatenate(outs), np.concatenate(el.physderiv(nel, deformed, df, f[0])), "PhysDeriv")
+    out = np.zeros(nel * el.nmTot)
+    coll.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
+    check(out, el.helmholtz(nel, deformed, jac, df, lam, x), "Helmholtz")
+    if shape in (po.QUAD, po.HEX):
+        out = np.zeros(nel * el.nmTot)
+        coll.ApplyOperator(nk.eIProductWRTDerivBase, *f, out)
+        check(out, el.iproductwrtderivbase(nel, deformed, jac, df, f), "IProductWRTDerivBase")
+    return coll
+
+
+@pytest.mark.parametrize("deformed", [False, True])
+@pytest.mark.parametrize("nm", list(range(2, 12)))
+def test_hex_all_operators_default_quadrature(nm, deformed):
+    """nm=2..11 (P=1..10), nq=nm+1: the TMA-fed compile-time kernels; 37 elements = ragged last batch."""
+    nk = nekmf()
+    coll = run_all_ops(nk, po.HEX, nm, nm + 1, 37, deformed, np.random.default_rng(100 + nm))
+    assert "hex_op_kernel" in coll.m_ops[nk.eBwdTrans].kernel_name
+
+
+@pytest.mark.parametrize("deformed", [False, True])
+@pytest.mark.parametrize("shape,nm,nq0", [
+    (po.HEX, 4, 6), (po.HEX, 5, 8), (po.HEX, 5, 10), (po.HEX, 4, 4),
+    (po.QUAD, 2, 3), (po.QUAD, 4, 5), (po.QUAD, 6, 7), (po.QUAD, 8, 9), (po.QUAD, 4, 8), (po.QUAD, 11, 12),
+    (po.TRI, 2, 3), (po.TRI, 4, 5), (po.TRI, 6, 7), (po.TRI, 8, 9), (po.TRI, 4, 8),
+    (po.PRISM, 2, 3), (po.PRISM, 4, 5), (po.PRISM, 7, 8), (po.PRISM, 8, 9), (po.PRISM, 4, 7),
+    (po.TET, 2, 3), (po.TET, 4, 5), (po.TET, 7, 8), (po.TET, 8, 9), (po.TET, 4, 7),
+])
+def test_all_shapes_runtime_kernels(shape, nm, nq0, deformed):
+    """collapsed-coordinate shapes (CORRECT terms of eModified_A), quads, over-integration (nq up to 2 nm)."""
+    run_all_ops(nekmf(), shape, nm, nq0, 13, deformed, np.random.default_rng(7 * nm + nq0 + shape))
+
+
+def golden_cases():
+    return sorted(set(k.rsplit("_", 1)[0] for k in GOLD.files if k.endswith("_x")))
+
+
+@pytest.mark.parametrize("key", golden_cases())
+def test_against_reference_golden_vectors(key):
+    """outputs of the reference's own kernels (oracle/_ref at fixture-generation time)"""
+    nk = nekmf()
+    name, nm, nq0, geo = key.split("_")
+    shape, nm, nq0, deformed = SHAPES[name], int(nm), int(nq0), geo == "def"
+    g = lambda s: GOLD[key + "_" + s]
+    std = nk.StdExpansion(shape, nm, nq0)
+    ncoef, nq = std.GetNcoeffs(), std.GetTotPoints()
+    nel = g("x").size // ncoef
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(g("jac"), g("df"), deformed))
+    out = np.zeros(nel * nq)
+    coll.ApplyOperator(nk.eBwdTrans, g("x"), out)
+    check(out, g("bwd"), "BwdTrans")
+    out = np.zeros(nel * ncoef)
+    coll.ApplyOperator(nk.eIProductWRTBase, g("f0"), out)
+    check(out, g("iprod"), "IProductWRTBase")
+    outs = [np.zeros(nel * nq) for _ in range(std.dim)]
+    coll.ApplyOperator(nk.ePhysDeriv, g("f0"), *outs)
+    check(np.concatenate(outs), np.concatenate([g("pd%d" % d) for d in range(std.dim)]), "PhysDeriv")
+    out = np.zeros(nel * ncoef)
+    coll.ApplyOperator(nk.eHelmholtz, g("x"), out, factors={nk.eFactorLambda: 1.5})
+    check(out, g("helm"), "Helmholtz")
+    if shape in (po.QUAD, po.HEX):
+        out = np.zeros(nel * ncoef)
+        coll.ApplyOperator(nk.eIProductWRTDerivBase, *[g("f%d" % d) for d in range(std.dim)], out)
+        check(out, g("ipwdb"), "IProductWRTDerivBase")
+
+
+def box_geometry(nel, hx, hy, hz):
+    jac = np.full(nel, hx * hy * hz / 8.0)
+    df = np.zeros((9, nel))
+    df[0], df[4], df[8] = 2.0 / hx, 2.0 / hy, 2.0 / hz
+    return jac, df.reshape(-1).copy()
+
+
+@pytest.mark.parametrize("nm", [2, 3, 4, 5, 6])
+@pytest.mark.parametrize("nel", [1, 31, 32, 33, 1000])
+def test_hex_helmholtz_coefficient_space_kernel(nm, nel):
+    """axis-aligned boxes (diagonal Laplacian metric) take the Kronecker coefficient-space kernel;
+    per-element box sizes vary so the per-element scalars are exercised."""
+    nk = nekmf()
+    rng = np.random.default_rng(nm * 1000 + nel)
+    el = po.Elem(po.HEX, nm, nm + 1)
+    std = nk.StdExpansion(nk.eHexahedron, nm, nm + 1)
+    h = rng.uniform(0.05, 2.0, (3, nel))
+    jac = h[0] * h[1] * h[2] / 8.0
+    df = np.zeros((9, nel))
+    df[0], df[4], df[8] = 2.0 / h[0], 2.0 / h[1], 2.0 / h[2]
+    df = df.reshape(-1).copy()
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, False))
+    x = rng.uniform(-1, 1, nel * el.nmTot)
+    for lam in (0.0, 1.0, 37.5):
+        out = np.zeros(nel * el.nmTot)
+        coll.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
+        check(out, el.helmholtz(nel, False, jac, df, lam, x), "Helmholtz(kron)")
+    assert "kron" in coll.m_ops[nk.eHelmholtz].kernel_name
+    # a sheared (non-diagonal metric) collection must NOT take it
+    jac2, df2 = random_geometry(rng, 3, nel, el.nqTot, False)
+    coll2 = nk.Collection(std, nel, nk.CoalescedGeomData(jac2, df2, False))
+    out = np.zeros(nel * el.nmTot)
+    coll2.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: 1.0})
+    check(out, el.helmholtz(nel, False, jac2, df2, 1.0, x), "Helmholtz(quad-space)")
+    assert "kron" not in coll2.m_ops[nk.eHelmholtz].kernel_name
+
+
+@pytest.mark.parametrize("nel", [0, 1, 2, 3, 5, 8, 9])
+def test_edge_element_counts(nel):
+    """empty, single-element and ragged collections (the reference pads to the SIMD width instead)."""
+    nk = nekmf()
+    rng = np.random.default_rng(nel)
+    if nel == 0:
+        std = nk.StdExpansion(nk.eHexahedron, 5, 6)
+        coll = nk.Collection(std, 0, nk.CoalescedGeomData(np.zeros(0), np.zeros(0), False))
+        coll.ApplyOperator(nk.eHelmholtz, np.zeros(1), np.zeros(1), factors={nk.eFactorLambda: 1.0})
+        return
+    for shape in (po.HEX, po.TET, po.QUAD):
+        run_all_ops(nk, shape, 5, 6, nel, True, rng)
+        run_all_ops(nk, shape, 5, 6, nel, False, rng)
+
+
+def test_device_resident_and_misaligned_arrays():
+    """torch CUDA tensors are used in place (no copies); pointers that are only 8-byte aligned (slices of
+    a larger field, as ExpList passes `in + offset`) take the non-TMA load path and must agree."""
+    torch = _torch()
+    nk = nekmf()
+    rng = np.random.default_rng(42)
+    nel, nm = 203, 5
+    el = po.Elem(po.HEX, nm, nm + 1)
+    std = nk.StdExpansion(nk.eHexahedron, nm, nm + 1)
+    for deformed in (False, True):
+        jac, df = random_geometry(rng, 3, nel, el.nqTot, deformed)
+        coll = nk.Collection(std, nel, nk.CoalescedGeomData(torch.tensor(jac, device="cuda"),
+                                                            torch.tensor(df, device="cuda"), deformed))
+        x = rng.uniform(-1, 1, nel * el.nmTot)
+        want = el.helmholtz(nel, deformed, jac, df, 0.9, x)
+        for off in (0, 1):
+            xin = torch.zeros(x.size + 3, dtype=torch.float64, device="cuda")
+            xin[off:off + x.size] = torch.tensor(x, device="cuda")
+            out = torch.zeros(x.size + 3, dtype=torch.float64, device="cuda")
+            coll.ApplyOperator(nk.eHelmholtz, xin[off:off + x.size], out[off:off + x.size],
+                               factors={nk.eFactorLambda: 0.9})
+            torch.cuda.synchronize()
+            check(out[off:off + x.size].cpu().numpy(), want, "Helmholtz device off=%d" % off)
+            assert float(out[off + x.size:].abs().max()) == 0.0 and (off == 0 or float(out[0]) == 0.0)
+        # box geometry -> coefficient-space kernel, also with misaligned pointers
+        if not deformed:
+            jb, dfb = box_geometry(nel, 0.3, 0.2, 0.5)
+            collb = nk.Collection(std, nel, nk.CoalescedGeomData(jb, dfb, False))
+            wantb = el.helmholtz(nel, False, jb, dfb, 0.9, x)
+            for off in (0, 1):
+                xin = torch.zeros(x.size + 3, dtype=torch.float64, device="cuda")
+                xin[off:off + x.size] = torch.tensor(x, device="cuda")
+                out = torch.zeros(x.size + 3, dtype=torch.float64, device="cuda")
+                collb.ApplyOperator(nk.eHelmholtz, xin[off:off + x.size], out[off:off + x.size],
+                                    factors={nk.eFactorLambda: 0.9})
+                torch.cuda.synchronize()
+                check(out[off:off + x.size].cpu().numpy(), wantb, "Helmholtz kron off=%d" % off)
+
+
+def test_physderiv_direction_overload_and_errors():
+    nk = nekmf()
+    rng = np.random.default_rng(9)
+    nel = 6
+    el = po.Elem(po.HEX, 4, 5)
+    std = nk.StdExpansion(nk.eHexahedron, 4, 5)
+    jac, df = random_geometry(rng, 3, nel, el.nqTot, True)
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, True))
+    f = rng.uniform(-1, 1, nel * el.nqTot)
+    want = el.physderiv(nel, True, df, f)
+    for d in range(3):
+        out = np.zeros(nel * el.nqTot)
+        coll.ApplyOperator(nk.ePhysDeriv, d, f, out)
+        check(out, want[d], "PhysDeriv dir %d" % d)
+    # operator()(dir, ...) is invalid for every other operator (reference: NEKERROR efatal)
+    with pytest.raises(nk.NekError):
+        coll.ApplyOperator(nk.eBwdTrans, 0, f, np.zeros(nel * el.nqTot))
+    # Helmholtz without eFactorLambda
+    with pytest.raises(nk.NekError):
+        coll.ApplyOperator(nk.eHelmholtz, np.zeros(nel * el.nmTot), np.zeros(nel * el.nmTot))
+    # geometry missing
+    coll2 = nk.Collection(std, nel, nk.CoalescedGeomData(None, None, True))
+    with pytest.raises(nk.NekError):
+        coll2.ApplyOperator(nk.eIProductWRTBase, f, np.zeros(nel * el.nmTot))
+    # unregistered implementation type
+    coll3 = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, True), nk.SetFixedImpType(nk.eStdMat))
+    with pytest.raises(nk.NekError):
+        coll3.Initialise(nk.eBwdTrans)
+
+
+def test_full_size_properties_hex_p4():
+    """BASELINE.json size (64^3 hex, P=4): size-independent properties instead of a CPU recompute:
+    linearity, symmetry x^T A y = y^T A x, positivity, BwdTrans/IProduct adjointness, and agreement of
+    the coefficient-space kernel with the quadrature-space kernel on the same box mesh."""
+    torch = _torch()
+    nk = nekmf()
+    nel, nm, nq = 64 ** 3, 5, 6
+    std = nk.StdExpansion(nk.eHexahedron, nm, nq)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.rand(nel * 125, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    y = torch.rand(nel * 125, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    h = 1.0 / 64
+    jac = torch.full((nel,), (h / 2) ** 3, dtype=torch.float64, device="cuda")
+    df = torch.zeros((9, nel), dtype=torch.float64, device="cuda")
+    df[0] = df[4] = df[8] = 2 / h
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df.reshape(-1), False))
+    # tiny shear on the LAST element only -> metric not exactly diagonal -> quadrature-space kernel
+    df2 = df.clone()
+    df2[1, -1] = 1e-300
+    coll_q = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df2.reshape(-1), False))
+    lam = {nk.eFactorLambda: 1.0}
+    Ax, Ay, Axy, Aq = (torch.empty_like(x) for _ in range(4))
+    coll.ApplyOperator(nk.eHelmholtz, x, Ax, factors=lam)
+    coll.ApplyOperator(nk.eHelmholtz, y, Ay, factors=lam)
+    coll.ApplyOperator(nk.eHelmholtz, (2.0 * x - 3.0 * y).contiguous(), Axy, factors=lam)
+    coll_q.ApplyOperator(nk.eHelmholtz, x, Aq, factors=lam)
+    torch.cuda.synchronize()
+    assert "kron" in coll.m_ops[nk.eHelmholtz].kernel_name
+    assert "kron" not in coll_q.m_ops[nk.eHelmholtz].kernel_name
+    nrm = float(torch.linalg.vector_norm(Ax))
+    assert float(torch.linalg.vector_norm(Axy - (2.0 * Ax - 3.0 * Ay))) < 1e-12 * nrm * 5
+    assert float(torch.linalg.vector_norm(Ax - Aq)) < 1e-12 * nrm
+    assert float((Ax - Aq).abs().max()) < 1e-12 * float(Aq.abs().max())
+    xAy, yAx = float(torch.dot(x, Ay)), float(torch.dot(y, Ax))
+    assert abs(xAy - yAx) < 1e-12 * max(abs(xAy), float(torch.dot(x, Ax)))
+    assert float(torch.dot(x, Ax)) > 0
+    # <B u, f>_{Jw} = <u, IProduct(f)>
+    fphys = torch.rand(nel * 216, dtype=torch.float64, device="cuda", generator=g)
+    Bu, Itf = torch.empty_like(fphys), torch.empty_like(x)
+    coll.ApplyOperator(nk.eBwdTrans, x, Bu)
+    coll.ApplyOperator(nk.eIProductWRTBase, fphys, Itf)
+    torch.cuda.synchronize()
+    z, w, _ = nk.points(nk.eGaussLobattoLegendre, nq)
+    wt = torch.tensor(w, device="cuda")
+    w3 = (wt[:, None, None] * wt[None, :, None] * wt[None, None, :]).reshape(-1) * (h / 2) ** 3
+    lhs = float(torch.sum(Bu.reshape(nel, 216) * fphys.reshape(nel, 216) * w3[None, :]))
+    rhs = float(torch.dot(x, Itf))
+    assert abs(lhs - rhs) < 1e-12 * abs(lhs)
