@@ -19,16 +19,24 @@
 // (double-buffered, mbarrier) and out with TMA bulk stores; per-element geometry is 4 doubles.
 #include "hex_kernels.cuh"
 #include "op_internal.h"
+#include <cmath>
 #include <string.h>
 
 namespace nekmf
 {
 
+// 1-D mass / stiffness matrices, upper triangles only (both are symmetric): Ms[tri(a,b)], a <= b.
+// 2 * NM(NM+1)/2 doubles -- 60 uniform registers at NM = 5, so every DFMA takes its matrix entry
+// from the uniform register file without reloads.
 template <int NM> struct KronTab
 {
-    double M[NM * NM];
-    double K[NM * NM];
+    double Ms[NM * (NM + 1) / 2];
+    double Ks[NM * (NM + 1) / 2];
 };
+__host__ __device__ constexpr int tri(int a, int b, int n)
+{
+    return a <= b ? a * n - a * (a - 1) / 2 + (b - a) : b * n - b * (b - 1) / 2 + (a - b);
+}
 
 struct KronArgs
 {
@@ -40,214 +48,238 @@ struct KronArgs
     double lambda;
 };
 
+constexpr int kron_pad(int minimum, int residue) // smallest v >= minimum with v % 16 == residue
+{
+    int v = minimum;
+    while (v % 16 != residue % 16) ++v;
+    return v;
+}
+
+// Every warp is an independent worker: it owns EPW elements per step, its own TMA-fed input
+// buffer, its own exchange/staging buffer and its own mbarrier -- no CTA-wide barrier in the loop.
 template <int NM> struct KronCfg
 {
     static constexpr int NM2 = NM * NM, NM3 = NM2 * NM;
-    // elements per batch: 3 buffers of EPB*NM3 doubles, two CTAs per SM
-    static constexpr int EPB_FIT = (104 * 1024) / (3 * NM3 * 8);
-    static constexpr int EPB_RAW = EPB_FIT > 32 ? 32 : EPB_FIT;
-    static constexpr int EPB     = (EPB_RAW / 2) * 2; // even: batches of odd-sized blocks stay 16-byte aligned
-    static constexpr int T       = round_up(EPB * NM, 32);
-    static constexpr int BUF     = EPB * NM3; // doubles, even
-    static constexpr size_t SMEM = (size_t)3 * BUF * 8 + 64;
+    static constexpr int EPW   = 32 / NM;                // elements per warp step (NM lanes per element)
+    static constexpr int INB   = round_up(EPW * NM3, 2); // doubles in the input buffer
+    // exchange layout X[e*ES + p*PS + q*NM + r]: writers (lanes = (e,r)) and readers (lanes = (e,p))
+    // both hit 16 distinct 8-byte banks per half-warp
+    static constexpr int PS = kron_pad(NM2, 1);
+    static constexpr int ES = kron_pad(NM * PS, NM);
+    static constexpr int XB = round_up(EPW * ES > EPW * NM3 ? EPW * ES : EPW * NM3, 2);
+    static constexpr int GEO = EPW * 4;
+    static constexpr int PER_WARP = INB + GEO + XB + 2; // doubles (+2: mbarrier, 16-byte slot)
+    // one CTA per SM; warps in multiples of 4 (one FP64 pipe per SM sub-partition)
+    static constexpr int W_FIT = (224 * 1024) / (PER_WARP * 8);
+    static constexpr int WARPS = W_FIT >= 12 ? 12 : (W_FIT >= 8 ? 8 : 4);
+    static constexpr int T     = WARPS * 32;
+    static constexpr size_t SMEM = (size_t)WARPS * PER_WARP * 8 + 16;
 };
 
-template <int NM>
-__global__ void __launch_bounds__(KronCfg<NM>::T, 2)
+// SPARSEK: the stiffness matrix has the structure of the modified C0 basis -- a 2x2 vertex block
+// plus a diagonal (interior modes have orthogonal derivatives) -- verified numerically at creation.
+template <int NM, bool SPARSEK>
+__global__ void __launch_bounds__(KronCfg<NM>::T, 1)
     hex_helm_kron_kernel(const __grid_constant__ KronTab<NM> tab, const __grid_constant__ KronArgs args)
 {
     using Cfg = KronCfg<NM>;
-    constexpr int NM2 = Cfg::NM2, NM3 = Cfg::NM3, EPB = Cfg::EPB, T = Cfg::T, BUF = Cfg::BUF;
+    constexpr int NM2 = Cfg::NM2, NM3 = Cfg::NM3, EPW = Cfg::EPW, INB = Cfg::INB, PS = Cfg::PS, ES = Cfg::ES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sIn0   = reinterpret_cast<double *>(smem_raw); // two input / output-staging buffers
-    double *sX     = sIn0 + 2 * BUF;                        // exchange buffer
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sX + BUF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *wbase = reinterpret_cast<double *>(smem_raw) + (size_t)warp * Cfg::PER_WARP;
+    double *sIn   = wbase;                  // [INB]  input block of the current step
+    double *sGeo  = wbase + INB;            // [GEO]  per-element scalars
+    double *sX    = sGeo + Cfg::GEO;        // [XB]   exchange, then output staging
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sX + Cfg::XB);
 
-    const int tid      = threadIdx.x;
-    const int nElmt    = args.nElmt;
-    const int nBatches = (nElmt + EPB - 1) / EPB;
-    const int e        = tid / NM;      // element within the batch
-    const int s1       = tid - e * NM;  // r in stage I, p' in stage II
-    const bool active  = tid < EPB * NM;
+    const int nElmt = args.nElmt;
+    const int nWB   = (nElmt + EPW - 1) / EPW;          // warp batches
+    const int GW    = gridDim.x * Cfg::WARPS;           // warps in the grid
+    const int gw    = blockIdx.x * Cfg::WARPS + warp;
+    const int e     = lane / NM;                        // element within the warp batch
+    const int s1    = lane - e * NM;                    // r in stage I, p' in stage II
+    const bool active = lane < EPW * NM;
+#define KM(a, b) tab.Ms[tri(a, b, NM)]
+#define KK(a, b) tab.Ks[tri(a, b, NM)]
+#define KNZ(a, b) (!SPARSEK || (a) == (b) || ((a) < 2 && (b) < 2))
 
-    if (tid == 0)
+    if (lane == 0)
     {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        mbar_init(bar, 1);
         mbar_fence_init();
     }
-    __syncthreads();
+    __syncwarp();
 
-    auto batch_ne = [&](int b) { int r = nElmt - b * EPB; return r < EPB ? r : EPB; };
-    auto tma_ok   = [&](int b) { return args.io_aligned && ((batch_ne(b) * NM3) & 1) == 0; };
-    auto issue    = [&](int b, int s) { // one thread
-        if (!tma_ok(b)) return;
-        const uint32_t bytes = (uint32_t)(batch_ne(b) * NM3 * 8);
-        mbar_expect_tx(&bars[s], bytes);
-        tma_load_1d(sIn0 + s * BUF, args.in + (size_t)b * BUF, bytes, &bars[s]);
+    auto batch_ne = [&](int wb) { int r = nElmt - wb * EPW; return r < EPW ? r : EPW; };
+    auto tma_ok   = [&](int wb) { return args.io_aligned && ((batch_ne(wb) * NM3) & 1) == 0 && (((wb * EPW * NM3) & 1) == 0); };
+    auto issue    = [&](int wb) { // lane 0; sIn and sGeo are free
+        const int ne   = batch_ne(wb);
+        uint32_t bytes = (uint32_t)(ne * 32);
+        if (tma_ok(wb)) bytes += (uint32_t)(ne * NM3 * 8);
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(sGeo, args.geo4 + (size_t)wb * EPW * 4, (uint32_t)(ne * 32), bar);
+        if (tma_ok(wb)) tma_load_1d(sIn, args.in + (size_t)wb * EPW * NM3, (uint32_t)(ne * NM3 * 8), bar);
     };
 
-    uint32_t ph0 = 0, ph1 = 0;
-    if (tid == 0 && (int)blockIdx.x < nBatches) issue(blockIdx.x, 0);
+    uint32_t phase = 0;
+    if (lane == 0 && gw < nWB) issue(gw);
 
-    int it = 0;
-    for (int b = blockIdx.x; b < nBatches; b += gridDim.x, ++it)
+    for (int wb = gw; wb < nWB; wb += GW)
     {
-        const int s     = it & 1;
-        const int ne    = batch_ne(b);
-        const int bnext = b + gridDim.x;
-        double *sIn     = sIn0 + s * BUF;
-        // prefetch the next batch into the other buffer once the bulk store that used it as
-        // staging (previous iteration) has finished reading shared memory
-        if (tid == 0 && bnext < nBatches)
+        const int ne      = batch_ne(wb);
+        const int wbnext  = wb + GW;
+        const bool tma_in = tma_ok(wb);
+        if (!tma_in)
         {
-            tma_store_wait_read0();
-            issue(bnext, s ^ 1);
+            // 8-byte aligned caller arrays or an odd-sized tail: plain loads by the warp
+            const double *src = args.in + (size_t)wb * EPW * NM3;
+            for (int i = lane; i < ne * NM3; i += 32) sIn[i] = __ldg(src + i);
         }
-        // per-element scalars (issued before the wait so their latency overlaps)
-        const int eg = (b * EPB + e) < nElmt ? (b * EPB + e) : (nElmt - 1);
-        const double2 g01 = __ldg(reinterpret_cast<const double2 *>(args.geo4 + (size_t)eg * 4));
-        const double2 g23 = __ldg(reinterpret_cast<const double2 *>(args.geo4 + (size_t)eg * 4 + 2));
-        const double lamJ = args.lambda * g01.x, jg00 = g01.y, jg11 = g23.x, jg22 = g23.y;
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        __syncwarp();
 
-        if (tma_ok(b))
-        {
-            mbar_wait(&bars[s], s ? ph1 : ph0);
-            if (s) ph1 ^= 1; else ph0 ^= 1;
-        }
-        else
-        {
-            if (tid == 0) tma_store_wait_read0();
-            __syncthreads();
-            const double *src = args.in + (size_t)b * BUF;
-            for (int i = tid; i < ne * NM3; i += T) sIn[i] = __ldg(src + i);
-            __syncthreads();
-        }
+        const double *g   = sGeo + (e < ne ? e : 0) * 4;
+        const double lamJ = args.lambda * g[0], jg00 = g[1], jg11 = g[2], jg22 = g[3];
 
-        // ---- stage I: thread (e, r): contract p then q in registers
-        double UM[NM][NM], UK[NM][NM];
+        // ---- stage I: lane (e, r): contract p then q in registers
+        //      A2 = (M (x) M) x,  R = jg00 (M (x) K) x + jg11 (K (x) M) x   for the lane's r-slab
+        double A2[NM][NM], R[NM][NM];
 #pragma unroll
         for (int a = 0; a < NM; ++a)
 #pragma unroll
-            for (int c = 0; c < NM; ++c) UM[a][c] = UK[a][c] = 0.0;
+            for (int c = 0; c < NM; ++c) A2[a][c] = R[a][c] = 0.0;
         if (active)
         {
             const double *xin = sIn + e * NM3 + s1 * NM2;
 #pragma unroll
             for (int q = 0; q < NM; ++q)
             {
-                double xr[NM], t1[NM], a11[NM], a22[NM];
+                double xr[NM], am[NM], bk[NM], a11[NM];
 #pragma unroll
                 for (int p = 0; p < NM; ++p) xr[p] = xin[q * NM + p];
 #pragma unroll
                 for (int pp = 0; pp < NM; ++pp)
                 {
-                    double am = tab.M[pp * NM] * xr[0], ak = tab.K[pp * NM] * xr[0];
+                    double m = KM(pp, 0) * xr[0], k = 0.0;
+                    bool kset = false;
 #pragma unroll
-                    for (int p = 1; p < NM; ++p)
-                    {
-                        am = fma(tab.M[pp * NM + p], xr[p], am);
-                        ak = fma(tab.K[pp * NM + p], xr[p], ak);
-                    }
-                    t1[pp]  = fma(lamJ, am, jg00 * ak);
-                    a11[pp] = jg11 * am;
-                    a22[pp] = jg22 * am;
+                    for (int p = 1; p < NM; ++p) m = fma(KM(pp, p), xr[p], m);
+#pragma unroll
+                    for (int p = 0; p < NM; ++p)
+                        if (KNZ(pp, p))
+                        {
+                            k    = kset ? fma(KK(pp, p), xr[p], k) : KK(pp, p) * xr[p];
+                            kset = true;
+                        }
+                    am[pp]  = m;
+                    bk[pp]  = jg00 * k;
+                    a11[pp] = jg11 * m;
                 }
 #pragma unroll
                 for (int qq = 0; qq < NM; ++qq)
 #pragma unroll
                     for (int pp = 0; pp < NM; ++pp)
                     {
-                        UM[qq][pp] = fma(tab.M[qq * NM + q], t1[pp], UM[qq][pp]);
-                        UM[qq][pp] = fma(tab.K[qq * NM + q], a11[pp], UM[qq][pp]);
-                        UK[qq][pp] = fma(tab.M[qq * NM + q], a22[pp], UK[qq][pp]);
+                        A2[qq][pp] = fma(KM(qq, q), am[pp], A2[qq][pp]);
+                        R[qq][pp]  = fma(KM(qq, q), bk[pp], R[qq][pp]);
+                        if (KNZ(qq, q)) R[qq][pp] = fma(KK(qq, q), a11[pp], R[qq][pp]);
                     }
             }
         }
-        // ---- exchange 1: U_M, transposed so that thread (e,p') finds its [r][q'] block contiguous
+        __syncwarp();
+        // sIn / sGeo are consumed: request the next warp batch now, it lands during the exchanges
+        if (lane == 0)
+        {
+            tma_store_wait_read0(); // the previous step's bulk store has finished reading sX
+            if (wbnext < nWB) issue(wbnext);
+        }
+        __syncwarp();
+        // ---- exchange 1: U_M = lamJ A2 + R.  lane (e,r) scatters, lane (e,p') gathers its [q'][r] block
         double acc[NM][NM];
         if (active)
         {
 #pragma unroll
             for (int qq = 0; qq < NM; ++qq)
 #pragma unroll
-                for (int pp = 0; pp < NM; ++pp) sX[e * NM3 + pp * NM2 + s1 * NM + qq] = UM[qq][pp];
+                for (int pp = 0; pp < NM; ++pp) sX[e * ES + pp * PS + qq * NM + s1] = fma(lamJ, A2[qq][pp], R[qq][pp]);
         }
-        __syncthreads(); // also: every stage-I read of sIn is complete
+        __syncwarp();
         if (active)
         {
-            const double *v = sX + e * NM3 + s1 * NM2;
+            const double *v = sX + e * ES + s1 * PS;
 #pragma unroll
             for (int qq = 0; qq < NM; ++qq)
             {
                 double col[NM];
 #pragma unroll
-                for (int r = 0; r < NM; ++r) col[r] = v[r * NM + qq];
+                for (int r = 0; r < NM; ++r) col[r] = v[qq * NM + r];
 #pragma unroll
                 for (int rr = 0; rr < NM; ++rr)
                 {
-                    double sacc = tab.M[rr * NM] * col[0];
+                    double sacc = KM(rr, 0) * col[0];
 #pragma unroll
-                    for (int r = 1; r < NM; ++r) sacc = fma(tab.M[rr * NM + r], col[r], sacc);
+                    for (int r = 1; r < NM; ++r) sacc = fma(KM(rr, r), col[r], sacc);
                     acc[rr][qq] = sacc;
                 }
             }
         }
-        __syncthreads();
-        // ---- exchange 2: U_K
+        __syncwarp();
+        // ---- exchange 2: U_K = jg22 A2
         if (active)
         {
 #pragma unroll
             for (int qq = 0; qq < NM; ++qq)
 #pragma unroll
-                for (int pp = 0; pp < NM; ++pp) sX[e * NM3 + pp * NM2 + s1 * NM + qq] = UK[qq][pp];
+                for (int pp = 0; pp < NM; ++pp) sX[e * ES + pp * PS + qq * NM + s1] = jg22 * A2[qq][pp];
         }
-        __syncthreads();
+        __syncwarp();
         if (active)
         {
-            const double *v = sX + e * NM3 + s1 * NM2;
+            const double *v = sX + e * ES + s1 * PS;
+            double col[NM][NM];
 #pragma unroll
             for (int qq = 0; qq < NM; ++qq)
-            {
-                double col[NM];
 #pragma unroll
-                for (int r = 0; r < NM; ++r) col[r] = v[r * NM + qq];
+                for (int r = 0; r < NM; ++r) col[qq][r] = v[qq * NM + r];
+#pragma unroll
+            for (int qq = 0; qq < NM; ++qq)
 #pragma unroll
                 for (int rr = 0; rr < NM; ++rr)
-                {
-                    double sacc = acc[rr][qq];
 #pragma unroll
-                    for (int r = 0; r < NM; ++r) sacc = fma(tab.K[rr * NM + r], col[r], sacc);
-                    acc[rr][qq] = sacc;
-                }
-            }
-            // ---- output staging in the (consumed) input buffer: out[e][r'][q'][p']
+                    for (int r = 0; r < NM; ++r)
+                        if (KNZ(rr, r)) acc[rr][qq] = fma(KK(rr, r), col[qq][r], acc[rr][qq]);
+        }
+        __syncwarp(); // every lane has read its exchange block: sX becomes the output staging buffer
+        if (active)
+        {
 #pragma unroll
             for (int rr = 0; rr < NM; ++rr)
 #pragma unroll
-                for (int qq = 0; qq < NM; ++qq) sIn[e * NM3 + rr * NM2 + qq * NM + s1] = acc[rr][qq];
+                for (int qq = 0; qq < NM; ++qq) sX[e * NM3 + rr * NM2 + qq * NM + s1] = acc[rr][qq];
         }
-        if (tma_ok(b))
+        if (tma_in)
         {
             fence_proxy_async();
-            __syncthreads();
-            if (tid == 0)
+            __syncwarp();
+            if (lane == 0)
             {
-                tma_store_1d(args.out + (size_t)b * BUF, sIn, (uint32_t)(ne * NM3 * 8));
+                tma_store_1d(args.out + (size_t)wb * EPW * NM3, sX, (uint32_t)(ne * NM3 * 8));
                 tma_store_commit();
             }
         }
         else
         {
-            __syncthreads();
-            double *dst = args.out + (size_t)b * BUF;
-            for (int i = tid; i < ne * NM3; i += T) dst[i] = sIn[i];
-            __syncthreads();
+            __syncwarp();
+            double *dst = args.out + (size_t)wb * EPW * NM3;
+            for (int i = lane; i < ne * NM3; i += 32) dst[i] = sX[i];
         }
-        // sX is rewritten only after the next iteration's first barrier-protected phase: the
-        // exchange-2 reads above are separated from it by the __syncthreads() just executed
+        __syncwarp();
     }
-    if (tid == 0) tma_store_wait0();
+    if (lane == 0) tma_store_wait0();
+#undef KM
+#undef KK
+#undef KNZ
 }
 
 // G off-diagonal == 0 for every element?  (computed exactly as the quadrature-space kernel would)
@@ -276,6 +308,7 @@ __global__ void kron_prepare_kernel(const double *__restrict__ jac, const double
 struct KronState
 {
     void *tab      = nullptr;
+    bool sparse_k  = false;
     double *d_geo4 = nullptr;
     int blocks_per_sm = 0;
     // the quadrature-space launcher this operator falls back to for non-diagonal metrics
@@ -298,7 +331,7 @@ template <int NM> static int kron_launch(nekmf_op_s *op, const double *const in[
         return rc;
     }
     using Cfg = KronCfg<NM>;
-    auto kern = hex_helm_kron_kernel<NM>;
+    auto kern = st->sparse_k ? hex_helm_kron_kernel<NM, true> : hex_helm_kron_kernel<NM, false>;
     if (st->blocks_per_sm == 0)
     {
         NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -311,7 +344,7 @@ template <int NM> static int kron_launch(nekmf_op_s *op, const double *const in[
     KronArgs a;
     a.in = in[0]; a.out = out[0]; a.geo4 = st->d_geo4; a.nElmt = op->nElmt; a.lambda = op->lambda;
     a.io_aligned = ((((uintptr_t)in[0]) | ((uintptr_t)out[0])) & 15) == 0;
-    const int nBatches = (op->nElmt + Cfg::EPB - 1) / Cfg::EPB;
+    const int nBatches = (op->nElmt + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
     int grid           = st->blocks_per_sm * NUM_SMS;
     if (grid > nBatches) grid = nBatches;
     if (grid < 1) return NEKMF_OK;
@@ -327,8 +360,9 @@ template <int NM> static void kron_wrap(nekmf_op_s *op)
     const int nq = op->nq[0];
     auto *tab    = new KronTab<NM>;
     const double *B = op->b[0].data(), *dB = op->db[0].data(), *w = op->ws[0].data();
+    double kmax = 0.0, koff = 0.0;
     for (int a = 0; a < NM; ++a)
-        for (int c = 0; c < NM; ++c)
+        for (int c = a; c < NM; ++c)
         {
             double m = 0.0, k = 0.0;
             for (int i = 0; i < nq; ++i)
@@ -336,11 +370,18 @@ template <int NM> static void kron_wrap(nekmf_op_s *op)
                 m += B[a * nq + i] * w[i] * B[c * nq + i];
                 k += dB[a * nq + i] * w[i] * dB[c * nq + i];
             }
-            tab->M[a * NM + c] = m;
-            tab->K[a * NM + c] = k;
+            tab->Ms[tri(a, c, NM)] = m;
+            tab->Ks[tri(a, c, NM)] = k;
+            const bool pattern = a == c || (a < 2 && c < 2);
+            if (pattern) kmax = std::fmax(kmax, std::fabs(k));
+            else koff = std::fmax(koff, std::fabs(k));
         }
+    // entries outside the (vertex block + diagonal) pattern are quadrature round-off for the modified
+    // basis; drop them only when they are at round-off level relative to the matrix
+    const bool sparse_k = koff <= 1e-14 * kmax;
     KronState *st      = new KronState;
     st->tab            = tab;
+    st->sparse_k       = sparse_k;
     st->fallback       = op->launch;
     st->fallback_state = op->kstate;
     st->fallback_free  = op->kstate_free;
@@ -393,7 +434,8 @@ int kron_geom_changed(nekmf_op_s *op)
     {
         st->use_kron = true;
         char name[96];
-        snprintf(name, sizeof(name), "hex_helm_kron_kernel<nm=%d>(regular,diagonal metric)", op->nm[0]);
+        snprintf(name, sizeof(name), "hex_helm_kron_kernel<nm=%d,%s>(regular,diagonal metric)", op->nm[0],
+                 st->sparse_k ? "sparseK" : "denseK");
         op->kname = name;
     }
     return NEKMF_OK;
