@@ -64,6 +64,7 @@ class ClockSampler:
         self.reasons = set()
         self.max_mhz = None
         self._stop = threading.Event()
+        self._ready = threading.Event()
         self._thr = None
 
     def _run(self):
@@ -80,17 +81,21 @@ class ClockSampler:
                 getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
             while not self._stop.is_set():
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self._ready.set()
                 r = int(get_reasons(h))
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
-                time.sleep(0.002)
+                time.sleep(0.0005)
         except Exception as ex:  # pragma: no cover
             self.error = repr(ex)
+            self._ready.set()
 
     def start(self):
         self._thr = threading.Thread(target=self._run, daemon=True)
         self._thr.start()
+        self._ready.wait(timeout=10)
+        self.samples.clear()  # keep only samples taken under load
 
     def stop(self):
         self._stop.set()
@@ -268,12 +273,13 @@ def main():
         del jac, df
         torch.cuda.empty_cache()
         op.SetLambda(LAMBDA)
-        for _ in range(W):
-            op.apply([x], [y])
         sampler = ClockSampler(local_rank)
         if variant == "regular":
             sampler.start()
+        for _ in range(W):
+            op.apply([x], [y])
         barrier()
+        sampler.samples.clear()
         l0 = nk.launch_count()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
         ev[0].record()

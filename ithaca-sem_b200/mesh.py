@@ -1,0 +1,139 @@
+"""Synthetic structured hexahedral meshes: the assembly-map data the CG path consumes.
+
+The reference builds `m_localToGlobalMap`, `m_localToGlobalSign`, the Dirichlet-first global numbering
+and the universal (cross-rank) numbering in AssemblyMapCG's constructor (MultiRegions/AssemblyMap/
+AssemblyMapCG.cpp, ~2.9k lines, out of scope: SURVEY.md section 2).  For the structured meshes of the
+benchmark configurations the same arrays are generated here directly:
+
+  * C0 connectivity of the modal hex expansion (StdRegions/StdHexExp.cpp:960-1240): in every direction
+    mode 0 is the vertex at xi=-1, mode 1 the vertex at xi=+1, modes >= 2 are interior; all elements
+    share the global axis orientation, so no sign changes are needed (m_signChange == false);
+  * global numbering with the Dirichlet DOFs (the surface of the box) first, as AssemblyMapCG orders
+    them (CG then runs on [nDir, nGlobal), NekLinSysIterCG.cpp:112-126);
+  * an element partition into z-slabs, one per rank, with the interface-plane DOF lists (identically
+    ordered on both sides) and the 0/1 ownership mask that Gs::Unique would produce
+    (AssemblyMapCG.cpp:2551-2569).
+
+Pure numpy: this is host-side setup, not the data path.
+"""
+import numpy as np
+
+
+def _gi(e, p, nm):
+    """1-D lattice index of local mode p of element e (vertex modes 0,1; interior 2..nm-1)."""
+    base = e * (nm - 1)
+    return base + np.where(p == 0, 0, np.where(p == 1, nm - 1, p - 1))
+
+
+class StructuredHexMesh:
+    """nx x ny x nz hexahedra on [0,Lx]x[0,Ly]x[0,Lz], nm modes per direction.  `slab=(rank, nranks)`
+    restricts the mesh to this rank's z-slab of elements; numbering is then rank-local."""
+
+    def __init__(self, nx, ny, nz, nm, lengths=(1.0, 1.0, 1.0), slab=(0, 1)):
+        self.nx, self.ny, self.nz, self.nm = nx, ny, nz, nm
+        self.L = tuple(float(v) for v in lengths)
+        self.rank, self.nranks = slab
+        if not 0 <= self.rank < self.nranks or self.nranks > nz:
+            raise ValueError("bad slab partition")
+        # contiguous z ranges, remainder spread over the first ranks
+        base, rem = divmod(nz, self.nranks)
+        counts = [base + (1 if r < rem else 0) for r in range(self.nranks)]
+        self.ez0 = sum(counts[:self.rank])
+        self.ez1 = self.ez0 + counts[self.rank]
+        self.nzl = self.ez1 - self.ez0
+        self.nElmt = nx * ny * self.nzl
+        self.h = (self.L[0] / nx, self.L[1] / ny, self.L[2] / nz)
+        m1 = nm - 1
+        self.Gx, self.Gy, self.Gz = nx * m1 + 1, ny * m1 + 1, nz * m1 + 1
+        self.gz0, self.gz1 = self.ez0 * m1, self.ez1 * m1  # inclusive global lattice planes of this slab
+        self.Gzl = self.gz1 - self.gz0 + 1
+        self._number()
+
+    # ------------------------------------------------------------------ numbering
+    def _number(self):
+        Gx, Gy, Gzl = self.Gx, self.Gy, self.Gzl
+        gz = np.arange(self.gz0, self.gz1 + 1)
+        on_bnd = np.zeros((Gzl, Gy, Gx), dtype=bool)
+        on_bnd[:, :, 0] = on_bnd[:, :, -1] = True
+        on_bnd[:, 0, :] = on_bnd[:, -1, :] = True
+        on_bnd[gz == 0] = True
+        on_bnd[gz == self.Gz - 1] = True
+        flat = on_bnd.reshape(-1)
+        self.nGlobal = flat.size
+        self.nDir = int(flat.sum())
+        ids = np.empty(flat.size, dtype=np.int64)
+        ids[flat] = np.arange(self.nDir)
+        ids[~flat] = self.nDir + np.arange(flat.size - self.nDir)
+        self.lattice_ids = ids.reshape(Gzl, Gy, Gx)  # rank-local global id of every lattice point
+        self.dirichlet = on_bnd
+        nm = self.nm
+        p = np.arange(nm)
+        ex, ey, ez = np.arange(self.nx), np.arange(self.ny), np.arange(self.nzl)
+        gx = _gi(ex[:, None], p[None, :], nm)                       # [nx, nm]
+        gy = _gi(ey[:, None], p[None, :], nm)
+        gzl = _gi(ez[:, None], p[None, :], nm)                      # slab-local lattice plane
+        # local index: e = ex + nx*(ey + ny*ez), mode = p + nm*(q + nm*r)
+        l2g = self.lattice_ids[gzl[:, None, None, :, None, None], gy[None, :, None, None, :, None],
+                               gx[None, None, :, None, None, :]]   # [ez, ey, ex, r, q, p]
+        self.localToGlobal = np.ascontiguousarray(l2g.reshape(-1), dtype=np.int32)
+        self.nLocal = self.localToGlobal.size
+        # ---- partition interfaces (z-slabs: at most two neighbours)
+        self.peers, self.interface_lists = [], []
+        mask = np.ones((Gzl, Gy, Gx))
+        if self.rank > 0:
+            plane = self.lattice_ids[0]
+            self.peers.append(self.rank - 1)
+            self.interface_lists.append(plane[~on_bnd[0]].astype(np.int32))
+            mask[0] = 0.0  # the lower rank owns the shared plane
+        if self.rank < self.nranks - 1:
+            plane = self.lattice_ids[-1]
+            self.peers.append(self.rank + 1)
+            self.interface_lists.append(plane[~on_bnd[-1]].astype(np.int32))
+        om = np.empty(self.nGlobal)
+        om[self.lattice_ids.reshape(-1)] = mask.reshape(-1)
+        self.ownerMask = om
+
+    # ------------------------------------------------------------------ geometry (regular boxes)
+    def geometry(self):
+        """jac[nElmt], df[9*nElmt] of the axis-aligned boxes (GeomFactors.cpp:399-474)."""
+        hx, hy, hz = self.h
+        jac = np.full(self.nElmt, hx * hy * hz / 8.0)
+        df = np.zeros((9, self.nElmt))
+        df[0], df[4], df[8] = 2.0 / hx, 2.0 / hy, 2.0 / hz
+        return jac, df.reshape(-1).copy()
+
+    def quad_coords(self, z):
+        """physical coordinates of every quadrature point, arrays [nElmt*nq^3] in the reference's
+        [elmt][k][j][i] order; z = 1-D quadrature nodes on [-1,1]."""
+        nq = len(z)
+        hx, hy, hz = self.h
+        X1 = (np.arange(self.nx)[:, None] + 0.5 * (z[None, :] + 1.0)) * hx
+        Y1 = (np.arange(self.ny)[:, None] + 0.5 * (z[None, :] + 1.0)) * hy
+        Z1 = (self.ez0 + np.arange(self.nzl)[:, None] + 0.5 * (z[None, :] + 1.0)) * hz
+        shape = (self.nzl, self.ny, self.nx, nq, nq, nq)
+        X = np.broadcast_to(X1[None, None, :, None, None, :], shape).reshape(-1)
+        Y = np.broadcast_to(Y1[None, :, None, None, :, None], shape).reshape(-1)
+        Z = np.broadcast_to(Z1[:, None, None, :, None, None], shape).reshape(-1)
+        return np.ascontiguousarray(X), np.ascontiguousarray(Y), np.ascontiguousarray(Z)
+
+    # ------------------------------------------------------------------ matrix-free Jacobi
+    def helmholtz_diagonal(self, basis, lam):
+        """Diagonal of the assembled Helmholtz matrix without forming elemental matrices (replaces
+        PreconditionerDiagonal::DiagonalPreconditionerSum, PreconditionerDiagonal.cpp:98-162): for an
+        axis-aligned box diag_e[pqr] = J (lam m_r m_q m_p + G00 m_r m_q k_p + G11 m_r k_q m_p +
+        G22 k_r m_q m_p) with m = diag(B W B^T), k = diag(DB W DB^T).  Returns this rank's LOCAL sum;
+        interface DOFs still need the cross-rank exchange."""
+        nm, nq = self.nm, basis.nq
+        B = basis.bdata.reshape(nm, nq)
+        dB = basis.dbdata.reshape(nm, nq)
+        m = (B * B) @ basis.W
+        k = (dB * dB) @ basis.W
+        hx, hy, hz = self.h
+        J = hx * hy * hz / 8.0
+        g0, g1, g2 = (2.0 / hx) ** 2, (2.0 / hy) ** 2, (2.0 / hz) ** 2
+        mr, mq, mp = m[:, None, None], m[None, :, None], m[None, None, :]
+        kr, kq, kp = k[:, None, None], k[None, :, None], k[None, None, :]
+        d = J * (lam * mr * mq * mp + g0 * mr * mq * kp + g1 * mr * kq * mp + g2 * kr * mq * mp)
+        diag = np.zeros(self.nGlobal)
+        np.add.at(diag, self.localToGlobal, np.tile(d.reshape(-1), self.nElmt))
+        return diag

@@ -1,0 +1,182 @@
+"""CPU suite, part 2: the library loads and exports its ABI, the host-side tables agree with the
+oracle, the library refuses to compute without a GPU, and the mesh / partition / sharded-CG host logic
+is right (world_size 2 over gloo)."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+import pyoracle as po
+from _util import ROOT, load_pkg_module, nekmf, rel_errs
+
+
+def test_library_exports_every_declared_symbol():
+    nk = nekmf()
+    hdr = open(os.path.join(ROOT, "include", "nekmf_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(nekmf_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 40
+    L = nk.lib()
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(nk.EXPORTS) == declared
+    assert L.nekmf_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    nk = nekmf()
+    if nk.device_count() > 0:
+        pytest.skip("a GPU is present")
+    std = nk.StdExpansion(nk.eHexahedron, 5, 6)
+    coll = nk.Collection(std, 4, nk.CoalescedGeomData(np.ones(4), np.ones(36), False))
+    with pytest.raises(nk.NekError, match="no CUDA device"):
+        coll.Initialise(nk.eHelmholtz)
+    with pytest.raises(nk.NekError, match="no CUDA device"):
+        nk.AssemblyMap(np.zeros(4, dtype=np.int32), 1)
+
+
+def test_argument_validation_needs_no_gpu():
+    nk = nekmf()
+    with pytest.raises(nk.NekError, match="out of range"):
+        nk.AssemblyMap(np.array([0, 5], dtype=np.int32), 2)
+    std = nk.StdExpansion(nk.eHexahedron, 5, 6)
+    assert std.GetNcoeffs() == 125 and std.GetTotPoints() == 216
+    assert nk.StdExpansion(nk.eTetrahedron, 7).GetNcoeffs() == 84
+    assert nk.StdExpansion(nk.ePrism, 7).GetNcoeffs() == 196
+    assert nk.StdExpansion(nk.eTetrahedron, 7).nq == [8, 7, 7]
+    assert nk.StdExpansion(nk.ePrism, 7).nq == [8, 8, 7]
+    with pytest.raises(nk.NekError):
+        nk.StdExpansion(nk.ePyramid, 4)
+    assert nk.ImplementationTypeMap[nk.eB200] == "B200" and nk.SIZE_ImplementationType == nk.eB200 + 1
+
+
+@pytest.mark.parametrize("ptype", [0, 1, 2])
+def test_product_points_match_oracle(ptype):
+    nk = nekmf()
+    for n in range(2, 16):
+        z, w, D = nk.points(ptype, n)
+        zo, wo, Do = po.points(ptype, n)
+        assert np.abs(z - zo).max() < 1e-14
+        assert np.abs(w - wo).max() < 1e-14 * np.abs(wo).max() * 10
+        assert np.abs(D - Do).max() < 1e-13 * np.abs(Do).max()
+
+
+@pytest.mark.parametrize("shape", [po.QUAD, po.TRI, po.HEX, po.PRISM, po.TET])
+def test_product_basis_tables_match_oracle(shape):
+    nk = nekmf()
+    for nm in range(2, 12):
+        e, s = po.Elem(shape, nm, nm + 1), nk.StdExpansion(shape, nm)
+        assert s.GetNcoeffs() == e.nmTot and s.GetTotPoints() == e.nqTot
+        for d in range(e.dim):
+            assert s.basis[d].rows == e.brows[d]
+            assert max(rel_errs(s.basis[d].bdata, e.bdata[d])) < 1e-13
+            assert max(rel_errs(s.basis[d].dbdata, e.dbdata[d])) < 1e-12
+
+
+def test_structured_mesh_numbering():
+    mesh_mod = load_pkg_module("mesh")
+    nm = 4
+    m = mesh_mod.StructuredHexMesh(3, 2, 4, nm)
+    G = (3 * 3 + 1) * (2 * 3 + 1) * (4 * 3 + 1)
+    assert m.nGlobal == G and m.nLocal == 24 * nm ** 3
+    interior = (3 * 3 - 1) * (2 * 3 - 1) * (4 * 3 - 1)
+    assert m.nDir == G - interior
+    l2g = m.localToGlobal
+    assert l2g.min() == 0 and l2g.max() == G - 1 and np.unique(l2g).size == G
+    # element-interior modes (p,q,r >= 2) are never shared; vertex modes are shared by up to 8 elements
+    counts = np.bincount(l2g, minlength=G)
+    assert counts.max() == 8 and (counts == 1).sum() >= 24 * (nm - 2) ** 3
+    # slabs: the two copies of the interface plane list the same DOFs in the same order
+    a = mesh_mod.StructuredHexMesh(3, 2, 4, nm, slab=(0, 2))
+    b = mesh_mod.StructuredHexMesh(3, 2, 4, nm, slab=(1, 2))
+    assert a.peers == [1] and b.peers == [0]
+    assert a.interface_lists[0].size == b.interface_lists[0].size == (3 * 3 - 1) * (2 * 3 - 1)
+    assert a.nElmt + b.nElmt == m.nElmt
+    # ownership: every DOF of the global problem is owned exactly once
+    assert int(a.ownerMask.sum() + b.ownerMask.sum()) == G
+
+
+def test_serial_cg_solves_helmholtz():
+    """oracle CG (NekLinSysIterCG restatement) on a 3x3x3 hex mesh, P=4: converges and the solution has
+    the expected spectral accuracy; the sharded reference with one rank is the same algorithm."""
+    import _sharded_ref as sr
+    mesh_mod = load_pkg_module("mesh")
+    nk = nekmf()
+    nm, lam = 5, 1.0
+    mesh = mesh_mod.StructuredHexMesh(3, 3, 3, nm)
+    el = po.Elem(po.HEX, nm, nm + 1)
+    jac, df = mesh.geometry()
+    rhs, u_exact = sr.helmholtz_rhs(None, mesh, el, jac, lam)
+    diag = mesh.helmholtz_diagonal(nk.StdExpansion(nk.eHexahedron, nm).basis[0], lam)
+    invdiag = 1.0 / diag[mesh.nDir:]
+    # different summation orders in the dot products: compare fully converged solutions
+    x, its, eps = el.cg(mesh.nElmt, False, jac, df, lam, mesh.nGlobal, mesh.nDir, mesh.localToGlobal, None,
+                        invdiag, rhs, tol=1e-13)
+    x2, its2, eps2 = sr.sharded_cg(None, mesh, el, jac, df, lam, rhs, invdiag, tol=1e-13)
+    assert abs(its - its2) <= 1 and np.abs(x - x2).max() < 1e-11 * np.abs(x).max()
+    uq = el.bwdtrans(mesh.nElmt, po.global_to_local(mesh.localToGlobal, None, x))
+    assert np.abs(uq - u_exact).max() < 2e-4
+    # the matrix-free diagonal equals the diagonal of the assembled operator
+    e0 = np.zeros(mesh.nGlobal)
+    probe = [mesh.nDir, mesh.nDir + 7, mesh.nGlobal - 1]
+    for g in probe:
+        e0[:] = 0
+        e0[g] = 1
+        col = po.assemble(mesh.localToGlobal, None,
+                          el.helmholtz(mesh.nElmt, False, jac, df, lam, po.global_to_local(mesh.localToGlobal, None, e0)),
+                          mesh.nGlobal)
+        assert abs(col[g] - diag[g]) < 1e-12 * abs(diag[g])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, nm, lam, out):
+    import torch.distributed as dist
+    import _sharded_ref as sr
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mesh_mod = load_pkg_module("mesh")
+    nk = nekmf()
+    mesh = mesh_mod.StructuredHexMesh(3, 2, 4, nm, slab=(rank, world))
+    el = po.Elem(po.HEX, nm, nm + 1)
+    jac, df = mesh.geometry()
+    rhs, _ = sr.helmholtz_rhs(dist, mesh, el, jac, lam)
+    diag = mesh.helmholtz_diagonal(nk.StdExpansion(nk.eHexahedron, nm).basis[0], lam)
+    sr.exchange_add(dist, diag, mesh.peers, mesh.interface_lists)
+    x, its, eps = sr.sharded_cg(dist, mesh, el, jac, df, lam, rhs, 1.0 / diag[mesh.nDir:], tol=1e-13)
+    # return the solution on the global lattice for comparison
+    np.save(os.path.join(out, "x_%d.npy" % rank), x[mesh.lattice_ids])
+    np.save(os.path.join(out, "meta_%d.npy" % rank), np.array([its, eps, mesh.gz0, mesh.gz1]))
+    dist.destroy_process_group()
+
+
+def test_sharded_cg_world_size_2_gloo(tmp_path):
+    """two ranks (z-slabs), gloo: interface exchange + masked dots + all-reduce reproduce the serial
+    solve (same iteration count, same solution)."""
+    import torch.multiprocessing as mp
+    import _sharded_ref as sr
+    nm, lam = 4, 1.0
+    mp.spawn(_gloo_worker, args=(2, _free_port(), nm, lam, str(tmp_path)), nprocs=2, join=True)
+    mesh_mod = load_pkg_module("mesh")
+    nk = nekmf()
+    mesh = mesh_mod.StructuredHexMesh(3, 2, 4, nm)
+    el = po.Elem(po.HEX, nm, nm + 1)
+    jac, df = mesh.geometry()
+    rhs, _ = sr.helmholtz_rhs(None, mesh, el, jac, lam)
+    diag = mesh.helmholtz_diagonal(nk.StdExpansion(nk.eHexahedron, nm).basis[0], lam)
+    x, its, eps = sr.sharded_cg(None, mesh, el, jac, df, lam, rhs, 1.0 / diag[mesh.nDir:], tol=1e-13)
+    xs = x[mesh.lattice_ids]
+    for r in range(2):
+        xr = np.load(os.path.join(str(tmp_path), "x_%d.npy" % r))
+        meta = np.load(os.path.join(str(tmp_path), "meta_%d.npy" % r))
+        assert abs(int(meta[0]) - its) <= 1
+        g0, g1 = int(meta[2]), int(meta[3])
+        assert np.abs(xr - xs[g0:g1 + 1]).max() < 1e-10 * np.abs(xs).max()

@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Matrix-free CG Helmholtz solve on a structured hex mesh at P=4, element-partitioned in z-slabs
+over the ranks of one box (BASELINE.json configs[4]).
+
+    python tools/bench_cg.py [--nx 64 --ny 128 --nz 128] [--iters 50] [--check]
+    torchrun --nproc-per-node N tools/bench_cg.py ...
+
+Every rank builds its slab (ithaca-sem_b200/mesh.py), creates the device operator / assembly map /
+NCCL exchange through the C ABI and runs nekmf_cg_solve with a fixed iteration cap.  --check solves to
+convergence and compares against the serial CPU oracle (small meshes only)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from _util import load_pkg_module, nekmf  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nx", type=int, default=64)
+    ap.add_argument("--ny", type=int, default=128)
+    ap.add_argument("--nz", type=int, default=128)
+    ap.add_argument("--nm", type=int, default=5)
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    nk = nekmf()
+    mesh_mod = load_pkg_module("mesh")
+    dist = None
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        comm = nk.Comm.from_torch_distributed()
+    lam = 1.0
+    mesh = mesh_mod.StructuredHexMesh(a.nx, a.ny, a.nz, a.nm, slab=(rank, world))
+    std = nk.StdExpansion(nk.eHexahedron, a.nm)
+    jac, df = mesh.geometry()
+    geom = nk.CoalescedGeomData(jac, df, False)
+    helm = nk.Operator(std, mesh.nElmt, geom, nk.eHelmholtz)
+    helm.SetLambda(lam)
+    ipr = nk.Operator(std, mesh.nElmt, geom, nk.eIProductWRTBase)
+    amap = nk.AssemblyMap(mesh.localToGlobal, mesh.nGlobal)
+    ex = nk.Exchange(comm, mesh.peers, mesh.interface_lists) if world > 1 else None
+    # right-hand side  -(v, f),  f = -(lam + 3 pi^2) sin sin sin  (device IProduct + Assemble + exchange)
+    z = std.basis[0].Z
+    X, Y, Z = mesh.quad_coords(z)
+    u_exact = np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z)
+    f = torch.tensor((lam + 3 * np.pi ** 2) * u_exact, device=dev)
+    del X, Y, Z
+    loc = torch.empty(mesh.nLocal, dtype=torch.float64, device=dev)
+    ipr.apply([f], [loc])
+    rhs = torch.empty(mesh.nGlobal, dtype=torch.float64, device=dev)
+    amap.Assemble(loc, rhs)
+    diag = torch.tensor(mesh.helmholtz_diagonal(std.basis[0], lam), device=dev)
+    if ex is not None:
+        ex.add(rhs)
+        ex.add(diag)
+    rhs[:mesh.nDir] = 0.0
+    torch.cuda.synchronize()
+    invdiag = (1.0 / diag[mesh.nDir:]).cpu().numpy()
+    cg = nk.HelmholtzCG(helm, amap, mesh.nDir, invdiag, exchange=ex, comm=comm, ownerMask=mesh.ownerMask)
+    x = torch.zeros(mesh.nGlobal, dtype=torch.float64, device=dev)
+    del f, loc
+    if a.check:
+        its, eps = cg.solve(rhs, x, tol=1e-13, maxiter=5000)
+        import pyoracle as po
+        import _sharded_ref as sr
+        full = mesh_mod.StructuredHexMesh(a.nx, a.ny, a.nz, a.nm)
+        el = po.Elem(po.HEX, a.nm, a.nm + 1)
+        jf, dff = full.geometry()
+        rhs_o, _ = sr.helmholtz_rhs(None, full, el, jf, lam)
+        dg = full.helmholtz_diagonal(std.basis[0], lam)
+        xo, itso, _ = el.cg(full.nElmt, False, jf, dff, lam, full.nGlobal, full.nDir, full.localToGlobal, None,
+                            1.0 / dg[full.nDir:], rhs_o, tol=1e-13)
+        mine = x.cpu().numpy()[mesh.lattice_ids]
+        want = xo[full.lattice_ids][mesh.gz0:mesh.gz1 + 1]
+        err = np.abs(mine - want).max() / np.abs(xo).max()
+        ok = err < 1e-10 and abs(its - itso) <= 2
+        t = torch.tensor([0.0 if ok else 1.0], device=dev)
+        if dist is not None:
+            dist.all_reduce(t)
+        if rank == 0:
+            print("rank0 its=%d (oracle %d) err=%.2e" % (its, itso, err))
+            print("CHECK OK" if float(t.item()) == 0.0 else "CHECK FAILED")
+        if dist is not None:
+            dist.destroy_process_group()
+        sys.exit(0 if float(t.item()) == 0.0 else 1)
+    # ---- timing: fixed iteration cap (tolerance 0 never triggers), max over ranks
+    cg.solve(rhs, x, tol=0.0, maxiter=3)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = nk.launch_count()
+    t0 = time.perf_counter()
+    its, eps = cg.solve(rhs, x, tol=0.0, maxiter=a.iters)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    nel_total = a.nx * a.ny * a.nz
+    gdof = (a.nx * (a.nm - 1) + 1) * (a.ny * (a.nm - 1) + 1) * (a.nz * (a.nm - 1) + 1)
+    if rank == 0:
+        print(json.dumps({"metric": "matrix-free CG Helmholtz, hex P=%d" % (a.nm - 1), "n_gpus": world,
+                          "elements": nel_total, "global_dof": gdof, "iterations": its,
+                          "ms_per_iteration": dt / its * 1e3,
+                          "gdof_per_s_local": nel_total * a.nm ** 3 * its / dt / 1e9,
+                          "launches": nk.launch_count() - l0, "final_eps": eps}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
