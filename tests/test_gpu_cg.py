@@ -79,7 +79,7 @@ def test_cg_matches_oracle(precon):
                            invdiag, rhs, tol=1e-9)
     # unpreconditioned CG on the (ill-conditioned) modal basis is rounding-sensitive: the iteration count
     # may drift with the summation order of the dot products; with Jacobi it is stable
-    assert abs(its - itso) <= (2 if precon else max(5, itso // 4)), (its, itso)
+    assert abs(its - itso) <= (max(3, itso // 10) if precon else max(5, itso // 4)), (its, itso)
     assert np.abs(x - xo).max() < 1e-6 * np.abs(xo).max()
     # fully converged: identical discrete solution
     x2 = np.zeros(mesh.nGlobal)
