@@ -1,0 +1,480 @@
+// NekB200Collections.hpp -- C++ host side above the C ABI: a self-contained mirror of the part of
+// library/Collections that selects and drives the matrix-free operators, with the new
+// ImplementationType eB200 registered in the operator factory.
+//
+// The reference's own headers cannot be compiled here (they include Boost), so the few types the
+// Collections interface exchanges are re-declared with the same names, argument meaning and error
+// behaviour:
+//
+//   Array<OneD, T>                 LibUtilities/BasicUtils/SharedArray.hpp  (ref-counted pointer + offset)
+//   LibUtilities::Basis            LibUtilities/Foundations/Basis.h         (GetBdata/GetDbdata/GetD/GetZ/GetW ...)
+//   StdRegions::StdExpansion       StdRegions/StdExpansion.h                (GetBasis, DetShapeType, GetNcoeffs ...)
+//                                  + the per-element geometric factors a LocalRegions::Expansion would own
+//   Collections::OperatorType / ImplementationType / OperatorKey / Operator / OperatorFactory /
+//   GetOperatorFactory / CoalescedGeomData / Collection / CollectionOptimisation / SetFixedImpType
+//                                  Collections/Operator.h:65-191, Collection.h:53-110,
+//                                  CoalescedGeomData.cpp:53-424, CollectionOptimisation.cpp:52-281
+//
+// Only eB200 operators are registered; asking the factory for any other key throws NekError exactly
+// as the reference's NekFactory does for an unregistered key (NekFactory.hpp:145-209).
+#pragma once
+#include "../../include/nekmf_b200.h"
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+namespace Nektar
+{
+typedef double NekDouble;
+
+namespace ErrorUtil
+{
+struct NekError : public std::runtime_error
+{
+    explicit NekError(const std::string &m) : std::runtime_error(m) {}
+};
+} // namespace ErrorUtil
+#define NEKB200_ERROR(msg)                                                              \
+    do                                                                                  \
+    {                                                                                   \
+        std::ostringstream _s;                                                          \
+        _s << "Fatal   : " << msg;                                                      \
+        throw ::Nektar::ErrorUtil::NekError(_s.str());                                  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ Array<OneD>
+struct OneD {};
+template <typename Dim, typename T> class Array;
+template <typename T> class Array<OneD, T>
+{
+public:
+    typedef typename std::remove_const<T>::type V;
+    Array() : m_size(0), m_off(0) {}
+    explicit Array(size_t n, V init = V()) : m_data(new V[n ? n : 1], std::default_delete<V[]>()), m_size(n), m_off(0)
+    {
+        for (size_t i = 0; i < n; ++i) m_data.get()[i] = init;
+    }
+    Array(size_t n, const V *src) : Array(n)
+    {
+        for (size_t i = 0; i < n; ++i) m_data.get()[i] = src[i];
+    }
+    // const view of a non-const array
+    template <typename U> Array(const Array<OneD, U> &o) : m_data(o.m_data), m_size(o.m_size), m_off(o.m_off) {}
+    size_t num_elements() const { return m_size - m_off; }
+    T *get() const { return m_data ? m_data.get() + m_off : nullptr; }
+    T &operator[](size_t i) const { return get()[i]; }
+    Array operator+(size_t off) const
+    {
+        Array r(*this);
+        r.m_off += off;
+        return r;
+    }
+    std::shared_ptr<V> m_data;
+    size_t m_size, m_off;
+};
+static const Array<OneD, NekDouble> NullNekDouble1DArray;
+
+// ------------------------------------------------------------------------------------------ LibUtilities
+namespace LibUtilities
+{
+enum ShapeType { eQuadrilateral = NEKMF_QUAD, eTriangle = NEKMF_TRI, eHexahedron = NEKMF_HEX, ePrism = NEKMF_PRISM,
+                 ePyramid = NEKMF_PYR, eTetrahedron = NEKMF_TET };
+enum BasisType { eModified_A = NEKMF_MODIFIED_A, eModified_B = NEKMF_MODIFIED_B, eModified_C = NEKMF_MODIFIED_C };
+enum PointsType { eGaussLobattoLegendre = NEKMF_GLL, eGaussRadauMAlpha1Beta0 = NEKMF_GRJM_A1B0,
+                  eGaussRadauMAlpha2Beta0 = NEKMF_GRJM_A2B0 };
+static const char *const ShapeTypeMap[] = {"Quadrilateral", "Triangle", "Hexahedron", "Prism", "Pyramid", "Tetrahedron"};
+
+class Basis
+{
+public:
+    Basis(BasisType bt, int nm, PointsType pt, int nq) : m_bt(bt), m_pt(pt), m_nm(nm), m_nq(nq), m_z(nq), m_w(nq), m_D(nq * nq)
+    {
+        if (nekmf_points(pt, nq, m_z.get(), m_w.get(), m_D.get())) NEKB200_ERROR("bad points key");
+        const int rows = nekmf_basis_rows(bt, nm);
+        m_b  = Array<OneD, NekDouble>(rows * nq);
+        m_db = Array<OneD, NekDouble>(rows * nq);
+        if (nekmf_basis(bt, nm, nq, m_z.get(), m_D.get(), m_b.get(), m_db.get())) NEKB200_ERROR("bad basis key");
+    }
+    const Array<OneD, NekDouble> &GetBdata() const { return m_b; }
+    const Array<OneD, NekDouble> &GetDbdata() const { return m_db; }
+    const Array<OneD, NekDouble> &GetD() const { return m_D; }
+    const Array<OneD, NekDouble> &GetZ() const { return m_z; }
+    const Array<OneD, NekDouble> &GetW() const { return m_w; }
+    int GetNumModes() const { return m_nm; }
+    int GetNumPoints() const { return m_nq; }
+    BasisType GetBasisType() const { return m_bt; }
+    PointsType GetPointsType() const { return m_pt; }
+
+private:
+    BasisType m_bt;
+    PointsType m_pt;
+    int m_nm, m_nq;
+    Array<OneD, NekDouble> m_z, m_w, m_D, m_b, m_db;
+};
+typedef std::shared_ptr<Basis> BasisSharedPtr;
+} // namespace LibUtilities
+
+// ------------------------------------------------------------------------------------------ StdRegions
+namespace StdRegions
+{
+enum ConstFactorType { eFactorLambda, eFactorTau };
+typedef std::map<ConstFactorType, NekDouble> ConstFactorMap;
+static const ConstFactorMap NullConstFactorMap;
+
+// the expansion of ONE element: reference-element bases + that element's geometric factors
+// (jac: 1 or nq values; df: ndf x (1 or nq), df[c*dim+d] = d xi_d / d x_c -- GeomFactors.cpp:399-474)
+class StdExpansion
+{
+public:
+    StdExpansion(LibUtilities::ShapeType shape, int nummodes, int numpoints0 = -1) : m_shape(shape), m_deformed(false)
+    {
+        using namespace LibUtilities;
+        const int nq0 = numpoints0 > 0 ? numpoints0 : nummodes + 1; // MeshGraph.cpp:1609-1762 defaults
+        m_dim         = (shape == eQuadrilateral || shape == eTriangle) ? 2 : 3;
+        BasisType bt[3]  = {eModified_A, eModified_A, eModified_A};
+        PointsType pt[3] = {eGaussLobattoLegendre, eGaussLobattoLegendre, eGaussLobattoLegendre};
+        int nq[3]        = {nq0, nq0, nq0};
+        if (shape == eTriangle) { bt[1] = eModified_B; pt[1] = eGaussRadauMAlpha1Beta0; nq[1] = nq0 - 1; }
+        else if (shape == ePrism) { bt[2] = eModified_B; pt[2] = eGaussRadauMAlpha1Beta0; nq[2] = nq0 - 1; }
+        else if (shape == eTetrahedron)
+        {
+            bt[1] = eModified_B; pt[1] = eGaussRadauMAlpha1Beta0; nq[1] = nq0 - 1;
+            bt[2] = eModified_C; pt[2] = eGaussRadauMAlpha2Beta0; nq[2] = nq0 - 1;
+        }
+        else if (shape != eQuadrilateral && shape != eHexahedron)
+            NEKB200_ERROR("shape " << ShapeTypeMap[shape] << " not supported");
+        m_ntot = 1;
+        for (int d = 0; d < m_dim; ++d)
+        {
+            m_base.push_back(std::make_shared<Basis>(bt[d], nummodes, pt[d], nq[d]));
+            m_ntot *= nq[d];
+        }
+        const int n = nummodes;
+        m_ncoeffs   = shape == eQuadrilateral ? n * n : shape == eTriangle ? n * (n + 1) / 2 : shape == eHexahedron ? n * n * n
+                      : shape == ePrism ? n * n * (n + 1) / 2 : n * (n + 1) * (n + 2) / 6;
+    }
+    // share the bases of an existing expansion, new geometry (what ExpList does for every element)
+    StdExpansion(const StdExpansion &o, bool deformed, const Array<OneD, NekDouble> &jac, const Array<OneD, NekDouble> &df)
+        : m_shape(o.m_shape), m_dim(o.m_dim), m_ncoeffs(o.m_ncoeffs), m_ntot(o.m_ntot), m_base(o.m_base),
+          m_deformed(deformed), m_jac(jac), m_df(df)
+    {
+        const size_t n = deformed ? m_ntot : 1;
+        if (jac.num_elements() != n || df.num_elements() != n * m_dim * m_dim)
+            NEKB200_ERROR("StdExpansion: geometric factor arrays have the wrong size");
+    }
+    const LibUtilities::BasisSharedPtr &GetBasis(int d) const { return m_base[d]; }
+    LibUtilities::ShapeType DetShapeType() const { return m_shape; }
+    int GetShapeDimension() const { return m_dim; }
+    int GetNcoeffs() const { return m_ncoeffs; }
+    int GetTotPoints() const { return m_ntot; }
+    bool IsDeformed() const { return m_deformed; }
+    const Array<OneD, NekDouble> &GetJac() const { return m_jac; }
+    const Array<OneD, NekDouble> &GetDerivFactors() const { return m_df; }
+
+private:
+    LibUtilities::ShapeType m_shape;
+    int m_dim, m_ncoeffs, m_ntot;
+    std::vector<LibUtilities::BasisSharedPtr> m_base;
+    bool m_deformed;
+    Array<OneD, NekDouble> m_jac, m_df;
+};
+typedef std::shared_ptr<StdExpansion> StdExpansionSharedPtr;
+} // namespace StdRegions
+
+// ------------------------------------------------------------------------------------------ Collections
+namespace Collections
+{
+enum OperatorType { eBwdTrans, eHelmholtz, eIProductWRTBase, eIProductWRTDerivBase, ePhysDeriv, SIZE_OperatorType };
+static const char *const OperatorTypeMap[] = {"BwdTrans", "Helmholtz", "IProductWRTBase", "IProductWRTDerivBase", "PhysDeriv"};
+enum ImplementationType { eNoImpType, eNoCollection, eIterPerExp, eStdMat, eSumFac, eMatrixFree, eB200, SIZE_ImplementationType };
+static const char *const ImplementationTypeMap[] = {"NoImplementationType", "NoCollection", "IterPerExp", "StdMat",
+                                                    "SumFac", "MatrixFree", "B200"};
+typedef bool ExpansionIsNodal;
+typedef std::map<OperatorType, ImplementationType> OperatorImpMap;
+inline OperatorImpMap SetFixedImpType(ImplementationType t) // Operator.cpp:128-138
+{
+    OperatorImpMap m;
+    for (int i = 0; i < SIZE_OperatorType; ++i) m[(OperatorType)i] = t;
+    return m;
+}
+
+// CoalescedGeomData.cpp:53-113 (GetJac), 251-313 (GetDerivFactors), 406-424 (IsDeformed)
+class CoalescedGeomData
+{
+public:
+    bool IsDeformed(const std::vector<StdRegions::StdExpansionSharedPtr> &e) const { return e[0]->IsDeformed(); }
+    const Array<OneD, NekDouble> &GetJac(const std::vector<StdRegions::StdExpansionSharedPtr> &e)
+    {
+        if (m_jac.num_elements() == 0 && !e.empty())
+        {
+            const size_t n = e[0]->GetJac().num_elements();
+            m_jac          = Array<OneD, NekDouble>(n * e.size());
+            for (size_t i = 0; i < e.size(); ++i)
+                for (size_t q = 0; q < n; ++q) m_jac[i * n + q] = e[i]->GetJac()[q];
+        }
+        return m_jac;
+    }
+    // [ndf][nElmt(*nq)] stored row after row (the reference returns Array<TwoD>)
+    const Array<OneD, NekDouble> &GetDerivFactors(const std::vector<StdRegions::StdExpansionSharedPtr> &e)
+    {
+        if (m_df.num_elements() == 0 && !e.empty())
+        {
+            const int dim = e[0]->GetShapeDimension(), ndf = dim * dim;
+            const size_t n = e[0]->GetJac().num_elements(), cols = n * e.size();
+            m_df = Array<OneD, NekDouble>(ndf * cols);
+            for (size_t i = 0; i < e.size(); ++i)
+                for (int r = 0; r < ndf; ++r)
+                    for (size_t q = 0; q < n; ++q) m_df[r * cols + i * n + q] = e[i]->GetDerivFactors()[r * n + q];
+        }
+        return m_df;
+    }
+
+private:
+    Array<OneD, NekDouble> m_jac, m_df;
+};
+typedef std::shared_ptr<CoalescedGeomData> CoalescedGeomDataSharedPtr;
+
+// Operator.h:113-165
+class Operator
+{
+public:
+    Operator(std::vector<StdRegions::StdExpansionSharedPtr> pCollExp, CoalescedGeomDataSharedPtr GeomData)
+        : m_isDeformed(GeomData->IsDeformed(pCollExp)), m_stdExp(pCollExp[0]), m_numElmt(pCollExp.size()),
+          m_nqe(pCollExp[0]->GetTotPoints()), m_wspSize(0)
+    {
+    }
+    virtual void operator()(const Array<OneD, const NekDouble> &input, Array<OneD, NekDouble> &output0,
+                            Array<OneD, NekDouble> &output1, Array<OneD, NekDouble> &output2,
+                            Array<OneD, NekDouble> &wsp, const StdRegions::ConstFactorMap &factors) = 0;
+    virtual void operator()(int dir, const Array<OneD, const NekDouble> &input, Array<OneD, NekDouble> &output,
+                            Array<OneD, NekDouble> &wsp) = 0;
+    virtual ~Operator() {}
+    unsigned int GetWspSize() { return m_wspSize; }
+    unsigned int GetNumElmt() { return m_numElmt; }
+    StdRegions::StdExpansionSharedPtr GetExpSharedPtr() { return m_stdExp; }
+
+protected:
+    bool m_isDeformed;
+    StdRegions::StdExpansionSharedPtr m_stdExp;
+    unsigned int m_numElmt, m_nqe, m_wspSize;
+};
+typedef std::shared_ptr<Operator> OperatorSharedPtr;
+typedef std::tuple<LibUtilities::ShapeType, OperatorType, ImplementationType, ExpansionIsNodal> OperatorKey;
+
+// NekFactory<OperatorKey, Operator, vector<StdExpansionSharedPtr>, CoalescedGeomDataSharedPtr>
+class OperatorFactory
+{
+public:
+    typedef OperatorSharedPtr (*CreatorFunction)(std::vector<StdRegions::StdExpansionSharedPtr>, CoalescedGeomDataSharedPtr);
+    OperatorKey RegisterCreatorFunction(OperatorKey key, CreatorFunction f, std::string desc = "")
+    {
+        m_map[key] = std::make_pair(f, desc);
+        return key;
+    }
+    OperatorSharedPtr CreateInstance(OperatorKey key, std::vector<StdRegions::StdExpansionSharedPtr> e,
+                                     CoalescedGeomDataSharedPtr g)
+    {
+        auto it = m_map.find(key);
+        if (it == m_map.end())
+            NEKB200_ERROR("No such module: (" << LibUtilities::ShapeTypeMap[std::get<0>(key)] << ", "
+                                              << OperatorTypeMap[std::get<1>(key)] << ", "
+                                              << ImplementationTypeMap[std::get<2>(key)] << ")");
+        return it->second.first(e, g);
+    }
+    bool ModuleExists(OperatorKey key) const { return m_map.count(key) != 0; }
+
+private:
+    std::map<OperatorKey, std::pair<CreatorFunction, std::string>> m_map;
+};
+inline OperatorFactory &GetOperatorFactory()
+{
+    static OperatorFactory f;
+    return f;
+}
+
+// ---- the eB200 operators: one class, five registrations per operator type
+class Operator_B200 : public Operator
+{
+public:
+    template <OperatorType OP>
+    static OperatorSharedPtr create(std::vector<StdRegions::StdExpansionSharedPtr> e, CoalescedGeomDataSharedPtr g)
+    {
+        return OperatorSharedPtr(new Operator_B200(OP, e, g));
+    }
+    ~Operator_B200() override { nekmf_op_destroy(m_op); }
+
+    void operator()(const Array<OneD, const NekDouble> &input, Array<OneD, NekDouble> &output0,
+                    Array<OneD, NekDouble> &output1, Array<OneD, NekDouble> &output2, Array<OneD, NekDouble> &,
+                    const StdRegions::ConstFactorMap &factors) override
+    {
+        if (m_type == eHelmholtz)
+        {
+            auto it = factors.find(StdRegions::eFactorLambda);
+            if (it == factors.end()) NEKB200_ERROR("Helmholtz_B200: eFactorLambda missing from the factor map");
+            Check(nekmf_op_set_lambda(m_op, it->second));
+        }
+        if (m_type == eIProductWRTDerivBase)
+        {
+            // reference convention (IProductWRTDerivBase.cpp:285-330): 2-D (in0, in1, out), 3-D (in0, in1, in2, out)
+            const bool d3 = m_stdExp->GetShapeDimension() == 3;
+            Check(nekmf_op_apply(m_op, input.get(), output0.get(), d3 ? output1.get() : nullptr,
+                                 d3 ? output2.get() : output1.get(), nullptr, nullptr, NEKMF_HOST));
+            return;
+        }
+        Check(nekmf_op_apply(m_op, input.get(), nullptr, nullptr, output0.get(), output1.get(), output2.get(), NEKMF_HOST));
+    }
+    void operator()(int dir, const Array<OneD, const NekDouble> &input, Array<OneD, NekDouble> &output,
+                    Array<OneD, NekDouble> &) override
+    {
+        if (m_type != ePhysDeriv)
+            NEKB200_ERROR(OperatorTypeMap[m_type] << "_B200: operator()(dir, ...) is not valid for this operator.");
+        // PhysDeriv.cpp:323-341: compute every direction, keep one
+        const int dim = m_stdExp->GetShapeDimension();
+        if (dir < 0 || dir >= dim) NEKB200_ERROR("PhysDeriv_B200: direction out of range");
+        Array<OneD, NekDouble> t[3];
+        for (int d = 0; d < dim; ++d) t[d] = d == dir ? output : Array<OneD, NekDouble>(m_numElmt * m_nqe);
+        Check(nekmf_op_apply(m_op, input.get(), nullptr, nullptr, t[0].get(), t[1].get(), dim == 3 ? t[2].get() : nullptr,
+                             NEKMF_HOST));
+    }
+    const char *KernelName() const { return nekmf_op_kernel_name(m_op); }
+
+private:
+    static void Check(int rc)
+    {
+        if (rc != NEKMF_OK) NEKB200_ERROR(nekmf_last_error());
+    }
+    Operator_B200(OperatorType type, std::vector<StdRegions::StdExpansionSharedPtr> pCollExp, CoalescedGeomDataSharedPtr pGeomData)
+        : Operator(pCollExp, pGeomData), m_type(type), m_op(nullptr)
+    {
+        const auto &exp = pCollExp[0];
+        const int dim   = exp->GetShapeDimension();
+        int nm[3] = {1, 1, 1}, nq[3] = {1, 1, 1}, bt[3] = {0, 0, 0}, pt[3] = {0, 0, 0};
+        const double *b[3] = {nullptr, nullptr, nullptr}, *db[3] = {nullptr, nullptr, nullptr}, *D[3] = {nullptr, nullptr, nullptr},
+                     *Z[3] = {nullptr, nullptr, nullptr}, *W[3] = {nullptr, nullptr, nullptr};
+        for (int d = 0; d < dim; ++d) // MatrixFreeOps/Operator.hpp:223-273
+        {
+            const auto &bas = exp->GetBasis(d);
+            nm[d] = bas->GetNumModes(); nq[d] = bas->GetNumPoints();
+            bt[d] = bas->GetBasisType(); pt[d] = bas->GetPointsType();
+            b[d] = bas->GetBdata().get(); db[d] = bas->GetDbdata().get(); D[d] = bas->GetD().get();
+            Z[d] = bas->GetZ().get(); W[d] = bas->GetW().get();
+        }
+        static const int abiop[] = {NEKMF_BWDTRANS, NEKMF_HELMHOLTZ, NEKMF_IPRODUCTWRTBASE, NEKMF_IPRODUCTWRTDERIVBASE, NEKMF_PHYSDERIV};
+        Check(nekmf_op_create(exp->DetShapeType(), abiop[type], nm, nq, bt, pt, b, db, D, Z, W, (int)pCollExp.size(),
+                              m_isDeformed, dim, &m_op));
+        const bool needJac = type == eHelmholtz || type == eIProductWRTBase || type == eIProductWRTDerivBase;
+        const bool needDF  = type == eHelmholtz || type == ePhysDeriv || type == eIProductWRTDerivBase;
+        if (needJac || needDF)
+            Check(nekmf_op_set_geom(m_op, needJac ? pGeomData->GetJac(pCollExp).get() : nullptr,
+                                    needDF ? pGeomData->GetDerivFactors(pCollExp).get() : nullptr, NEKMF_HOST));
+    }
+    OperatorType m_type;
+    nekmf_op_t m_op;
+};
+
+namespace detail
+{
+template <OperatorType OP> inline void RegisterB200(bool withCollapsed)
+{
+    using namespace LibUtilities;
+    auto &f = GetOperatorFactory();
+    const std::string n = std::string(OperatorTypeMap[OP]) + "_B200_";
+    f.RegisterCreatorFunction(OperatorKey(eQuadrilateral, OP, eB200, false), Operator_B200::create<OP>, n + "Quad");
+    f.RegisterCreatorFunction(OperatorKey(eHexahedron, OP, eB200, false), Operator_B200::create<OP>, n + "Hex");
+    if (withCollapsed)
+    {
+        f.RegisterCreatorFunction(OperatorKey(eTriangle, OP, eB200, false), Operator_B200::create<OP>, n + "Tri");
+        f.RegisterCreatorFunction(OperatorKey(ePrism, OP, eB200, false), Operator_B200::create<OP>, n + "Prism");
+        f.RegisterCreatorFunction(OperatorKey(eTetrahedron, OP, eB200, false), Operator_B200::create<OP>, n + "Tet");
+    }
+}
+struct Registrar
+{
+    Registrar()
+    {
+        RegisterB200<eBwdTrans>(true);
+        RegisterB200<eHelmholtz>(true);
+        RegisterB200<eIProductWRTBase>(true);
+        RegisterB200<ePhysDeriv>(true);
+        RegisterB200<eIProductWRTDerivBase>(false);
+    }
+};
+static Registrar g_registrar; // static registration, as the reference's m_typeArr[] initialisers
+} // namespace detail
+
+// CollectionOptimisation.cpp:52-281 reduced to what the unit tests use: a fixed implementation type,
+// no session file (the reference's tests pass a null session pointer, TestHexCollection.cpp:3699-3704)
+class CollectionOptimisation
+{
+public:
+    CollectionOptimisation(void *pSession, ImplementationType defaultType = eB200) : m_default(defaultType)
+    {
+        if (pSession) NEKB200_ERROR("CollectionOptimisation: session files are not supported by this mirror");
+    }
+    OperatorImpMap GetOperatorImpMap(StdRegions::StdExpansionSharedPtr) { return SetFixedImpType(m_default); }
+
+private:
+    ImplementationType m_default;
+};
+
+// Collection.h:53-110, Collection.cpp:46-87
+class Collection
+{
+public:
+    Collection(std::vector<StdRegions::StdExpansionSharedPtr> pCollExp, OperatorImpMap &impTypes)
+        : m_geomData(std::make_shared<CoalescedGeomData>()), m_collExp(pCollExp), m_impTypes(impTypes)
+    {
+    }
+    void Initialise(const OperatorType opType)
+    {
+        if (m_ops.count(opType)) return;
+        if (m_collExp.empty()) return;
+        OperatorKey key(m_collExp[0]->DetShapeType(), opType, m_impTypes[opType], false);
+        m_ops[opType] = GetOperatorFactory().CreateInstance(key, m_collExp, m_geomData);
+    }
+    void ApplyOperator(const OperatorType &op, const Array<OneD, const NekDouble> &in, Array<OneD, NekDouble> &out,
+                       const StdRegions::ConstFactorMap &factors = StdRegions::NullConstFactorMap)
+    {
+        Array<OneD, NekDouble> wsp(Op(op)->GetWspSize()), n1, n2;
+        (*Op(op))(in, out, n1, n2, wsp, factors);
+    }
+    void ApplyOperator(const OperatorType &op, const Array<OneD, const NekDouble> &in, Array<OneD, NekDouble> &out0,
+                       Array<OneD, NekDouble> &out1)
+    {
+        Array<OneD, NekDouble> wsp(Op(op)->GetWspSize()), n2;
+        (*Op(op))(in, out0, out1, n2, wsp, StdRegions::NullConstFactorMap);
+    }
+    void ApplyOperator(const OperatorType &op, const Array<OneD, const NekDouble> &in, Array<OneD, NekDouble> &out0,
+                       Array<OneD, NekDouble> &out1, Array<OneD, NekDouble> &out2,
+                       const StdRegions::ConstFactorMap &factors = StdRegions::NullConstFactorMap)
+    {
+        Array<OneD, NekDouble> wsp(Op(op)->GetWspSize());
+        (*Op(op))(in, out0, out1, out2, wsp, factors);
+    }
+    void ApplyOperator(const OperatorType &op, int dir, const Array<OneD, const NekDouble> &in, Array<OneD, NekDouble> &out)
+    {
+        Array<OneD, NekDouble> wsp(Op(op)->GetWspSize());
+        (*Op(op))(dir, in, out, wsp);
+    }
+    bool HasOperator(const OperatorType &op) { return m_ops.count(op) != 0; }
+    OperatorSharedPtr GetOpSharedPtr(const OperatorType &op) { return m_ops[op]; }
+    CoalescedGeomDataSharedPtr GetGeomSharedPtr() { return m_geomData; }
+
+protected:
+    OperatorSharedPtr &Op(OperatorType op)
+    {
+        Initialise(op);
+        return m_ops[op];
+    }
+    std::map<OperatorType, OperatorSharedPtr> m_ops;
+    CoalescedGeomDataSharedPtr m_geomData;
+    std::vector<StdRegions::StdExpansionSharedPtr> m_collExp;
+    OperatorImpMap m_impTypes;
+};
+
+} // namespace Collections
+} // namespace Nektar

@@ -277,3 +277,16 @@ def test_full_size_properties_hex_p4():
     lhs = float(torch.sum(Bu.reshape(nel, 216) * fphys.reshape(nel, 216) * w3[None, :]))
     rhs = float(torch.dot(x, Itf))
     assert abs(lhs - rhs) < 1e-12 * abs(lhs)
+
+
+def test_cpp_collections_mirror():
+    """the C++ host side (ithaca-sem_b200/host/NekB200Collections.hpp: Collection / OperatorFactory /
+    eB200 operators over the C ABI) through tests/cpp/TestCollectionB200.cpp, the analogue of
+    library/UnitTests/Collections/TestHexCollection.cpp"""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "cpp", "TestCollectionB200")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "PASSED" in r.stdout

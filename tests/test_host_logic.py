@@ -180,3 +180,13 @@ def test_sharded_cg_world_size_2_gloo(tmp_path):
         assert abs(int(meta[0]) - its) <= 1
         g0, g1 = int(meta[2]), int(meta[3])
         assert np.abs(xr - xs[g0:g1 + 1]).max() < 1e-10 * np.abs(xs).max()
+
+
+def test_cpp_collections_mirror_builds_and_refuses_without_gpu():
+    import subprocess
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    nk = nekmf()
+    if nk.device_count() > 0:
+        pytest.skip("a GPU is present: the real run is in the gpu suite")
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "TestCollectionB200")], capture_output=True, text=True)
+    assert r.returncode == 77 and "no CUDA device" in r.stdout
