@@ -82,7 +82,8 @@ enum nekmf_pointstype
 /* where the caller's arrays live */
 enum nekmf_memkind
 {
-    NEKMF_HOST   = 0, /* pageable or pinned host memory: staged H2D / D2H inside the call */
+    NEKMF_HOST   = 0, /* pageable or pinned host memory: H2D -> kernel -> D2H pipelined over element
+                         chunks inside the call (3 streams), returns when the outputs are complete */
     NEKMF_DEVICE = 1  /* device pointers: no copies, asynchronous on the operator's stream */
 };
 
@@ -117,6 +118,11 @@ int nekmf_malloc_device(void **ptr, size_t bytes);
 int nekmf_free_device(void *ptr);
 int nekmf_malloc_pinned(void **ptr, size_t bytes);
 int nekmf_free_pinned(void *ptr);
+/* page-lock an existing host allocation (e.g. the Array<OneD> storage behind ExpList::m_coeffs /
+ * m_phys, LibUtilities/BasicUtils/SharedArray.hpp) so NEKMF_HOST applies copy at full PCIe rate and
+ * overlap H2D / kernel / D2H; without it the driver stages pageable memory through its own buffers */
+int nekmf_host_register(void *ptr, size_t bytes);
+int nekmf_host_unregister(void *ptr);
 int nekmf_memcpy_h2d(void *dst, const void *src, size_t bytes);
 int nekmf_memcpy_d2h(void *dst, const void *src, size_t bytes);
 int nekmf_memset_device(void *dst, int value, size_t bytes);

@@ -91,6 +91,17 @@ int nekmf_free_pinned(void *ptr)
     NEKMF_CUDA(cudaFreeHost(ptr));
     return NEKMF_OK;
 }
+int nekmf_host_register(void *ptr, size_t bytes)
+{
+    if (!ptr) { set_error("nekmf_host_register: null ptr"); return NEKMF_ERR_ARG; }
+    NEKMF_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return NEKMF_OK;
+}
+int nekmf_host_unregister(void *ptr)
+{
+    NEKMF_CUDA(cudaHostUnregister(ptr));
+    return NEKMF_OK;
+}
 int nekmf_memcpy_h2d(void *dst, const void *src, size_t bytes)
 {
     NEKMF_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
@@ -396,6 +407,9 @@ int nekmf_op_apply(nekmf_op_t op, const double *in0, const double *in1, const do
     {
         const double *din[3] = {ins[0], nin > 1 ? ins[1] : ins[0], nin > 2 ? ins[2] : ins[0]};
         double *dout[3]      = {outs[0], nout > 1 ? outs[1] : outs[0], nout > 2 ? outs[2] : outs[0]};
+        op->run_e0     = 0;
+        op->run_ne     = op->nElmt;
+        op->run_stream = op->stream;
         if (op->timing) NEKMF_CUDA(cudaEventRecord(op->ev0, op->stream));
         rc = op->launch(op, din, dout);
         if (rc) return rc;
@@ -408,7 +422,10 @@ int nekmf_op_apply(nekmf_op_t op, const double *in0, const double *in1, const do
     }
     if (memkind != NEKMF_HOST) { set_error("nekmf_op_apply: bad memkind %d", memkind); return NEKMF_ERR_ARG; }
 
-    // host arrays (the literal Array<OneD> drop-in): stage H2D, run, stage D2H, synchronous
+    // Host arrays (the literal Array<OneD> drop-in).  The collection is cut into element chunks that
+    // flow through a 3-stream pipeline: H2D of chunk c+1, the kernel on chunk c and D2H of chunk c-1
+    // overlap (PCIe is full duplex and the copy engines are independent), so the call costs about
+    // max(H2D, D2H) instead of H2D + kernel + D2H.  Synchronous: returns when `out` is complete.
     if (op->stage_in_sz < in_sz * nin)
     {
         if (op->d_stage_in) cudaFree(op->d_stage_in);
@@ -423,27 +440,71 @@ int nekmf_op_apply(nekmf_op_t op, const double *in0, const double *in1, const do
         NEKMF_CUDA(cudaMalloc(&op->d_stage_out, out_sz * nout * 8));
         op->stage_out_sz = out_sz * nout;
     }
-    const double *din[3];
-    double *dout[3];
-    for (int a = 0; a < 3; ++a)
+    if (!op->pipe_stream[0])
     {
-        din[a]  = op->d_stage_in + (a < nin ? a : 0) * in_sz;
-        dout[a] = op->d_stage_out + (a < nout ? a : 0) * out_sz;
+        for (int s = 0; s < 3; ++s) NEKMF_CUDA(cudaStreamCreateWithFlags(&op->pipe_stream[s], cudaStreamNonBlocking));
+        NEKMF_CUDA(cudaEventCreateWithFlags(&op->pipe_done, cudaEventDisableTiming));
     }
-    for (int a = 0; a < nin; ++a)
-        NEKMF_CUDA(cudaMemcpyAsync(op->d_stage_in + a * in_sz, ins[a], in_sz * 8, cudaMemcpyHostToDevice, op->stream));
-    if (op->timing) NEKMF_CUDA(cudaEventRecord(op->ev0, op->stream));
-    rc = op->launch(op, din, dout);
-    if (rc) return rc;
-    if (op->timing)
+    const size_t in_el  = cin ? op->nmTot : op->nqTot;
+    const size_t out_el = cout ? op->nmTot : op->nqTot;
+    // chunk: about 8 MB of the larger of (inputs, outputs); element counts even so that every chunk
+    // of every array stays 16-byte aligned for the TMA-fed kernels
+    const size_t el_bytes = 8 * (in_el * nin > out_el * nout ? in_el * nin : out_el * nout);
+    int chunk = (int)((size_t)(8u << 20) / el_bytes);
+    chunk &= ~1;
+    if (chunk < 2) chunk = 2;
+    // work queued earlier on the operator's stream (e.g. a device-array apply) stays ordered before us
+    NEKMF_CUDA(cudaEventRecord(op->pipe_done, op->stream));
+    for (int s = 0; s < 3; ++s) NEKMF_CUDA(cudaStreamWaitEvent(op->pipe_stream[s], op->pipe_done, 0));
+    if (op->timing) NEKMF_CUDA(cudaEventRecord(op->ev0, op->pipe_stream[0]));
+    int c = 0;
+    for (int e0 = 0; e0 < op->nElmt; e0 += chunk, ++c)
     {
-        NEKMF_CUDA(cudaEventRecord(op->ev1, op->stream));
+        const int ne      = op->nElmt - e0 < chunk ? op->nElmt - e0 : chunk;
+        cudaStream_t st   = op->pipe_stream[c % 3];
+        const double *din[3];
+        double *dout[3];
+        for (int a = 0; a < 3; ++a)
+        {
+            din[a]  = op->d_stage_in + (a < nin ? a : 0) * in_sz + (size_t)e0 * in_el;
+            dout[a] = op->d_stage_out + (a < nout ? a : 0) * out_sz + (size_t)e0 * out_el;
+        }
+        for (int a = 0; a < nin; ++a)
+            NEKMF_CUDA(cudaMemcpyAsync(const_cast<double *>(din[a]), ins[a] + (size_t)e0 * in_el, (size_t)ne * in_el * 8,
+                                       cudaMemcpyHostToDevice, st));
+        op->run_e0     = e0;
+        op->run_ne     = ne;
+        op->run_stream = st;
+        rc             = op->launch(op, din, dout);
+        if (rc) break;
+        for (int a = 0; a < nout; ++a)
+            NEKMF_CUDA(cudaMemcpyAsync(outs[a] + (size_t)e0 * out_el, dout[a], (size_t)ne * out_el * 8,
+                                       cudaMemcpyDeviceToHost, st));
+    }
+    op->run_e0     = 0;
+    op->run_ne     = op->nElmt;
+    op->run_stream = op->stream;
+    if (op->timing && rc == NEKMF_OK)
+    {
+        // ev0/ev1 bracket the whole pipelined call (copies included) for host-array applies
+        for (int s = 1; s < 3; ++s)
+        {
+            NEKMF_CUDA(cudaEventRecord(op->pipe_done, op->pipe_stream[s]));
+            NEKMF_CUDA(cudaStreamWaitEvent(op->pipe_stream[0], op->pipe_done, 0));
+        }
+        NEKMF_CUDA(cudaEventRecord(op->ev1, op->pipe_stream[0]));
         op->timed_once = true;
     }
-    for (int a = 0; a < nout; ++a)
-        NEKMF_CUDA(cudaMemcpyAsync(outs[a], op->d_stage_out + a * out_sz, out_sz * 8, cudaMemcpyDeviceToHost, op->stream));
-    NEKMF_CUDA(cudaStreamSynchronize(op->stream));
-    return NEKMF_OK;
+    for (int s = 0; s < 3; ++s)
+    {
+        cudaError_t e = cudaStreamSynchronize(op->pipe_stream[s]);
+        if (e != cudaSuccess && rc == NEKMF_OK)
+        {
+            set_error("nekmf_op_apply: host pipeline failed: %s", cudaGetErrorString(e));
+            rc = NEKMF_ERR_CUDA;
+        }
+    }
+    return rc;
 }
 
 int nekmf_op_destroy(nekmf_op_t op)
@@ -455,6 +516,9 @@ int nekmf_op_destroy(nekmf_op_t op)
     cudaFree(op->d_df);
     cudaFree(op->d_stage_in);
     cudaFree(op->d_stage_out);
+    for (int s = 0; s < 3; ++s)
+        if (op->pipe_stream[s]) cudaStreamDestroy(op->pipe_stream[s]);
+    if (op->pipe_done) cudaEventDestroy(op->pipe_done);
     if (op->ev0) cudaEventDestroy(op->ev0);
     if (op->ev1) cudaEventDestroy(op->ev1);
     delete op;

@@ -119,10 +119,10 @@ static int cg_matvec_device(nekmf_cg_s *cg, const double *w, double *s)
     if (rc) return rc;
     const double *in[3] = {cg->d_lin, cg->d_lin, cg->d_lin};
     double *out[3]      = {cg->d_lout, cg->d_lout, cg->d_lout};
-    cudaStream_t saved  = cg->op->stream;
-    cg->op->stream      = cg->stream;
+    cg->op->run_e0      = 0;
+    cg->op->run_ne      = cg->op->nElmt;
+    cg->op->run_stream  = cg->stream;
     rc                  = cg->op->launch(cg->op, in, out);
-    cg->op->stream      = saved;
     if (rc) return rc;
     rc = map_assemble_device(cg->map, cg->d_lout, s, cg->stream);
     if (rc) return rc;

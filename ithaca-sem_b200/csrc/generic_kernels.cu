@@ -30,6 +30,7 @@ struct GenArgs
     int off[3][5];
     int nm, nq0, nq1, nq2;
     int nmTot, nqTot, nElmt, deformed, optype;
+    size_t dfStride; // df row stride (whole collection); jac/df already point at this launch's first element
     int N; // doubles per work buffer
     double lambda;
 };
@@ -572,7 +573,7 @@ template <int SHAPE> __global__ void __launch_bounds__(256) gen_kernel(const __g
 
     const bool deformed = a.deformed != 0;
     const int nmTot = a.nmTot, nqTot = a.nqTot;
-    const size_t dfs = deformed ? (size_t)a.nElmt * nqTot : (size_t)a.nElmt;
+    const size_t dfs = a.dfStride;
     const bool coeff_in  = a.optype == NEKMF_BWDTRANS || a.optype == NEKMF_HELMHOLTZ;
     const bool coeff_out = a.optype != NEKMF_BWDTRANS && a.optype != NEKMF_PHYSDERIV;
     const int nin = coeff_in ? nmTot : nqTot, nout = coeff_out ? nmTot : nqTot;
@@ -695,16 +696,20 @@ template <int SHAPE> static int gen_launch(nekmf_op_s *op, const double *const i
     GenArgs a;
     a.in0 = in[0]; a.in1 = in[1]; a.in2 = in[2];
     a.out0 = out[0]; a.out1 = out[1]; a.out2 = out[2];
-    a.jac = op->d_jac; a.df = op->d_df; a.tab = op->d_tab; a.tab_len = op->tab_len;
+    const size_t gstep = op->deformed ? (size_t)op->nqTot : 1;
+    a.jac = op->d_jac ? op->d_jac + (size_t)op->run_e0 * gstep : nullptr;
+    a.df  = op->d_df ? op->d_df + (size_t)op->run_e0 * gstep : nullptr;
+    a.dfStride = (size_t)op->nElmt * gstep;
+    a.tab = op->d_tab; a.tab_len = op->tab_len;
     for (int d = 0; d < 3; ++d)
         for (int t = 0; t < 5; ++t) a.off[d][t] = op->tab_off[d][t];
     a.nm = op->nm[0]; a.nq0 = op->nq[0]; a.nq1 = op->nq[1]; a.nq2 = op->nq[2];
-    a.nmTot = op->nmTot; a.nqTot = op->nqTot; a.nElmt = op->nElmt; a.deformed = op->deformed;
+    a.nmTot = op->nmTot; a.nqTot = op->nqTot; a.nElmt = op->run_ne; a.deformed = op->deformed;
     a.optype = op->optype; a.N = st->N; a.lambda = op->lambda;
     int grid = st->blocks_per_sm * NUM_SMS;
-    if (grid > op->nElmt) grid = op->nElmt;
+    if (grid > op->run_ne) grid = op->run_ne;
     if (grid < 1) return NEKMF_OK;
-    kern<<<grid, 256, st->smem, op->stream>>>(a);
+    kern<<<grid, 256, st->smem, op->run_stream>>>(a);
     ++g_launches;
     NEKMF_CUDA(cudaGetLastError());
     return NEKMF_OK;

@@ -35,16 +35,19 @@ template <int OP, int NM, int NQ, bool DEF> static int hex_launch(nekmf_op_s *op
     HexArgs a;
     a.in0 = in[0]; a.in1 = in[1]; a.in2 = in[2];
     a.out0 = out[0]; a.out1 = out[1]; a.out2 = out[2];
-    a.jac = op->d_jac; a.df = op->d_df;
-    a.nElmt  = op->nElmt;
-    a.lambda = op->lambda;
+    const size_t gstep = DEF ? (size_t)op->geo_pitch : 1; // geometry entries per element
+    a.jac = op->d_jac ? op->d_jac + (size_t)op->run_e0 * gstep : nullptr;
+    a.df  = op->d_df ? op->d_df + (size_t)op->run_e0 * gstep : nullptr;
+    a.nElmt    = op->run_ne;
+    a.dfStride = (size_t)op->nElmt * gstep;
+    a.lambda   = op->lambda;
     a.in_aligned = (((uintptr_t)in[0] | (uintptr_t)in[1] | (uintptr_t)in[2]) & 15) == 0;
-    const int nBatches = (op->nElmt + Cfg::E - 1) / Cfg::E;
+    const int nBatches = (op->run_ne + Cfg::E - 1) / Cfg::E;
     int grid           = blocks_per_sm * NUM_SMS;
     if (grid > nBatches) grid = nBatches;
     if (grid < 1) return NEKMF_OK;
     const HexTab<NM, NQ> *tab = static_cast<const HexTab<NM, NQ> *>(op->kstate);
-    kern<<<grid, Cfg::T, Cfg::SMEM, op->stream>>>(*tab, a);
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*tab, a);
     ++g_launches;
     NEKMF_CUDA(cudaGetLastError());
     return NEKMF_OK;

@@ -50,7 +50,8 @@ struct HexArgs
     double *out0, *out1, *out2;
     const double *jac; // [nElmt] | [nElmt*NQ3]
     const double *df;  // [9][nElmt] | [9][nElmt*NQ3]
-    int nElmt;
+    int nElmt;       // elements this launch covers (jac/df already point at the first of them)
+    size_t dfStride; // distance between df rows: nElmt of the whole collection (* pitch when deformed)
     int in_aligned; // all input pointers 16-byte aligned
     double lambda;
 };
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T)
         // internal geometry layout: [array][element][NQ3P] (op_internal.h: geo_pitch), always 16-byte aligned
         const int ne         = batch_ne(b);
         const uint32_t bytes = (uint32_t)(ne * NQ3P * 8);
-        const size_t dfs     = (size_t)nElmt * NQ3P;
+        const size_t dfs     = args.dfStride;
         fence_proxy_async();
         mbar_expect_tx(&bars[1], bytes * NGEO);
         if (OP == HEX_IPROD)
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T)
                 if (OP != HEX_IPROD)
                 {
 #pragma unroll
-                    for (int n = 0; n < 9; ++n) rdf[n] = __ldg(args.df + (size_t)n * nElmt + eg);
+                    for (int n = 0; n < 9; ++n) rdf[n] = __ldg(args.df + (size_t)n * args.dfStride + eg);
                 }
                 if (OP != HEX_PD) rjac = __ldg(args.jac + eg);
             }

@@ -342,13 +342,13 @@ template <int NM> static int kron_launch(nekmf_op_s *op, const double *const in[
         st->blocks_per_sm = nb;
     }
     KronArgs a;
-    a.in = in[0]; a.out = out[0]; a.geo4 = st->d_geo4; a.nElmt = op->nElmt; a.lambda = op->lambda;
+    a.in = in[0]; a.out = out[0]; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
     a.io_aligned = ((((uintptr_t)in[0]) | ((uintptr_t)out[0])) & 15) == 0;
-    const int nBatches = (op->nElmt + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
+    const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
     int grid           = st->blocks_per_sm * NUM_SMS;
     if (grid > nBatches) grid = nBatches;
     if (grid < 1) return NEKMF_OK;
-    kern<<<grid, Cfg::T, Cfg::SMEM, op->stream>>>(*static_cast<const KronTab<NM> *>(st->tab), a);
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const KronTab<NM> *>(st->tab), a);
     ++g_launches;
     NEKMF_CUDA(cudaGetLastError());
     return NEKMF_OK;

@@ -27,9 +27,17 @@ struct nekmf_op_s
     double *d_df      = nullptr;
     int geo_pitch     = 0;
     cudaStream_t stream = nullptr;
-    // staging for NEKMF_HOST applies
+    // what one launch covers: elements [run_e0, run_e0 + run_ne) on run_stream.  nekmf_op_apply sets these
+    // before every launch (whole collection on `stream` for device arrays; one chunk per pipeline stage for
+    // host arrays).  in/out pointers handed to the launcher already point at element run_e0; launchers
+    // offset the geometry themselves (the df row stride stays nElmt).
+    int run_e0 = 0, run_ne = 0;
+    cudaStream_t run_stream = nullptr;
+    // staging + copy pipeline for NEKMF_HOST applies
     double *d_stage_in = nullptr, *d_stage_out = nullptr;
     size_t stage_in_sz = 0, stage_out_sz = 0;
+    cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_done = nullptr;
     // launcher: device pointers only
     int (*launch)(nekmf_op_s *, const double *const in[3], double *const out[3]) = nullptr;
     std::string kname;

@@ -46,7 +46,8 @@ _vp = C.c_void_p
 
 EXPORTS = [
     "nekmf_abi_version", "nekmf_last_error", "nekmf_device_count", "nekmf_set_device", "nekmf_launch_count",
-    "nekmf_malloc_device", "nekmf_free_device", "nekmf_malloc_pinned", "nekmf_free_pinned", "nekmf_memcpy_h2d",
+    "nekmf_malloc_device", "nekmf_free_device", "nekmf_malloc_pinned", "nekmf_free_pinned", "nekmf_host_register",
+    "nekmf_host_unregister", "nekmf_memcpy_h2d",
     "nekmf_memcpy_d2h", "nekmf_memset_device", "nekmf_sync", "nekmf_points", "nekmf_basis_rows", "nekmf_basis",
     "nekmf_op_create", "nekmf_op_set_geom", "nekmf_op_set_lambda", "nekmf_op_apply", "nekmf_op_set_stream",
     "nekmf_op_ncoeff", "nekmf_op_nphys", "nekmf_op_kernel_name", "nekmf_op_enable_timing", "nekmf_op_last_ms",

@@ -290,3 +290,62 @@ def test_cpp_collections_mirror():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "PASSED" in r.stdout
+
+
+@pytest.mark.parametrize("case", ["hex_regular_diag", "hex_regular_sheared", "hex_deformed", "tet_deformed", "quad_regular"])
+def test_host_array_pipeline_many_chunks(case):
+    """NEKMF_HOST applies are cut into ~8 MB element chunks over a 3-stream H2D/kernel/D2H pipeline
+    (abi.cu): collections large enough for several chunks (ragged last one) must give exactly the
+    device-array result for every operator (incl. 3-input / 3-output ones), and match the oracle."""
+    torch = _torch()
+    nk = nekmf()
+    rng = np.random.default_rng(hash(case) % 1000)
+    shape, nm, nq0, nel, deformed = {
+        "hex_regular_diag": (po.HEX, 5, 6, 20001, False), "hex_regular_sheared": (po.HEX, 5, 6, 20001, False),
+        "hex_deformed": (po.HEX, 4, 5, 25003, True), "tet_deformed": (po.TET, 5, 6, 40001, True),
+        "quad_regular": (po.QUAD, 6, 7, 90001, False)}[case]
+    el = po.Elem(shape, nm, nq0)
+    jac, df = random_geometry(rng, el.dim, nel, el.nqTot, deformed)
+    if case == "hex_regular_diag":
+        df = df.reshape(9, nel).copy()
+        for n in range(9):
+            if n not in (0, 4, 8):
+                df[n] = 0.0
+        df = df.reshape(-1)
+    std = nk.StdExpansion(shape, nm, nq0)
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, deformed))
+    x = rng.uniform(-1, 1, nel * el.nmTot)
+    f = [rng.uniform(-1, 1, nel * el.nqTot) for _ in range(el.dim)]
+    dev = torch.device("cuda", 0)
+    tx = torch.from_numpy(x).to(dev)
+    tf = [torch.from_numpy(a).to(dev) for a in f]
+
+    def both(op, ins_h, ins_d, nout, out_len, **kw):
+        oh = [np.zeros(out_len) for _ in range(nout)]
+        od = [torch.zeros(out_len, dtype=torch.float64, device=dev) for _ in range(nout)]
+        if op == nk.eIProductWRTDerivBase:
+            coll.ApplyOperator(op, *ins_h, oh[0])
+            coll.ApplyOperator(op, *ins_d, od[0])
+        else:
+            coll.ApplyOperator(op, ins_h[0], *oh, **kw)
+            coll.ApplyOperator(op, ins_d[0], *od, **kw)
+        torch.cuda.synchronize()
+        for a, b in zip(oh, od):
+            assert np.array_equal(a, b.cpu().numpy()), "host-array and device-array results differ (op %d)" % op
+        return oh
+
+    both(nk.eBwdTrans, [x], [tx], 1, nel * el.nqTot)
+    both(nk.eIProductWRTBase, [f[0]], [tf[0]], 1, nel * el.nmTot)
+    both(nk.ePhysDeriv, [f[0]], [tf[0]], el.dim, nel * el.nqTot)
+    if case == "hex_regular_diag":
+        assert "kron" in coll.m_ops[nk.eHelmholtz].kernel_name if nk.eHelmholtz in coll.m_ops else True
+    h = both(nk.eHelmholtz, [x], [tx], 1, nel * el.nmTot, factors={nk.eFactorLambda: 0.7})[0]
+    if shape in (po.QUAD, po.HEX):
+        both(nk.eIProductWRTDerivBase, f, tf, 1, nel * el.nmTot)
+    # oracle on the last 300 elements (covers the ragged last chunk and its geometry offsets)
+    ns = 300
+    e0 = nel - ns
+    gs = el.nqTot if deformed else 1
+    jac_s = jac[e0 * gs:]
+    df_s = np.ascontiguousarray(df.reshape(el.dim * el.dim, -1)[:, e0 * gs:]).reshape(-1)
+    check(h[e0 * el.nmTot:], el.helmholtz(ns, deformed, jac_s, df_s, 0.7, x[e0 * el.nmTot:]), "Helmholtz tail")

@@ -87,7 +87,9 @@ def main():
         mine = x.cpu().numpy()[mesh.lattice_ids]
         want = xo[full.lattice_ids][mesh.gz0:mesh.gz1 + 1]
         err = np.abs(mine - want).max() / np.abs(xo).max()
-        ok = err < 1e-10 and abs(its - itso) <= 2
+        # tol=1e-13 is at the round-off plateau: the iteration at which r.r crosses it depends on the
+        # summation order of the (ownership-masked, all-reduced) dot products, so allow a few percent
+        ok = err < 1e-10 and abs(its - itso) <= max(2, 0.05 * itso)
         t = torch.tensor([0.0 if ok else 1.0], device=dev)
         if dist is not None:
             dist.all_reduce(t)
