@@ -1,5 +1,6 @@
 // abi.cu -- the C ABI of include/nekmf_b200.h: library, memory helpers and the elemental
 // operator object (create / set_geom / set_lambda / apply / destroy).
+#include <stdlib.h>
 #include "op_internal.h"
 #include <stdarg.h>
 #include <string.h>
@@ -274,7 +275,7 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
     bool ok       = false;
     op->geo_pitch = op->nqTot;
     if (shape == NEKMF_HEX) ok = select_hex_fast(op);
-    if (!ok && shape == NEKMF_QUAD) ok = select_quad_fast(op);
+    if (!ok && shape != NEKMF_HEX) ok = select_shape_fast(op);
     if (!ok) ok = select_generic(op);
     if (!ok)
     {
@@ -450,7 +451,12 @@ int nekmf_op_apply(nekmf_op_t op, const double *in0, const double *in1, const do
     // chunk: about 8 MB of the larger of (inputs, outputs); element counts even so that every chunk
     // of every array stays 16-byte aligned for the TMA-fed kernels
     const size_t el_bytes = 8 * (in_el * nin > out_el * nout ? in_el * nin : out_el * nout);
-    int chunk = (int)((size_t)(8u << 20) / el_bytes);
+    static const size_t chunk_bytes = [] {
+        const char *v = getenv("NEKMF_HOST_CHUNK_MB"); // tuning knob; default 8 MB
+        const long mb = v ? atol(v) : 0;
+        return (size_t)(mb > 0 ? mb : 8) << 20;
+    }();
+    int chunk = (int)(chunk_bytes / el_bytes);
     chunk &= ~1;
     if (chunk < 2) chunk = 2;
     // work queued earlier on the operator's stream (e.g. a device-array apply) stays ordered before us

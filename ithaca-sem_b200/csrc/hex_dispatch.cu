@@ -34,6 +34,26 @@ bool select_hex_fast(nekmf_op_s *op)
     return ok;
 }
 
-bool select_quad_fast(nekmf_op_s *) { return false; }
+#define SHP_DECL(n) bool shape_try_nm##n(nekmf_op_s *op);
+SHP_DECL(2) SHP_DECL(3) SHP_DECL(4) SHP_DECL(5) SHP_DECL(6) SHP_DECL(7) SHP_DECL(8) SHP_DECL(9)
+#undef SHP_DECL
+
+// Quad / Tri / Prism / Tet with the default quadrature: compile-time sized kernels (shape_kernels.cuh)
+bool select_shape_fast(nekmf_op_s *op)
+{
+    if (op->shape == NEKMF_HEX || op->shape == NEKMF_PYR) return false;
+    switch (op->nm[0])
+    {
+        case 2: return shape_try_nm2(op);
+        case 3: return shape_try_nm3(op);
+        case 4: return shape_try_nm4(op);
+        case 5: return shape_try_nm5(op);
+        case 6: return shape_try_nm6(op);
+        case 7: return shape_try_nm7(op);
+        case 8: return shape_try_nm8(op);
+        case 9: return shape_try_nm9(op);
+    }
+    return false;
+}
 void notify_geom_changed(nekmf_op_s *op) { kron_geom_changed(op); }
 } // namespace nekmf

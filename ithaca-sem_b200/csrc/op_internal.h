@@ -53,7 +53,7 @@ namespace nekmf
 {
 // each returns true if it installed a launcher for this operator
 bool select_hex_fast(nekmf_op_s *op);
-bool select_quad_fast(nekmf_op_s *op);
+bool select_shape_fast(nekmf_op_s *op);
 bool select_generic(nekmf_op_s *op);
 // called after set_geom / set_lambda so launchers can precompute (e.g. detect diagonal metrics)
 void notify_geom_changed(nekmf_op_s *op);

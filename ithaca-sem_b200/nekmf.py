@@ -110,6 +110,8 @@ def lib():
         L.nekmf_free_device.argtypes = [_vp]
         L.nekmf_malloc_pinned.argtypes = [C.POINTER(_vp), C.c_size_t]
         L.nekmf_free_pinned.argtypes = [_vp]
+        L.nekmf_host_register.argtypes = [_vp, C.c_size_t]
+        L.nekmf_host_unregister.argtypes = [_vp]
         L.nekmf_memcpy_h2d.argtypes = [_vp, _vp, C.c_size_t]
         L.nekmf_memcpy_d2h.argtypes = [_vp, _vp, C.c_size_t]
         L.nekmf_memset_device.argtypes = [_vp, C.c_int, C.c_size_t]

@@ -349,3 +349,17 @@ def test_host_array_pipeline_many_chunks(case):
     jac_s = jac[e0 * gs:]
     df_s = np.ascontiguousarray(df.reshape(el.dim * el.dim, -1)[:, e0 * gs:]).reshape(-1)
     check(h[e0 * el.nmTot:], el.helmholtz(ns, deformed, jac_s, df_s, 0.7, x[e0 * el.nmTot:]), "Helmholtz tail")
+
+
+@pytest.mark.parametrize("deformed", [False, True])
+@pytest.mark.parametrize("nm", list(range(2, 10)))
+@pytest.mark.parametrize("shape", ["Quad", "Tri", "Prism", "Tet"])
+def test_shape_fast_kernels(shape, nm, deformed):
+    """compile-time sized Quad/Tri/Prism/Tet kernels (shape_kernels.cuh), nm=2..9 with the default quadrature:
+    several batches per CTA plus a ragged last batch; singular vertex/edge (CORRECT) terms folded into the
+    sum-factorisation intermediates must reproduce the reference's separate correction loops."""
+    nk = nekmf()
+    nel = {"Quad": 331, "Tri": 331, "Prism": 67, "Tet": 67}[shape]
+    coll = run_all_ops(nk, SHAPES[shape], nm, nm + 1, nel, deformed, np.random.default_rng(31 * nm + len(shape)))
+    for op in (nk.eBwdTrans, nk.eIProductWRTBase, nk.ePhysDeriv, nk.eHelmholtz):
+        assert "shape_op_kernel" in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
