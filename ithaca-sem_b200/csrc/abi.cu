@@ -161,11 +161,6 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
         set_error("nekmf_op_create: coordim %d != element dimension %d is not supported", coordim, dim);
         return NEKMF_ERR_UNSUPPORTED;
     }
-    if (optype == NEKMF_IPRODUCTWRTDERIVBASE && shape != NEKMF_QUAD && shape != NEKMF_HEX)
-    {
-        set_error("nekmf_op_create: IProductWRTDerivBase is implemented for Quad and Hex only");
-        return NEKMF_ERR_UNSUPPORTED;
-    }
     // expected basis / points per direction (SpatialDomains/MeshGraph.cpp:1609-1762) and the
     // isotropy preconditions asserted by the reference (Helmholtz.h:42-44,329-331,1042-1046,2017-2021)
     int ebt[3] = {NEKMF_MODIFIED_A, NEKMF_MODIFIED_A, NEKMF_MODIFIED_A};

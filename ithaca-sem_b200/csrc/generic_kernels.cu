@@ -628,15 +628,44 @@ template <int SHAPE> __global__ void __launch_bounds__(256) gen_kernel(const __g
                     if (dim == 3)
                     {
                         const double x = sIn[t], y = s3[t], z = s4[t];
-                        sIn[t] = GDF(0) * x + GDF(3) * y + GDF(6) * z;
-                        s3[t]  = GDF(1) * x + GDF(4) * y + GDF(7) * z;
-                        s4[t]  = GDF(2) * x + GDF(5) * y + GDF(8) * z;
+                        double t0 = GDF(0) * x + GDF(3) * y + GDF(6) * z;
+                        double t1 = GDF(1) * x + GDF(4) * y + GDF(7) * z;
+                        const double t2 = GDF(2) * x + GDF(5) * y + GDF(8) * z;
+                        if (SHAPE == NEKMF_PRISM)
+                        {
+                            // collapsed (xi_0, xi_2): IProductWRTDerivBase.h:1697-1733
+                            const int i = t % c.nq0, k = t / (c.nq0 * c.nq1);
+                            const double f0 = 2.0 / (1.0 - c.Z[2][k]), hf1 = 0.5 * (1.0 + c.Z[0][i]);
+                            t0 = t0 * f0 + (hf1 * t2) * f0;
+                        }
+                        else if (SHAPE == NEKMF_TET)
+                        {
+                            // IProductWRTDerivBase.h:2551-2603
+                            const int i = t % c.nq0, j = (t / c.nq0) % c.nq1, k = t / (c.nq0 * c.nq1);
+                            const double z1 = c.Z[1][j];
+                            const double f2 = 2.0 / (1.0 - c.Z[2][k]), f3 = 0.5 * (1.0 + z1), f0 = 2.0 * f2 / (1.0 - z1);
+                            const double f1 = 0.5 * (1.0 + c.Z[0][i]);
+                            t0 = (t0 + (t1 + t2) * f1) * f0;
+                            t1 = (t1 + t2 * f3) * f2;
+                        }
+                        sIn[t] = t0;
+                        s3[t]  = t1;
+                        s4[t]  = t2;
                     }
                     else
                     {
                         const double x = sIn[t], y = s3[t];
-                        sIn[t] = GDF(0) * x + GDF(2) * y;
-                        s3[t]  = GDF(1) * x + GDF(3) * y;
+                        double t0 = GDF(0) * x + GDF(2) * y;
+                        const double t1 = GDF(1) * x + GDF(3) * y;
+                        if (SHAPE == NEKMF_TRI)
+                        {
+                            // IProductWRTDerivBase.h:1006-1036
+                            const int i = t % c.nq0, j = t / c.nq0;
+                            const double f0 = 2.0 / (1.0 - c.Z[1][j]), hf1 = 0.5 * (1.0 + c.Z[0][i]);
+                            t0 = t0 * f0 + (hf1 * t1) * f0;
+                        }
+                        sIn[t] = t0;
+                        s3[t]  = t1;
                     }
                 }
                 __syncthreads();

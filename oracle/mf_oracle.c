@@ -1414,7 +1414,6 @@ int mfo_iproductwrtderivbase(const mfo_elem *e, int nElmt, int DEF, const double
                              const double *in0, const double *in1, const double *in2, double *out)
 {
     const size_t dfs = DEF ? (size_t)nElmt * e->nqTot : (size_t)nElmt;
-    if (e->shape != MFO_HEX && e->shape != MFO_QUAD) return -1;
 #pragma omp parallel num_threads(g_threads)
     {
         scratch s = scratch_new(e->nqTot, e->nmTot);
@@ -1432,9 +1431,31 @@ int mfo_iproductwrtderivbase(const mfo_elem *e, int nElmt, int DEF, const double
                 for (pt = 0; pt < e->nqTot; ++pt)
                 {
                     double a = in0[qoff + pt], b = in1[qoff + pt], c = in2[qoff + pt];
-                    t0[pt] = DFE(0) * a + DFE(3) * b + DFE(6) * c;
-                    t1[pt] = DFE(1) * a + DFE(4) * b + DFE(7) * c;
-                    t2[pt] = DFE(2) * a + DFE(5) * b + DFE(8) * c;
+                    double v0 = DFE(0) * a + DFE(3) * b + DFE(6) * c;
+                    double v1 = DFE(1) * a + DFE(4) * b + DFE(7) * c;
+                    double v2 = DFE(2) * a + DFE(5) * b + DFE(8) * c;
+                    if (e->shape == MFO_PRISM)
+                    {
+                        /* IProductWRTDerivBase.h:1697-1733 */
+                        int i = pt % e->nq[0], k = pt / (e->nq[0] * e->nq[1]);
+                        double f0 = 2.0 / (1.0 - e->z[2][k]), hf1 = 0.5 * (1.0 + e->z[0][i]), f1t2;
+                        v0 *= f0;
+                        f1t2 = hf1 * v2;
+                        v0 += f1t2 * f0;
+                    }
+                    else if (e->shape == MFO_TET)
+                    {
+                        /* IProductWRTDerivBase.h:2551-2603 */
+                        int i = pt % e->nq[0], j = (pt / e->nq[0]) % e->nq[1], k = pt / (e->nq[0] * e->nq[1]);
+                        double z1 = e->z[1][j];
+                        double f2 = 2.0 / (1.0 - e->z[2][k]), f3 = 0.5 * (1.0 + z1), f0 = 2.0 * f2 / (1.0 - z1);
+                        double f1 = 0.5 * (1.0 + e->z[0][i]);
+                        v0 += (v1 + v2) * f1;
+                        v0 *= f0;
+                        v1 += v2 * f3;
+                        v1 *= f2;
+                    }
+                    t0[pt] = v0; t1[pt] = v1; t2[pt] = v2;
                 }
                 ip_one(e, t0, e->db[0], e->b[1], e->b[2], jc, DEF, out + moff, 1.0, 0, 0, &s);
                 ip_one(e, t1, e->b[0], e->db[1], e->b[2], jc, DEF, out + moff, 1.0, 0, 1, &s);
@@ -1445,8 +1466,18 @@ int mfo_iproductwrtderivbase(const mfo_elem *e, int nElmt, int DEF, const double
                 for (pt = 0; pt < e->nqTot; ++pt)
                 {
                     double a = in0[qoff + pt], b = in1[qoff + pt];
-                    t0[pt] = DFE(0) * a + DFE(2) * b;
-                    t1[pt] = DFE(1) * a + DFE(3) * b;
+                    double v0 = DFE(0) * a + DFE(2) * b;
+                    double v1 = DFE(1) * a + DFE(3) * b;
+                    if (e->shape == MFO_TRI)
+                    {
+                        /* IProductWRTDerivBase.h:1006-1036 */
+                        int i = pt % e->nq[0], j = pt / e->nq[0];
+                        double f0 = 2.0 / (1.0 - e->z[1][j]), hf1 = 0.5 * (1.0 + e->z[0][i]), c1;
+                        v0 *= f0;
+                        c1 = hf1 * v1;
+                        v0 += c1 * f0;
+                    }
+                    t0[pt] = v0; t1[pt] = v1;
                 }
                 ip_one(e, t0, e->db[0], e->b[1], NULL, jc, DEF, out + moff, 1.0, 0, 0, &s);
                 ip_one(e, t1, e->b[0], e->db[1], NULL, jc, DEF, out + moff, 1.0, 0, 1, &s);

@@ -64,7 +64,7 @@ void mfo_physderiv(const mfo_elem *e, int nElmt, int deformed, const double *df,
                    double *out0, double *out1, double *out2);
 void mfo_helmholtz(const mfo_elem *e, int nElmt, int deformed, const double *jac, const double *df,
                    double lambda, const double *in, double *out);
-/* hex and quad only */
+/* Quad, Tri, Hex, Prism, Tet (IProductWRTDerivBase.h:542,891,1232,1630,2484) */
 int mfo_iproductwrtderivbase(const mfo_elem *e, int nElmt, int deformed, const double *jac, const double *df,
                              const double *in0, const double *in1, const double *in2, double *out);
 

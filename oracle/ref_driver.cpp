@@ -404,7 +404,53 @@ template <int NM, int NQ, bool DEF> struct TriOps
         }
         PAR_BLOCKS_END
     }
-    static void ipwdb(Ctx &) {}
+    // IProductWRTDerivBase.h:891-1060 (coordim 2)
+    static void ipwdb(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        const size_t dfSize = DEF ? (size_t)ndf * nqTot : ndf;
+        PAR_BLOCKS_BEGIN(c)
+        vec_t sums_j[NQ1 > NM ? NQ1 : NM];
+        VecVec i0(nqTot), i1(nqTot), t0v(nqTot), t1v(nqTot), tmpOut(nmTot);
+        vec_t df0, df1, df2, df3;
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            const vec_t *df_ptr  = &c.df[e * dfSize];
+            const vec_t *jac_ptr = DEF ? &c.jac[(size_t)nqTot * e] : &c.jac[e];
+            load_interleave(c.in[0] + (size_t)e * nqTot * W, nqTot, i0);
+            load_interleave(c.in[1] + (size_t)e * nqTot * W, nqTot, i1);
+            if (!DEF) { df0 = df_ptr[0]; df1 = df_ptr[1]; df2 = df_ptr[2]; df3 = df_ptr[3]; }
+            size_t cnt = 0;
+            for (size_t j = 0; j < NQ1; ++j)
+            {
+                vec_t f0 = 2.0 / (1.0 - c.Z[1][j]);
+                for (size_t i = 0; i < NQ; ++i, ++cnt)
+                {
+                    if (DEF)
+                    {
+                        df0 = df_ptr[cnt * ndf]; df1 = df_ptr[cnt * ndf + 1];
+                        df2 = df_ptr[cnt * ndf + 2]; df3 = df_ptr[cnt * ndf + 3];
+                    }
+                    vec_t a = i0[cnt], b = i1[cnt];
+                    vec_t t0 = df0 * a + df2 * b;
+                    vec_t t1 = df1 * a + df3 * b;
+                    vec_t hf1 = 0.5 * (1.0 + c.Z[0][i]);
+                    t0 *= f0;
+                    vec_t c1 = hf1 * t1;
+                    t0.fma(c1, f0);
+                    t0v[cnt] = t0;
+                    t1v[cnt] = t1;
+                }
+            }
+            IProductTriKernel<NM, NM, NQ, NQ1, CORRECT, false, false, DEF>(
+                t0v, c.dbdata[0], c.bdata[1], c.w[0], c.w[1], jac_ptr, sums_j, tmpOut);
+            IProductTriKernel<NM, NM, NQ, NQ1, CORRECT, false, true, DEF>(
+                t1v, c.bdata[0], c.dbdata[1], c.w[0], c.w[1], jac_ptr, sums_j, tmpOut);
+            deinterleave_store(tmpOut, nmTot, c.out[0] + (size_t)e * nmTot * W);
+        }
+        PAR_BLOCKS_END
+    }
 };
 
 // =============================================================== HEX
@@ -715,7 +761,62 @@ template <int NM, int NQ, bool DEF> struct PrismOps
         }
         PAR_BLOCKS_END
     }
-    static void ipwdb(Ctx &) {}
+    // IProductWRTDerivBase.h:1630-1778
+    static void ipwdb(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        const size_t dfSize = DEF ? (size_t)ndf * nqTot : ndf;
+        PAR_BLOCKS_BEGIN(c)
+        vec_t wsp1[NQ * NQ2 > NM * NM ? NQ * NQ2 : NM * NM], wsp2[NQ2 > NM ? NQ2 : NM], wsp3[NM];
+        VecVec i0(nqTot), i1(nqTot), i2(nqTot), t0v(nqTot), t1v(nqTot), t2v(nqTot), tmpOut(nmTot);
+        vec_t df0, df1, df2, df3, df4, df5, df6, df7, df8;
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            const vec_t *df_ptr  = &c.df[e * dfSize];
+            const vec_t *jac_ptr = DEF ? &c.jac[(size_t)nqTot * e] : &c.jac[e];
+            load_interleave(c.in[0] + (size_t)e * nqTot * W, nqTot, i0);
+            load_interleave(c.in[1] + (size_t)e * nqTot * W, nqTot, i1);
+            load_interleave(c.in[2] + (size_t)e * nqTot * W, nqTot, i2);
+            if (!DEF)
+            {
+                df0 = df_ptr[0]; df1 = df_ptr[1]; df2 = df_ptr[2];
+                df3 = df_ptr[3]; df4 = df_ptr[4]; df5 = df_ptr[5];
+                df6 = df_ptr[6]; df7 = df_ptr[7]; df8 = df_ptr[8];
+            }
+            for (size_t k = 0, cnt = 0; k < NQ2; ++k)
+            {
+                vec_t f0 = 2.0 / (1.0 - c.Z[2][k]);
+                for (size_t j = 0; j < NQ; ++j)
+                    for (size_t i = 0; i < NQ; ++i, ++cnt)
+                    {
+                        if (DEF)
+                        {
+                            df0 = df_ptr[cnt * ndf]; df1 = df_ptr[cnt * ndf + 1]; df2 = df_ptr[cnt * ndf + 2];
+                            df3 = df_ptr[cnt * ndf + 3]; df4 = df_ptr[cnt * ndf + 4]; df5 = df_ptr[cnt * ndf + 5];
+                            df6 = df_ptr[cnt * ndf + 6]; df7 = df_ptr[cnt * ndf + 7]; df8 = df_ptr[cnt * ndf + 8];
+                        }
+                        vec_t a = i0[cnt], b = i1[cnt], g = i2[cnt];
+                        vec_t t0 = df0 * a + df3 * b + df6 * g;
+                        vec_t t1 = df1 * a + df4 * b + df7 * g;
+                        vec_t t2 = df2 * a + df5 * b + df8 * g;
+                        vec_t hf1 = 0.5 * (1.0 + c.Z[0][i]);
+                        t0 *= f0;
+                        vec_t f1t2 = hf1 * t2;
+                        t0.fma(f1t2, f0);
+                        t0v[cnt] = t0; t1v[cnt] = t1; t2v[cnt] = t2;
+                    }
+            }
+            IProductPrismKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT, false, false, DEF>(
+                t0v, c.dbdata[0], c.bdata[1], c.bdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp1, wsp2, wsp3, tmpOut);
+            IProductPrismKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT, false, true, DEF>(
+                t1v, c.bdata[0], c.dbdata[1], c.bdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp1, wsp2, wsp3, tmpOut);
+            IProductPrismKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT, false, true, DEF>(
+                t2v, c.bdata[0], c.bdata[1], c.dbdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp1, wsp2, wsp3, tmpOut);
+            deinterleave_store(tmpOut, nmTot, c.out[0] + (size_t)e * nmTot * W);
+        }
+        PAR_BLOCKS_END
+    }
 };
 
 // =============================================================== TET (nq = NQ,NQ-1,NQ-1)
@@ -853,7 +954,68 @@ template <int NM, int NQ, bool DEF> struct TetOps
         }
         PAR_BLOCKS_END
     }
-    static void ipwdb(Ctx &) {}
+    // IProductWRTDerivBase.h:2484-2640
+    static void ipwdb(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        const size_t dfSize = DEF ? (size_t)ndf * nqTot : ndf;
+        PAR_BLOCKS_BEGIN(c)
+        vec_t wsp[NQ1 * NQ2 + NQ2];
+        VecVec i0(nqTot), i1(nqTot), i2(nqTot), t0v(nqTot), t1v(nqTot), t2v(nqTot), tmpOut(nmTot);
+        vec_t df0, df1, df2, df3, df4, df5, df6, df7, df8;
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            const vec_t *df_ptr  = &c.df[e * dfSize];
+            const vec_t *jac_ptr = DEF ? &c.jac[(size_t)nqTot * e] : &c.jac[e];
+            load_interleave(c.in[0] + (size_t)e * nqTot * W, nqTot, i0);
+            load_interleave(c.in[1] + (size_t)e * nqTot * W, nqTot, i1);
+            load_interleave(c.in[2] + (size_t)e * nqTot * W, nqTot, i2);
+            if (!DEF)
+            {
+                df0 = df_ptr[0]; df1 = df_ptr[1]; df2 = df_ptr[2];
+                df3 = df_ptr[3]; df4 = df_ptr[4]; df5 = df_ptr[5];
+                df6 = df_ptr[6]; df7 = df_ptr[7]; df8 = df_ptr[8];
+            }
+            for (size_t k = 0, cnt = 0; k < NQ2; ++k)
+            {
+                vec_t f2 = 2.0 / (1.0 - c.Z[2][k]);
+                for (size_t j = 0; j < NQ1; ++j)
+                {
+                    vec_t Z1Load = c.Z[1][j];
+                    vec_t f3 = 0.5 * (1.0 + Z1Load);
+                    vec_t f0 = 2.0 * f2 / (1.0 - Z1Load);
+                    for (size_t i = 0; i < NQ; ++i, ++cnt)
+                    {
+                        if (DEF)
+                        {
+                            df0 = df_ptr[cnt * ndf]; df1 = df_ptr[cnt * ndf + 1]; df2 = df_ptr[cnt * ndf + 2];
+                            df3 = df_ptr[cnt * ndf + 3]; df4 = df_ptr[cnt * ndf + 4]; df5 = df_ptr[cnt * ndf + 5];
+                            df6 = df_ptr[cnt * ndf + 6]; df7 = df_ptr[cnt * ndf + 7]; df8 = df_ptr[cnt * ndf + 8];
+                        }
+                        vec_t a = i0[cnt], b = i1[cnt], g = i2[cnt];
+                        vec_t t0 = df0 * a + df3 * b + df6 * g;
+                        vec_t t1 = df1 * a + df4 * b + df7 * g;
+                        vec_t t2 = df2 * a + df5 * b + df8 * g;
+                        vec_t f1 = 0.5 * (1.0 + c.Z[0][i]);
+                        t0.fma(t1 + t2, f1);
+                        t0 *= f0;
+                        t1.fma(t2, f3);
+                        t1 *= f2;
+                        t0v[cnt] = t0; t1v[cnt] = t1; t2v[cnt] = t2;
+                    }
+                }
+            }
+            IProductTetKernel<NM, NM, NM, NQ, NQ1, NQ2, CORRECT, false, false, DEF>(
+                t0v, c.dbdata[0], c.bdata[1], c.bdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp, tmpOut);
+            IProductTetKernel<NM, NM, NM, NQ, NQ1, NQ2, CORRECT, false, true, DEF>(
+                t1v, c.bdata[0], c.dbdata[1], c.bdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp, tmpOut);
+            IProductTetKernel<NM, NM, NM, NQ, NQ1, NQ2, CORRECT, false, true, DEF>(
+                t2v, c.bdata[0], c.bdata[1], c.dbdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp, tmpOut);
+            deinterleave_store(tmpOut, nmTot, c.out[0] + (size_t)e * nmTot * W);
+        }
+        PAR_BLOCKS_END
+    }
 };
 
 template <class Ops> int run_op(int op, Ctx &c)

@@ -58,8 +58,7 @@ def main():
             for d in range(el.dim):
                 out[key + "_pd%d" % d] = pd[d]
             out[key + "_helm"] = ref.operator(po.OP_HELM, el, NEL, deformed, jac, df)(x, lam=LAMBDA)
-            if shape in (po.QUAD, po.HEX):
-                out[key + "_ipwdb"] = ref.operator(po.OP_IPWDB, el, NEL, deformed, jac, df)(f)
+            out[key + "_ipwdb"] = ref.operator(po.OP_IPWDB, el, NEL, deformed, jac, df)(f)
     np.savez_compressed(os.path.join(HERE, "ref_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -46,10 +46,9 @@ def run_all_ops(nk, shape, nm, nq0, nel, deformed, rng, lam=1.3, geometry=None):
     out = np.zeros(nel * el.nmTot)
     coll.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
     check(out, el.helmholtz(nel, deformed, jac, df, lam, x), "Helmholtz")
-    if shape in (po.QUAD, po.HEX):
-        out = np.zeros(nel * el.nmTot)
-        coll.ApplyOperator(nk.eIProductWRTDerivBase, *f, out)
-        check(out, el.iproductwrtderivbase(nel, deformed, jac, df, f), "IProductWRTDerivBase")
+    out = np.zeros(nel * el.nmTot)
+    coll.ApplyOperator(nk.eIProductWRTDerivBase, *f, out)
+    check(out, el.iproductwrtderivbase(nel, deformed, jac, df, f), "IProductWRTDerivBase")
     return coll
 
 
@@ -102,10 +101,9 @@ def test_against_reference_golden_vectors(key):
     out = np.zeros(nel * ncoef)
     coll.ApplyOperator(nk.eHelmholtz, g("x"), out, factors={nk.eFactorLambda: 1.5})
     check(out, g("helm"), "Helmholtz")
-    if shape in (po.QUAD, po.HEX):
-        out = np.zeros(nel * ncoef)
-        coll.ApplyOperator(nk.eIProductWRTDerivBase, *[g("f%d" % d) for d in range(std.dim)], out)
-        check(out, g("ipwdb"), "IProductWRTDerivBase")
+    out = np.zeros(nel * ncoef)
+    coll.ApplyOperator(nk.eIProductWRTDerivBase, *[g("f%d" % d) for d in range(std.dim)], out)
+    check(out, g("ipwdb"), "IProductWRTDerivBase")
 
 
 def box_geometry(nel, hx, hy, hz):
@@ -340,8 +338,7 @@ def test_host_array_pipeline_many_chunks(case):
     if case == "hex_regular_diag":
         assert "kron" in coll.m_ops[nk.eHelmholtz].kernel_name if nk.eHelmholtz in coll.m_ops else True
     h = both(nk.eHelmholtz, [x], [tx], 1, nel * el.nmTot, factors={nk.eFactorLambda: 0.7})[0]
-    if shape in (po.QUAD, po.HEX):
-        both(nk.eIProductWRTDerivBase, f, tf, 1, nel * el.nmTot)
+    both(nk.eIProductWRTDerivBase, f, tf, 1, nel * el.nmTot)
     # oracle on the last 300 elements (covers the ragged last chunk and its geometry offsets)
     ns = 300
     e0 = nel - ns
