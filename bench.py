@@ -299,7 +299,6 @@ def main():
                         op.apply([x], [y])
                     torch.cuda.synchronize()
             clocks = sampler.stop()
-            launches = K
         total_ms = ev[0].elapsed_time(ev[K])
         per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(K))
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)

@@ -69,6 +69,45 @@ __global__ void assemble_kernel(const int *__restrict__ rowptr, const int *__res
     glob[g] = s;
 }
 
+// Assemble fused with the CG dot product mu = sum_{g >= nDir} mask[g] * glob[g] * w[g] (the s.w of
+// NekLinSysIterCG.cpp:226-235): fixed grid, grid-stride, one partial sum per block -> deterministic.
+__global__ void __launch_bounds__(256)
+    assemble_dot_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ sign,
+                        const double *__restrict__ loc, double *__restrict__ glob, int nGlobal,
+                        const double *__restrict__ w, const double *__restrict__ mask, int nDir,
+                        double *__restrict__ part)
+{
+    __shared__ double sh[8];
+    double mu = 0.0;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nGlobal; g += gridDim.x * blockDim.x)
+    {
+        const int b = rowptr[g], e = rowptr[g + 1];
+        double s = 0.0;
+        for (int k = b; k < e; ++k)
+        {
+            const int i = col[k];
+            s += sign ? sign[i] * __ldg(loc + i) : __ldg(loc + i);
+        }
+        glob[g] = s;
+        if (g >= nDir)
+        {
+            const double wg = mask ? w[g] * mask[g] : w[g];
+            mu = fma(s, wg, mu);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mu;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        double r = threadIdx.x < 8 ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (threadIdx.x == 0) part[blockIdx.x] = r;
+    }
+}
+
 } // namespace nekmf
 
 using namespace nekmf;
@@ -159,6 +198,15 @@ int map_assemble_device(nekmf_map_s *m, const double *loc, double *glob, cudaStr
     const int threads = 256;
     assemble_kernel<<<(m->nGlobal + threads - 1) / threads, threads, 0, st>>>(m->d_rowptr, m->d_col, m->d_sign, loc,
                                                                                glob, m->nGlobal);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+int map_assemble_dot_device(nekmf_map_s *m, const double *loc, double *glob, const double *w, const double *mask,
+                            int nDir, double *part, int nBlocks, cudaStream_t st)
+{
+    assemble_dot_kernel<<<nBlocks, 256, 0, st>>>(m->d_rowptr, m->d_col, m->d_sign, loc, glob, m->nGlobal, w, mask, nDir,
+                                                 part);
     ++g_launches;
     NEKMF_CUDA(cudaGetLastError());
     return NEKMF_OK;

@@ -6,11 +6,17 @@
 // (MultiRegions/GlobalLinSysIterativeFull.cpp:215-257) and a diagonal (or identity)
 // preconditioner (MultiRegions/PreconditionerDiagonal.cpp).
 //
-// Device design: all vectors resident; the four axpy updates and the preconditioner are one
-// fused elementwise kernel; the three dot products are one fused two-stage deterministic
-// reduction (fixed grid, fixed order, ownership-masked for multi-rank runs) followed by a single
-// ncclAllReduce of 3 doubles; local/global work buffers are allocated once (the reference
-// allocates 2 x nLocal every mat-vec, GlobalLinSysIterativeFull.cpp:225-226).
+// Device design: all vectors resident.  One iteration is four kernels:
+//   cg_update_dots       the four axpy updates + preconditioner + partial sums of r.w and r.r
+//   Helmholtz (gather)   GlobalToLocal fused into the operator's loads (hex_kron.cu GATHER variant:
+//                        cp.async indirect loads straight into shared memory); other operator
+//                        kernels are preceded by the separate gather kernel
+//   assemble_dot         transpose-CSR Assemble + partial sums of s.w (a separate dot pass after
+//                        the NCCL interface exchange when the solve is sharded)
+//   dot3_final           fixed-order reduction of the partials -> one ncclAllReduce of 3 doubles
+// Reductions use a fixed grid and order (deterministic, ownership-masked for multi-rank runs);
+// work buffers are allocated once (the reference allocates 2 x nLocal every mat-vec,
+// GlobalLinSysIterativeFull.cpp:225-226).
 #include "map_internal.h"
 
 struct nekmf_cg_s
@@ -32,7 +38,7 @@ struct nekmf_cg_s
 
 namespace nekmf
 {
-constexpr int RED_BLOCKS = 592; // 4 x 148
+constexpr int RED_BLOCKS = 1184; // 8 x 148: every SM holds its 2048 threads
 constexpr int RED_T      = 256;
 
 __device__ __forceinline__ double block_sum(double v, double *sh)
@@ -91,21 +97,51 @@ __global__ void __launch_bounds__(RED_T) dot3_final(const double *__restrict__ p
 }
 
 // p = beta p + w ; q = beta q + s ; x += alpha p ; r -= alpha q ; w = M^-1 r
-// (NekLinSysIterCG.cpp:209-220); w,s,x are offset to the first non-Dirichlet DOF
-__global__ void cg_update(double *__restrict__ p, double *__restrict__ q, double *__restrict__ x, double *__restrict__ r,
-                          double *__restrict__ w, const double *__restrict__ s, const double *__restrict__ invdiag,
-                          double alpha, double beta, int n)
+// (NekLinSysIterCG.cpp:209-220); w,s,x are offset to the first non-Dirichlet DOF.
+// Fused with the two dot products that do not depend on the next mat-vec:
+// rho = r.w and eps = r.r (ownership-masked).  Fixed grid, grid-stride -> deterministic partial sums in
+// part[0..RED_BLOCKS) (rho) and part[2*RED_BLOCKS..) (eps); the s.w partials come from the assemble kernel.
+__global__ void __launch_bounds__(RED_T)
+    cg_update_dots(double *__restrict__ p, double *__restrict__ q, double *__restrict__ x, double *__restrict__ r,
+                   double *__restrict__ w, const double *__restrict__ s, const double *__restrict__ invdiag,
+                   const double *__restrict__ mask, double alpha, double beta, int n, double *__restrict__ part)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double pi = fma(beta, p[i], w[i]);
-    const double qi = fma(beta, q[i], s[i]);
-    const double ri = fma(-alpha, qi, r[i]);
-    p[i] = pi;
-    q[i] = qi;
-    x[i] = fma(alpha, pi, x[i]);
-    r[i] = ri;
-    w[i] = invdiag ? ri * invdiag[i] : ri;
+    __shared__ double sh[RED_T / 32];
+    double rho = 0.0, eps = 0.0;
+    for (int i = blockIdx.x * RED_T + threadIdx.x; i < n; i += RED_BLOCKS * RED_T)
+    {
+        const double pi = fma(beta, p[i], w[i]);
+        const double qi = fma(beta, q[i], s[i]);
+        const double ri = fma(-alpha, qi, r[i]);
+        const double wi = invdiag ? ri * invdiag[i] : ri;
+        p[i] = pi;
+        q[i] = qi;
+        x[i] = fma(alpha, pi, x[i]);
+        r[i] = ri;
+        w[i] = wi;
+        const double rm = mask ? ri * mask[i] : ri;
+        rho = fma(rm, wi, rho);
+        eps = fma(rm, ri, eps);
+    }
+    rho = block_sum(rho, sh);
+    eps = block_sum(eps, sh);
+    if (threadIdx.x == 0)
+    {
+        part[blockIdx.x]                  = rho;
+        part[2 * RED_BLOCKS + blockIdx.x] = eps;
+    }
+}
+// partial sums of one masked product into part[0..RED_BLOCKS)
+__global__ void __launch_bounds__(RED_T)
+    dot1_partial(const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ mask, int n,
+                 double *__restrict__ part)
+{
+    __shared__ double sh[RED_T / 32];
+    double s0 = 0.0;
+    for (int i = blockIdx.x * RED_T + threadIdx.x; i < n; i += RED_BLOCKS * RED_T)
+        s0 = fma(mask ? a[i] * mask[i] : a[i], b[i], s0);
+    s0 = block_sum(s0, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = s0;
 }
 __global__ void cg_precon(double *__restrict__ w, const double *__restrict__ r, const double *__restrict__ invdiag, int n)
 {
@@ -113,21 +149,58 @@ __global__ void cg_precon(double *__restrict__ w, const double *__restrict__ r, 
     if (i < n) w[i] = invdiag ? r[i] * invdiag[i] : r[i];
 }
 
-static int cg_matvec_device(nekmf_cg_s *cg, const double *w, double *s)
+// s = Assemble(Helmholtz(GlobalToLocal(w))) (+ interface exchange).  When the operator kernel can gather
+// (op->gather_ok) the GlobalToLocal pass is fused into its loads and no local input vector is written.
+// mu_part != null: the assemble kernel also leaves the partial sums of s.w over [nDir, nGlobal) there
+// (only valid without an exchange step: the interface contributions arrive after the assemble).
+static int cg_matvec_device(nekmf_cg_s *cg, const double *w, double *s, double *mu_part = nullptr)
 {
-    int rc = map_g2l_device(cg->map, w, cg->d_lin, cg->stream);
+    int rc;
+    nekmf_op_s *op = cg->op;
+    double *out[3] = {cg->d_lout, cg->d_lout, cg->d_lout};
+    op->run_e0     = 0;
+    op->run_ne     = op->nElmt;
+    op->run_stream = cg->stream;
+    if (op->gather_ok)
+    {
+        const double *in[3] = {w, w, w};
+        op->gather_map      = cg->map->d_map;
+        op->gather_sign     = cg->map->d_sign;
+        rc                  = op->launch(op, in, out);
+        op->gather_map      = nullptr;
+        op->gather_sign     = nullptr;
+    }
+    else
+    {
+        rc = map_g2l_device(cg->map, w, cg->d_lin, cg->stream);
+        if (rc) return rc;
+        const double *in[3] = {cg->d_lin, cg->d_lin, cg->d_lin};
+        rc                  = op->launch(op, in, out);
+    }
     if (rc) return rc;
-    const double *in[3] = {cg->d_lin, cg->d_lin, cg->d_lin};
-    double *out[3]      = {cg->d_lout, cg->d_lout, cg->d_lout};
-    cg->op->run_e0      = 0;
-    cg->op->run_ne      = cg->op->nElmt;
-    cg->op->run_stream  = cg->stream;
-    rc                  = cg->op->launch(cg->op, in, out);
-    if (rc) return rc;
-    rc = map_assemble_device(cg->map, cg->d_lout, s, cg->stream);
+    if (mu_part && cg->nGlobal > 0)
+        rc = map_assemble_dot_device(cg->map, cg->d_lout, s, w, cg->d_mask, cg->nDir, mu_part, RED_BLOCKS, cg->stream);
+    else
+        rc = map_assemble_device(cg->map, cg->d_lout, s, cg->stream);
     if (rc) return rc;
     if (cg->ex) rc = exchange_add_device(cg->ex, s, cg->stream);
     return rc;
+}
+
+// reduce the three partial-sum rows in d_part, all-reduce across ranks, bring the 3 values to the host
+static int cg_finish_dots(nekmf_cg_s *cg, double out[3])
+{
+    dot3_final<<<1, RED_T, 0, cg->stream>>>(cg->d_part, cg->d_red);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    int rc = comm_allreduce_sum(cg->comm, cg->d_red, 3, cg->stream);
+    if (rc) return rc;
+    NEKMF_CUDA(cudaMemcpyAsync(cg->h_red, cg->d_red, 3 * 8, cudaMemcpyDeviceToHost, cg->stream));
+    NEKMF_CUDA(cudaStreamSynchronize(cg->stream));
+    out[0] = cg->h_red[0];
+    out[1] = cg->h_red[1];
+    out[2] = cg->h_red[2];
+    return NEKMF_OK;
 }
 
 static int cg_dots(nekmf_cg_s *cg, const double *a, const double *b, const double *c, const double *d, const double *e,
@@ -241,13 +314,22 @@ int nekmf_cg_solve(nekmf_cg_t cg, const double *rhs_in, double *x_out, int memki
         for (;;)
         {
             if (k >= maxiter) break;
-            if (B > 0)
-                cg_update<<<B, T, 0, st>>>(cg->d_p, cg->d_q, x + nDir, cg->d_r, cg->d_w + nDir, cg->d_s + nDir,
-                                           cg->d_invdiag, alpha, beta, nN);
+            // update + (rho, eps) partials | mat-vec with the gather fused into the operator and the mu
+            // partials fused into the assemble | one final reduction + all-reduce + 24-byte D2H
+            cg_update_dots<<<RED_BLOCKS, RED_T, 0, st>>>(cg->d_p, cg->d_q, x + nDir, cg->d_r, cg->d_w + nDir,
+                                                         cg->d_s + nDir, cg->d_invdiag, mask_nd, alpha, beta, nN,
+                                                         cg->d_part);
             ++g_launches;
-            rc = cg_matvec_device(cg, cg->d_w, cg->d_s);
+            rc = cg_matvec_device(cg, cg->d_w, cg->d_s, cg->ex ? nullptr : cg->d_part + RED_BLOCKS);
             if (rc) return rc;
-            rc = cg_dots(cg, cg->d_r, cg->d_w + nDir, cg->d_s + nDir, cg->d_w + nDir, cg->d_r, cg->d_r, mask_nd, nN, red);
+            if (cg->ex)
+            {
+                // interface contributions arrive after the assemble: s.w needs its own pass
+                dot1_partial<<<RED_BLOCKS, RED_T, 0, st>>>(cg->d_s + nDir, cg->d_w + nDir, mask_nd, nN,
+                                                           cg->d_part + RED_BLOCKS);
+                ++g_launches;
+            }
+            rc = cg_finish_dots(cg, red);
             if (rc) return rc;
             rho_new = red[0]; mu = red[1]; eps = red[2];
             ++its;

@@ -46,6 +46,10 @@ struct KronArgs
     int nElmt;
     int io_aligned; // in and out 16-byte aligned
     double lambda;
+    // GATHER variant (CG mat-vec): `in` is the GLOBAL vector, the coefficient block of local DOF i is
+    // sign[i] * in[map[i]] (AssemblyMapCG::v_GlobalToLocal fused into the operator's load)
+    const int *map;
+    const double *sign;
 };
 
 constexpr int kron_pad(int minimum, int residue) // smallest v >= minimum with v % 16 == residue
@@ -57,7 +61,7 @@ constexpr int kron_pad(int minimum, int residue) // smallest v >= minimum with v
 
 // Every warp is an independent worker: it owns EPW elements per step, its own TMA-fed input
 // buffer, its own exchange/staging buffer and its own mbarrier -- no CTA-wide barrier in the loop.
-template <int NM> struct KronCfg
+template <int NM, bool GATHER = false> struct KronCfg
 {
     static constexpr int NM2 = NM * NM, NM3 = NM2 * NM;
     static constexpr int EPW   = 32 / NM;                // elements per warp step (NM lanes per element)
@@ -68,7 +72,8 @@ template <int NM> struct KronCfg
     static constexpr int ES = kron_pad(NM * PS, NM);
     static constexpr int XB = round_up(EPW * ES > EPW * NM3 ? EPW * ES : EPW * NM3, 2);
     static constexpr int GEO = EPW * 4;
-    static constexpr int PER_WARP = INB + GEO + XB + 2; // doubles (+2: mbarrier, 16-byte slot)
+    static constexpr int MAPB = GATHER ? round_up(EPW * NM3, 4) / 2 : 0; // doubles holding EPW*NM3 ints
+    static constexpr int PER_WARP = INB + GEO + XB + 2 + MAPB; // doubles (+2: mbarrier, 16-byte slot)
     // one CTA per SM; warps in multiples of 4 (one FP64 pipe per SM sub-partition)
     static constexpr int W_FIT = (224 * 1024) / (PER_WARP * 8);
     static constexpr int WARPS = W_FIT >= 12 ? 12 : (W_FIT >= 8 ? 8 : 4);
@@ -78,11 +83,23 @@ template <int NM> struct KronCfg
 
 // SPARSEK: the stiffness matrix has the structure of the modified C0 basis -- a 2x2 vertex block
 // plus a diagonal (interior modes have orthogonal derivatives) -- verified numerically at creation.
-template <int NM, bool SPARSEK>
-__global__ void __launch_bounds__(KronCfg<NM>::T, 1)
+// 4/8-byte asynchronous global -> shared copies (LDGSTS): the gather lands in shared memory without
+// passing through registers, so a whole batch of indirect loads is in flight per warp
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int NM, bool SPARSEK, bool GATHER = false>
+__global__ void __launch_bounds__(KronCfg<NM, GATHER>::T, 1)
     hex_helm_kron_kernel(const __grid_constant__ KronTab<NM> tab, const __grid_constant__ KronArgs args)
 {
-    using Cfg = KronCfg<NM>;
+    using Cfg = KronCfg<NM, GATHER>;
     constexpr int NM2 = Cfg::NM2, NM3 = Cfg::NM3, EPW = Cfg::EPW, INB = Cfg::INB, PS = Cfg::PS, ES = Cfg::ES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,6 +108,7 @@ __global__ void __launch_bounds__(KronCfg<NM>::T, 1)
     double *sGeo  = wbase + INB;            // [GEO]  per-element scalars
     double *sX    = sGeo + Cfg::GEO;        // [XB]   exchange, then output staging
     uint64_t *bar = reinterpret_cast<uint64_t *>(sX + Cfg::XB);
+    int *sMap     = reinterpret_cast<int *>(sX + Cfg::XB + 2); // [EPW*NM3] (GATHER only)
 
     const int nElmt = args.nElmt;
     const int nWB   = (nElmt + EPW - 1) / EPW;          // warp batches
@@ -111,7 +129,20 @@ __global__ void __launch_bounds__(KronCfg<NM>::T, 1)
     __syncwarp();
 
     auto batch_ne = [&](int wb) { int r = nElmt - wb * EPW; return r < EPW ? r : EPW; };
-    auto tma_ok   = [&](int wb) { return args.io_aligned && ((batch_ne(wb) * NM3) & 1) == 0 && (((wb * EPW * NM3) & 1) == 0); };
+    auto tma_ok   = [&](int wb) { return !GATHER && args.io_aligned && ((batch_ne(wb) * NM3) & 1) == 0 && (((wb * EPW * NM3) & 1) == 0); };
+    auto out_tma_ok = [&](int wb) { return args.io_aligned && ((batch_ne(wb) * NM3) & 1) == 0 && (((wb * EPW * NM3) & 1) == 0); };
+    // GATHER: whole warp.  fetch_map(wb): local-to-global indices of batch wb -> sMap;
+    // gather(wb): sIn[i] <- in[sMap[i]] (asynchronous, completes at the next cp_async_wait_all)
+    auto fetch_map = [&](int wb) {
+        const int n    = batch_ne(wb) * NM3;
+        const int *src = args.map + (size_t)wb * EPW * NM3;
+        for (int i = lane; i < n; i += 32) cp_async4(sMap + i, src + i);
+    };
+    auto gather = [&](int wb) {
+        const int n = batch_ne(wb) * NM3;
+#pragma unroll 4
+        for (int i = lane; i < n; i += 32) cp_async8(sIn + i, args.in + sMap[i]);
+    };
     auto issue    = [&](int wb) { // lane 0; sIn and sGeo are free
         const int ne   = batch_ne(wb);
         uint32_t bytes = (uint32_t)(ne * 32);
@@ -123,13 +154,32 @@ __global__ void __launch_bounds__(KronCfg<NM>::T, 1)
 
     uint32_t phase = 0;
     if (lane == 0 && gw < nWB) issue(gw);
+    if (GATHER && gw < nWB)
+    {
+        fetch_map(gw);
+        cp_async_wait_all();
+        __syncwarp();
+        gather(gw);
+        __syncwarp(); // every lane has read its sMap entries
+        if (gw + GW < nWB) fetch_map(gw + GW);
+    }
 
     for (int wb = gw; wb < nWB; wb += GW)
     {
         const int ne      = batch_ne(wb);
         const int wbnext  = wb + GW;
         const bool tma_in = tma_ok(wb);
-        if (!tma_in)
+        if (GATHER)
+        {
+            cp_async_wait_all(); // this batch's gathered block (and the next batch's indices) have landed
+            if (args.sign)
+            {
+                __syncwarp();
+                const double *sg = args.sign + (size_t)wb * EPW * NM3;
+                for (int i = lane; i < ne * NM3; i += 32) sIn[i] *= __ldg(sg + i);
+            }
+        }
+        else if (!tma_in)
         {
             // 8-byte aligned caller arrays or an odd-sized tail: plain loads by the warp
             const double *src = args.in + (size_t)wb * EPW * NM3;
@@ -193,6 +243,12 @@ __global__ void __launch_bounds__(KronCfg<NM>::T, 1)
         {
             tma_store_wait_read0(); // the previous step's bulk store has finished reading sX
             if (wbnext < nWB) issue(wbnext);
+        }
+        if (GATHER && wbnext < nWB)
+        {
+            gather(wbnext); // sMap holds the indices of the next batch; sIn is consumed
+            __syncwarp();
+            if (wbnext + GW < nWB) fetch_map(wbnext + GW);
         }
         __syncwarp();
         // ---- exchange 1: U_M = lamJ A2 + R.  lane (e,r) scatters, lane (e,p') gathers its [q'][r] block
@@ -258,7 +314,7 @@ __global__ void __launch_bounds__(KronCfg<NM>::T, 1)
 #pragma unroll
                 for (int qq = 0; qq < NM; ++qq) sX[e * NM3 + rr * NM2 + qq * NM + s1] = acc[rr][qq];
         }
-        if (tma_in)
+        if (GATHER ? out_tma_ok(wb) : tma_in)
         {
             fence_proxy_async();
             __syncwarp();
@@ -310,7 +366,7 @@ struct KronState
     void *tab      = nullptr;
     bool sparse_k  = false;
     double *d_geo4 = nullptr;
-    int blocks_per_sm = 0;
+    int blocks_per_sm = 0, blocks_per_sm_gather = 0;
     // the quadrature-space launcher this operator falls back to for non-diagonal metrics
     int (*fallback)(nekmf_op_s *, const double *const in[3], double *const out[3]) = nullptr;
     void *fallback_state                                                           = nullptr;
@@ -319,39 +375,48 @@ struct KronState
     bool use_kron = false;
 };
 
-template <int NM> static int kron_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
+template <int NM, bool GATHER> static int kron_launch_t(nekmf_op_s *op, KronState *st, const double *in, double *out)
 {
-    KronState *st = static_cast<KronState *>(op->kstate);
-    if (!st->use_kron)
-    {
-        void *saved = op->kstate;
-        op->kstate  = st->fallback_state;
-        const int rc = st->fallback(op, in, out);
-        op->kstate  = saved;
-        return rc;
-    }
-    using Cfg = KronCfg<NM>;
-    auto kern = st->sparse_k ? hex_helm_kron_kernel<NM, true> : hex_helm_kron_kernel<NM, false>;
-    if (st->blocks_per_sm == 0)
+    using Cfg = KronCfg<NM, GATHER>;
+    auto kern = st->sparse_k ? hex_helm_kron_kernel<NM, true, GATHER> : hex_helm_kron_kernel<NM, false, GATHER>;
+    int &bps  = GATHER ? st->blocks_per_sm_gather : st->blocks_per_sm;
+    if (bps == 0)
     {
         NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int nb = 0;
         NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
         if (nb < 1) { set_error("kron kernel does not fit on an SM"); return NEKMF_ERR_CUDA; }
-        st->blocks_per_sm = nb;
+        bps = nb;
     }
     KronArgs a;
-    a.in = in[0]; a.out = out[0]; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
-    a.io_aligned = ((((uintptr_t)in[0]) | ((uintptr_t)out[0])) & 15) == 0;
+    a.in = in; a.out = out; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
+    a.map  = GATHER ? op->gather_map + (size_t)op->run_e0 * Cfg::NM3 : nullptr;
+    a.sign = GATHER && op->gather_sign ? op->gather_sign + (size_t)op->run_e0 * Cfg::NM3 : nullptr;
+    a.io_aligned = GATHER ? ((((uintptr_t)out) & 15) == 0) : ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
     const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
-    int grid           = st->blocks_per_sm * NUM_SMS;
+    int grid           = bps * NUM_SMS;
     if (grid > nBatches) grid = nBatches;
     if (grid < 1) return NEKMF_OK;
     kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const KronTab<NM> *>(st->tab), a);
     ++g_launches;
     NEKMF_CUDA(cudaGetLastError());
     return NEKMF_OK;
+}
+
+template <int NM> static int kron_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
+{
+    KronState *st = static_cast<KronState *>(op->kstate);
+    if (!st->use_kron)
+    {
+        if (op->gather_map) { set_error("fused gather requested from a kernel that does not provide it"); return NEKMF_ERR_ARG; }
+        void *saved = op->kstate;
+        op->kstate  = st->fallback_state;
+        const int rc = st->fallback(op, in, out);
+        op->kstate  = saved;
+        return rc;
+    }
+    return op->gather_map ? kron_launch_t<NM, true>(op, st, in[0], out[0]) : kron_launch_t<NM, false>(op, st, in[0], out[0]);
 }
 
 template <int NM> static void kron_wrap(nekmf_op_s *op)
@@ -419,6 +484,7 @@ int kron_geom_changed(nekmf_op_s *op)
     if (!op->kron) return NEKMF_OK;
     KronState *st = static_cast<KronState *>(op->kstate);
     st->use_kron  = false;
+    op->gather_ok = false;
     op->kname     = st->fallback_name;
     if (!op->has_jac || !op->has_df || op->nElmt == 0) return NEKMF_OK;
     if (!st->d_geo4) NEKMF_CUDA(cudaMalloc(&st->d_geo4, (size_t)op->nElmt * 4 * 8));
@@ -432,7 +498,8 @@ int kron_geom_changed(nekmf_op_s *op)
     cudaFree(d_flag);
     if (flag == 0)
     {
-        st->use_kron = true;
+        st->use_kron  = true;
+        op->gather_ok = true;
         char name[96];
         snprintf(name, sizeof(name), "hex_helm_kron_kernel<nm=%d,%s>(regular,diagonal metric)", op->nm[0],
                  st->sparse_k ? "sparseK" : "denseK");

@@ -33,6 +33,9 @@ namespace nekmf
 {
 int map_g2l_device(nekmf_map_s *m, const double *glob, double *loc, cudaStream_t st);
 int map_assemble_device(nekmf_map_s *m, const double *loc, double *glob, cudaStream_t st);
+// Assemble + partial sums (one per block, nBlocks blocks of 256 threads) of sum_{g>=nDir} mask*glob*w
+int map_assemble_dot_device(nekmf_map_s *m, const double *loc, double *glob, const double *w, const double *mask,
+                            int nDir, double *part, int nBlocks, cudaStream_t st);
 int exchange_add_device(nekmf_exchange_s *ex, double *glob, cudaStream_t st);
 int comm_allreduce_sum(nekmf_comm_s *c, double *d_buf, int n, cudaStream_t st);
 } // namespace nekmf

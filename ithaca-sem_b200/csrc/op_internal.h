@@ -43,6 +43,11 @@ struct nekmf_op_s
     std::string kname;
     void *kstate = nullptr; // launcher-private (constant tables etc.)
     void (*kstate_free)(void *) = nullptr;
+    // fused AssemblyMap gather (CG mat-vec): when gather_ok, a caller may set gather_map (+ optional sign) and
+    // pass the GLOBAL vector as in[0]; the kernel then loads sign[i]*in[map[i]] itself.  Reset to null after.
+    bool gather_ok           = false;
+    const int *gather_map    = nullptr;
+    const double *gather_sign = nullptr;
     bool kron        = false; // Helmholtz/hex/regular: coefficient-space kernel available (hex_kron.cu)
     bool timing      = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -117,3 +117,42 @@ def test_sharded_cg_two_gpus():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "CHECK OK" in r.stdout
+
+
+@pytest.mark.parametrize("geometry", ["box", "sheared"])
+@pytest.mark.parametrize("nm", [2, 3, 4, 5, 6, 7])
+def test_matvec_fused_gather_with_sign_changes(nm, geometry):
+    """A = Assemble o Helmholtz o GlobalToLocal with a +-1 localToGlobalSign (AssemblyMapCG.cpp:2853-2910).
+    box: the coefficient-space kernel loads sign[i]*glob[map[i]] itself (nm <= 6; cp.async gather, ragged last
+    warp batch); sheared / nm = 7: the separate gather kernel feeds the quadrature-space kernel."""
+    import torch
+    nk = nekmf()
+    mesh_mod = load_pkg_module("mesh")
+    mesh = mesh_mod.StructuredHexMesh(5, 3, 7, nm)  # 105 elements: not a multiple of any warp batch
+    el = po.Elem(po.HEX, nm, nm + 1)
+    jac, df = mesh.geometry()
+    if geometry == "sheared":
+        d = df.reshape(9, -1)
+        d[1] = 0.3 * d[0]
+        df = d.reshape(-1).copy()
+    rng = np.random.default_rng(nm)
+    sign = rng.choice([-1.0, 1.0], mesh.nLocal)
+    lam = 0.8
+    helm = nk.Operator(nk.StdExpansion(nk.eHexahedron, nm), mesh.nElmt, nk.CoalescedGeomData(jac, df, False),
+                       nk.eHelmholtz)
+    helm.SetLambda(lam)
+    fused = geometry == "box" and nm <= 6
+    assert ("kron" in helm.kernel_name) == fused
+    for sg in (None, sign):
+        amap = nk.AssemblyMap(mesh.localToGlobal, mesh.nGlobal, sg)
+        cg = nk.HelmholtzCG(helm, amap, mesh.nDir, None)
+        w = rng.uniform(-1, 1, mesh.nGlobal)
+        w_d = torch.tensor(w, device="cuda")
+        s_d = torch.zeros(mesh.nGlobal, dtype=torch.float64, device="cuda")
+        cg.matvec(w_d, s_d)
+        torch.cuda.synchronize()
+        want = po.assemble(mesh.localToGlobal, sg,
+                           el.helmholtz(mesh.nElmt, False, jac, df, lam, po.global_to_local(mesh.localToGlobal, sg, w)),
+                           mesh.nGlobal)
+        assert max(rel_errs(s_d.cpu().numpy(), want)) < 1e-12
+        del cg, amap

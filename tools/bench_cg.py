@@ -115,8 +115,22 @@ def main():
     dt = float(t.item())
     nel_total = a.nx * a.ny * a.nz
     gdof = (a.nx * (a.nm - 1) + 1) * (a.ny * (a.nm - 1) + 1) * (a.nz * (a.nm - 1) + 1)
+    # per-rank bytes one iteration must move with the kernels as fused: update 7 reads + 5 writes
+    # of nNonDir doubles; mat-vec: map (4 B) + local output written and read back (16 B) + transpose-CSR column
+    # (4 B) per local DOF, gathered w + rowptr + s written + w re-read for s.w per global DOF
+    nN = mesh.nGlobal - mesh.nDir
+    by = 12 * 8 * nN + mesh.nLocal * (4 + 16 + 4) + mesh.nGlobal * (8 + 4 + 8 + 8) + mesh.nElmt * 32
+    if world > 1:
+        by += 3 * 8 * nN  # separate masked s.w pass after the interface exchange
+    sys.path.insert(0, ROOT)
+    import bench
+    peak, peak_src = bench.measured_peaks()
     if rank == 0:
+        gbs = by * its / dt / 1e9
         print(json.dumps({"metric": "matrix-free CG Helmholtz, hex P=%d" % (a.nm - 1), "n_gpus": world,
+                          "kernel": helm.kernel_name,
+                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                       "bytes_per_iteration_per_rank": by, "peak_source": peak_src},
                           "elements": nel_total, "global_dof": gdof, "iterations": its,
                           "ms_per_iteration": dt / its * 1e3,
                           "gdof_per_s_local": nel_total * a.nm ** 3 * its / dt / 1e9,
