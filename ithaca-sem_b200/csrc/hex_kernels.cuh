@@ -90,8 +90,12 @@ template <int OP, int NM, int NQ, bool DEF> struct HexCfg
     static constexpr int NM3 = NM * NM * NM, NQ3 = NQ * NQ * NQ, NQ2 = NQ * NQ;
     static constexpr int NQ3P = round_up(NQ3, 2); // element pitch of the (internal) geometry arrays
     static constexpr int NGEO = DEF ? HexOpTraits<OP>::NGEO : 0;
-    // doubles of shared memory per element: 4 work buffers + coefficient staging + geometry
-    static constexpr int PER_ELMT = 4 * NQ3 + round_up(NM3, 2) + NGEO * NQ3P;
+    // work buffers actually live at the same time (the others alias them, see the kernel):
+    //   BwdTrans: P1 -> sA, P2 -> sB, P3 -> sU = sA           IProductWRTBase: sU, sA, sB, sC = sA
+    static constexpr int NBUF    = OP == HEX_BWD ? 2 : (OP == HEX_IPROD ? 3 : 4);
+    static constexpr bool HASCIN = HexOpTraits<OP>::COEFF_IN;
+    // doubles of shared memory per element: work buffers + coefficient staging + geometry
+    static constexpr int PER_ELMT = NBUF * NQ3 + (HASCIN ? round_up(NM3, 2) : 0) + NGEO * NQ3P;
     static constexpr int SMEM_BUDGET = 100 * 1024; // aim at >= 2 CTAs per SM
     static constexpr int E_FIT       = SMEM_BUDGET / (PER_ELMT * 8);
     // E even when possible (keeps every full batch of odd-sized coefficient blocks 16-byte aligned)
@@ -100,9 +104,14 @@ template <int OP, int NM, int NQ, bool DEF> struct HexCfg
     static constexpr int E_MIN = E_RAW < E_THR ? E_RAW : E_THR;
     static constexpr int E     = (E_MIN >= 2 && (E_MIN % 2)) ? E_MIN - 1 : E_MIN;
     static constexpr int T     = round_up(E * NQ2, 32);
-    static constexpr int CIN   = round_up(E * NM3, 2);
+    static constexpr int CIN   = HASCIN ? round_up(E * NM3, 2) : 0;
     static constexpr int BUF   = round_up(E * NQ3, 2); // work-buffer pitch (keeps every buffer 16-byte aligned)
-    static constexpr size_t SMEM = (size_t)(4 * BUF + CIN + NGEO * E * NQ3P + NQ) * 8 + 64;
+    static constexpr size_t SMEM = (size_t)(NBUF * BUF + CIN + NGEO * E * NQ3P + NQ) * 8 + 64;
+    // regular-geometry Helmholtz is FP64-latency bound: the compiler hoists the per-element metric and
+    // unrolls into >160 registers, which leaves ONE CTA per SM.  Bound the allocation so that two CTAs are
+    // resident (measured: nm=5 1.25 -> 1.15 ms, nm=8 1.74 -> 1.18 ms, nm=11 2.42 -> 1.70 ms; the same bound
+    // on IProductWRTDerivBase lost more than it won and is not applied).
+    static constexpr int MINB = (!DEF && OP == HEX_HELM && 2 * SMEM <= 220 * 1024) ? 2 : 1;
 };
 
 // y[b] = sum_a M[a*NOUT+b] x[a]          (forward: basis / derivative evaluation)
@@ -131,7 +140,7 @@ template <int NIN, int NOUT> __device__ __forceinline__ void mat_tr(const double
 }
 
 template <int OP, int NM, int NQ, bool DEF>
-__global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T)
+__global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T, HexCfg<OP, NM, NQ, DEF>::MINB)
     hex_op_kernel(const __grid_constant__ HexTab<NM, NQ> tab, const __grid_constant__ HexArgs args)
 {
     using Cfg = HexCfg<OP, NM, NQ, DEF>;
@@ -143,11 +152,13 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T)
     constexpr int NIN  = OP == HEX_IPWDB ? 3 : 1;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sU   = reinterpret_cast<double *>(smem_raw);
-    double *sA   = sU + Cfg::BUF;
+    // BwdTrans: sU aliases sA (P3 reads sB; sA is dead after P2).  IProductWRTBase: sC aliases sA (P9 reads
+    // sB; sA is dead after P8; the next write of sA is P7c of the following batch, two barriers later).
+    double *sA   = reinterpret_cast<double *>(smem_raw);
     double *sB   = sA + Cfg::BUF;
-    double *sC   = sB + Cfg::BUF;
-    double *sCin = sC + Cfg::BUF;
+    double *sU   = OP == HEX_BWD ? sA : sB + Cfg::BUF;
+    double *sC   = OP == HEX_IPROD ? sA : sU + Cfg::BUF; // unused by BwdTrans
+    double *sCin = reinterpret_cast<double *>(smem_raw) + Cfg::NBUF * Cfg::BUF;
     double *sGeo = sCin + Cfg::CIN;
     double *sW   = sGeo + NGEO * GEOA;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sW + NQ); // [0] inputs, [1] geometry
