@@ -379,6 +379,23 @@ static int op_check_ready(nekmf_op_t op)
     return NEKMF_OK;
 }
 
+// Device-side aliases of page-locked host arrays (cudaHostAlloc / cudaHostRegister); false if any array is
+// pageable or not mapped into the device address space.
+static bool host_arrays_device_pointers(const double *const ins[3], int nin, double *const outs[3], int nout,
+                                        const double *din[3], double *dout[3])
+{
+    auto devptr = [](const void *p) -> void * {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+    };
+    for (int a = 0; a < nin; ++a)
+        if (!(din[a] = static_cast<const double *>(devptr(ins[a])))) return false;
+    for (int a = 0; a < nout; ++a)
+        if (!(dout[a] = static_cast<double *>(devptr(outs[a])))) return false;
+    return true;
+}
+
 int nekmf_op_apply(nekmf_op_t op, const double *in0, const double *in1, const double *in2, double *out0,
                    double *out1, double *out2, int memkind)
 {
@@ -418,10 +435,40 @@ int nekmf_op_apply(nekmf_op_t op, const double *in0, const double *in1, const do
     }
     if (memkind != NEKMF_HOST) { set_error("nekmf_op_apply: bad memkind %d", memkind); return NEKMF_ERR_ARG; }
 
-    // Host arrays (the literal Array<OneD> drop-in).  The collection is cut into element chunks that
-    // flow through a 3-stream pipeline: H2D of chunk c+1, the kernel on chunk c and D2H of chunk c-1
-    // overlap (PCIe is full duplex and the copy engines are independent), so the call costs about
-    // max(H2D, D2H) instead of H2D + kernel + D2H.  Synchronous: returns when `out` is complete.
+    // Host arrays (the literal Array<OneD> drop-in).  The collection is cut into element chunks that flow
+    // through three role streams: every H2D copy is queued back to back on the copy-in stream, the kernel on
+    // chunk c waits (event) for its copy, the D2H copy of chunk c waits for its kernel.  The staging buffers
+    // hold the whole collection, so no copy ever waits for a later stage: both PCIe directions stay busy and
+    // the call costs about max(H2D, D2H) of a full-duplex link instead of H2D + kernel + D2H.
+    // Synchronous: returns when `out` is complete.
+    // Page-locked host arrays are addressable from the device (unified virtual addressing), so the kernels can
+    // read their inputs from and write their results to host memory themselves: one launch over the whole
+    // collection, no staging memory.  Opt-in (NEKMF_HOST_ZEROCOPY=1) for callers short of device memory:
+    // measured on the 64^3 P=4 bench it is slower than the staged pipeline below (6.8 vs 6.3 ms; letting only
+    // the outputs go direct while inputs use the copy engine is worse still, 7.3+ ms, the SM-issued PCIe
+    // writes and the DMA reads throttle each other).
+    const char *zc_env   = getenv("NEKMF_HOST_ZEROCOPY"); // read per call: a caller may switch it at run time
+    const bool zero_copy = zc_env && atoi(zc_env) > 0;
+    const double *zin[3] = {nullptr, nullptr, nullptr};
+    double *zout[3]      = {nullptr, nullptr, nullptr};
+    if (zero_copy && host_arrays_device_pointers(ins, nin, outs, nout, zin, zout))
+    {
+        for (int a = nin; a < 3; ++a) zin[a] = zin[0];
+        for (int a = nout; a < 3; ++a) zout[a] = zout[0];
+        op->run_e0     = 0;
+        op->run_ne     = op->nElmt;
+        op->run_stream = op->stream;
+        if (op->timing) NEKMF_CUDA(cudaEventRecord(op->ev0, op->stream));
+        rc = op->launch(op, zin, zout);
+        if (rc) return rc;
+        if (op->timing)
+        {
+            NEKMF_CUDA(cudaEventRecord(op->ev1, op->stream));
+            op->timed_once = true;
+        }
+        NEKMF_CUDA(cudaStreamSynchronize(op->stream));
+        return NEKMF_OK;
+    }
     if (op->stage_in_sz < in_sz * nin)
     {
         if (op->d_stage_in) cudaFree(op->d_stage_in);
@@ -443,57 +490,102 @@ int nekmf_op_apply(nekmf_op_t op, const double *in0, const double *in1, const do
     }
     const size_t in_el  = cin ? op->nmTot : op->nqTot;
     const size_t out_el = cout ? op->nmTot : op->nqTot;
-    // chunk: about 8 MB of the larger of (inputs, outputs); element counts even so that every chunk
-    // of every array stays 16-byte aligned for the TMA-fed kernels
     const size_t el_bytes = 8 * (in_el * nin > out_el * nout ? in_el * nin : out_el * nout);
     static const size_t chunk_bytes = [] {
-        const char *v = getenv("NEKMF_HOST_CHUNK_MB"); // tuning knob; default 8 MB
+        const char *v = getenv("NEKMF_HOST_CHUNK_MB"); // tuning knob
         const long mb = v ? atol(v) : 0;
-        return (size_t)(mb > 0 ? mb : 8) << 20;
+        return (size_t)(mb > 0 ? mb : 16) << 20;
     }();
-    int chunk = (int)(chunk_bytes / el_bytes);
-    chunk &= ~1;
-    if (chunk < 2) chunk = 2;
+    cudaStream_t sH = op->pipe_stream[0], sK = op->pipe_stream[1], sD = op->pipe_stream[2];
+
+    // Chunk schedule: the first and the last chunks are small (the first H2D and the last D2H copy overlap
+    // nothing, and the D2H stream trails the H2D stream by one chunk), sizes double towards the middle up to
+    // NEKMF_HOST_CHUNK_MB (default 16 MB; every copy carries ~15 us of engine set-up, measured with chunk sweeps
+    // both directly issued and replayed from a CUDA graph, so small uniform chunks lose).  Element counts are
+    // even so that every chunk of every array stays 16-byte aligned for the TMA-fed kernels; an odd leftover
+    // element goes to the last chunk.
+    auto schedule = [&](size_t first_bytes, size_t max_bytes) {
+        std::vector<int> sched, back;
+        auto even      = [](size_t n) { int v = (int)n & ~1; return v < 2 ? 2 : v; };
+        const int smax = even(max_bytes / el_bytes);
+        int sz         = even(first_bytes / el_bytes);
+        if (sz > smax) sz = smax;
+        int remaining = op->nElmt & ~1;
+        while (remaining > 0)
+        {
+            int t = sz < remaining ? sz : remaining;
+            sched.push_back(t);
+            remaining -= t;
+            if (remaining > 0)
+            {
+                t = sz < remaining ? sz : remaining;
+                back.push_back(t);
+                remaining -= t;
+            }
+            sz = 2 * sz < smax ? 2 * sz : smax;
+        }
+        sched.insert(sched.end(), back.rbegin(), back.rend());
+        if (op->nElmt & 1)
+        {
+            if (sched.empty()) sched.push_back(1);
+            else sched.back() += 1;
+        }
+        return sched;
+    };
+    // queues the whole pipeline on (sH, sK, sD); used directly and under stream capture
+    auto issue = [&](const std::vector<int> &sched) -> int {
+        const int nChunks = (int)sched.size();
+        while ((int)op->pipe_ev.size() < 2 * nChunks)
+        {
+            cudaEvent_t ev;
+            NEKMF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            op->pipe_ev.push_back(ev);
+        }
+        int e0 = 0;
+        for (int c = 0; c < nChunks; e0 += sched[c], ++c)
+        {
+            const int ne = sched[c];
+            const double *din[3];
+            double *dout[3];
+            for (int a = 0; a < 3; ++a)
+            {
+                din[a]  = op->d_stage_in + (a < nin ? a : 0) * in_sz + (size_t)e0 * in_el;
+                dout[a] = op->d_stage_out + (a < nout ? a : 0) * out_sz + (size_t)e0 * out_el;
+            }
+            for (int a = 0; a < nin; ++a)
+                NEKMF_CUDA(cudaMemcpyAsync(const_cast<double *>(din[a]), ins[a] + (size_t)e0 * in_el,
+                                           (size_t)ne * in_el * 8, cudaMemcpyHostToDevice, sH));
+            NEKMF_CUDA(cudaEventRecord(op->pipe_ev[2 * c], sH));
+            NEKMF_CUDA(cudaStreamWaitEvent(sK, op->pipe_ev[2 * c], 0));
+            op->run_e0     = e0;
+            op->run_ne     = ne;
+            op->run_stream = sK;
+            const int lrc  = op->launch(op, din, dout);
+            if (lrc) return lrc;
+            NEKMF_CUDA(cudaEventRecord(op->pipe_ev[2 * c + 1], sK));
+            NEKMF_CUDA(cudaStreamWaitEvent(sD, op->pipe_ev[2 * c + 1], 0));
+            for (int a = 0; a < nout; ++a)
+                NEKMF_CUDA(cudaMemcpyAsync(outs[a] + (size_t)e0 * out_el, dout[a], (size_t)ne * out_el * 8,
+                                           cudaMemcpyDeviceToHost, sD));
+        }
+        return NEKMF_OK;
+    };
+
     // work queued earlier on the operator's stream (e.g. a device-array apply) stays ordered before us
     NEKMF_CUDA(cudaEventRecord(op->pipe_done, op->stream));
     for (int s = 0; s < 3; ++s) NEKMF_CUDA(cudaStreamWaitEvent(op->pipe_stream[s], op->pipe_done, 0));
-    if (op->timing) NEKMF_CUDA(cudaEventRecord(op->ev0, op->pipe_stream[0]));
-    int c = 0;
-    for (int e0 = 0; e0 < op->nElmt; e0 += chunk, ++c)
-    {
-        const int ne      = op->nElmt - e0 < chunk ? op->nElmt - e0 : chunk;
-        cudaStream_t st   = op->pipe_stream[c % 3];
-        const double *din[3];
-        double *dout[3];
-        for (int a = 0; a < 3; ++a)
-        {
-            din[a]  = op->d_stage_in + (a < nin ? a : 0) * in_sz + (size_t)e0 * in_el;
-            dout[a] = op->d_stage_out + (a < nout ? a : 0) * out_sz + (size_t)e0 * out_el;
-        }
-        for (int a = 0; a < nin; ++a)
-            NEKMF_CUDA(cudaMemcpyAsync(const_cast<double *>(din[a]), ins[a] + (size_t)e0 * in_el, (size_t)ne * in_el * 8,
-                                       cudaMemcpyHostToDevice, st));
-        op->run_e0     = e0;
-        op->run_ne     = ne;
-        op->run_stream = st;
-        rc             = op->launch(op, din, dout);
-        if (rc) break;
-        for (int a = 0; a < nout; ++a)
-            NEKMF_CUDA(cudaMemcpyAsync(outs[a] + (size_t)e0 * out_el, dout[a], (size_t)ne * out_el * 8,
-                                       cudaMemcpyDeviceToHost, st));
-    }
+    if (op->timing) NEKMF_CUDA(cudaEventRecord(op->ev0, sH));
+
+    rc = issue(schedule((size_t)2 << 20, chunk_bytes));
     op->run_e0     = 0;
     op->run_ne     = op->nElmt;
     op->run_stream = op->stream;
     if (op->timing && rc == NEKMF_OK)
     {
         // ev0/ev1 bracket the whole pipelined call (copies included) for host-array applies
-        for (int s = 1; s < 3; ++s)
-        {
-            NEKMF_CUDA(cudaEventRecord(op->pipe_done, op->pipe_stream[s]));
-            NEKMF_CUDA(cudaStreamWaitEvent(op->pipe_stream[0], op->pipe_done, 0));
-        }
-        NEKMF_CUDA(cudaEventRecord(op->ev1, op->pipe_stream[0]));
+        NEKMF_CUDA(cudaEventRecord(op->pipe_done, sD));
+        NEKMF_CUDA(cudaStreamWaitEvent(sH, op->pipe_done, 0));
+        NEKMF_CUDA(cudaEventRecord(op->ev1, sH));
         op->timed_once = true;
     }
     for (int s = 0; s < 3; ++s)
@@ -520,6 +612,7 @@ int nekmf_op_destroy(nekmf_op_t op)
     for (int s = 0; s < 3; ++s)
         if (op->pipe_stream[s]) cudaStreamDestroy(op->pipe_stream[s]);
     if (op->pipe_done) cudaEventDestroy(op->pipe_done);
+    for (cudaEvent_t ev : op->pipe_ev) cudaEventDestroy(ev);
     if (op->ev0) cudaEventDestroy(op->ev0);
     if (op->ev1) cudaEventDestroy(op->ev1);
     delete op;

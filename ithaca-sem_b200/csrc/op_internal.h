@@ -38,6 +38,7 @@ struct nekmf_op_s
     size_t stage_in_sz = 0, stage_out_sz = 0;
     cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_done = nullptr;
+    std::vector<cudaEvent_t> pipe_ev; // [2*chunk]: copy-in done, kernel done 
     // launcher: device pointers only
     int (*launch)(nekmf_op_s *, const double *const in[3], double *const out[3]) = nullptr;
     std::string kname;

@@ -292,7 +292,7 @@ def test_cpp_collections_mirror():
 
 @pytest.mark.parametrize("case", ["hex_regular_diag", "hex_regular_sheared", "hex_deformed", "tet_deformed", "quad_regular"])
 def test_host_array_pipeline_many_chunks(case):
-    """NEKMF_HOST applies are cut into ~8 MB element chunks over a 3-stream H2D/kernel/D2H pipeline
+    """NEKMF_HOST applies are cut into element chunks (2 MB ramping to 32 MB) over a 3-stream H2D/kernel/D2H pipeline
     (abi.cu): collections large enough for several chunks (ragged last one) must give exactly the
     device-array result for every operator (incl. 3-input / 3-output ones), and match the oracle."""
     torch = _torch()
@@ -360,3 +360,43 @@ def test_shape_fast_kernels(shape, nm, deformed):
     coll = run_all_ops(nk, SHAPES[shape], nm, nm + 1, nel, deformed, np.random.default_rng(31 * nm + len(shape)))
     for op in (nk.eBwdTrans, nk.eIProductWRTBase, nk.ePhysDeriv, nk.eHelmholtz):
         assert "shape_op_kernel" in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
+
+
+@pytest.mark.parametrize("zero_copy", ["0", "1"])
+def test_host_array_pinned_and_pageable_repeated(zero_copy, monkeypatch):
+    """Repeated NEKMF_HOST applies.  NEKMF_HOST_ZEROCOPY=1: page-locked arrays are read and written by the
+    kernels directly over PCIe (abi.cu); otherwise, and always for pageable arrays, the staged copy pipeline
+    runs.  New input VALUES, a new lambda and alternating array kinds must all be honoured and both routes
+    must agree bit for bit."""
+    monkeypatch.setenv("NEKMF_HOST_ZEROCOPY", zero_copy)
+    torch = _torch()
+    nk = nekmf()
+    rng = np.random.default_rng(5)
+    nm, nel = 5, 30011
+    el = po.Elem(po.HEX, nm, nm + 1)
+    jac, df = box_geometry(nel, 0.1, 0.2, 0.3)
+    std = nk.StdExpansion(po.HEX, nm, nm + 1)
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, False))
+    xh = torch.empty(nel * el.nmTot, dtype=torch.float64).pin_memory()
+    yh = torch.empty(nel * el.nmTot, dtype=torch.float64).pin_memory()
+    ns = 200  # oracle on the last elements (ragged tail of the chunk schedule)
+    js, dfs = jac[-ns:], np.ascontiguousarray(df.reshape(9, -1)[:, -ns:]).reshape(-1)
+    for it, lam in enumerate([1.0, 1.0, 1.0, 2.5, 2.5, 2.5]):
+        x = rng.uniform(-1, 1, nel * el.nmTot)
+        xh.copy_(torch.from_numpy(x))
+        yh.zero_()
+        coll.ApplyOperator(nk.eHelmholtz, xh, yh, factors={nk.eFactorLambda: lam})
+        check(yh.numpy()[-ns * el.nmTot:], el.helmholtz(ns, False, js, dfs, lam, x[-ns * el.nmTot:]), "replay %d" % it)
+        check(yh.numpy()[:ns * el.nmTot], el.helmholtz(ns, False, jac[:ns], np.ascontiguousarray(
+            df.reshape(9, -1)[:, :ns]).reshape(-1), lam, x[:ns * el.nmTot]), "replay head %d" % it)
+    # pageable numpy arrays in between, then the pinned pair again
+    x = rng.uniform(-1, 1, nel * el.nmTot)
+    y = np.zeros(nel * el.nmTot)
+    for _ in range(3):
+        coll.ApplyOperator(nk.eHelmholtz, x, y, factors={nk.eFactorLambda: 2.5})
+    check(y[-ns * el.nmTot:], el.helmholtz(ns, False, js, dfs, 2.5, x[-ns * el.nmTot:]), "pageable")
+    xh.copy_(torch.from_numpy(x))
+    for _ in range(3):
+        yh.zero_()
+        coll.ApplyOperator(nk.eHelmholtz, xh, yh, factors={nk.eFactorLambda: 2.5})
+        assert np.array_equal(yh.numpy(), y)
