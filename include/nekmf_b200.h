@@ -70,7 +70,8 @@ enum nekmf_basistype
 {
     NEKMF_MODIFIED_A = 0,
     NEKMF_MODIFIED_B = 1,
-    NEKMF_MODIFIED_C = 2
+    NEKMF_MODIFIED_C = 2,
+    NEKMF_MODIFIEDPYR_C = 3 /* eModifiedPyr_C: rows (p,q,r), r fastest, nm - max(p,q) rows per (p,q) */
 };
 enum nekmf_pointstype
 {

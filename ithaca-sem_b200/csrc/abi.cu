@@ -25,6 +25,7 @@ static int basis_rows(int btype, int nm)
         case NEKMF_MODIFIED_A: return nm;
         case NEKMF_MODIFIED_B: return nm * (nm + 1) / 2;
         case NEKMF_MODIFIED_C: return nm * (nm + 1) * (nm + 2) / 6;
+        case NEKMF_MODIFIEDPYR_C: return nm * (nm + 1) * (2 * nm + 1) / 6;
     }
     return -1;
 }
@@ -39,6 +40,7 @@ static int count_modes(int shape, int nm)
         case NEKMF_HEX: return nm * nm * nm;
         case NEKMF_PRISM: return nm * nm * (nm + 1) / 2;
         case NEKMF_TET: return nm * (nm + 1) * (nm + 2) / 6;
+        case NEKMF_PYR: return nm * (nm + 1) * (2 * nm + 1) / 6;
     }
     return -1;
 }
@@ -138,12 +140,8 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
         set_error("nekmf_op_create: null table argument");
         return NEKMF_ERR_ARG;
     }
-    if (shape == NEKMF_PYR)
-    {
-        set_error("nekmf_op_create: Pyramid operators are not implemented");
-        return NEKMF_ERR_UNSUPPORTED;
-    }
-    if (shape != NEKMF_QUAD && shape != NEKMF_TRI && shape != NEKMF_HEX && shape != NEKMF_PRISM && shape != NEKMF_TET)
+    if (shape != NEKMF_QUAD && shape != NEKMF_TRI && shape != NEKMF_HEX && shape != NEKMF_PRISM && shape != NEKMF_PYR &&
+        shape != NEKMF_TET)
     {
         set_error("nekmf_op_create: unknown shape %d", shape);
         return NEKMF_ERR_ARG;
@@ -162,7 +160,7 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
         return NEKMF_ERR_UNSUPPORTED;
     }
     // expected basis / points per direction (SpatialDomains/MeshGraph.cpp:1609-1762) and the
-    // isotropy preconditions asserted by the reference (Helmholtz.h:42-44,329-331,1042-1046,2017-2021)
+    // isotropy preconditions asserted by the reference (Helmholtz.h:42-44,329-331,1042-1046,1519-1525,2017-2021)
     int ebt[3] = {NEKMF_MODIFIED_A, NEKMF_MODIFIED_A, NEKMF_MODIFIED_A};
     int ept[3] = {NEKMF_GLL, NEKMF_GLL, NEKMF_GLL};
     int enq[3] = {nq[0], nq[0], nq[0]};
@@ -170,6 +168,7 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
     {
         case NEKMF_TRI: ebt[1] = NEKMF_MODIFIED_B; ept[1] = NEKMF_GRJM_A1B0; enq[1] = nq[0] - 1; break;
         case NEKMF_PRISM: ebt[2] = NEKMF_MODIFIED_B; ept[2] = NEKMF_GRJM_A1B0; enq[2] = nq[0] - 1; break;
+        case NEKMF_PYR: ebt[2] = NEKMF_MODIFIEDPYR_C; ept[2] = NEKMF_GRJM_A2B0; enq[2] = nq[0] - 1; break;
         case NEKMF_TET:
             ebt[1] = NEKMF_MODIFIED_B; ept[1] = NEKMF_GRJM_A1B0; enq[1] = nq[0] - 1;
             ebt[2] = NEKMF_MODIFIED_C; ept[2] = NEKMF_GRJM_A2B0; enq[2] = nq[0] - 1;
@@ -270,7 +269,7 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
     bool ok       = false;
     op->geo_pitch = op->nqTot;
     if (shape == NEKMF_HEX) ok = select_hex_fast(op);
-    if (!ok && shape != NEKMF_HEX) ok = select_shape_fast(op);
+    if (!ok && shape != NEKMF_HEX && shape != NEKMF_PYR) ok = select_shape_fast(op);
     if (!ok) ok = select_generic(op);
     if (!ok)
     {

@@ -205,6 +205,7 @@ int nekmf_basis_rows(int basistype, int nm)
         case NEKMF_MODIFIED_A: return nm;
         case NEKMF_MODIFIED_B: return nm * (nm + 1) / 2;
         case NEKMF_MODIFIED_C: return nm * (nm + 1) * (nm + 2) / 6;
+        case NEKMF_MODIFIEDPYR_C: return nm * (nm + 1) * (2 * nm + 1) / 6;
     }
     return -1;
 }
@@ -219,6 +220,36 @@ int nekmf_basis(int basistype, int nm, int np, const double *z, const double *D,
         modified_a_rows(nm, np, z, bdata);
     else if (basistype == NEKMF_MODIFIED_B)
         modified_b_rows(nm, np, z, bdata);
+    else if (basistype == NEKMF_MODIFIEDPYR_C)
+    {
+        // ModifiedPyr_C(p,q,r), r < nm - max(p,q) (Foundations/Basis.cpp:569-669):
+        //   p < 2 or q < 2 (vertices, edges, triangular faces): Modified_B(max(p,q), r)
+        //   p,q >= 2: ((1-z)/2)^(p+q-2) for r = 0 (base face), times (1+z)/2 P_{r-1}^{(2p+2q-3,1)} for r >= 1
+        std::vector<double> B((size_t)nm * (nm + 1) / 2 * np);
+        modified_b_rows(nm, np, z, B.data());
+        std::vector<int> boff(nm + 1, 0); // first Modified_B row of block m
+        for (int m = 0; m < nm; ++m) boff[m + 1] = boff[m] + (nm - m);
+        int row = 0;
+        for (int p = 0; p < nm; ++p)
+            for (int q = 0; q < nm; ++q)
+            {
+                const int m = p > q ? p : q;
+                for (int r = 0; r < nm - m; ++r, ++row)
+                    for (int i = 0; i < np; ++i)
+                    {
+                        double v;
+                        if (p < 2 || q < 2)
+                            v = B[(size_t)(boff[m] + r) * np + i];
+                        else
+                        {
+                            const double om = 0.5 * (1.0 - z[i]), op = 0.5 * (1.0 + z[i]);
+                            v = std::pow(om, p + q - 2);
+                            if (r > 0) v *= op * jacobi(r - 1, 2.0 * p + 2.0 * q - 3.0, 1.0, z[i]);
+                        }
+                        bdata[(size_t)row * np + i] = v;
+                    }
+            }
+    }
     else
     {
         // Modified_C(p,q,r) = Modified_B(p+q, r): for every p the tail of the B table starting at block p

@@ -1,5 +1,5 @@
 // generic_kernels.cu -- runtime-sized sum-factorisation kernels for every shape the path
-// supports (Quad, Tri, Hex, Prism, Tet) and any (nm, nq).  These are the complete-coverage
+// supports (Quad, Tri, Hex, Prism, Pyr, Tet) and any (nm, nq).  These are the complete-coverage
 // kernels: collapsed-coordinate shapes, over-integrated quadrature and any order the
 // compile-time specialised hex/quad kernels do not instantiate run here.
 //
@@ -14,7 +14,11 @@
 //   IProductWRTBase MatrixFreeOps/IProductKernels.hpp:76-133, 135-234, 236-314, 316-450, 600-761
 //   PhysDeriv       MatrixFreeOps/PhysDerivKernels.hpp:39-90, 153-217, 219-372, 376-461, 555-696
 //   Helmholtz       MatrixFreeOps/Helmholtz.h:138-275, 506-635, 764-993, 1291-1458, 2266-2448
-//   IProductWRTDerivBase (Quad/Hex) MatrixFreeOps/IProductWRTDerivBase.h:542-, 1232-1345
+//   IProductWRTDerivBase MatrixFreeOps/IProductWRTDerivBase.h:542- (Quad) 891- (Tri) 1232- (Hex) 1630- (Prism)
+//                   2056- (Pyr) 2484- (Tet)
+//   Pyramid         BwdTransKernels.hpp:131-222, IProductKernels.hpp:455-598, PhysDerivKernels.hpp:464-553,
+//                   Helmholtz.h:1771-1955 (modes (p,q,r), r fastest, nm - max(p,q) per (p,q); the rows of the
+//                   eModifiedPyr_C table are indexed by the mode itself)
 #include "op_internal.h"
 
 namespace nekmf
@@ -41,6 +45,7 @@ struct GenCtx
     const double *b[3], *db[3], *D[3], *Z[3], *w[3];
     int *offP;  // offP[p] = sum_{p'<p} (nm-p')                       (Tri / Prism / Tet dir-1 rows)
     int *offPQ; // Tet: mode offset of (p,q), running index cpq       (size nm(nm+1)/2 + 1)
+                // Pyr: mode offset of (p,q) at [p*nm+q]              (size nm*nm + 1)
     int *cpqP;  // Tet: cpq offset of p
 };
 
@@ -154,6 +159,41 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
         }
         __syncthreads();
     }
+    else if (SHAPE == NEKMF_PYR)
+    {
+        // fpq[k][p][q] = sum_r in[m] b2[m][k]
+        GEN_FOR(t, nq2 * nm * nm)
+        {
+            const int k = t / (nm * nm), pq = t - k * nm * nm;
+            const int m0 = c.offPQ[pq], len = c.offPQ[pq + 1] - m0;
+            double s = 0.0;
+            for (int r = 0; r < len; ++r) s = fma(in[m0 + r], b2[(m0 + r) * nq2 + k], s);
+            w1[t] = s;
+        }
+        __syncthreads();
+        // fp[k][j][p]
+        GEN_FOR(t, nq2 * nq1 * nm)
+        {
+            const int k = t / (nq1 * nm), jp = t - k * nq1 * nm;
+            const int j = jp / nm, p = jp - j * nm;
+            double s = 0.0;
+            for (int q = 0; q < nm; ++q) s = fma(w1[(k * nm + p) * nm + q], b1[q * nq1 + j], s);
+            w2[t] = s;
+        }
+        __syncthreads();
+        GEN_FOR(t, nq0 * nq1 * nq2)
+        {
+            const int k = t / (nq0 * nq1), ji = t - k * nq0 * nq1;
+            const int j = ji / nq0, i = ji - j * nq0;
+            double s = 0.0;
+            for (int p = 0; p < nm; ++p) s = fma(w2[(k * nq1 + j) * nm + p], b0[p * nq0 + i], s);
+            // CORRECT: top vertex (mode 1)
+            const double t1 = b0[i] * b1[nq1 + j] + b0[nq0 + i] * b1[j] + b0[nq0 + i] * b1[nq1 + j];
+            s = fma(t1 * b2[nq2 + k], in[1], s);
+            out[t] = s;
+        }
+        __syncthreads();
+    }
     else // TET
     {
         const int npq = nm * (nm + 1) / 2;
@@ -255,7 +295,7 @@ __device__ void gen_ip(const GenCtx &c, const double *f, const double *B0, const
         w1[t] = s;
     }
     __syncthreads();
-    if (SHAPE == NEKMF_HEX || SHAPE == NEKMF_PRISM)
+    if (SHAPE == NEKMF_HEX || SHAPE == NEKMF_PRISM || SHAPE == NEKMF_PYR)
     {
         // s2[k][q][p]
         GEN_FOR(t, nq2 * nm * nm)
@@ -274,6 +314,30 @@ __device__ void gen_ip(const GenCtx &c, const double *f, const double *B0, const
                 const int r = t / (nm * nm), qp = t - r * nm * nm;
                 double s = 0.0;
                 for (int k = 0; k < nq2; ++k) s = fma(w2[k * nm * nm + qp], B2[r * nq2 + k], s);
+                out[t] = append ? out[t] + s * scale : s * scale;
+            }
+        }
+        else if (SHAPE == NEKMF_PYR)
+        {
+            GEN_FOR(t, c.nmTot)
+            {
+                // mode -> (p,q): last pq with offPQ[pq] <= t
+                int lo = 0, hi = nm * nm - 1;
+                while (lo < hi)
+                {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (c.offPQ[mid] <= t) lo = mid;
+                    else hi = mid - 1;
+                }
+                const int p = lo / nm, q = lo - p * nm;
+                double s = 0.0;
+                for (int k = 0; k < nq2; ++k) s = fma(w2[(k * nm + q) * nm + p], B2[t * nq2 + k], s);
+                if (t == 1)
+                {
+                    // CORRECT: top vertex collects the (p,q) = (0,1), (1,0), (1,1) lines
+                    for (int k = 0; k < nq2; ++k)
+                        s = fma(w2[(k * nm + 1) * nm] + w2[k * nm * nm + 1] + w2[(k * nm + 1) * nm + 1], B2[nq2 + k], s);
+                }
                 out[t] = append ? out[t] + s * scale : s * scale;
             }
         }
@@ -422,6 +486,15 @@ __device__ void gen_pd_apply(const GenCtx &c, double *d0, double *d1, double *d2
                 a = a * (2.0 / (1.0 - c.Z[2][k]));
                 g = fma(0.5 * (1.0 + c.Z[0][i]), a, g);
             }
+            else if (SHAPE == NEKMF_PYR)
+            {
+                // PhysDerivKernels.hpp:505-527
+                const double x2 = 2.0 / (1.0 - c.Z[2][k]);
+                a = a * x2;
+                b = b * x2;
+                g = fma(0.5 * (1.0 + c.Z[0][i]), a, g);
+                g = fma(0.5 * (1.0 + c.Z[1][j]), b, g);
+            }
             else if (SHAPE == NEKMF_TET)
             {
                 const double x2 = 2.0 / (1.0 - c.Z[2][k]), x1 = 2.0 / (1.0 - c.Z[1][j]);
@@ -499,6 +572,20 @@ __device__ void gen_metric(const GenCtx &c, double *g0, double *g1, double *g2, 
                 m22 = df2 * df2 + df5 * df5 + df8 * df8;
                 m12 = df1 * df2 + df4 * df5 + df7 * df8;
             }
+            else if (SHAPE == NEKMF_PYR)
+            {
+                // Helmholtz.h:1845-1905
+                const double h0 = 0.5 * (1.0 + c.Z[0][i]), h1 = 0.5 * (1.0 + c.Z[1][j]), h2 = 2.0 / (1.0 - c.Z[2][k]);
+                const double h1h2 = h1 * h2, h0h2 = h0 * h2;
+                const double t0 = h2 * df0 + h0h2 * df2, t1 = h2 * df3 + h0h2 * df5, t2 = h2 * df6 + h0h2 * df8;
+                const double t3 = h2 * df1 + h1h2 * df2, t4 = h2 * df4 + h1h2 * df5, t5 = h2 * df7 + h1h2 * df8;
+                m00 = t0 * t0 + t1 * t1 + t2 * t2;
+                m11 = t3 * t3 + t4 * t4 + t5 * t5;
+                m22 = df2 * df2 + df5 * df5 + df8 * df8;
+                m01 = t0 * t3 + t1 * t4 + t2 * t5;
+                m02 = df2 * t0 + df5 * t1 + df8 * t2;
+                m12 = df2 * t3 + df5 * t4 + df8 * t5;
+            }
             else
             {
                 const double h0 = 0.5 * (1.0 + c.Z[0][i]), h1 = 0.5 * (1.0 + c.Z[1][j]);
@@ -560,12 +647,24 @@ template <int SHAPE> __global__ void __launch_bounds__(256) gen_kernel(const __g
             if (p < nm)
             {
                 o += nm - p;
-                for (int q = 0; q < nm - p; ++q, ++cq)
-                {
-                    c.offPQ[cq] = m;
-                    m += nm - p - q;
-                }
+                if (SHAPE != NEKMF_PYR)
+                    for (int q = 0; q < nm - p; ++q, ++cq)
+                    {
+                        c.offPQ[cq] = m;
+                        m += nm - p - q;
+                    }
             }
+        }
+        if (SHAPE == NEKMF_PYR)
+        {
+            // mode offset of every (p,q): nm - max(p,q) modes each, r fastest
+            for (int pq = 0; pq < nm * nm; ++pq)
+            {
+                const int p = pq / nm, q = pq - p * nm;
+                c.offPQ[pq] = m;
+                m += nm - (p > q ? p : q);
+            }
+            cq = nm * nm;
         }
         c.offPQ[cq] = m;
     }
@@ -637,6 +736,14 @@ template <int SHAPE> __global__ void __launch_bounds__(256) gen_kernel(const __g
                             const int i = t % c.nq0, k = t / (c.nq0 * c.nq1);
                             const double f0 = 2.0 / (1.0 - c.Z[2][k]), hf1 = 0.5 * (1.0 + c.Z[0][i]);
                             t0 = t0 * f0 + (hf1 * t2) * f0;
+                        }
+                        else if (SHAPE == NEKMF_PYR)
+                        {
+                            // IProductWRTDerivBase.h:2121-2168
+                            const int i = t % c.nq0, j = (t / c.nq0) % c.nq1, k = t / (c.nq0 * c.nq1);
+                            const double f0 = 2.0 / (1.0 - c.Z[2][k]);
+                            t0 = t0 * f0 + (0.5 * (1.0 + c.Z[0][i]) * t2) * f0;
+                            t1 = t1 * f0 + (0.5 * (1.0 + c.Z[1][j]) * t2) * f0;
                         }
                         else if (SHAPE == NEKMF_TET)
                         {
@@ -753,7 +860,7 @@ bool select_generic(nekmf_op_s *op)
     for (int v : cands)
         if (v > N) N = v;
     N = (N + 1) & ~1;
-    const size_t smem = (size_t)(op->tab_len + 7 * N) * 8 + (size_t)(2 * (nm + 1) + nm * (nm + 1) / 2 + 2) * 4 + 16;
+    const size_t smem = (size_t)(op->tab_len + 7 * N) * 8 + (size_t)(2 * (nm + 1) + nm * nm + 2) * 4 + 16;
     if (smem > 227 * 1024) return false;
     GenState *st    = new GenState{N, smem, 0};
     op->kstate      = st;
@@ -768,6 +875,7 @@ bool select_generic(nekmf_op_s *op)
         case NEKMF_TRI: op->launch = gen_launch<NEKMF_TRI>; break;
         case NEKMF_HEX: op->launch = gen_launch<NEKMF_HEX>; break;
         case NEKMF_PRISM: op->launch = gen_launch<NEKMF_PRISM>; break;
+        case NEKMF_PYR: op->launch = gen_launch<NEKMF_PYR>; break;
         case NEKMF_TET: op->launch = gen_launch<NEKMF_TET>; break;
         default: return false;
     }

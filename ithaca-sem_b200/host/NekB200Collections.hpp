@@ -83,7 +83,8 @@ namespace LibUtilities
 {
 enum ShapeType { eQuadrilateral = NEKMF_QUAD, eTriangle = NEKMF_TRI, eHexahedron = NEKMF_HEX, ePrism = NEKMF_PRISM,
                  ePyramid = NEKMF_PYR, eTetrahedron = NEKMF_TET };
-enum BasisType { eModified_A = NEKMF_MODIFIED_A, eModified_B = NEKMF_MODIFIED_B, eModified_C = NEKMF_MODIFIED_C };
+enum BasisType { eModified_A = NEKMF_MODIFIED_A, eModified_B = NEKMF_MODIFIED_B, eModified_C = NEKMF_MODIFIED_C,
+                 eModifiedPyr_C = NEKMF_MODIFIEDPYR_C };
 enum PointsType { eGaussLobattoLegendre = NEKMF_GLL, eGaussRadauMAlpha1Beta0 = NEKMF_GRJM_A1B0,
                   eGaussRadauMAlpha2Beta0 = NEKMF_GRJM_A2B0 };
 static const char *const ShapeTypeMap[] = {"Quadrilateral", "Triangle", "Hexahedron", "Prism", "Pyramid", "Tetrahedron"};
@@ -140,6 +141,7 @@ public:
         int nq[3]        = {nq0, nq0, nq0};
         if (shape == eTriangle) { bt[1] = eModified_B; pt[1] = eGaussRadauMAlpha1Beta0; nq[1] = nq0 - 1; }
         else if (shape == ePrism) { bt[2] = eModified_B; pt[2] = eGaussRadauMAlpha1Beta0; nq[2] = nq0 - 1; }
+        else if (shape == ePyramid) { bt[2] = eModifiedPyr_C; pt[2] = eGaussRadauMAlpha2Beta0; nq[2] = nq0 - 1; }
         else if (shape == eTetrahedron)
         {
             bt[1] = eModified_B; pt[1] = eGaussRadauMAlpha1Beta0; nq[1] = nq0 - 1;
@@ -155,7 +157,8 @@ public:
         }
         const int n = nummodes;
         m_ncoeffs   = shape == eQuadrilateral ? n * n : shape == eTriangle ? n * (n + 1) / 2 : shape == eHexahedron ? n * n * n
-                      : shape == ePrism ? n * n * (n + 1) / 2 : n * (n + 1) * (n + 2) / 6;
+                      : shape == ePrism ? n * n * (n + 1) / 2 : shape == ePyramid ? n * (n + 1) * (2 * n + 1) / 6
+                      : n * (n + 1) * (n + 2) / 6;
     }
     // share the bases of an existing expansion, new geometry (what ExpList does for every element)
     StdExpansion(const StdExpansion &o, bool deformed, const Array<OneD, NekDouble> &jac, const Array<OneD, NekDouble> &df)
@@ -389,6 +392,7 @@ template <OperatorType OP> inline void RegisterB200(bool withCollapsed)
     {
         f.RegisterCreatorFunction(OperatorKey(eTriangle, OP, eB200, false), Operator_B200::create<OP>, n + "Tri");
         f.RegisterCreatorFunction(OperatorKey(ePrism, OP, eB200, false), Operator_B200::create<OP>, n + "Prism");
+        f.RegisterCreatorFunction(OperatorKey(ePyramid, OP, eB200, false), Operator_B200::create<OP>, n + "Pyr");
         f.RegisterCreatorFunction(OperatorKey(eTetrahedron, OP, eB200, false), Operator_B200::create<OP>, n + "Tet");
     }
 }
@@ -400,7 +404,7 @@ struct Registrar
         RegisterB200<eHelmholtz>(true);
         RegisterB200<eIProductWRTBase>(true);
         RegisterB200<ePhysDeriv>(true);
-        RegisterB200<eIProductWRTDerivBase>(false);
+        RegisterB200<eIProductWRTDerivBase>(true);
     }
 };
 static Registrar g_registrar; // static registration, as the reference's m_typeArr[] initialisers

@@ -35,7 +35,7 @@ OperatorTypeMap = ["BwdTrans", "Helmholtz", "IProductWRTBase", "IProductWRTDeriv
 ImplementationTypeMap = ["NoImplementationType", "NoCollection", "IterPerExp", "StdMat", "SumFac", "MatrixFree",
                          "B200"]
 # basis / points types
-eModified_A, eModified_B, eModified_C = 0, 1, 2
+eModified_A, eModified_B, eModified_C, eModifiedPyr_C = 0, 1, 2, 3
 eGaussLobattoLegendre, eGaussRadauMAlpha1Beta0, eGaussRadauMAlpha2Beta0 = 0, 1, 2
 HOST, DEVICE = 0, 1
 eFactorLambda = "FactorLambda"
@@ -196,7 +196,8 @@ class Basis:
 def num_coeffs(shape, nm):
     """LibUtilities::StdXxxData::getNumberOfCoefficients (BasicUtils/ShapeType.hpp:111-337)."""
     return {eQuadrilateral: nm * nm, eTriangle: nm * (nm + 1) // 2, eHexahedron: nm ** 3,
-            ePrism: nm * nm * (nm + 1) // 2, eTetrahedron: nm * (nm + 1) * (nm + 2) // 6}[shape]
+            ePrism: nm * nm * (nm + 1) // 2, eTetrahedron: nm * (nm + 1) * (nm + 2) // 6,
+            ePyramid: nm * (nm + 1) * (2 * nm + 1) // 6}[shape]
 
 
 class StdExpansion:
@@ -216,6 +217,9 @@ class StdExpansion:
             bt[1], pt[1], nq[1] = eModified_B, eGaussRadauMAlpha1Beta0, nq0 - 1
         elif shape == ePrism:
             bt[2], pt[2], nq[2] = eModified_B, eGaussRadauMAlpha1Beta0, nq0 - 1
+        elif shape == ePyramid:
+            # nq2 = nq0 - 1 is what the MatrixFree operators require (Helmholtz.h:1519-1525)
+            bt[2], pt[2], nq[2] = eModifiedPyr_C, eGaussRadauMAlpha2Beta0, nq0 - 1
         elif shape == eTetrahedron:
             bt[1], pt[1], nq[1] = eModified_B, eGaussRadauMAlpha1Beta0, nq0 - 1
             bt[2], pt[2], nq[2] = eModified_C, eGaussRadauMAlpha2Beta0, nq0 - 1

@@ -321,6 +321,7 @@ int mfo_basis_rows(int btype, int nm)
         case MFO_MOD_A: return nm;
         case MFO_MOD_B: return nm * (nm + 1) / 2;
         case MFO_MOD_C: return nm * (nm + 1) * (nm + 2) / 6;
+        case MFO_MOD_PYR_C: return nm * (nm + 1) * (2 * nm + 1) / 6;
     }
     return 0;
 }
@@ -390,6 +391,53 @@ void mfo_basis(int btype, int nm, int np, const double *z, const double *D, doub
         modified_a(nm, np, z, bdata);
     else if (btype == MFO_MOD_B)
         modified_b(nm, np, z, bdata);
+    else if (btype == MFO_MOD_PYR_C)
+    {
+        /* ModifiedPyr_C: Basis.cpp:569-669.  Rows ordered (p, q, r) with r fastest and nm - max(p,q) rows per
+         * (p,q); vertex/edge/face rows are copies of Modified_B rows, face-0 rows are powers of (1-z)/2,
+         * interior rows [(1-z)/2]^{p+q-2} (1+z)/2 P_{r-1}^{2p+2q-3,1}. */
+        int nb       = mfo_basis_rows(MFO_MOD_B, nm), p, q, r;
+        double *modb = (double *)malloc((size_t)nb * np * sizeof(double));
+        size_t N, boff = 0, off = 0;
+        double *mode;
+        const double *one_p_z;
+        modified_b(nm, np, z, modb);
+        N = (size_t)np * nm * (nm + 1) / 2;
+        memcpy(bdata, modb, N * sizeof(double));
+        off += N;
+        boff += (size_t)np * nm;
+        N = (size_t)np * (nm - 1);
+        memcpy(bdata + off, modb + boff, N * sizeof(double));
+        off += N;
+        N = (size_t)np * (nm - 1) * nm / 2;
+        memcpy(bdata + off, modb + boff, N * sizeof(double));
+        off += N;
+        boff += (size_t)np * (nm - 1);
+        mode = bdata + off;
+        for (p = 2; p < nm; ++p)
+        {
+            N = (size_t)np * (nm - p);
+            memcpy(mode, modb + boff, N * sizeof(double));
+            mode += N;
+            memcpy(mode, modb + boff, N * sizeof(double));
+            mode += N;
+            boff += N;
+            one_p_z = bdata + np;
+            for (q = 2; q < nm; ++q)
+            {
+                double *one_m_z_pow = mode;
+                for (i = 0; i < np; ++i) mode[i] = pow(bdata[i], p + q - 2);
+                mode += np;
+                for (r = 1; r < nm - (p > q ? p : q); ++r)
+                {
+                    mfo_jacobfd(np, z, mode, NULL, r - 1, 2 * p + 2 * q - 3, 1.0);
+                    for (i = 0; i < np; ++i) mode[i] *= one_m_z_pow[i] * one_p_z[i];
+                    mode += np;
+                }
+            }
+        }
+        free(modb);
+    }
     else
     {
         /* Modified_C = re-indexed copy of Modified_B (phi^c_{pqr} = phi^b_{p+q,r}): Basis.cpp:513-558 */
@@ -436,6 +484,7 @@ static int count_modes(int shape, int nm)
         case MFO_HEX: return nm * nm * nm;
         case MFO_PRISM: return nm * nm * (nm + 1) / 2;
         case MFO_TET: return nm * (nm + 1) * (nm + 2) / 6;
+        case MFO_PYR: return nm * (nm + 1) * (2 * nm + 1) / 6;
     }
     return -1;
 }
@@ -468,6 +517,9 @@ mfo_elem *mfo_create(int shape, int nm, int nq0)
             e->nq[1] = nq0 - 1; e->ptype[1] = MFO_GRJM_A1; e->btype[1] = MFO_MOD_B;
             e->nq[2] = nq0 - 1; e->ptype[2] = MFO_GRJM_A2; e->btype[2] = MFO_MOD_C;
             break;
+        case MFO_PYR: /* MatrixFree precondition nq2 = nq0 - 1: Helmholtz.h:1519-1525 */
+            e->nq[2] = nq0 - 1; e->ptype[2] = MFO_GRJM_A2; e->btype[2] = MFO_MOD_PYR_C;
+            break;
         default: free(e); return NULL;
     }
     e->nmTot = count_modes(shape, nm);
@@ -498,6 +550,16 @@ mfo_elem *mfo_create(int shape, int nm, int nq0)
         e->h1  = (double *)malloc(sizeof(double) * e->nq[dl]);
         for (i = 0; i < e->nq[0]; ++i) e->h0[i] = 0.5 * (1 + e->z[0][i]);
         for (i = 0; i < e->nq[dl]; ++i) e->h1[i] = 2.0 / (1 - e->z[dl][i]);
+    }
+    else if (shape == MFO_PYR)
+    {
+        /* Helmholtz.h:1489-1507 */
+        e->h0 = (double *)malloc(sizeof(double) * e->nq[0]);
+        e->h1 = (double *)malloc(sizeof(double) * e->nq[1]);
+        e->h2 = (double *)malloc(sizeof(double) * e->nq[2]);
+        for (i = 0; i < e->nq[0]; ++i) e->h0[i] = 0.5 * (1 + e->z[0][i]);
+        for (i = 0; i < e->nq[1]; ++i) e->h1[i] = 0.5 * (1 + e->z[1][i]);
+        for (i = 0; i < e->nq[2]; ++i) e->h2[i] = 2.0 / (1 - e->z[2][i]);
     }
     else if (shape == MFO_TET)
     {
@@ -926,6 +988,112 @@ static void k_ip_prism(int nm, int nq0, int nq1, int nq2, const double *in, cons
     }
 }
 
+/* ---------------- Pyr.  BwdTransKernels.hpp:131-222 (isotropic modes) */
+static void k_bwd_pyr(int nm, int nq0, int nq1, int nq2, const double *in, const double *b0, const double *b1,
+                      const double *b2, double *fpq, double *fp, double *out)
+{
+    int i, j, k, p, q, r, c = 0;
+    for (k = 0; k < nq2; ++k)
+    {
+        int mpqr = 0, mpq = 0;
+        for (p = 0; p < nm; ++p)
+            for (q = 0; q < nm; ++q, ++mpq)
+            {
+                int len  = nm - (p > q ? p : q);
+                double s = 0.0;
+                for (r = 0; r < len; ++r, ++mpqr) s += in[mpqr] * b2[mpqr * nq2 + k];
+                fpq[mpq] = s;
+            }
+        for (j = 0; j < nq1; ++j)
+        {
+            mpq = 0;
+            for (p = 0; p < nm; ++p)
+            {
+                double s = 0.0;
+                for (q = 0; q < nm; ++q, ++mpq) s += fpq[mpq] * b1[q * nq1 + j];
+                fp[p] = s;
+            }
+            for (i = 0; i < nq0; ++i, ++c)
+            {
+                double v = 0.0, t1;
+                for (p = 0; p < nm; ++p) v += fp[p] * b0[p * nq0 + i];
+                /* CORRECT: top vertex */
+                t1 = b0[i] * b1[nq1 + j];
+                t1 += b0[nq0 + i] * b1[j];
+                t1 += b0[nq0 + i] * b1[nq1 + j];
+                t1 = t1 * b2[nq2 + k];
+                v += t1 * in[1];
+                out[c] = v;
+            }
+        }
+    }
+}
+
+/* IProductKernels.hpp:455-598 */
+static void k_ip_pyr(int nm, int nq0, int nq1, int nq2, const double *in, const double *b0, const double *b1,
+                     const double *b2, const double *w0, const double *w1, const double *w2, const double *jac, int DEF,
+                     double *s_kj, double *s_k, double *out, double scale, int SCALE, int APPEND)
+{
+    int i, j, k, p, q, r, mpqr = 0;
+    for (p = 0; p < nm; ++p)
+    {
+        int ckji = 0, ckj = 0;
+        for (k = 0; k < nq2; ++k)
+            for (j = 0; j < nq1; ++j, ++ckj)
+            {
+                double s = 0.0;
+                for (i = 0; i < nq0; ++i, ++ckji)
+                {
+                    double jv   = DEF ? jac[nq0 * nq1 * k + nq0 * j + i] : jac[0];
+                    double prod = b0[nq0 * p + i] * jv * w0[i];
+                    s += prod * in[ckji];
+                }
+                s_kj[ckj] = s;
+            }
+        for (q = 0; q < nm; ++q)
+        {
+            int len = nm - (p > q ? p : q);
+            ckj     = 0;
+            for (k = 0; k < nq2; ++k)
+            {
+                double s = 0.0;
+                for (j = 0; j < nq1; ++j, ++ckj) s += (b1[q * nq1 + j] * w1[j]) * s_kj[ckj];
+                s_k[k] = s;
+            }
+            for (r = 0; r < len; ++r, ++mpqr)
+            {
+                double s = 0.0;
+                for (k = 0; k < nq2; ++k) s += (b2[mpqr * nq2 + k] * w2[k]) * s_k[k];
+                scale_append(&out[mpqr], s, scale, SCALE, APPEND);
+            }
+        }
+    }
+    /* CORRECT: top vertex, accumulated point by point into mode 1 */
+    {
+        int c = 0;
+        for (k = 0; k < nq2; ++k)
+        {
+            double kw = w2[k];
+            if (!DEF) kw = kw * jac[0];
+            for (j = 0; j < nq1; ++j)
+            {
+                double kjw = kw * w1[j];
+                for (i = 0; i < nq0; ++i, ++c)
+                {
+                    double q3 = kjw * w0[i], t;
+                    if (DEF) q3 = q3 * jac[k * nq0 * nq1 + j * nq0 + i];
+                    t = b0[i] * b1[nq1 + j];
+                    t += b0[nq0 + i] * b1[j];
+                    t += b0[nq0 + i] * b1[nq1 + j];
+                    t = t * b2[nq2 + k];
+                    t = t * in[c];
+                    scale_append(&out[1], t * q3, scale, SCALE, 1);
+                }
+            }
+        }
+    }
+}
+
 /* ---------------- Tet.  BwdTransKernels.hpp:374-484 */
 static void k_bwd_tet(int nm, int nq0, int nq1, int nq2, const double *in, const double *b0, const double *b1,
                       const double *b2, double *fpq, double *fp, double *out)
@@ -1105,6 +1273,9 @@ static void bwd_one(const mfo_elem *e, const double *in, double *out, scratch *s
         case MFO_TET:
             k_bwd_tet(e->nm, e->nq[0], e->nq[1], e->nq[2], in, e->b[0], e->b[1], e->b[2], s->a, s->b, out);
             break;
+        case MFO_PYR:
+            k_bwd_pyr(e->nm, e->nq[0], e->nq[1], e->nq[2], in, e->b[0], e->b[1], e->b[2], s->a, s->b, out);
+            break;
     }
 }
 
@@ -1132,6 +1303,10 @@ static void ip_one(const mfo_elem *e, const double *in, const double *B0, const 
         case MFO_TET:
             k_ip_tet(e->nm, e->nq[0], e->nq[1], e->nq[2], in, B0, B1, B2, e->ws[0], e->ws[1], e->ws[2], jac, DEF,
                      s->a, out, scale, SCALE, APPEND);
+            break;
+        case MFO_PYR:
+            k_ip_pyr(e->nm, e->nq[0], e->nq[1], e->nq[2], in, B0, B1, B2, e->ws[0], e->ws[1], e->ws[2], jac, DEF,
+                     s->a, s->b, out, scale, SCALE, APPEND);
             break;
     }
 }
@@ -1223,12 +1398,22 @@ static void pd_one(const mfo_elem *e, const double *in, const double *df, size_t
     }
     for (k = 0, pt = 0; k < nq2; ++k)
     {
-        double xe2 = e->shape == MFO_PRISM ? 2.0 / (1.0 - e->z[2][k]) : 0.0;
+        double xe2 = (e->shape == MFO_PRISM || e->shape == MFO_PYR) ? 2.0 / (1.0 - e->z[2][k]) : 0.0;
         for (j = 0; j < nq1; ++j)
             for (i = 0; i < nq0; ++i, ++pt)
             {
                 double d0 = o0[pt], d1 = o1[pt], d2 = o2[pt], r0, r1, r2;
-                if (e->shape == MFO_PRISM)
+                if (e->shape == MFO_PYR)
+                {
+                    /* PhysDerivKernels.hpp:505-527 */
+                    double xe1 = 0.5 * (1 + e->z[1][j]), xe0;
+                    d0  = o0[pt] * xe2;
+                    d1  = o1[pt] * xe2;
+                    xe0 = 0.5 * (1 + e->z[0][i]);
+                    d2 += xe0 * d0;
+                    d2 += xe1 * d1;
+                }
+                else if (e->shape == MFO_PRISM)
                 {
                     /* PhysDerivKernels.hpp:417-428 */
                     double xe0;
@@ -1315,6 +1500,25 @@ static void helm_one(const mfo_elem *e, const double *in, const double *jac, con
                     m11 = df1 * df1; m11 += df4 * df4; m11 += df7 * df7; /* g1 */
                     m22 = df2 * df2; m22 += df5 * df5; m22 += df8 * df8; /* g2 */
                     m12 = df1 * df2; m12 += df4 * df5; m12 += df7 * df8; /* g5 */
+                }
+                else if (e->shape == MFO_PYR)
+                {
+                    /* Helmholtz.h:1845-1905 */
+                    double h2 = e->h2[k], h1 = e->h1[j], h0 = e->h0[i];
+                    double h1h2 = h1 * h2, h0h2 = h0 * h2;
+                    double t0, t1, t2, t3, t4, t5;
+                    t0 = h2 * df0; t0 += h0h2 * df2;
+                    t1 = h2 * df3; t1 += h0h2 * df5;
+                    t2 = h2 * df6; t2 += h0h2 * df8;
+                    t3 = h2 * df1; t3 += h1h2 * df2;
+                    t4 = h2 * df4; t4 += h1h2 * df5;
+                    t5 = h2 * df7; t5 += h1h2 * df8;
+                    m00 = t0 * t0; m00 += t1 * t1; m00 += t2 * t2;       /* g0 */
+                    m11 = t3 * t3; m11 += t4 * t4; m11 += t5 * t5;       /* g1 */
+                    m22 = df2 * df2; m22 += df5 * df5; m22 += df8 * df8; /* g2 */
+                    m01 = t0 * t3; m01 += t1 * t4; m01 += t2 * t5;       /* g3 */
+                    m02 = df2 * t0; m02 += df5 * t1; m02 += df8 * t2;    /* g4 */
+                    m12 = df2 * t3; m12 += df5 * t4; m12 += df8 * t5;    /* g5 */
                 }
                 else
                 {
@@ -1442,6 +1646,19 @@ int mfo_iproductwrtderivbase(const mfo_elem *e, int nElmt, int DEF, const double
                         v0 *= f0;
                         f1t2 = hf1 * v2;
                         v0 += f1t2 * f0;
+                    }
+                    else if (e->shape == MFO_PYR)
+                    {
+                        /* IProductWRTDerivBase.h:2121-2168 */
+                        int i = pt % e->nq[0], j = (pt / e->nq[0]) % e->nq[1], k = pt / (e->nq[0] * e->nq[1]);
+                        double f0 = 2.0 / (1.0 - e->z[2][k]), hf2 = 0.5 * (1.0 + e->z[1][j]);
+                        double hf1 = 0.5 * (1.0 + e->z[0][i]), f1t2;
+                        v0 *= f0;
+                        f1t2 = hf1 * v2;
+                        v0 += f1t2 * f0;
+                        v1 *= f0;
+                        f1t2 = hf2 * v2;
+                        v1 += f1t2 * f0;
                     }
                     else if (e->shape == MFO_TET)
                     {

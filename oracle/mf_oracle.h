@@ -22,7 +22,7 @@ enum { MFO_QUAD = 0, MFO_TRI = 1, MFO_HEX = 2, MFO_PRISM = 3, MFO_PYR = 4, MFO_T
 /* points types: Gauss-Lobatto-Legendre, Gauss-Radau-M (alpha=1|2, beta=0) */
 enum { MFO_GLL = 0, MFO_GRJM_A1 = 1, MFO_GRJM_A2 = 2 };
 /* basis types */
-enum { MFO_MOD_A = 0, MFO_MOD_B = 1, MFO_MOD_C = 2 };
+enum { MFO_MOD_A = 0, MFO_MOD_B = 1, MFO_MOD_C = 2, MFO_MOD_PYR_C = 3 };
 
 /* ---- Polylib restatement (LibUtilities/Polylib/Polylib.cpp) */
 void mfo_jacobfd(int np, const double *z, double *poly, double *polyd, int n, double alpha, double beta);

@@ -1018,6 +1018,203 @@ template <int NM, int NQ, bool DEF> struct TetOps
     }
 };
 
+// =============================================================== PYR  (nq2 = nq0 - 1)
+template <int NM, int NQ, bool DEF> struct PyrOps
+{
+    static constexpr int NQ2 = NQ - 1;
+    static constexpr int nmTot = NM * (NM + 1) * (2 * NM + 1) / 6, nqTot = NQ * NQ * NQ2, ndf = 9;
+    static constexpr bool CORRECT = true;
+
+    static void bwd(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        PAR_BLOCKS_BEGIN(c)
+        vec_t fpq[NM * NM], fp[NM];
+        VecVec tmpIn(nmTot), tmpOut(nqTot);
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            load_interleave(c.in[0] + (size_t)e * nmTot * W, nmTot, tmpIn);
+            BwdTransPyrKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT>(tmpIn, c.bdata[0], c.bdata[1], c.bdata[2], fpq, fp, tmpOut);
+            deinterleave_store(tmpOut, nqTot, c.out[0] + (size_t)e * nqTot * W);
+        }
+        PAR_BLOCKS_END
+    }
+    static void iprod(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        PAR_BLOCKS_BEGIN(c)
+        vec_t wsp1[NQ * NQ2], wsp2[NQ2];
+        VecVec tmpIn(nqTot), tmpOut(nmTot);
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            const vec_t *jac_ptr = DEF ? &c.jac[(size_t)nqTot * e] : &c.jac[e];
+            load_interleave(c.in[0] + (size_t)e * nqTot * W, nqTot, tmpIn);
+            IProductPyrKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT, false, false, DEF>(
+                tmpIn, c.bdata[0], c.bdata[1], c.bdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp1, wsp2, tmpOut);
+            deinterleave_store(tmpOut, nmTot, c.out[0] + (size_t)e * nmTot * W);
+        }
+        PAR_BLOCKS_END
+    }
+    static void physderiv(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        const size_t dfSize = DEF ? (size_t)ndf * nqTot : ndf;
+        PAR_BLOCKS_BEGIN(c)
+        VecVec tmpIn(nqTot), o0(nqTot), o1(nqTot), o2(nqTot);
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            const vec_t *df_ptr = &c.df[e * dfSize];
+            load_interleave(c.in[0] + (size_t)e * nqTot * W, nqTot, tmpIn);
+            PhysDerivPyrKernel<NQ, NQ, NQ2, DEF>(tmpIn, c.Z[0], c.Z[1], c.Z[2], c.D[0], c.D[1], c.D[2], df_ptr, o0, o1, o2);
+            deinterleave_store(o0, nqTot, c.out[0] + (size_t)e * nqTot * W);
+            deinterleave_store(o1, nqTot, c.out[1] + (size_t)e * nqTot * W);
+            deinterleave_store(o2, nqTot, c.out[2] + (size_t)e * nqTot * W);
+        }
+        PAR_BLOCKS_END
+    }
+    // Helmholtz.h:1771-1955
+    static void helm(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        const size_t dfSize = DEF ? (size_t)ndf * nqTot : ndf;
+        PAR_BLOCKS_BEGIN(c)
+        vec_t wsp1[NQ * NQ2 > NM * NM ? NQ * NQ2 : NM * NM], wsp2[NQ2 > NM ? NQ2 : NM];
+        VecVec tmpIn(nmTot), tmpOut(nmTot), bwd(nqTot), deriv0(nqTot), deriv1(nqTot), deriv2(nqTot);
+        vec_t df0, df1, df2, df3, df4, df5, df6, df7, df8;
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            const vec_t *df_ptr = &c.df[e * dfSize];
+            const vec_t *jac_ptr;
+            load_interleave(c.in[0] + (size_t)e * nmTot * W, nmTot, tmpIn);
+            if (!DEF)
+            {
+                df0 = df_ptr[0]; df1 = df_ptr[1]; df2 = df_ptr[2];
+                df3 = df_ptr[3]; df4 = df_ptr[4]; df5 = df_ptr[5];
+                df6 = df_ptr[6]; df7 = df_ptr[7]; df8 = df_ptr[8];
+                jac_ptr = &c.jac[e];
+            }
+            else
+            {
+                jac_ptr = &c.jac[(size_t)e * nqTot];
+            }
+            BwdTransPyrKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT>(tmpIn, c.bdata[0], c.bdata[1], c.bdata[2], wsp1, wsp2, bwd);
+            IProductPyrKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT, true, false, DEF>(
+                bwd, c.bdata[0], c.bdata[1], c.bdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp1, wsp2, tmpOut, c.lambda);
+            PhysDerivTensor3DKernel<NQ, NQ, NQ2>(bwd, c.D[0], c.D[1], c.D[2], deriv0, deriv1, deriv2);
+            for (size_t k = 0, cnt = 0; k < NQ2; ++k)
+            {
+                vec_t h2 = c.h2[k];
+                for (size_t j = 0; j < NQ; ++j)
+                {
+                    vec_t h1 = c.h1[j];
+                    vec_t h1h2 = h1 * h2;
+                    for (size_t i = 0; i < NQ; ++i, cnt++)
+                    {
+                        vec_t h0 = c.h0[i];
+                        vec_t h0h2 = h0 * h2;
+                        if (DEF)
+                        {
+                            df0 = df_ptr[cnt * ndf]; df1 = df_ptr[cnt * ndf + 1]; df2 = df_ptr[cnt * ndf + 2];
+                            df3 = df_ptr[cnt * ndf + 3]; df4 = df_ptr[cnt * ndf + 4]; df5 = df_ptr[cnt * ndf + 5];
+                            df6 = df_ptr[cnt * ndf + 6]; df7 = df_ptr[cnt * ndf + 7]; df8 = df_ptr[cnt * ndf + 8];
+                        }
+                        vec_t tmp0 = h2 * df0; tmp0.fma(h0h2, df2);
+                        vec_t tmp1 = h2 * df3; tmp1.fma(h0h2, df5);
+                        vec_t tmp2 = h2 * df6; tmp2.fma(h0h2, df8);
+                        vec_t tmp3 = h2 * df1; tmp3.fma(h1h2, df2);
+                        vec_t tmp4 = h2 * df4; tmp4.fma(h1h2, df5);
+                        vec_t tmp5 = h2 * df7; tmp5.fma(h1h2, df8);
+                        vec_t g0 = tmp0 * tmp0; g0.fma(tmp1, tmp1); g0.fma(tmp2, tmp2);
+                        vec_t g1 = tmp3 * tmp3; g1.fma(tmp4, tmp4); g1.fma(tmp5, tmp5);
+                        vec_t g2 = df2 * df2; g2.fma(df5, df5); g2.fma(df8, df8);
+                        vec_t g3 = tmp0 * tmp3; g3.fma(tmp1, tmp4); g3.fma(tmp2, tmp5);
+                        vec_t g4 = df2 * tmp0; g4.fma(df5, tmp1); g4.fma(df8, tmp2);
+                        vec_t g5 = df2 * tmp3; g5.fma(df5, tmp4); g5.fma(df8, tmp5);
+                        vec_t d0 = deriv0[cnt], d1 = deriv1[cnt], d2 = deriv2[cnt];
+                        tmp1 = g0 * d0; tmp1.fma(g3, d1); tmp1.fma(g4, d2); deriv0[cnt] = tmp1;
+                        tmp2 = g3 * d0; tmp2.fma(g1, d1); tmp2.fma(g5, d2); deriv1[cnt] = tmp2;
+                        tmp3 = g4 * d0; tmp3.fma(g5, d1); tmp3.fma(g2, d2); deriv2[cnt] = tmp3;
+                    }
+                }
+            }
+            IProductPyrKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT, false, true, DEF>(
+                deriv0, c.dbdata[0], c.bdata[1], c.bdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp1, wsp2, tmpOut);
+            IProductPyrKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT, false, true, DEF>(
+                deriv1, c.bdata[0], c.dbdata[1], c.bdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp1, wsp2, tmpOut);
+            IProductPyrKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT, false, true, DEF>(
+                deriv2, c.bdata[0], c.bdata[1], c.dbdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp1, wsp2, tmpOut);
+            deinterleave_store(tmpOut, nmTot, c.out[0] + (size_t)e * nmTot * W);
+        }
+        PAR_BLOCKS_END
+    }
+    // IProductWRTDerivBase.h:2056-2200
+    static void ipwdb(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        const size_t dfSize = DEF ? (size_t)ndf * nqTot : ndf;
+        PAR_BLOCKS_BEGIN(c)
+        vec_t wsp1[NQ * NQ2], wsp2[NQ2];
+        VecVec i0(nqTot), i1(nqTot), i2(nqTot), t0v(nqTot), t1v(nqTot), t2v(nqTot), tmpOut(nmTot);
+        vec_t df0, df1, df2, df3, df4, df5, df6, df7, df8;
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            const vec_t *df_ptr  = &c.df[e * dfSize];
+            const vec_t *jac_ptr = DEF ? &c.jac[(size_t)nqTot * e] : &c.jac[e];
+            load_interleave(c.in[0] + (size_t)e * nqTot * W, nqTot, i0);
+            load_interleave(c.in[1] + (size_t)e * nqTot * W, nqTot, i1);
+            load_interleave(c.in[2] + (size_t)e * nqTot * W, nqTot, i2);
+            if (!DEF)
+            {
+                df0 = df_ptr[0]; df1 = df_ptr[1]; df2 = df_ptr[2];
+                df3 = df_ptr[3]; df4 = df_ptr[4]; df5 = df_ptr[5];
+                df6 = df_ptr[6]; df7 = df_ptr[7]; df8 = df_ptr[8];
+            }
+            for (size_t k = 0, cnt = 0; k < NQ2; ++k)
+            {
+                vec_t f0 = 2.0 / (1.0 - c.Z[2][k]);
+                for (size_t j = 0; j < NQ; ++j)
+                {
+                    vec_t hf2 = 0.5 * (1.0 + c.Z[1][j]);
+                    for (size_t i = 0; i < NQ; ++i, ++cnt)
+                    {
+                        if (DEF)
+                        {
+                            df0 = df_ptr[cnt * ndf]; df1 = df_ptr[cnt * ndf + 1]; df2 = df_ptr[cnt * ndf + 2];
+                            df3 = df_ptr[cnt * ndf + 3]; df4 = df_ptr[cnt * ndf + 4]; df5 = df_ptr[cnt * ndf + 5];
+                            df6 = df_ptr[cnt * ndf + 6]; df7 = df_ptr[cnt * ndf + 7]; df8 = df_ptr[cnt * ndf + 8];
+                        }
+                        vec_t a = i0[cnt], b = i1[cnt], g = i2[cnt];
+                        vec_t t0 = df0 * a + df3 * b + df6 * g;
+                        vec_t t1 = df1 * a + df4 * b + df7 * g;
+                        vec_t t2 = df2 * a + df5 * b + df8 * g;
+                        t0 *= f0;
+                        vec_t hf1 = 0.5 * (1.0 + c.Z[0][i]);
+                        vec_t f1t2 = hf1 * t2;
+                        t0.fma(f1t2, f0);
+                        t1 *= f0;
+                        f1t2 = hf2 * t2;
+                        t1.fma(f1t2, f0);
+                        t0v[cnt] = t0; t1v[cnt] = t1; t2v[cnt] = t2;
+                    }
+                }
+            }
+            IProductPyrKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT, false, false, DEF>(
+                t0v, c.dbdata[0], c.bdata[1], c.bdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp1, wsp2, tmpOut);
+            IProductPyrKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT, false, true, DEF>(
+                t1v, c.bdata[0], c.dbdata[1], c.bdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp1, wsp2, tmpOut);
+            IProductPyrKernel<NM, NM, NM, NQ, NQ, NQ2, CORRECT, false, true, DEF>(
+                t2v, c.bdata[0], c.bdata[1], c.dbdata[2], c.w[0], c.w[1], c.w[2], jac_ptr, wsp1, wsp2, tmpOut);
+            deinterleave_store(tmpOut, nmTot, c.out[0] + (size_t)e * nmTot * W);
+        }
+        PAR_BLOCKS_END
+    }
+};
+
 template <class Ops> int run_op(int op, Ctx &c)
 {
     switch (op)
@@ -1048,6 +1245,7 @@ int dispatch_tri(int nm, int nq, int op, bool def, Ctx &c);
 int dispatch_hex(int nm, int nq, int op, bool def, Ctx &c);
 int dispatch_prism(int nm, int nq, int op, bool def, Ctx &c);
 int dispatch_tet(int nm, int nq, int op, bool def, Ctx &c);
+int dispatch_pyr(int nm, int nq, int op, bool def, Ctx &c);
 
 #define X(A, B)                                                                \
     if (nm == A && nq == B) return run_def<OPS, A, B>(op, def, c);
@@ -1063,6 +1261,9 @@ int dispatch_hex(int nm, int nq, int op, bool def, Ctx &c) { REF_PAIRS_HEX(X) re
 #elif defined(REF_TU_SHAPE) && REF_TU_SHAPE == 3
 #define OPS PrismOps
 int dispatch_prism(int nm, int nq, int op, bool def, Ctx &c) { REF_PAIRS_BASE(X) return -3; }
+#elif defined(REF_TU_SHAPE) && REF_TU_SHAPE == 4
+#define OPS PyrOps
+int dispatch_pyr(int nm, int nq, int op, bool def, Ctx &c) { REF_PAIRS_BASE(X) return -3; }
 #elif defined(REF_TU_SHAPE) && REF_TU_SHAPE == 5
 #define OPS TetOps
 int dispatch_tet(int nm, int nq, int op, bool def, Ctx &c) { REF_PAIRS_BASE(X) return -3; }
@@ -1128,6 +1329,7 @@ void *nekref_create(int op, int shape, int nm, int nq0, int deformed, const doub
         case SH_HEX: c.nmTot = nm * nm * nm; break;
         case SH_PRISM: c.nmTot = nm * nm * (nm + 1) / 2; break;
         case SH_TET: c.nmTot = nm * (nm + 1) * (nm + 2) / 6; break;
+        case SH_PYR: c.nmTot = nm * (nm + 1) * (2 * nm + 1) / 6; break;
         default: delete h; return nullptr;
     }
     for (int d = 0; d < c.dim; ++d)
@@ -1152,6 +1354,14 @@ void *nekref_create(int op, int shape, int nm, int nq0, int deformed, const doub
         c.h0.resize(nqd[0]); c.h1.resize(nqd[2]);
         for (int i = 0; i < nqd[0]; ++i) c.h0[i] = vec_t(0.5 * (1 + Z[0][i]));
         for (int k = 0; k < nqd[2]; ++k) c.h1[k] = vec_t(2.0 / (1 - Z[2][k]));
+    }
+    else if (shape == SH_PYR)
+    {
+        // Helmholtz.h:1489-1507
+        c.h0.resize(nqd[0]); c.h1.resize(nqd[1]); c.h2.resize(nqd[2]);
+        for (int i = 0; i < nqd[0]; ++i) c.h0[i] = vec_t(0.5 * (1 + Z[0][i]));
+        for (int j = 0; j < nqd[1]; ++j) c.h1[j] = vec_t(0.5 * (1 + Z[1][j]));
+        for (int k = 0; k < nqd[2]; ++k) c.h2[k] = vec_t(2.0 / (1 - Z[2][k]));
     }
     else if (shape == SH_TET)
     {
@@ -1221,6 +1431,7 @@ int nekref_run(void *handle, const double *in0, const double *in1, const double 
         case SH_TRI: rc = dispatch_tri(h->nm, h->nq0, h->op, def, c); break;
         case SH_HEX: rc = dispatch_hex(h->nm, h->nq0, h->op, def, c); break;
         case SH_PRISM: rc = dispatch_prism(h->nm, h->nq0, h->op, def, c); break;
+        case SH_PYR: rc = dispatch_pyr(h->nm, h->nq0, h->op, def, c); break;
         case SH_TET: rc = dispatch_tet(h->nm, h->nq0, h->op, def, c); break;
     }
     if (rc == 0 && padded)

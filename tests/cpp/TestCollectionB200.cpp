@@ -185,8 +185,12 @@ static void TestUnregisteredImplementation()
     try { col.Initialise(eBwdTrans); } catch (const ErrorUtil::NekError &) { threw = true; }
     CHECK(threw, "factory must reject (Hex, BwdTrans, StdMat)");
     CHECK(GetOperatorFactory().ModuleExists(OperatorKey(LibUtilities::eTetrahedron, eHelmholtz, eB200, false)), "Tet Helmholtz registered");
-    CHECK(!GetOperatorFactory().ModuleExists(OperatorKey(LibUtilities::eTetrahedron, eIProductWRTDerivBase, eB200, false)),
-          "Tet IProductWRTDerivBase not registered");
+    // every shape x operator pair the reference registers for eMatrixFree (Collections/*.cpp m_typeArr) exists
+    CHECK(GetOperatorFactory().ModuleExists(OperatorKey(LibUtilities::eTetrahedron, eIProductWRTDerivBase, eB200, false)),
+          "Tet IProductWRTDerivBase registered");
+    CHECK(GetOperatorFactory().ModuleExists(OperatorKey(LibUtilities::ePyramid, eHelmholtz, eB200, false)), "Pyr Helmholtz registered");
+    CHECK(!GetOperatorFactory().ModuleExists(OperatorKey(LibUtilities::eTetrahedron, eHelmholtz, eStdMat, false)),
+          "only eB200 is registered here");
     mfo_destroy(c.el);
 }
 

@@ -26,6 +26,7 @@ CASES = [  # shape, nm, nq0
     (po.HEX, 3, 4), (po.HEX, 5, 6), (po.HEX, 4, 6), (po.HEX, 8, 9),
     (po.PRISM, 4, 5), (po.PRISM, 7, 8),
     (po.TET, 4, 5), (po.TET, 7, 8), (po.TET, 5, 8),
+    (po.PYR, 4, 5), (po.PYR, 6, 7), (po.PYR, 4, 6),  # appended last: earlier cases keep their random streams
 ]
 NEL = 2
 LAMBDA = 1.5

@@ -13,7 +13,7 @@ from _util import ROOT, nekmf, random_geometry, rel_errs
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
-SHAPES = {"Quad": po.QUAD, "Tri": po.TRI, "Hex": po.HEX, "Prism": po.PRISM, "Tet": po.TET}
+SHAPES = {"Quad": po.QUAD, "Tri": po.TRI, "Hex": po.HEX, "Prism": po.PRISM, "Pyr": po.PYR, "Tet": po.TET}
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"))
 
 
@@ -68,6 +68,7 @@ def test_hex_all_operators_default_quadrature(nm, deformed):
     (po.TRI, 2, 3), (po.TRI, 4, 5), (po.TRI, 6, 7), (po.TRI, 8, 9), (po.TRI, 4, 8),
     (po.PRISM, 2, 3), (po.PRISM, 4, 5), (po.PRISM, 7, 8), (po.PRISM, 8, 9), (po.PRISM, 4, 7),
     (po.TET, 2, 3), (po.TET, 4, 5), (po.TET, 7, 8), (po.TET, 8, 9), (po.TET, 4, 7),
+    (po.PYR, 2, 3), (po.PYR, 3, 4), (po.PYR, 4, 5), (po.PYR, 5, 6), (po.PYR, 7, 8), (po.PYR, 8, 9), (po.PYR, 4, 7),
 ])
 def test_all_shapes_runtime_kernels(shape, nm, nq0, deformed):
     """collapsed-coordinate shapes (CORRECT terms of eModified_A), quads, over-integration (nq up to 2 nm)."""

@@ -46,8 +46,9 @@ def test_argument_validation_needs_no_gpu():
     assert nk.StdExpansion(nk.ePrism, 7).GetNcoeffs() == 196
     assert nk.StdExpansion(nk.eTetrahedron, 7).nq == [8, 7, 7]
     assert nk.StdExpansion(nk.ePrism, 7).nq == [8, 8, 7]
+    assert nk.StdExpansion(nk.ePyramid, 7).GetNcoeffs() == 140 and nk.StdExpansion(nk.ePyramid, 7).nq == [8, 8, 7]
     with pytest.raises(nk.NekError):
-        nk.StdExpansion(nk.ePyramid, 4)
+        nk.StdExpansion(99, 4)
     assert nk.ImplementationTypeMap[nk.eB200] == "B200" and nk.SIZE_ImplementationType == nk.eB200 + 1
 
 
@@ -62,7 +63,7 @@ def test_product_points_match_oracle(ptype):
         assert np.abs(D - Do).max() < 1e-13 * np.abs(Do).max()
 
 
-@pytest.mark.parametrize("shape", [po.QUAD, po.TRI, po.HEX, po.PRISM, po.TET])
+@pytest.mark.parametrize("shape", [po.QUAD, po.TRI, po.HEX, po.PRISM, po.PYR, po.TET])
 def test_product_basis_tables_match_oracle(shape):
     nk = nekmf()
     for nm in range(2, 12):

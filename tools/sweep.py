@@ -45,7 +45,7 @@ def main():
     dev = torch.device("cuda", 0)
     lo, hi = (a.nm.split("..") + [a.nm])[:2] if ".." in a.nm else (a.nm, a.nm)
     shapes = {"Quad": nk.eQuadrilateral, "Tri": nk.eTriangle, "Hex": nk.eHexahedron, "Prism": nk.ePrism,
-              "Tet": nk.eTetrahedron}
+              "Pyr": nk.ePyramid, "Tet": nk.eTetrahedron}
     ops = list(OPS) if a.ops == "all" else a.ops.split(",")
     peak, peak_src = bench.measured_peaks()
     gen = torch.Generator(device=dev).manual_seed(1234)
@@ -71,8 +71,6 @@ def main():
                 geom = nk.CoalescedGeomData(jac, df.reshape(-1), deformed)
                 coll = nk.Collection(std, nel, geom)
                 for opn in ops:
-                    if opn == "IProductWRTDerivBase" and sname in ("Tri", "Prism", "Tet") and not nk_has_ipwdb(nk, coll):
-                        continue
                     op = OPS[opn]
                     cin = opn in ("BwdTrans", "Helmholtz")
                     cout = opn not in ("BwdTrans", "PhysDeriv")
@@ -114,14 +112,6 @@ def main():
     if out:
         out.write(json.dumps({"hbm_peak_gb_per_s": peak, "peak_source": peak_src}) + "\n")
         out.close()
-
-
-def nk_has_ipwdb(nk, coll):
-    try:
-        coll.Initialise(nk.eIProductWRTDerivBase)
-        return True
-    except nk.NekError:
-        return False
 
 
 if __name__ == "__main__":
