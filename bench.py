@@ -214,6 +214,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=NX, help="elements per direction (default 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4],
+                    help="BASELINE.json configuration, 1-based: 2 (default) = configs[1], the metric's workload; "
+                         "1 = 2-D quad Helmholtz P=5; 4 = mixed Hex/Prism/Tet Helmholtz P=6 (bench_configs.py)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -253,6 +256,15 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.config != 2:
+        if world > 1:
+            raise SystemExit("bench.py --config %d is a single-GPU measurement" % args.config)
+        import pyoracle as po
+        import bench_configs
+        peak, peak_src = measured_peaks()
+        bench_configs.run(args, torch, nk, po, peak, peak_src, ClockSampler)
+        return
 
     nel = args.nx ** 3
     ndof = nel * NM ** 3

@@ -1,0 +1,253 @@
+"""bench.py --config 1 | 4: the BASELINE.json configurations that are neither the default (configs[1], bench.py
+itself), the per-order sweep (configs[2], tools/sweep.py) nor the sharded CG (configs[4], tools/bench_cg.py).
+
+  config 1  2-D Helmholtz on a structured N x N quad mesh, P=5 (nm=6, nq=7), lambda=1 -- the reference's
+            Helmholtz2D_modal session scaled up: operator apply (device-resident and host arrays) and the
+            device CG iteration on the assembled problem.
+  config 4  Tet and Prism (plus the hexahedra they are mixed with) Helmholtz apply at P=6 on a synthetic mixed
+            mesh: an n^3 structured grid of cubes, 60 % kept as hexahedra, 30 % cut into 2 prisms, 10 % into 6
+            tetrahedra (equal element counts per shape), one collection per shape as CreateCollections forms
+            them (MultiRegions/ExpList.cpp:5005-5151).  All elements are affine (regular geometry).
+
+Every line carries `roofline` (dominant kernel, algorithmic bytes of SURVEY.md 8(d)) and `cpu_baseline` (the
+reference's own kernels from oracle/_ref on a bounded sample, all host threads).  Imported by bench.py only."""
+import itertools
+import json
+import os
+import time
+
+import numpy as np
+
+LAMBDA = 1.0
+
+
+def _time_apply(torch, op, ins, outs, reps, warm=3):
+    for _ in range(warm):
+        op.apply(ins, outs)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
+        op.apply(ins, outs)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+    return ts[len(ts) // 2], ev[0].elapsed_time(ev[reps]) / reps
+
+
+def _cpu_helmholtz(po, shape, nm, nq0, nel, jac, df, seconds=4.0):
+    """reference MatrixFree Helmholtz (AVX2 build) on `nel` affine elements, all host threads; GDOF/s"""
+    el = po.Elem(shape, nm, nq0)
+    try:
+        ref = po.Ref("avx2")
+        kind = "reference"
+    except Exception:
+        ref, kind = None, "port"
+    threads = os.cpu_count() or 1
+    x = np.random.default_rng(1234).uniform(-1, 1, nel * el.nmTot)
+    if ref is not None:
+        op = ref.operator(po.OP_HELM, el, nel, False, jac, df)
+        out = [np.zeros(nel * el.nmTot)]
+        run = lambda: op(x, lam=LAMBDA, nthreads=threads, outs=out)
+    else:
+        po.set_threads(threads)
+        run = lambda: el.helmholtz(nel, False, jac, df, LAMBDA, x)
+    run()
+    t0 = time.perf_counter()
+    run()
+    t1 = time.perf_counter() - t0
+    reps = max(3, min(100, int(seconds / max(t1, 1e-4))))
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        run()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return nel * el.nmTot / ts[len(ts) // 2] / 1e9, ts[len(ts) // 2], kind, threads, reps
+
+
+def config1(args, torch, nk, po, peak, peak_src, ClockSampler):
+    from _util import load_pkg_module
+    mesh_mod = load_pkg_module("mesh")
+    dev = torch.device("cuda", 0)
+    nm, nq, N = 6, 7, args.nx if args.nx != 64 else 1024
+    mesh = mesh_mod.StructuredQuadMesh(N, N, nm)
+    std = nk.StdExpansion(nk.eQuadrilateral, nm)
+    jac, df = mesh.geometry()
+    geom = nk.CoalescedGeomData(jac, df, False)
+    helm = nk.Operator(std, mesh.nElmt, geom, nk.eHelmholtz)
+    helm.SetLambda(LAMBDA)
+    ndof = mesh.nLocal
+    gen = torch.Generator(device="cpu").manual_seed(1234)
+    x_host = (torch.rand(ndof, dtype=torch.float64, generator=gen) * 2 - 1).pin_memory()
+    y_host = torch.empty(ndof, dtype=torch.float64).pin_memory()
+    x, y = x_host.to(dev), torch.empty(ndof, dtype=torch.float64, device=dev)
+    sampler = ClockSampler(0)
+    sampler.start()
+    med, avg = _time_apply(torch, helm, [x], [y], args.steps, max(args.warmup, 3))
+    if len(sampler.samples) < 8:
+        t_end = time.perf_counter() + 0.4
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                helm.apply([x], [y])
+            torch.cuda.synchronize()
+    clocks = sampler.stop()
+    for _ in range(2):
+        helm.apply([x_host], [y_host])
+    t0 = time.perf_counter()
+    Ke = 5
+    for _ in range(Ke):
+        helm.apply([x_host], [y_host])
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / Ke
+    # device CG on the assembled problem (Jacobi preconditioned), fixed iteration count
+    amap = nk.AssemblyMap(mesh.localToGlobal, mesh.nGlobal)
+    diag = mesh.helmholtz_diagonal(std.basis[0], LAMBDA)
+    cg = nk.HelmholtzCG(helm, amap, mesh.nDir, 1.0 / diag[mesh.nDir:])
+    rhs = torch.rand(mesh.nGlobal, dtype=torch.float64, device=dev)
+    rhs[:mesh.nDir] = 0.0
+    xs = torch.zeros(mesh.nGlobal, dtype=torch.float64, device=dev)
+    cg.solve(rhs, xs, tol=0.0, maxiter=3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    its, _ = cg.solve(rhs, xs, tol=0.0, maxiter=30)
+    torch.cuda.synchronize()
+    cg_ms = (time.perf_counter() - t0) / its * 1e3
+    bytes_el = 8 * (2 * nm * nm + 5)  # 616 B per quad at P=5, regular geometry
+    ach = bytes_el * mesh.nElmt / (avg * 1e-3) / 1e9
+    ns = 65536
+    cpu, cpu_t, kind, threads, reps = _cpu_helmholtz(po, po.QUAD, nm, nq, ns, jac[:ns].copy(),
+                                                     df.reshape(4, -1)[:, :ns].reshape(-1).copy())
+    return {
+        "metric": "GDOF/s FP64 Helmholtz apply (quad P=5)", "value": ndof / (avg * 1e-3) / 1e9, "unit": "GDOF/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": avg, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "2D Helmholtz, structured %dx%d quad mesh, P=5 (nm=6, nq=7), lambda=1 "
+                               "(BASELINE configs[0], Helmholtz2D_modal scaled up)" % (N, N),
+                   "elements": mesh.nElmt, "l2": "inputs larger than L2 (in+out %d MB), no flush" % (ndof * 16 >> 20)},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_element": bytes_el, "kernel": helm.kernel_name,
+                     "kernel_ms": avg},
+        "e2e": {"value": ndof / e2e_s / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": ndof * 8,
+                "d2h_bytes_per_step": ndof * 8, "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": args.steps, "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+        "cg": {"ms_per_iteration": cg_ms, "iterations": its, "global_dof": mesh.nGlobal,
+               "note": "Jacobi-preconditioned device CG, gather -> quad Helmholtz -> assemble per iteration"},
+        "cpu_baseline": {"value": cpu, "unit": "GDOF/s", "cores": threads, "kind": kind,
+                         "sample": "%d of %d quads, median of %d applies, reference MatrixFreeOps kernels "
+                                   "(oracle/_ref AVX2 build)" % (ns, mesh.nElmt, reps)},
+    }
+
+
+def affine_factors(edges):
+    """jac, df[9] of the affine map x = x0 + sum_d (xi_d + 1)/2 * edges[d]  (GeomFactors.cpp:399-474:
+    df[c*3+d] = d xi_d / d x_c, jac = det(dx/dxi))"""
+    J = np.stack(edges, axis=1) / 2.0          # dx_c / dxi_d
+    Ji = np.linalg.inv(J)                       # dxi_d / dx_c  at [d][c]
+    df = np.array([Ji[d, c] for c in range(3) for d in range(3)])
+    return float(np.linalg.det(J)), df
+
+
+def mixed_mesh(n, h):
+    """element geometry of the synthetic mixed mesh: returns {shape: (nElmt, jac[nElmt], df[9*nElmt])}.
+    Cube c (lexicographic) keeps its type by c mod 10: 0-5 hex, 6-8 two prisms, 9 six tetrahedra."""
+    ex, ey, ez = np.eye(3) * h
+    hexf = [affine_factors([ex, ey, ez])]
+    # prism reference: triangle in (xi_0, xi_2) extruded along xi_1; second prism is the point-reflected half
+    prf = [affine_factors([ex, ey, ez]), affine_factors([-ex, ey, -ez])]
+    tetf = []
+    for perm in itertools.permutations(range(3)):
+        e = [ex, ey, ez]
+        a, b, c = e[perm[0]], e[perm[1]], e[perm[2]]
+        v1, v2, v3 = a, a + b, a + b + c          # Kuhn simplex of this permutation
+        E = [v1, v2, v3]
+        if np.linalg.det(np.stack(E, axis=1)) < 0:
+            E = [v2, v1, v3]
+        tetf.append(affine_factors(E))
+    ncube = n ** 3
+    kinds = np.arange(ncube) % 10
+    counts = {"Hex": int((kinds < 6).sum()), "Prism": int(((kinds >= 6) & (kinds < 9)).sum()) * 2,
+              "Tet": int((kinds == 9).sum()) * 6}
+    out = {}
+    for name, fac in (("Hex", hexf), ("Prism", prf), ("Tet", tetf)):
+        nel = counts[name]
+        k = len(fac)
+        jac = np.tile(np.array([f[0] for f in fac]), nel // k)
+        df = np.tile(np.stack([f[1] for f in fac], axis=1), (1, nel // k))  # [9][nel]
+        out[name] = (nel, jac, np.ascontiguousarray(df).reshape(-1))
+    return out
+
+
+def config4(args, torch, nk, po, peak, peak_src, ClockSampler):
+    dev = torch.device("cuda", 0)
+    nm, n = 7, args.nx if args.nx != 64 else 60
+    mesh = mixed_mesh(n, 1.0 / n)
+    shapes = {"Hex": (nk.eHexahedron, po.HEX), "Prism": (nk.ePrism, po.PRISM), "Tet": (nk.eTetrahedron, po.TET)}
+    per, ops, bufs = {}, {}, {}
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    for name, (nshape, _) in shapes.items():
+        nel, jac, df = mesh[name]
+        std = nk.StdExpansion(nshape, nm)
+        op = nk.Operator(std, nel, nk.CoalescedGeomData(jac, df, False), nk.eHelmholtz)
+        op.SetLambda(LAMBDA)
+        x = torch.rand(nel * std.GetNcoeffs(), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+        y = torch.empty_like(x)
+        ops[name], bufs[name] = op, (x, y, std)
+    sampler = ClockSampler(0)
+    sampler.start()
+    for name in shapes:
+        x, y, std = bufs[name]
+        med, avg = _time_apply(torch, ops[name], [x], [y], args.steps, max(args.warmup, 3))
+        nel = mesh[name][0]
+        by = 8 * (2 * std.GetNcoeffs() + 10)
+        per[name] = {"elements": nel, "ncoeffs": std.GetNcoeffs(), "ms": avg, "gdof_per_s": nel * std.GetNcoeffs() / (avg * 1e-3) / 1e9,
+                     "algorithmic_bytes_per_element": by, "gb_per_s": by * nel / (avg * 1e-3) / 1e9,
+                     "frac_hbm": by * nel / (avg * 1e-3) / 1e9 / peak, "kernel": ops[name].kernel_name}
+    clocks = sampler.stop()
+    # one step = the three collections back to back (what ExpList::GeneralMatrixOp does), timed as a whole
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        for name in shapes:
+            x, y, _ = bufs[name]
+            ops[name].apply([x], [y])
+    ev1.record()
+    torch.cuda.synchronize()
+    step_ms = ev0.elapsed_time(ev1) / args.steps
+    ndof = sum(p["elements"] * p["ncoeffs"] for p in per.values())
+    dom = max(per, key=lambda k: per[k]["ms"])
+    # CPU baseline: the same three collections, a bounded sample of each, aggregated by DOF / time
+    cpu_dof, cpu_t, kind, threads = 0.0, 0.0, "reference", 1
+    for name, (_, pshape) in shapes.items():
+        nel, jac, df = mesh[name]
+        ns = min(nel, 6000)
+        ns -= ns % 12
+        g, t, kind, threads, _ = _cpu_helmholtz(po, pshape, nm, nm + 1, ns, jac[:ns].copy(),
+                                                df.reshape(9, -1)[:, :ns].reshape(-1).copy(), seconds=3.0)
+        cpu_dof += ns * per[name]["ncoeffs"] * (nel / ns)
+        cpu_t += t * (nel / ns)
+    return {
+        "metric": "GDOF/s FP64 Helmholtz apply (mixed Hex/Prism/Tet mesh, P=6)", "value": ndof / (step_ms * 1e-3) / 1e9,
+        "unit": "GDOF/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Helmholtz apply on a synthetic mixed mesh: %d^3 cubes, 60%% hexahedra, 30%% cut into 2 "
+                               "prisms, 10%% into 6 tetrahedra, P=6 (nm=7), regular geometry, one collection per shape "
+                               "(BASELINE configs[3])" % n,
+                   "elements": {k: v["elements"] for k, v in per.items()},
+                   "l2": "coefficient arrays of the three collections total %d MB per apply, no flush" % (ndof * 16 >> 20)},
+        "roofline": {"bound": "hbm", "achieved": per[dom]["gb_per_s"], "peak": peak, "unit": "GB/s",
+                     "frac": per[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_element": per[dom]["algorithmic_bytes_per_element"], "kernel": per[dom]["kernel"],
+                     "kernel_ms": per[dom]["ms"],
+                     "note": "regular-geometry Helmholtz at P=6 is FP64/shared-memory bound, not HBM bound"},
+        "per_shape": per, "gpu_launches": 3 * args.steps,
+        "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+        "cpu_baseline": {"value": cpu_dof / cpu_t / 1e9, "unit": "GDOF/s", "cores": threads, "kind": kind,
+                         "sample": "up to 6000 elements of each shape, scaled to the mesh's element counts, reference "
+                                   "MatrixFreeOps kernels (oracle/_ref AVX2 build)"},
+    }
+
+
+def run(args, torch, nk, po, peak, peak_src, ClockSampler):
+    fn = {1: config1, 4: config4}[args.config]
+    print(json.dumps(fn(args, torch, nk, po, peak, peak_src, ClockSampler)))

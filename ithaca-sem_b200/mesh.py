@@ -137,3 +137,73 @@ class StructuredHexMesh:
         diag = np.zeros(self.nGlobal)
         np.add.at(diag, self.localToGlobal, np.tile(d.reshape(-1), self.nElmt))
         return diag
+
+
+class StructuredQuadMesh:
+    """nx x ny quadrilaterals on [0,Lx]x[0,Ly], nm modes per direction: the 2-D counterpart of
+    StructuredHexMesh for BASELINE configs[0] (the reference's Helmholtz2D_modal session: structured quads,
+    P=5, homogeneous Dirichlet on the whole boundary).  C0 connectivity of the modal quad expansion
+    (StdRegions/StdQuadExp.cpp): mode 0 / 1 are the vertices at xi=-1 / +1, modes >= 2 interior; all
+    elements share the global orientation, so no sign changes.  Dirichlet DOFs are numbered first."""
+
+    def __init__(self, nx, ny, nm, lengths=(1.0, 1.0)):
+        self.nx, self.ny, self.nm = nx, ny, nm
+        self.L = tuple(float(v) for v in lengths)
+        self.h = (self.L[0] / nx, self.L[1] / ny)
+        self.nElmt = nx * ny
+        m1 = nm - 1
+        self.Gx, self.Gy = nx * m1 + 1, ny * m1 + 1
+        on_bnd = np.zeros((self.Gy, self.Gx), dtype=bool)
+        on_bnd[:, 0] = on_bnd[:, -1] = True
+        on_bnd[0, :] = on_bnd[-1, :] = True
+        flat = on_bnd.reshape(-1)
+        self.nGlobal, self.nDir = flat.size, int(flat.sum())
+        ids = np.empty(flat.size, dtype=np.int64)
+        ids[flat] = np.arange(self.nDir)
+        ids[~flat] = self.nDir + np.arange(flat.size - self.nDir)
+        self.lattice_ids = ids.reshape(self.Gy, self.Gx)
+        p = np.arange(nm)
+        gx = _gi(np.arange(nx)[:, None], p[None, :], nm)  # [nx, nm]
+        gy = _gi(np.arange(ny)[:, None], p[None, :], nm)
+        # local index: e = ex + nx*ey, mode = p + nm*q
+        l2g = self.lattice_ids[gy[:, None, :, None], gx[None, :, None, :]]  # [ey, ex, q, p]
+        self.localToGlobal = np.ascontiguousarray(l2g.reshape(-1), dtype=np.int32)
+        self.nLocal = self.localToGlobal.size
+        self.ownerMask = np.ones(self.nGlobal)
+        self.peers, self.interface_lists = [], []
+
+    def geometry(self):
+        """jac[nElmt], df[4*nElmt] of the axis-aligned rectangles (df[c*2+d] = d xi_d / d x_c)."""
+        hx, hy = self.h
+        jac = np.full(self.nElmt, hx * hy / 4.0)
+        df = np.zeros((4, self.nElmt))
+        df[0], df[3] = 2.0 / hx, 2.0 / hy
+        return jac, df.reshape(-1).copy()
+
+    def quad_coords(self, z):
+        """physical coordinates of every quadrature point, [nElmt*nq^2] in [elmt][j][i] order."""
+        nq = len(z)
+        hx, hy = self.h
+        X1 = (np.arange(self.nx)[:, None] + 0.5 * (z[None, :] + 1.0)) * hx
+        Y1 = (np.arange(self.ny)[:, None] + 0.5 * (z[None, :] + 1.0)) * hy
+        shape = (self.ny, self.nx, nq, nq)
+        X = np.broadcast_to(X1[None, :, None, :], shape).reshape(-1)
+        Y = np.broadcast_to(Y1[:, None, :, None], shape).reshape(-1)
+        return np.ascontiguousarray(X), np.ascontiguousarray(Y)
+
+    def helmholtz_diagonal(self, basis, lam):
+        """matrix-free Jacobi diagonal, as StructuredHexMesh.helmholtz_diagonal"""
+        nm, nq = self.nm, basis.nq
+        B = basis.bdata.reshape(nm, nq)
+        dB = basis.dbdata.reshape(nm, nq)
+        m = (B * B) @ basis.W
+        k = (dB * dB) @ basis.W
+        hx, hy = self.h
+        J = hx * hy / 4.0
+        g0, g1 = (2.0 / hx) ** 2, (2.0 / hy) ** 2
+        mq, mp = m[:, None], m[None, :]
+        kq, kp = k[:, None], k[None, :]
+        d = J * (lam * mq * mp + g0 * mq * kp + g1 * kq * mp)
+        diag = np.zeros(self.nGlobal)
+        np.add.at(diag, self.localToGlobal, np.tile(d.reshape(-1), self.nElmt))
+        return diag

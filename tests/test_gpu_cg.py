@@ -112,8 +112,8 @@ def test_sharded_cg_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tools", "bench_cg.py"), "--nx", "6", "--ny", "5",
-           "--nz", "8", "--check"]
+           "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "_cg_check.py"), "--nx", "6", "--ny", "5",
+           "--nz", "8"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "CHECK OK" in r.stdout
@@ -156,3 +156,46 @@ def test_matvec_fused_gather_with_sign_changes(nm, geometry):
                            mesh.nGlobal)
         assert max(rel_errs(s_d.cpu().numpy(), want)) < 1e-12
         del cg, amap
+
+
+def test_config1_quad_helmholtz_solve_device():
+    """BASELINE configs[0] on the device: the 2-D quad P=5 Helmholtz solve (reference session
+    Helmholtz2D_modal: lambda=1, u = sin(pi x) sin(pi y)) through the C ABI -- device IProduct for the forcing,
+    device assembly map, device CG with the quad Helmholtz kernel -- against the oracle solve and the exact
+    solution."""
+    import torch
+    nk = nekmf()
+    mesh_mod = load_pkg_module("mesh")
+    nm, lam = 6, 1.0
+    mesh = mesh_mod.StructuredQuadMesh(8, 6, nm)
+    el = po.Elem(po.QUAD, nm, nm + 1)
+    jac, df = mesh.geometry()
+    std = nk.StdExpansion(nk.eQuadrilateral, nm)
+    geom = nk.CoalescedGeomData(jac, df, False)
+    X, Y = mesh.quad_coords(el.Z[0])
+    u = np.sin(np.pi * X) * np.sin(np.pi * Y)
+    f = -(lam + 2 * np.pi ** 2) * u
+    loc = np.zeros(mesh.nLocal)
+    nk.Operator(std, mesh.nElmt, geom, nk.eIProductWRTBase).apply([f], [loc])
+    amap = nk.AssemblyMap(mesh.localToGlobal, mesh.nGlobal)
+    rhs = np.zeros(mesh.nGlobal)
+    amap.Assemble(-loc, rhs)
+    rhs[:mesh.nDir] = 0.0
+    helm = nk.Operator(std, mesh.nElmt, geom, nk.eHelmholtz)
+    helm.SetLambda(lam)
+    diag = mesh.helmholtz_diagonal(std.basis[0], lam)
+    invdiag = 1.0 / diag[mesh.nDir:]
+    cg = nk.HelmholtzCG(helm, amap, mesh.nDir, invdiag)
+    x = np.zeros(mesh.nGlobal)
+    its, eps = cg.solve(rhs, x, tol=1e-12)
+    rhs_o = po.assemble(mesh.localToGlobal, None, -el.iproduct(mesh.nElmt, False, jac, f), mesh.nGlobal)
+    rhs_o[:mesh.nDir] = 0.0
+    xo, itso, _ = el.cg(mesh.nElmt, False, jac, df, lam, mesh.nGlobal, mesh.nDir, mesh.localToGlobal, None, invdiag,
+                        rhs_o, tol=1e-12)
+    assert abs(its - itso) <= max(3, itso // 10)
+    assert np.abs(x - xo).max() < 1e-10 * np.abs(xo).max()
+    uq = np.zeros(mesh.nElmt * el.nqTot)
+    xl = np.zeros(mesh.nLocal)
+    amap.GlobalToLocal(x, xl)
+    nk.Operator(std, mesh.nElmt, geom, nk.eBwdTrans).apply([xl], [uq])
+    assert np.abs(uq - u).max() < 1e-6

@@ -191,3 +191,37 @@ def test_cpp_collections_mirror_builds_and_refuses_without_gpu():
         pytest.skip("a GPU is present: the real run is in the gpu suite")
     r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "TestCollectionB200")], capture_output=True, text=True)
     assert r.returncode == 77 and "no CUDA device" in r.stdout
+
+
+def test_config1_quad_helmholtz_solve_oracle():
+    """BASELINE configs[0] on the CPU: 2-D Helmholtz on a structured quad mesh at P=5 (nm=6, nq=7), the
+    reference's Helmholtz2D_modal set-up (lambda=1, u = sin(pi x) sin(pi y), homogeneous Dirichlet).  The
+    MatrixFree-path CG solve converges to the analytic solution with spectral accuracy, and the matrix-free
+    operator equals the StdMat-style dense elemental matrix applied element by element."""
+    mesh_mod = load_pkg_module("mesh")
+    nk = nekmf()
+    nm, lam = 6, 1.0
+    mesh = mesh_mod.StructuredQuadMesh(4, 4, nm)
+    el = po.Elem(po.QUAD, nm, nm + 1)
+    jac, df = mesh.geometry()
+    X, Y = mesh.quad_coords(el.Z[0])
+    u = np.sin(np.pi * X) * np.sin(np.pi * Y)
+    rhs = po.assemble(mesh.localToGlobal, None, -el.iproduct(mesh.nElmt, False, jac, -(lam + 2 * np.pi ** 2) * u),
+                      mesh.nGlobal)
+    rhs[:mesh.nDir] = 0.0
+    diag = mesh.helmholtz_diagonal(nk.StdExpansion(nk.eQuadrilateral, nm).basis[0], lam)
+    x, its, eps = el.cg(mesh.nElmt, False, jac, df, lam, mesh.nGlobal, mesh.nDir, mesh.localToGlobal, None,
+                        1.0 / diag[mesh.nDir:], rhs, tol=1e-12)
+    uq = el.bwdtrans(mesh.nElmt, po.global_to_local(mesh.localToGlobal, None, x))
+    assert np.abs(uq - u).max() < 5e-6 and its < 200
+    # StdMat comparator: dense elemental matrix from unit vectors (all elements are congruent)
+    n = el.nmTot
+    A = np.zeros((n, n))
+    for j in range(n):
+        e = np.zeros(n)
+        e[j] = 1.0
+        A[:, j] = el.helmholtz(1, False, jac[:1], df.reshape(4, -1)[:, :1].reshape(-1).copy(), lam, e)
+    loc = np.random.default_rng(0).uniform(-1, 1, mesh.nLocal)
+    mf = el.helmholtz(mesh.nElmt, False, jac, df, lam, loc)
+    sm = (loc.reshape(mesh.nElmt, n) @ A.T).reshape(-1)
+    assert max(rel_errs(mf, sm)) < 1e-12

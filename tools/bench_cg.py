@@ -2,12 +2,12 @@
 """Matrix-free CG Helmholtz solve on a structured hex mesh at P=4, element-partitioned in z-slabs
 over the ranks of one box (BASELINE.json configs[4]).
 
-    python tools/bench_cg.py [--nx 64 --ny 128 --nz 128] [--iters 50] [--check]
+    python tools/bench_cg.py [--nx 64 --ny 128 --nz 128] [--iters 50]
     torchrun --nproc-per-node N tools/bench_cg.py ...
 
 Every rank builds its slab (ithaca-sem_b200/mesh.py), creates the device operator / assembly map /
-NCCL exchange through the C ABI and runs nekmf_cg_solve with a fixed iteration cap.  --check solves to
-convergence and compares against the serial CPU oracle (small meshes only)."""
+NCCL exchange through the C ABI and runs nekmf_cg_solve with a fixed iteration cap.  The convergence /
+parity check against the serial CPU oracle lives in tests/_cg_check.py (it reuses setup() from here)."""
 import argparse
 import json
 import os
@@ -16,21 +16,23 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from _util import load_pkg_module, nekmf  # noqa: E402
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--nx", type=int, default=64)
     ap.add_argument("--ny", type=int, default=128)
     ap.add_argument("--nz", type=int, default=128)
     ap.add_argument("--nm", type=int, default=5)
     ap.add_argument("--iters", type=int, default=50)
-    ap.add_argument("--check", action="store_true")
-    a = ap.parse_args()
+    return ap.parse_args(argv)
+
+
+def setup(a):
+    """builds this rank's slab, operators, assembly map, exchange, right-hand side and the CG object"""
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -73,32 +75,14 @@ def main():
     cg = nk.HelmholtzCG(helm, amap, mesh.nDir, invdiag, exchange=ex, comm=comm, ownerMask=mesh.ownerMask)
     x = torch.zeros(mesh.nGlobal, dtype=torch.float64, device=dev)
     del f, loc
-    if a.check:
-        its, eps = cg.solve(rhs, x, tol=1e-13, maxiter=5000)
-        import pyoracle as po
-        import _sharded_ref as sr
-        full = mesh_mod.StructuredHexMesh(a.nx, a.ny, a.nz, a.nm)
-        el = po.Elem(po.HEX, a.nm, a.nm + 1)
-        jf, dff = full.geometry()
-        rhs_o, _ = sr.helmholtz_rhs(None, full, el, jf, lam)
-        dg = full.helmholtz_diagonal(std.basis[0], lam)
-        xo, itso, _ = el.cg(full.nElmt, False, jf, dff, lam, full.nGlobal, full.nDir, full.localToGlobal, None,
-                            1.0 / dg[full.nDir:], rhs_o, tol=1e-13)
-        mine = x.cpu().numpy()[mesh.lattice_ids]
-        want = xo[full.lattice_ids][mesh.gz0:mesh.gz1 + 1]
-        err = np.abs(mine - want).max() / np.abs(xo).max()
-        # tol=1e-13 is at the round-off plateau: the iteration at which r.r crosses it depends on the
-        # summation order of the (ownership-masked, all-reduced) dot products, so allow a few percent
-        ok = err < 1e-10 and abs(its - itso) <= max(2, 0.05 * itso)
-        t = torch.tensor([0.0 if ok else 1.0], device=dev)
-        if dist is not None:
-            dist.all_reduce(t)
-        if rank == 0:
-            print("rank0 its=%d (oracle %d) err=%.2e" % (its, itso, err))
-            print("CHECK OK" if float(t.item()) == 0.0 else "CHECK FAILED")
-        if dist is not None:
-            dist.destroy_process_group()
-        sys.exit(0 if float(t.item()) == 0.0 else 1)
+    return dict(rank=rank, world=world, dev=dev, nk=nk, mesh_mod=mesh_mod, dist=dist, mesh=mesh, std=std, lam=lam, helm=helm,
+                cg=cg, rhs=rhs, x=x, keepalive=(amap, ex, comm, geom, ipr))
+
+
+def main():
+    a = parse_args()
+    S = setup(a)
+    rank, world, dev, nk, dist, mesh, helm, cg, rhs, x = (S[k] for k in ("rank", "world", "dev", "nk", "dist", "mesh", "helm", "cg", "rhs", "x"))
     # ---- timing: fixed iteration cap (tolerance 0 never triggers), max over ranks
     cg.solve(rhs, x, tol=0.0, maxiter=3)
     if dist is not None:
