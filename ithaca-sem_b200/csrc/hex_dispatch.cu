@@ -42,18 +42,25 @@ SHP_DECL(2) SHP_DECL(3) SHP_DECL(4) SHP_DECL(5) SHP_DECL(6) SHP_DECL(7) SHP_DECL
 bool select_shape_fast(nekmf_op_s *op)
 {
     if (op->shape == NEKMF_HEX || op->shape == NEKMF_PYR) return false;
+    bool ok = false;
     switch (op->nm[0])
     {
-        case 2: return shape_try_nm2(op);
-        case 3: return shape_try_nm3(op);
-        case 4: return shape_try_nm4(op);
-        case 5: return shape_try_nm5(op);
-        case 6: return shape_try_nm6(op);
-        case 7: return shape_try_nm7(op);
-        case 8: return shape_try_nm8(op);
-        case 9: return shape_try_nm9(op);
+        case 2: ok = shape_try_nm2(op); break;
+        case 3: ok = shape_try_nm3(op); break;
+        case 4: ok = shape_try_nm4(op); break;
+        case 5: ok = shape_try_nm5(op); break;
+        case 6: ok = shape_try_nm6(op); break;
+        case 7: ok = shape_try_nm7(op); break;
+        case 8: ok = shape_try_nm8(op); break;
+        case 9: ok = shape_try_nm9(op); break;
     }
-    return false;
+    // regular quad Helmholtz: add the coefficient-space kernel (used when the metric is diagonal)
+    if (ok) quad_kron_maybe_wrap(op);
+    return ok;
 }
-void notify_geom_changed(nekmf_op_s *op) { kron_geom_changed(op); }
+void notify_geom_changed(nekmf_op_s *op)
+{
+    kron_geom_changed(op);
+    quad_kron_geom_changed(op);
+}
 } // namespace nekmf

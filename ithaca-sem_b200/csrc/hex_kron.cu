@@ -475,13 +475,13 @@ void kron_maybe_wrap(nekmf_op_s *op)
         case 6: kron_wrap<6>(op); break;
         default: return;
     }
-    op->kron = true;
+    op->kron = 1;
 }
 
 // called after set_geom: decide between the coefficient-space and the quadrature-space kernel
 int kron_geom_changed(nekmf_op_s *op)
 {
-    if (!op->kron) return NEKMF_OK;
+    if (op->kron != 1) return NEKMF_OK;
     KronState *st = static_cast<KronState *>(op->kstate);
     st->use_kron  = false;
     op->gather_ok = false;

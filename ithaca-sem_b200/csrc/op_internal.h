@@ -49,7 +49,7 @@ struct nekmf_op_s
     bool gather_ok           = false;
     const int *gather_map    = nullptr;
     const double *gather_sign = nullptr;
-    bool kron        = false; // Helmholtz/hex/regular: coefficient-space kernel available (hex_kron.cu)
+    int kron         = 0; // regular Helmholtz: coefficient-space kernel available (1 hex_kron.cu, 2 quad_kron.cu)
     bool timing      = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed_once = false;
@@ -65,4 +65,6 @@ bool select_generic(nekmf_op_s *op);
 void notify_geom_changed(nekmf_op_s *op);
 void kron_maybe_wrap(nekmf_op_s *op);
 int kron_geom_changed(nekmf_op_s *op);
+void quad_kron_maybe_wrap(nekmf_op_s *op);
+int quad_kron_geom_changed(nekmf_op_s *op);
 } // namespace nekmf

@@ -1,0 +1,359 @@
+// quad_kron.cu -- Helmholtz on REGULAR (affine) quadrilaterals whose Laplacian metric is diagonal
+// (axis-aligned rectangles: every structured mesh), evaluated entirely in coefficient space.
+//
+// Reference semantics: MatrixFreeOps/Helmholtz.h:138-275 (HelmholtzQuadImpl, DEFORMED=false).  As for the
+// hexahedron (hex_kron.cu) the chain BwdTrans -> lambda*IProduct -> PhysDerivTensor -> G -> 2x IProduct(dbdata)
+// is, for constant geometric factors, the Kronecker sum
+//     out = J [ lambda M(x)M + G00 M(x)K + G11 K(x)M ] in
+// of the nm x nm 1-D mass M = B W B^T and stiffness K = (DB) W (DB)^T built from the operator's own tables.
+//
+// B200 mapping: one LANE owns one element.  Its nm x nm coefficient block lives in registers, the matrices are
+// kernel-parameter constants (uniform-register operands of every DFMA), one output column at a time is formed
+// and written back into the lane's own shared-memory slot -- no exchange between lanes, no barrier.  A warp is
+// an independent worker with two TMA-fed 32-element buffers: the next batch lands while the current one is
+// computed, results leave by TMA bulk stores.  Even nm: one bulk copy per element into a padded slot (stride
+// nm^2+2 doubles: 2-way bank conflicts instead of up to 16-way); odd nm: one bulk copy per batch (stride nm^2 is
+// odd: conflict free).
+#include "hex_kernels.cuh"
+#include "op_internal.h"
+#include <cmath>
+#include <string.h>
+#include <string>
+
+namespace nekmf
+{
+
+template <int NM> struct QKronTab
+{
+    double Ms[NM * (NM + 1) / 2]; // upper triangles, both matrices are symmetric
+    double Ks[NM * (NM + 1) / 2];
+};
+__host__ __device__ constexpr int qtri(int a, int b, int n)
+{
+    return a <= b ? a * n - a * (a - 1) / 2 + (b - a) : b * n - b * (b - 1) / 2 + (a - b);
+}
+
+struct QKronArgs
+{
+    const double *in;
+    double *out;
+    const double *geo4; // [nElmt][4] = J, J*G00, J*G11, 0
+    int nElmt;
+    int io_aligned; // in and out 16-byte aligned
+    double lambda;
+};
+
+template <int NM> struct QKronCfg
+{
+    static constexpr int NM2      = NM * NM;
+    static constexpr bool PADDED  = (NM % 2) == 0;
+    static constexpr int ES       = PADDED ? NM2 + 2 : NM2; // element stride in shared memory (doubles)
+    static constexpr int BUF      = round_up(32 * ES, 2);
+    static constexpr int GEO      = 32 * 4;
+    static constexpr int PER_WARP = 2 * BUF + 2 * GEO + 2; // + two mbarriers
+    static constexpr int W_FIT    = (200 * 1024) / (PER_WARP * 8);
+    static constexpr int WARPS    = W_FIT >= 16 ? 16 : (W_FIT >= 12 ? 12 : (W_FIT >= 8 ? 8 : 4));
+    static constexpr int T        = WARPS * 32;
+    static constexpr size_t SMEM  = (size_t)WARPS * PER_WARP * 8 + 16;
+};
+
+// SPARSEK: K = 2x2 vertex block + diagonal (modified C0 basis), verified numerically at creation
+template <int NM, bool SPARSEK>
+__global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
+    quad_helm_kron_kernel(const __grid_constant__ QKronTab<NM> tab, const __grid_constant__ QKronArgs args)
+{
+    using Cfg = QKronCfg<NM>;
+    constexpr int NM2 = Cfg::NM2, ES = Cfg::ES, BUF = Cfg::BUF;
+    constexpr bool PADDED = Cfg::PADDED;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *wbase  = reinterpret_cast<double *>(smem_raw) + (size_t)warp * Cfg::PER_WARP;
+    double *sBuf   = wbase;                 // [2][BUF]
+    double *sGeo   = wbase + 2 * BUF;       // [2][GEO]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sGeo + 2 * Cfg::GEO); // [2]
+#define QM(a, b) tab.Ms[qtri(a, b, NM)]
+#define QK(a, b) tab.Ks[qtri(a, b, NM)]
+#define QNZ(a, b) (!SPARSEK || (a) == (b) || ((a) < 2 && (b) < 2))
+
+    const int nElmt = args.nElmt;
+    const int nB    = (nElmt + 31) / 32;
+    const int GW    = gridDim.x * Cfg::WARPS;
+    const int gw    = blockIdx.x * Cfg::WARPS + warp;
+    if (lane == 0)
+    {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    auto batch_ne = [&](int b) { int r = nElmt - b * 32; return r < 32 ? r : 32; };
+    // TMA eligibility of a batch: 16-byte aligned arrays and (unpadded layout) an even number of doubles
+    auto tma_ok = [&](int b) { return args.io_aligned && (PADDED || ((batch_ne(b) * NM2) & 1) == 0); };
+    auto issue  = [&](int b, int s) { // whole warp
+        const int ne    = batch_ne(b);
+        const bool tma  = tma_ok(b);
+        double *dst     = sBuf + s * BUF;
+        const double *g = args.in + (size_t)b * 32 * NM2;
+        if (lane == 0)
+        {
+            mbar_expect_tx(&bars[s], (uint32_t)(ne * 32 + (tma ? ne * NM2 * 8 : 0)));
+            tma_load_1d(sGeo + s * Cfg::GEO, args.geo4 + (size_t)b * 32 * 4, (uint32_t)(ne * 32), &bars[s]);
+            if (tma && !PADDED) tma_load_1d(dst, g, (uint32_t)(ne * NM2 * 8), &bars[s]);
+        }
+        __syncwarp();
+        if (tma && PADDED && lane < ne) tma_load_1d(dst + lane * ES, g + (size_t)lane * NM2, (uint32_t)(NM2 * 8), &bars[s]);
+    };
+
+    uint32_t phase[2] = {0u, 0u};
+    if (gw < nB) issue(gw, 0);
+    int it = 0;
+    for (int b = gw; b < nB; b += GW, ++it)
+    {
+        const int s = it & 1, ne = batch_ne(b), bnext = b + GW;
+        const bool tma = tma_ok(b);
+        double *buf    = sBuf + s * BUF;
+        if (bnext < nB)
+        {
+            // the other buffer was the source of the previous iteration's bulk stores: wait until they have
+            // been read (each lane waits for its own bulk groups), then let the next batch land in it
+            tma_store_wait_read0();
+            __syncwarp();
+            issue(bnext, s ^ 1);
+        }
+        if (!tma)
+        {
+            const double *g = args.in + (size_t)b * 32 * NM2;
+            for (int i = lane; i < ne * NM2; i += 32) buf[(i / NM2) * ES + (i % NM2)] = __ldg(g + i);
+        }
+        mbar_wait(&bars[s], phase[s]);
+        phase[s] ^= 1;
+        __syncwarp();
+
+        if (lane < ne)
+        {
+            double *xe        = buf + lane * ES;
+            const double *geo = sGeo + s * Cfg::GEO + lane * 4;
+            const double lamJ = args.lambda * geo[0], jg00 = geo[1], jg11 = geo[2];
+            double x[NM][NM]; // x[q][p]
+#pragma unroll
+            for (int q = 0; q < NM; ++q)
+#pragma unroll
+                for (int p = 0; p < NM; ++p) x[q][p] = xe[q * NM + p];
+            // one output column p' at a time:  a = (M x^T)[p'], b = (K x^T)[p'] over q, then the q-contraction
+#pragma unroll
+            for (int pp = 0; pp < NM; ++pp)
+            {
+                double a[NM], bk[NM];
+#pragma unroll
+                for (int q = 0; q < NM; ++q)
+                {
+                    double m = QM(pp, 0) * x[q][0], k = 0.0;
+                    bool kset = false;
+#pragma unroll
+                    for (int p = 1; p < NM; ++p) m = fma(QM(pp, p), x[q][p], m);
+#pragma unroll
+                    for (int p = 0; p < NM; ++p)
+                        if (QNZ(pp, p))
+                        {
+                            k    = kset ? fma(QK(pp, p), x[q][p], k) : QK(pp, p) * x[q][p];
+                            kset = true;
+                        }
+                    // fold the per-element scalars in here: u = lamJ a + jg00 b (goes through M), v = jg11 a (through K)
+                    a[q]  = fma(lamJ, m, jg00 * k);
+                    bk[q] = jg11 * m;
+                }
+#pragma unroll
+                for (int qq = 0; qq < NM; ++qq)
+                {
+                    double o = QM(qq, 0) * a[0];
+#pragma unroll
+                    for (int q = 1; q < NM; ++q) o = fma(QM(qq, q), a[q], o);
+#pragma unroll
+                    for (int q = 0; q < NM; ++q)
+                        if (QNZ(qq, q)) o = fma(QK(qq, q), bk[q], o);
+                    xe[qq * NM + pp] = o; // the lane's own slot: x is in registers, nobody else reads it
+                }
+            }
+        }
+        double *dstg = args.out + (size_t)b * 32 * NM2;
+        if (tma)
+        {
+            fence_proxy_async();
+            __syncwarp();
+            if (PADDED)
+            {
+                if (lane < ne) tma_store_1d(dstg + (size_t)lane * NM2, buf + lane * ES, (uint32_t)(NM2 * 8));
+            }
+            else if (lane == 0)
+                tma_store_1d(dstg, buf, (uint32_t)(ne * NM2 * 8));
+            tma_store_commit();
+        }
+        else
+        {
+            __syncwarp();
+            for (int i = lane; i < ne * NM2; i += 32) dstg[i] = buf[(i / NM2) * ES + (i % NM2)];
+            __syncwarp();
+        }
+    }
+    tma_store_wait0();
+#undef QM
+#undef QK
+#undef QNZ
+}
+
+// G01 == 0 for every element?  (computed exactly as the quadrature-space kernel would, Helmholtz.h:205-215)
+__global__ void quad_kron_prepare_kernel(const double *__restrict__ jac, const double *__restrict__ df, int nElmt,
+                                         double *__restrict__ geo4, int *__restrict__ nondiag)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nElmt) return;
+    const double f0 = df[e], f1 = df[(size_t)nElmt + e], f2 = df[(size_t)2 * nElmt + e], f3 = df[(size_t)3 * nElmt + e];
+    const double m00 = f0 * f0 + f2 * f2, m01 = f0 * f1 + f2 * f3, m11 = f1 * f1 + f3 * f3;
+    if (m01 != 0.0) atomicOr(nondiag, 1);
+    const double j           = jac[e];
+    geo4[(size_t)e * 4 + 0] = j;
+    geo4[(size_t)e * 4 + 1] = j * m00;
+    geo4[(size_t)e * 4 + 2] = j * m11;
+    geo4[(size_t)e * 4 + 3] = 0.0;
+}
+
+struct QKronState
+{
+    void *tab      = nullptr;
+    void (*tab_free)(void *) = nullptr;
+    bool sparse_k  = false;
+    double *d_geo4 = nullptr;
+    int blocks_per_sm = 0;
+    int (*fallback)(nekmf_op_s *, const double *const in[3], double *const out[3]) = nullptr;
+    void *fallback_state                                                           = nullptr;
+    void (*fallback_free)(void *)                                                  = nullptr;
+    std::string fallback_name;
+    bool use_kron = false;
+};
+
+template <int NM> static int quad_kron_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
+{
+    QKronState *st = static_cast<QKronState *>(op->kstate);
+    if (!st->use_kron)
+    {
+        void *saved  = op->kstate;
+        op->kstate   = st->fallback_state;
+        const int rc = st->fallback(op, in, out);
+        op->kstate   = saved;
+        return rc;
+    }
+    using Cfg = QKronCfg<NM>;
+    auto kern = st->sparse_k ? quad_helm_kron_kernel<NM, true> : quad_helm_kron_kernel<NM, false>;
+    if (st->blocks_per_sm == 0)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int nb = 0;
+        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
+        if (nb < 1) { set_error("quad kron kernel does not fit on an SM"); return NEKMF_ERR_CUDA; }
+        st->blocks_per_sm = nb;
+    }
+    QKronArgs a;
+    a.in = in[0]; a.out = out[0]; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
+    a.io_aligned = ((((uintptr_t)in[0]) | ((uintptr_t)out[0])) & 15) == 0;
+    const int nBatches = (op->run_ne + 32 * Cfg::WARPS - 1) / (32 * Cfg::WARPS);
+    int grid           = st->blocks_per_sm * NUM_SMS;
+    if (grid > nBatches) grid = nBatches;
+    if (grid < 1) return NEKMF_OK;
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const QKronTab<NM> *>(st->tab), a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+
+template <int NM> static void quad_kron_wrap(nekmf_op_s *op)
+{
+    const int nq = op->nq[0];
+    auto *tab    = new QKronTab<NM>;
+    const double *B = op->b[0].data(), *dB = op->db[0].data(), *w = op->ws[0].data();
+    double kmax = 0.0, koff = 0.0;
+    for (int a = 0; a < NM; ++a)
+        for (int c = a; c < NM; ++c)
+        {
+            double m = 0.0, k = 0.0;
+            for (int i = 0; i < nq; ++i)
+            {
+                m += B[a * nq + i] * w[i] * B[c * nq + i];
+                k += dB[a * nq + i] * w[i] * dB[c * nq + i];
+            }
+            tab->Ms[qtri(a, c, NM)] = m;
+            tab->Ks[qtri(a, c, NM)] = k;
+            const bool pattern = a == c || (a < 2 && c < 2);
+            if (pattern) kmax = std::fmax(kmax, std::fabs(k));
+            else koff = std::fmax(koff, std::fabs(k));
+        }
+    QKronState *st     = new QKronState;
+    st->tab            = tab;
+    st->tab_free       = [](void *p) { delete static_cast<QKronTab<NM> *>(p); };
+    st->sparse_k       = koff <= 1e-14 * kmax;
+    st->fallback       = op->launch;
+    st->fallback_state = op->kstate;
+    st->fallback_free  = op->kstate_free;
+    st->fallback_name  = op->kname;
+    op->kstate         = st;
+    op->kstate_free    = [](void *p) {
+        QKronState *s = static_cast<QKronState *>(p);
+        if (s->fallback_state && s->fallback_free) s->fallback_free(s->fallback_state);
+        if (s->tab && s->tab_free) s->tab_free(s->tab);
+        cudaFree(s->d_geo4);
+        delete s;
+    };
+    op->launch = quad_kron_launch<NM>;
+}
+
+// called from select_shape_fast after the quadrature-space launcher is installed
+void quad_kron_maybe_wrap(nekmf_op_s *op)
+{
+    if (op->shape != NEKMF_QUAD || op->optype != NEKMF_HELMHOLTZ || op->deformed) return;
+    if (op->nm[1] != op->nm[0] || op->nq[1] != op->nq[0] || op->b[1] != op->b[0] || op->db[1] != op->db[0] ||
+        op->ws[1] != op->ws[0])
+        return;
+    switch (op->nm[0])
+    {
+        case 2: quad_kron_wrap<2>(op); break;
+        case 3: quad_kron_wrap<3>(op); break;
+        case 4: quad_kron_wrap<4>(op); break;
+        case 5: quad_kron_wrap<5>(op); break;
+        case 6: quad_kron_wrap<6>(op); break;
+        case 7: quad_kron_wrap<7>(op); break;
+        case 8: quad_kron_wrap<8>(op); break;
+        default: return;
+    }
+    op->kron = 2;
+}
+
+// called after set_geom: decide between the coefficient-space and the quadrature-space kernel
+int quad_kron_geom_changed(nekmf_op_s *op)
+{
+    if (op->kron != 2) return NEKMF_OK;
+    QKronState *st = static_cast<QKronState *>(op->kstate);
+    st->use_kron   = false;
+    op->kname      = st->fallback_name;
+    if (!op->has_jac || !op->has_df || op->nElmt == 0) return NEKMF_OK;
+    if (!st->d_geo4) NEKMF_CUDA(cudaMalloc(&st->d_geo4, (size_t)op->nElmt * 4 * 8));
+    int *d_flag = nullptr;
+    NEKMF_CUDA(cudaMalloc(&d_flag, 4));
+    NEKMF_CUDA(cudaMemset(d_flag, 0, 4));
+    quad_kron_prepare_kernel<<<(op->nElmt + 255) / 256, 256>>>(op->d_jac, op->d_df, op->nElmt, st->d_geo4, d_flag);
+    ++g_launches;
+    int flag = 1;
+    NEKMF_CUDA(cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_flag);
+    if (flag == 0)
+    {
+        st->use_kron = true;
+        char name[96];
+        snprintf(name, sizeof(name), "quad_helm_kron_kernel<nm=%d,%s>(regular,diagonal metric)", op->nm[0],
+                 st->sparse_k ? "sparseK" : "denseK");
+        op->kname = name;
+    }
+    return NEKMF_OK;
+}
+
+} // namespace nekmf

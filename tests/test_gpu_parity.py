@@ -144,6 +144,46 @@ def test_hex_helmholtz_coefficient_space_kernel(nm, nel):
     assert "kron" not in coll2.m_ops[nk.eHelmholtz].kernel_name
 
 
+@pytest.mark.parametrize("nm", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("nel", [1, 31, 32, 33, 4097])
+def test_quad_helmholtz_coefficient_space_kernel(nm, nel):
+    """Axis-aligned regular quads (diagonal Laplacian metric) take quad_kron.cu: one lane per element, padded
+    per-element TMA copies for even nm, one bulk copy per batch for odd nm, ragged last batch, device arrays that
+    are only 8-byte aligned; rotated / sheared elements must fall back to the quadrature-space kernel."""
+    torch = _torch()
+    nk = nekmf()
+    rng = np.random.default_rng(nm * 977 + nel)
+    el = po.Elem(po.QUAD, nm, nm + 1)
+    std = nk.StdExpansion(nk.eQuadrilateral, nm, nm + 1)
+    h = rng.uniform(0.05, 2.0, (2, nel))
+    jac = h[0] * h[1] / 4.0
+    df = np.zeros((4, nel))
+    df[0], df[3] = 2.0 / h[0], 2.0 / h[1]
+    df = df.reshape(-1).copy()
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, False))
+    x = rng.uniform(-1, 1, nel * el.nmTot)
+    for lam in (0.0, 1.0, 37.5):
+        out = np.zeros(nel * el.nmTot)
+        coll.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
+        check(out, el.helmholtz(nel, False, jac, df, lam, x), "Helmholtz(quad kron)")
+    assert "quad_helm_kron" in coll.m_ops[nk.eHelmholtz].kernel_name
+    # device-resident arrays: 16-byte aligned (TMA) and offset by one double (plain loads / stores)
+    want = el.helmholtz(nel, False, jac, df, 1.0, x)
+    for off in (0, 1):
+        xd = torch.zeros(x.size + off, dtype=torch.float64, device="cuda")
+        xd[off:] = torch.from_numpy(x).cuda()
+        yd = torch.zeros(x.size + off, dtype=torch.float64, device="cuda")
+        coll.ApplyOperator(nk.eHelmholtz, xd[off:], yd[off:], factors={nk.eFactorLambda: 1.0})
+        torch.cuda.synchronize()
+        check(yd[off:].cpu().numpy(), want, "Helmholtz(quad kron, device, offset %d)" % off)
+    jac2, df2 = random_geometry(rng, 2, nel, el.nqTot, False)
+    coll2 = nk.Collection(std, nel, nk.CoalescedGeomData(jac2, df2, False))
+    out = np.zeros(nel * el.nmTot)
+    coll2.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: 1.0})
+    check(out, el.helmholtz(nel, False, jac2, df2, 1.0, x), "Helmholtz(quad-space)")
+    assert "kron" not in coll2.m_ops[nk.eHelmholtz].kernel_name
+
+
 @pytest.mark.parametrize("nel", [0, 1, 2, 3, 5, 8, 9])
 def test_edge_element_counts(nel):
     """empty, single-element and ragged collections (the reference pads to the SIMD width instead)."""
