@@ -2,7 +2,9 @@
 // direction, NQ = NM+1 and NM+2 quadrature points) and provides their launchers.  Compiled once per order so the
 // orders build in parallel.
 #include "hex_kernels.cuh"
+#include "hex_slab.cuh"
 #include "op_internal.h"
+#include <stdlib.h>
 #include <string.h>
 
 #ifndef HEX_NM
@@ -53,6 +55,63 @@ template <int OP, int NM, int NQ, bool DEF> static int hex_launch(nekmf_op_s *op
     return NEKMF_OK;
 }
 
+// register-slab kernels (hex_slab.cuh) for BwdTrans / IProductWRTBase (regular geometry) with the default
+// quadrature.  Measured against the pencil kernels (fraction of HBM peak, nm = 2..6): BwdTrans .58->.63, .61->.70,
+// .64->.87, .73->.93, .73->.78; IProductWRTBase .50->.78, .66->.65, .69->.83, .77->.80, .64->.72.  From nm = 7 the
+// slab (nm^2 doubles plus a line) no longer fits the register file without spilling and the pencil kernels win.
+#ifndef HEX_SLAB_MAX_NM
+#define HEX_SLAB_MAX_NM 6
+#endif
+template <int OP, int NM> static int hex_slab_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
+{
+    using Cfg = SlabCfg<OP, NM>;
+    static int blocks_per_sm = 0;
+    auto kern                = hex_slab_kernel<OP, NM>;
+    if (blocks_per_sm == 0)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int nb = 0;
+        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
+        if (nb < 1)
+        {
+            set_error("hex slab kernel <%d,%d> does not fit on an SM (smem %zu)", OP, NM, (size_t)Cfg::SMEM);
+            return NEKMF_ERR_CUDA;
+        }
+        blocks_per_sm = nb;
+    }
+    SlabArgs a;
+    a.in  = in[0];
+    a.out = out[0];
+    a.jac   = op->d_jac ? op->d_jac + (size_t)op->run_e0 : nullptr;
+    a.nElmt = op->run_ne;
+    a.io_aligned = (((uintptr_t)in[0] | (uintptr_t)out[0]) & 15) == 0;
+    const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
+    int grid           = blocks_per_sm * NUM_SMS;
+    if (grid > nBatches) grid = nBatches;
+    if (grid < 1) return NEKMF_OK;
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const HexTab<NM, NM + 1> *>(op->kstate), a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+template <int NM, int NQ> static bool hex_slab_install(nekmf_op_s *op)
+{
+    if constexpr (NQ == NM + 1 && NM <= HEX_SLAB_MAX_NM)
+    {
+        const char *v = getenv("NEKMF_HEX_SLAB"); // NEKMF_HEX_SLAB=0: keep the pencil kernels (A/B comparisons)
+        if (v && v[0] == '0') return false;
+        if (op->optype != HEX_BWD && !(op->optype == HEX_IPROD && !op->deformed)) return false;
+        char name[96];
+        snprintf(name, sizeof(name), "hex_slab_kernel<%s,nm=%d,nq=%d,%s>", op->optype == HEX_BWD ? "bwd" : "iprod", NM, NQ,
+                 op->deformed ? "deformed" : "regular");
+        op->kname = name;
+        op->launch = op->optype == HEX_BWD ? hex_slab_launch<HEX_BWD, NM> : hex_slab_launch<HEX_IPROD, NM>;
+        return true;
+    }
+    return false;
+}
+
 template <int NM, int NQ> static bool hex_install(nekmf_op_s *op)
 {
     auto *tab = new HexTab<NM, NQ>;
@@ -66,6 +125,7 @@ template <int NM, int NQ> static bool hex_install(nekmf_op_s *op)
     const char *opn[5] = {"bwd", "helm", "iprod", "ipwdb", "physderiv"};
     snprintf(name, sizeof(name), "hex_op_kernel<%s,nm=%d,nq=%d,%s>", opn[op->optype], NM, NQ, op->deformed ? "deformed" : "regular");
     op->kname = name;
+    if (hex_slab_install<NM, NQ>(op)) return true;
 #define HEX_CASE(OPC)                                                                     \
     case OPC:                                                                             \
         op->launch = op->deformed ? hex_launch<OPC, NM, NQ, true> : hex_launch<OPC, NM, NQ, false>; \

@@ -1,0 +1,301 @@
+// hex_slab.cuh -- BwdTrans and IProductWRTBase on hexahedra as warp-independent register-slab kernels.
+//
+// Reference semantics (what is computed, not how):
+//   BwdTrans         MatrixFreeOps/BwdTransKernels.hpp:302-372   u[k][j][i] = sum_pqr c[r][q][p] B[p][i] B[q][j] B[r][k]
+//   IProductWRTBase  MatrixFreeOps/IProductKernels.hpp:236-314   c[r][q][p] = sum_kji f[k][j][i] J w_i w_j w_k B[p][i] B[q][j] B[r][k]
+//
+// The pencil kernels of hex_kernels.cuh are bound by shared-memory wavefronts (three passes, each value read and
+// written once per pass, 35-40 % bank conflicts).  Here a LANE owns a whole 2-D slab of its element in registers
+// and does TWO of the three contractions there; one transposing exchange through a conflict-free padded layout
+// feeds the third:
+//   BwdTrans : lane (e,r) holds c[r][.][.], contracts p->i and q->j, scatters w[r][j][i]; lane (e,j) then gathers
+//              the r-lines of its (j,.) row and contracts r->k into the output staging block;
+//   IProduct : lane (e,k) holds (f J w)[k][.][.], contracts i->p and j->q, scatters v[k][q][p]; lane (e,q) gathers
+//              the k-lines of its (q,.) row and contracts k->r.
+// Every warp is an independent worker (own TMA-fed input buffer, own mbarrier, own bulk stores; no CTA barrier).
+// Slabs whose length is even (coefficient slabs for even nm, quadrature slabs for odd nm) are copied by one bulk
+// copy per slab into slots padded by two doubles, odd-length slabs by one bulk copy per batch: in both cases the
+// lane-strided slab reads are at most 2-way bank conflicted.  Matrix entries are kernel-parameter constants.
+#pragma once
+#include "hex_kernels.cuh"
+
+namespace nekmf
+{
+
+constexpr int slab_pad16(int minimum, int residue) // smallest v >= minimum with v % 16 == residue % 16
+{
+    int v = minimum;
+    while (v % 16 != residue % 16) ++v;
+    return v;
+}
+
+template <int OP, int NM> struct SlabCfg
+{
+    static constexpr int NQ = NM + 1, NM2 = NM * NM, NM3 = NM2 * NM, NQ2 = NQ * NQ, NQ3 = NQ2 * NQ;
+    // elements per warp step: the wider stage uses NQ lanes per element; kept even because one of nm^3, nq^3 is
+    // always odd and a batch must be a whole number of 16-byte units to travel by TMA
+    static constexpr int EPW = (32 / NQ) >= 2 ? ((32 / NQ) & ~1) : 1;
+    // coefficient block [e][r][q][p]: slab stride CS, element stride CE
+    static constexpr bool CPAD = (NM % 2) == 0;
+    static constexpr int CS = CPAD ? NM2 + 2 : NM2, CE = NM * CS, CBUF = round_up(EPW * CE, 2);
+    // quadrature block [e][k][j][i]: slab stride PS, element stride PE
+    static constexpr bool PPAD = (NQ % 2) == 0;
+    static constexpr int PS = PPAD ? NQ2 + 2 : NQ2, PE = NQ * PS, PBUF = round_up(EPW * PE, 2);
+    // exchange block.  BwdTrans: X[e*EX + j*LS + i*NM + r] (r-lines of length NM, rows j of NQ lines);
+    //                  IProduct: X[e*EX + q*LS + p*NQ + k] (k-lines of length NQ, rows q of NM lines)
+    static constexpr int LINE = OP == HEX_BWD ? NM : NQ;   // line length = lanes per element of stage I
+    static constexpr int ROWS = OP == HEX_BWD ? NQ : NM;   // rows = lanes per element of stage II
+    static constexpr int LPR  = OP == HEX_BWD ? NQ : NM;   // lines per row
+    static constexpr int LS   = (LPR * LINE) | 1;          // odd row stride: stage II lanes hit distinct banks
+    static constexpr int EX   = slab_pad16(ROWS * LS, LINE); // stage I: the elements of a half-warp tile the banks
+    static constexpr int XBUF = round_up(EPW * EX, 2);
+    static constexpr int INBUF  = OP == HEX_BWD ? CBUF : PBUF;
+    static constexpr int OUTBUF = OP == HEX_BWD ? PBUF : CBUF;
+    static constexpr int PER_WARP = INBUF + XBUF + OUTBUF + 2; // doubles (+2: mbarrier slot)
+    static constexpr int W_FIT  = (216 * 1024) / (PER_WARP * 8);
+    static constexpr int WARPS  = W_FIT >= 12 ? 12 : (W_FIT >= 8 ? 8 : (W_FIT >= 1 ? W_FIT : 1));
+    static constexpr int T      = WARPS * 32;
+    static constexpr size_t SMEM = (size_t)WARPS * PER_WARP * 8 + 16;
+};
+
+struct SlabArgs
+{
+    const double *in;
+    double *out;
+    const double *jac; // IProduct: [nElmt] (regular geometry; deformed collections keep the pencil kernel, which
+                       // already streams the per-point Jacobian at 0.9-1.0 of the HBM peak)
+    int nElmt;
+    int io_aligned; // in and out 16-byte aligned
+};
+
+template <int OP, int NM>
+__global__ void __launch_bounds__(SlabCfg<OP, NM>::T, 1)
+    hex_slab_kernel(const __grid_constant__ HexTab<NM, NM + 1> tab, const __grid_constant__ SlabArgs args)
+{
+    using Cfg = SlabCfg<OP, NM>;
+    constexpr int NQ = Cfg::NQ, NM2 = Cfg::NM2, NM3 = Cfg::NM3, NQ2 = Cfg::NQ2, NQ3 = Cfg::NQ3, EPW = Cfg::EPW;
+    constexpr int CS = Cfg::CS, CE = Cfg::CE, PS = Cfg::PS, PE = Cfg::PE, LS = Cfg::LS, EX = Cfg::EX;
+    constexpr bool BWD = OP == HEX_BWD;
+    // input side / output side geometry of the shared-memory blocks
+    constexpr int IN_SLABS = BWD ? NM : NQ, IN_SLEN = BWD ? NM2 : NQ2, IN_SS = BWD ? CS : PS, IN_ES = BWD ? CE : PE;
+    constexpr int IN_EL = BWD ? NM3 : NQ3;
+    constexpr bool IN_PAD = BWD ? Cfg::CPAD : Cfg::PPAD;
+    constexpr int OUT_SLABS = BWD ? NQ : NM, OUT_SLEN = BWD ? NQ2 : NM2, OUT_SS = BWD ? PS : CS, OUT_ES = BWD ? PE : CE;
+    constexpr int OUT_EL = BWD ? NQ3 : NM3;
+    constexpr bool OUT_PAD = BWD ? Cfg::PPAD : Cfg::CPAD;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *wbase  = reinterpret_cast<double *>(smem_raw) + (size_t)warp * Cfg::PER_WARP;
+    double *sIn    = wbase;
+    double *sX     = sIn + Cfg::INBUF;
+    double *sOut   = sX + Cfg::XBUF;
+    uint64_t *bar  = reinterpret_cast<uint64_t *>(sOut + Cfg::OUTBUF);
+
+    const int nElmt = args.nElmt;
+    const int nWB   = (nElmt + EPW - 1) / EPW;
+    const int GW    = gridDim.x * Cfg::WARPS;
+    const int gw    = blockIdx.x * Cfg::WARPS + warp;
+    // stage I lane = (e1, s1): s1 < IN_SLABS ; stage II lane = (e2, s2): s2 < OUT rows
+    const int e1 = lane / IN_SLABS, s1 = lane - e1 * IN_SLABS;
+    const int e2 = lane / Cfg::ROWS, s2 = lane - e2 * Cfg::ROWS;
+    // bulk-store issuers: lane = (eo, so): so < OUT_SLABS
+    const int eo = lane / OUT_SLABS, so = lane - eo * OUT_SLABS;
+
+    if (lane == 0)
+    {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    auto batch_ne = [&](int wb) { int r = nElmt - wb * EPW; return r < EPW ? r : EPW; };
+    auto in_tma   = [&](int wb) { return args.io_aligned && (IN_PAD || (((batch_ne(wb) * IN_EL) & 1) == 0 && ((wb * EPW * IN_EL) & 1) == 0)); };
+    auto out_tma  = [&](int wb) { return args.io_aligned && (OUT_PAD || (((batch_ne(wb) * OUT_EL) & 1) == 0 && ((wb * EPW * OUT_EL) & 1) == 0)); };
+    auto issue    = [&](int wb) { // whole warp; the input buffer is free
+        const int ne      = batch_ne(wb);
+        if (!in_tma(wb)) return;
+        const double *src = args.in + (size_t)wb * EPW * IN_EL;
+        if (lane == 0)
+        {
+            mbar_expect_tx(bar, (uint32_t)(ne * IN_EL * 8));
+            if (!IN_PAD) tma_load_1d(sIn, src, (uint32_t)(ne * IN_EL * 8), bar);
+        }
+        __syncwarp();
+        if (IN_PAD && e1 < ne && lane < EPW * IN_SLABS)
+            tma_load_1d(sIn + e1 * IN_ES + s1 * IN_SS, src + (size_t)e1 * IN_EL + s1 * IN_SLEN, (uint32_t)(IN_SLEN * 8), bar);
+    };
+
+    uint32_t phase = 0;
+    if (gw < nWB) issue(gw);
+    for (int wb = gw; wb < nWB; wb += GW)
+    {
+        const int ne = batch_ne(wb), wbnext = wb + GW;
+        const bool tin = in_tma(wb), tout = out_tma(wb);
+        if (!tin)
+        {
+            const double *src = args.in + (size_t)wb * EPW * IN_EL;
+            for (int i = lane; i < ne * IN_EL; i += 32)
+            {
+                const int e = i / IN_EL, w = i - e * IN_EL, s = w / IN_SLEN;
+                sIn[e * IN_ES + s * IN_SS + (w - s * IN_SLEN)] = __ldg(src + i);
+            }
+        }
+        else
+        {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------------------ stage I
+        if (lane < EPW * IN_SLABS && e1 < ne)
+        {
+            const double *xs = sIn + e1 * IN_ES + s1 * IN_SS;
+            double *X        = sX + e1 * EX;
+            if (BWD)
+            {
+                // lane (e, r): c[q][p] -> w[j][i] = sum_q B[q][j] sum_p B[p][i] c[q][p]
+                double c[NM][NM];
+#pragma unroll
+                for (int q = 0; q < NM; ++q)
+#pragma unroll
+                    for (int p = 0; p < NM; ++p) c[q][p] = xs[q * NM + p];
+#pragma unroll
+                for (int i = 0; i < NQ; ++i)
+                {
+                    double t[NM];
+#pragma unroll
+                    for (int q = 0; q < NM; ++q)
+                    {
+                        double s = tab.B[i] * c[q][0];
+#pragma unroll
+                        for (int p = 1; p < NM; ++p) s = fma(tab.B[p * NQ + i], c[q][p], s);
+                        t[q] = s;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j)
+                    {
+                        double s = tab.B[j] * t[0];
+#pragma unroll
+                        for (int q = 1; q < NM; ++q) s = fma(tab.B[q * NQ + j], t[q], s);
+                        X[j * LS + i * NM + s1] = s;
+                    }
+                }
+            }
+            else
+            {
+                // lane (e, k): g[j][i] = f[j][i] J w_k w_j w_i -> v[q][p] = sum_j B[q][j] sum_i B[p][i] g[j][i]
+                double g[NQ][NQ];
+                const double jk = __ldg(args.jac + (size_t)wb * EPW + e1) * tab.w[s1];
+#pragma unroll
+                for (int j = 0; j < NQ; ++j)
+#pragma unroll
+                    for (int i = 0; i < NQ; ++i)
+                    {
+                        g[j][i] = xs[j * NQ + i] * ((jk * tab.w[j]) * tab.w[i]);
+                    }
+#pragma unroll
+                for (int p = 0; p < NM; ++p)
+                {
+                    double t[NQ];
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j)
+                    {
+                        double s = tab.B[p * NQ] * g[j][0];
+#pragma unroll
+                        for (int i = 1; i < NQ; ++i) s = fma(tab.B[p * NQ + i], g[j][i], s);
+                        t[j] = s;
+                    }
+#pragma unroll
+                    for (int q = 0; q < NM; ++q)
+                    {
+                        double s = tab.B[q * NQ] * t[0];
+#pragma unroll
+                        for (int j = 1; j < NQ; ++j) s = fma(tab.B[q * NQ + j], t[j], s);
+                        X[q * LS + p * NQ + s1] = s;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // the input buffer is consumed: request the next batch now, it lands during stage II and the store; the
+        // staging buffer must no longer be read by the previous batch's bulk stores (each issuing lane waits for
+        // its own groups)
+        if (wbnext < nWB) issue(wbnext);
+        tma_store_wait_read0();
+        __syncwarp();
+
+        // ------------------------------------------------------------------ stage II
+        if (lane < EPW * Cfg::ROWS && e2 < ne)
+        {
+            const double *X = sX + e2 * EX + s2 * LS;
+            double *O       = sOut + e2 * OUT_ES;
+            if (BWD)
+            {
+                // lane (e, j): u[k][j][i] = sum_r B[r][k] w[r][j][i]
+#pragma unroll
+                for (int i = 0; i < NQ; ++i)
+                {
+                    double v[NM];
+#pragma unroll
+                    for (int r = 0; r < NM; ++r) v[r] = X[i * NM + r];
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k)
+                    {
+                        double s = tab.B[k] * v[0];
+#pragma unroll
+                        for (int r = 1; r < NM; ++r) s = fma(tab.B[r * NQ + k], v[r], s);
+                        O[k * OUT_SS + s2 * NQ + i] = s;
+                    }
+                }
+            }
+            else
+            {
+                // lane (e, q): c[r][q][p] = sum_k B[r][k] v[k][q][p]
+#pragma unroll
+                for (int p = 0; p < NM; ++p)
+                {
+                    double v[NQ];
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k) v[k] = X[p * NQ + k];
+#pragma unroll
+                    for (int r = 0; r < NM; ++r)
+                    {
+                        double s = tab.B[r * NQ] * v[0];
+#pragma unroll
+                        for (int k = 1; k < NQ; ++k) s = fma(tab.B[r * NQ + k], v[k], s);
+                        O[r * OUT_SS + s2 * NM + p] = s;
+                    }
+                }
+            }
+        }
+        double *dst = args.out + (size_t)wb * EPW * OUT_EL;
+        if (tout)
+        {
+            fence_proxy_async();
+            __syncwarp();
+            if (OUT_PAD)
+            {
+                if (lane < EPW * OUT_SLABS && eo < ne)
+                    tma_store_1d(dst + (size_t)eo * OUT_EL + so * OUT_SLEN, sOut + eo * OUT_ES + so * OUT_SS, (uint32_t)(OUT_SLEN * 8));
+            }
+            else if (lane == 0)
+                tma_store_1d(dst, sOut, (uint32_t)(ne * OUT_EL * 8));
+            tma_store_commit();
+        }
+        else
+        {
+            __syncwarp();
+            for (int i = lane; i < ne * OUT_EL; i += 32)
+            {
+                const int e = i / OUT_EL, w = i - e * OUT_EL, s = w / OUT_SLEN;
+                dst[i] = sOut[e * OUT_ES + s * OUT_SS + (w - s * OUT_SLEN)];
+            }
+            __syncwarp();
+        }
+    }
+    tma_store_wait0();
+}
+
+} // namespace nekmf
