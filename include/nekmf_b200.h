@@ -51,8 +51,9 @@ enum nekmf_shape
     NEKMF_TRI   = 1,
     NEKMF_HEX   = 2,
     NEKMF_PRISM = 3,
-    NEKMF_PYR   = 4, /* declared for completeness; create returns NEKMF_ERR_UNSUPPORTED */
-    NEKMF_TET   = 5
+    NEKMF_PYR   = 4,
+    NEKMF_TET   = 5,
+    NEKMF_SEG   = 6 /* 1-D element embedded in 1, 2 or 3 space dimensions (coordim) */
 };
 
 /* Collections::OperatorType, same order (Collections/Operator.h:65-73) */
@@ -144,7 +145,9 @@ int nekmf_basis(int basistype, int nm, int np, const double *z, const double *D,
  * D[k*nq+i] = dh_k/dz(z_i); Z[d], W[d]: points and raw quadrature weights (the collapsed-
  * coordinate 0.5 / 0.25 weight scaling of MatrixFreeOps/Operator.hpp:244-258 is applied here).
  * All tables are copied.  deformed: 0 = one jac/df entry per element, 1 = per quadrature point.
- * coordim must equal dim (the reference's 2-D kernels reject 3 outputs, PhysDeriv.h:285-286). */
+ * coordim must equal dim (the reference's 2-D kernels reject 3 outputs, PhysDeriv.h:285-286), except for
+ * NEKMF_SEG where coordim = 1, 2 or 3 gives the number of PhysDeriv outputs / IProductWRTDerivBase inputs and of
+ * derivative-factor rows (PhysDeriv.h:60-250, IProductWRTDerivBase.h:182-365); Helmholtz has no segment variant. */
 int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], const int basistype[3],
                     const int pointstype[3], const double *const bdata[3], const double *const dbdata[3],
                     const double *const D[3], const double *const Z[3], const double *const W[3], int nElmt,

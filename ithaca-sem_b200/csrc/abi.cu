@@ -41,6 +41,7 @@ static int count_modes(int shape, int nm)
         case NEKMF_PRISM: return nm * nm * (nm + 1) / 2;
         case NEKMF_TET: return nm * (nm + 1) * (nm + 2) / 6;
         case NEKMF_PYR: return nm * (nm + 1) * (2 * nm + 1) / 6;
+        case NEKMF_SEG: return nm;
     }
     return -1;
 }
@@ -141,7 +142,7 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
         return NEKMF_ERR_ARG;
     }
     if (shape != NEKMF_QUAD && shape != NEKMF_TRI && shape != NEKMF_HEX && shape != NEKMF_PRISM && shape != NEKMF_PYR &&
-        shape != NEKMF_TET)
+        shape != NEKMF_TET && shape != NEKMF_SEG)
     {
         set_error("nekmf_op_create: unknown shape %d", shape);
         return NEKMF_ERR_ARG;
@@ -152,8 +153,29 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
         return NEKMF_ERR_ARG;
     }
     if (nElmt < 0) { set_error("nekmf_op_create: negative element count"); return NEKMF_ERR_ARG; }
-    const int dim = (shape == NEKMF_QUAD || shape == NEKMF_TRI) ? 2 : 3;
-    if (coordim != dim)
+    const int dim = shape == NEKMF_SEG ? 1 : ((shape == NEKMF_QUAD || shape == NEKMF_TRI) ? 2 : 3);
+    if (shape == NEKMF_SEG)
+    {
+        if (coordim < 1 || coordim > 3)
+        {
+            set_error("nekmf_op_create: segment coordim %d out of range 1..3", coordim);
+            return NEKMF_ERR_ARG;
+        }
+        if (optype == NEKMF_HELMHOLTZ)
+        {
+            // the reference registers no (eSegment, eHelmholtz, eMatrixFree) operator (Collections/Helmholtz.cpp:484-504)
+            set_error("nekmf_op_create: Helmholtz has no segment variant");
+            return NEKMF_ERR_UNSUPPORTED;
+        }
+        if (optype == NEKMF_IPRODUCTWRTDERIVBASE && coordim == 3 && !deformed)
+        {
+            // the reference's regular coordim-3 branch multiplies the third input by df[1] (IProductWRTDerivBase.h:321-323);
+            // neither that nor a silently different result is offered
+            set_error("nekmf_op_create: IProductWRTDerivBase on regular segments in 3 space dimensions is not supported");
+            return NEKMF_ERR_UNSUPPORTED;
+        }
+    }
+    else if (coordim != dim)
     {
         // the reference's 2-D kernels reject a third output (PhysDeriv.h:285-286,412-413)
         set_error("nekmf_op_create: coordim %d != element dimension %d is not supported", coordim, dim);
@@ -210,9 +232,10 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
     op->shape    = shape;
     op->optype   = optype;
     op->dim      = dim;
+    op->coordim  = coordim;
     op->nElmt    = nElmt;
     op->deformed = deformed ? 1 : 0;
-    op->ndf      = dim * dim;
+    op->ndf      = dim * coordim;
     op->nmTot    = count_modes(shape, nm[0]);
     op->nqTot    = 1;
     int off      = 0;
@@ -268,9 +291,10 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
     }
     bool ok       = false;
     op->geo_pitch = op->nqTot;
-    if (shape == NEKMF_HEX) ok = select_hex_fast(op);
-    if (!ok && shape != NEKMF_HEX && shape != NEKMF_PYR) ok = select_shape_fast(op);
-    if (!ok) ok = select_generic(op);
+    if (shape == NEKMF_SEG) ok = select_seg(op);
+    if (!ok && shape == NEKMF_HEX) ok = select_hex_fast(op);
+    if (!ok && shape != NEKMF_HEX && shape != NEKMF_PYR && shape != NEKMF_SEG) ok = select_shape_fast(op);
+    if (!ok && shape != NEKMF_SEG) ok = select_generic(op);
     if (!ok)
     {
         set_error("nekmf_op_create: no kernel for shape %d op %d nm %d nq %d", shape, optype, nm[0], nq[0]);
@@ -401,8 +425,8 @@ int nekmf_op_apply(nekmf_op_t op, const double *in0, const double *in1, const do
     if (!op) { set_error("nekmf_op_apply: null operator"); return NEKMF_ERR_ARG; }
     int rc = op_check_ready(op);
     if (rc) return rc;
-    const int nin   = op->optype == NEKMF_IPRODUCTWRTDERIVBASE ? op->dim : 1;
-    const int nout  = op->optype == NEKMF_PHYSDERIV ? op->dim : 1;
+    const int nin   = op->optype == NEKMF_IPRODUCTWRTDERIVBASE ? op->coordim : 1;
+    const int nout  = op->optype == NEKMF_PHYSDERIV ? op->coordim : 1;
     const bool cin  = op->optype == NEKMF_BWDTRANS || op->optype == NEKMF_HELMHOLTZ;
     const bool cout = op->optype != NEKMF_BWDTRANS && op->optype != NEKMF_PHYSDERIV;
     const size_t in_sz  = (size_t)op->nElmt * (cin ? op->nmTot : op->nqTot);

@@ -7,7 +7,7 @@
 
 struct nekmf_op_s
 {
-    int shape = 0, optype = 0, dim = 0;
+    int shape = 0, optype = 0, dim = 0, coordim = 0; // coordim != dim only for segments
     int nm[3] = {1, 1, 1}, nq[3] = {1, 1, 1}, btype[3] = {0, 0, 0}, ptype[3] = {0, 0, 0}, rows[3] = {0, 0, 0};
     int nmTot = 0, nqTot = 0, nElmt = 0, deformed = 0, ndf = 0;
     double lambda       = 0.0;
@@ -61,6 +61,7 @@ namespace nekmf
 bool select_hex_fast(nekmf_op_s *op);
 bool select_shape_fast(nekmf_op_s *op);
 bool select_generic(nekmf_op_s *op);
+bool select_seg(nekmf_op_s *op);
 // called after set_geom / set_lambda so launchers can precompute (e.g. detect diagonal metrics)
 void notify_geom_changed(nekmf_op_s *op);
 void kron_maybe_wrap(nekmf_op_s *op);

@@ -24,8 +24,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnekmf_b200.so")
 
 # LibUtilities::ShapeType subset, ABI numbering
-eQuadrilateral, eTriangle, eHexahedron, ePrism, ePyramid, eTetrahedron = 0, 1, 2, 3, 4, 5
-ShapeTypeMap = {0: "Quadrilateral", 1: "Triangle", 2: "Hexahedron", 3: "Prism", 4: "Pyramid", 5: "Tetrahedron"}
+eQuadrilateral, eTriangle, eHexahedron, ePrism, ePyramid, eTetrahedron, eSegment = 0, 1, 2, 3, 4, 5, 6
+ShapeTypeMap = {0: "Quadrilateral", 1: "Triangle", 2: "Hexahedron", 3: "Prism", 4: "Pyramid", 5: "Tetrahedron", 6: "Segment"}
 # Collections::OperatorType (Operator.h:65-73)
 eBwdTrans, eHelmholtz, eIProductWRTBase, eIProductWRTDerivBase, ePhysDeriv, SIZE_OperatorType = 0, 1, 2, 3, 4, 5
 OperatorTypeMap = ["BwdTrans", "Helmholtz", "IProductWRTBase", "IProductWRTDerivBase", "PhysDeriv"]
@@ -197,7 +197,7 @@ def num_coeffs(shape, nm):
     """LibUtilities::StdXxxData::getNumberOfCoefficients (BasicUtils/ShapeType.hpp:111-337)."""
     return {eQuadrilateral: nm * nm, eTriangle: nm * (nm + 1) // 2, eHexahedron: nm ** 3,
             ePrism: nm * nm * (nm + 1) // 2, eTetrahedron: nm * (nm + 1) * (nm + 2) // 6,
-            ePyramid: nm * (nm + 1) * (2 * nm + 1) // 6}[shape]
+            ePyramid: nm * (nm + 1) * (2 * nm + 1) // 6, eSegment: nm}[shape]
 
 
 class StdExpansion:
@@ -205,11 +205,13 @@ class StdExpansion:
     Basis objects with Nektar's default point distributions (SpatialDomains/MeshGraph.cpp:1609-1762:
     nq = nm+1 Gauss-Lobatto-Legendre in tensor directions, Gauss-Radau in collapsed ones)."""
 
-    def __init__(self, shape, nummodes, numpoints=None):
+    def __init__(self, shape, nummodes, numpoints=None, coordim=None):
         nm = nummodes
         nq0 = numpoints if numpoints is not None else nm + 1
         self.shape, self.nm = shape, nm
-        self.dim = 2 if shape in (eQuadrilateral, eTriangle) else 3
+        self.dim = 1 if shape == eSegment else (2 if shape in (eQuadrilateral, eTriangle) else 3)
+        # GetCoordim(): space dimension; differs from the element dimension only for segments (1..3)
+        self.coordim = self.dim if coordim is None else int(coordim)
         bt = [eModified_A] * 3
         pt = [eGaussLobattoLegendre] * 3
         nq = [nq0] * 3
@@ -223,7 +225,7 @@ class StdExpansion:
         elif shape == eTetrahedron:
             bt[1], pt[1], nq[1] = eModified_B, eGaussRadauMAlpha1Beta0, nq0 - 1
             bt[2], pt[2], nq[2] = eModified_C, eGaussRadauMAlpha2Beta0, nq0 - 1
-        elif shape not in (eQuadrilateral, eHexahedron):
+        elif shape not in (eQuadrilateral, eHexahedron, eSegment):
             raise NekError("shape %s not supported" % ShapeTypeMap.get(shape, shape))
         self.basis = [Basis(bt[d], nm, pt[d], nq[d]) for d in range(self.dim)]
         self.nq = nq[:self.dim]
@@ -274,7 +276,7 @@ class Operator:
 
         deformed = bool(geom.IsDeformed()) if geom is not None else False
         check(lib().nekmf_op_create(stdexp.shape, optype, nm, nq, bt, pt, arr("bdata"), arr("dbdata"), arr("D"),
-                                    arr("Z"), arr("W"), self.nElmt, int(deformed), dim, C.byref(self.h)),
+                                    arr("Z"), arr("W"), self.nElmt, int(deformed), stdexp.coordim, C.byref(self.h)),
               "nekmf_op_create")
         self.m_isDeformed = deformed
         self.ncoeff = int(lib().nekmf_op_ncoeff(self.h))
@@ -284,7 +286,7 @@ class Operator:
             pd, kd, _ = _ptr(geom.GetDerivFactors())
             kind = _kind(geom.GetJac(), geom.GetDerivFactors())
             npt = self.nElmt * (self.nphys if deformed else 1)
-            for a, n, nmq in ((geom.GetJac(), npt, "jac"), (geom.GetDerivFactors(), npt * dim * dim, "df")):
+            for a, n, nmq in ((geom.GetJac(), npt, "jac"), (geom.GetDerivFactors(), npt * dim * stdexp.coordim, "df")):
                 if a is not None and (a.numel() if _is_torch(a) else a.size) != n:
                     raise NekError("CoalescedGeomData: %s has %d entries, expected %d" % (
                         nmq, a.numel() if _is_torch(a) else a.size, n))
@@ -349,7 +351,7 @@ class Operator:
     def apply_dir(self, dir, input, output):
         if self.optype != ePhysDeriv:
             raise NekError("%s: operator()(dir, ...) is not valid for this operator" % OperatorTypeMap[self.optype])
-        dim = self.stdexp.dim
+        dim = self.stdexp.coordim
         if not 0 <= dir < dim:
             raise NekError("PhysDeriv: direction %d out of range" % dir)
         n = self.nElmt * self.nphys

@@ -469,7 +469,7 @@ void mfo_basis(int btype, int nm, int np, const double *z, const double *D, doub
 
 struct mfo_elem
 {
-    int shape, dim, nm, nmTot, nqTot;
+    int shape, dim, coordim, nm, nmTot, nqTot;
     int nq[3], ptype[3], btype[3], rows[3];
     double *z[3], *w[3], *ws[3], *D[3], *b[3], *db[3];
     double *h0, *h1, *h2, *h3;
@@ -485,6 +485,7 @@ static int count_modes(int shape, int nm)
         case MFO_PRISM: return nm * nm * (nm + 1) / 2;
         case MFO_TET: return nm * (nm + 1) * (nm + 2) / 6;
         case MFO_PYR: return nm * (nm + 1) * (2 * nm + 1) / 6;
+        case MFO_SEG: return nm;
     }
     return -1;
 }
@@ -495,7 +496,8 @@ mfo_elem *mfo_create(int shape, int nm, int nq0)
     int d, i;
     e->shape = shape;
     e->nm    = nm;
-    e->dim   = (shape == MFO_QUAD || shape == MFO_TRI) ? 2 : 3;
+    e->dim   = shape == MFO_SEG ? 1 : ((shape == MFO_QUAD || shape == MFO_TRI) ? 2 : 3);
+    e->coordim = e->dim;
     for (d = 0; d < 3; ++d)
     {
         e->nq[d]    = nq0;
@@ -505,6 +507,7 @@ mfo_elem *mfo_create(int shape, int nm, int nq0)
     /* MeshGraph.cpp:1609-1762 defaults; MatrixFree preconditions Helmholtz.h:329-331,1042-1046,2017-2021 */
     switch (shape)
     {
+        case MFO_SEG:
         case MFO_QUAD:
         case MFO_HEX: break;
         case MFO_TRI:
@@ -591,6 +594,7 @@ void mfo_destroy(mfo_elem *e)
 }
 
 int mfo_dim(const mfo_elem *e) { return e->dim; }
+void mfo_set_coordim(mfo_elem *e, int c) { if (e->shape == MFO_SEG && c >= 1 && c <= 3) e->coordim = c; }
 int mfo_nmtot(const mfo_elem *e) { return e->nmTot; }
 int mfo_nqtot(const mfo_elem *e) { return e->nqTot; }
 int mfo_nq(const mfo_elem *e, int d) { return e->nq[d]; }
@@ -1264,6 +1268,18 @@ static void bwd_one(const mfo_elem *e, const double *in, double *out, scratch *s
 {
     switch (e->shape)
     {
+        case MFO_SEG:
+        {
+            /* BwdTransKernels.hpp:14-33 */
+            int i, p, nq = e->nq[0], nm = e->nm;
+            for (i = 0; i < nq; ++i)
+            {
+                double t = in[0] * e->b[0][i];
+                for (p = 1; p < nm; ++p) t += in[p] * e->b[0][p * nq + i];
+                out[i] = t;
+            }
+            break;
+        }
         case MFO_QUAD: k_bwd_quad(e->nm, e->nq[0], in, e->b[0], e->b[1], s->a, out); break;
         case MFO_TRI: k_bwd_tri(e->nm, e->nq[0], e->nq[1], in, e->b[0], e->b[1], s->a, out); break;
         case MFO_HEX: k_bwd_hex(e->nm, e->nq[0], in, e->b[0], e->b[1], e->b[2], s->a, s->b, out); break;
@@ -1285,6 +1301,22 @@ static void ip_one(const mfo_elem *e, const double *in, const double *B0, const 
 {
     switch (e->shape)
     {
+        case MFO_SEG:
+        {
+            /* IProductKernels.hpp:39-75 */
+            int i, p, nq = e->nq[0], nm = e->nm;
+            for (p = 0; p < nm; ++p)
+            {
+                double sum = 0.0;
+                for (i = 0; i < nq; ++i)
+                {
+                    double prod = in[i] * B0[p * nq + i] * (DEF ? jac[i] : jac[0]);
+                    sum += prod * e->ws[0][i];
+                }
+                scale_append(&out[p], sum, scale, SCALE, APPEND);
+            }
+            break;
+        }
         case MFO_QUAD:
             k_ip_quad(e->nm, e->nq[0], in, B0, B1, e->ws[0], e->ws[1], jac, DEF, s->a, out, scale, SCALE, APPEND);
             break;
@@ -1319,6 +1351,20 @@ static void pd_one(const mfo_elem *e, const double *in, const double *df, size_t
 {
     const int nq0 = e->nq[0], nq1 = e->nq[1], nq2 = e->nq[2];
     int i, j, k, pt;
+    if (e->dim == 1)
+    {
+        /* PhysDerivKernels.hpp:13-38 + PhysDeriv.h:60-250 (one output per space dimension) */
+        double *outs[3] = {o0, o1, o2};
+        for (i = 0; i < nq0; ++i)
+        {
+            double d = 0.0;
+            int c;
+            for (k = 0; k < nq0; ++k) d += e->D[0][k * nq0 + i] * in[k];
+            pt = i;
+            for (c = e->coordim - 1; c >= 0; --c) outs[c][i] = d * DFV(c);
+        }
+        return;
+    }
     if (e->dim == 2)
     {
         k_dtensor2(nq0, nq1, in, e->D[0], e->D[1], o0, o1);
@@ -1588,7 +1634,8 @@ void mfo_physderiv(const mfo_elem *e, int nElmt, int DEF, const double *df, cons
         for (el = 0; el < nElmt; ++el)
         {
             size_t off = (size_t)el * e->nqTot;
-            pd_one(e, in + off, DEF ? df + off : df + el, dfs, DEF, o0 + off, o1 + off, o2 ? o2 + off : NULL, &s);
+            pd_one(e, in + off, DEF ? df + off : df + el, dfs, DEF, o0 + off, o1 ? o1 + off : NULL,
+                   o2 ? o2 + off : NULL, &s);
         }
         scratch_free(&s);
     }
@@ -1630,7 +1677,21 @@ int mfo_iproductwrtderivbase(const mfo_elem *e, int nElmt, int DEF, const double
             double *t0 = s.c, *t1 = s.d, *t2 = s.e;
             int pt;
 #define DFE(n) (DEF ? dfe[(size_t)(n) * dfs + pt] : dfe[(size_t)(n) * dfs])
-            if (e->dim == 3)
+            if (e->dim == 1)
+            {
+                /* IProductWRTDerivBase.h:182-365: t = sum_c df[c] in_c, then one IProduct with dbdata.  The
+                 * reference's regular coordim-3 branch reads df[1] for the third factor (:321-323); it is
+                 * restated as written there. */
+                for (pt = 0; pt < e->nqTot; ++pt)
+                {
+                    double v = DFE(0) * in0[qoff + pt];
+                    if (e->coordim >= 2) v = v + DFE(1) * in1[qoff + pt];
+                    if (e->coordim == 3) v = v + (DEF ? DFE(2) : DFE(1)) * in2[qoff + pt];
+                    t0[pt] = v;
+                }
+                ip_one(e, t0, e->db[0], NULL, NULL, jc, DEF, out + moff, 1.0, 0, 0, &s);
+            }
+            else if (e->dim == 3)
             {
                 for (pt = 0; pt < e->nqTot; ++pt)
                 {

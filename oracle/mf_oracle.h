@@ -18,7 +18,7 @@ extern "C" {
 #endif
 
 /* LibUtilities::ShapeType subset, numbered like the C-ABI (include/nekmf_b200.h) */
-enum { MFO_QUAD = 0, MFO_TRI = 1, MFO_HEX = 2, MFO_PRISM = 3, MFO_PYR = 4, MFO_TET = 5 };
+enum { MFO_QUAD = 0, MFO_TRI = 1, MFO_HEX = 2, MFO_PRISM = 3, MFO_PYR = 4, MFO_TET = 5, MFO_SEG = 6 };
 /* points types: Gauss-Lobatto-Legendre, Gauss-Radau-M (alpha=1|2, beta=0) */
 enum { MFO_GLL = 0, MFO_GRJM_A1 = 1, MFO_GRJM_A2 = 2 };
 /* basis types */
@@ -45,6 +45,8 @@ typedef struct mfo_elem mfo_elem;
 mfo_elem *mfo_create(int shape, int nm, int nq0);
 void mfo_destroy(mfo_elem *e);
 int mfo_dim(const mfo_elem *e);
+/* segments only: number of space dimensions the 1-D element is embedded in (1..3, default 1) */
+void mfo_set_coordim(mfo_elem *e, int coordim);
 int mfo_nmtot(const mfo_elem *e);
 int mfo_nqtot(const mfo_elem *e);
 int mfo_nq(const mfo_elem *e, int dir);

@@ -15,8 +15,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-QUAD, TRI, HEX, PRISM, PYR, TET = 0, 1, 2, 3, 4, 5
-SHAPE_NAMES = {QUAD: "Quad", TRI: "Tri", HEX: "Hex", PRISM: "Prism", PYR: "Pyr", TET: "Tet"}
+QUAD, TRI, HEX, PRISM, PYR, TET, SEG = 0, 1, 2, 3, 4, 5, 6
+SHAPE_NAMES = {QUAD: "Quad", TRI: "Tri", HEX: "Hex", PRISM: "Prism", PYR: "Pyr", TET: "Tet", SEG: "Seg"}
 OP_BWD, OP_HELM, OP_IPROD, OP_IPWDB, OP_PHYSDERIV = 0, 1, 2, 3, 4
 
 _dp = C.POINTER(C.c_double)
@@ -46,6 +46,7 @@ def oracle_lib():
         L.mfo_destroy.argtypes = [C.c_void_p]
         for f in ("mfo_dim", "mfo_nmtot", "mfo_nqtot"):
             getattr(L, f).argtypes = [C.c_void_p]
+        L.mfo_set_coordim.argtypes = [C.c_void_p, C.c_int]
         for f in ("mfo_nq", "mfo_ptype", "mfo_btype", "mfo_brows"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int]
         L.mfo_table.restype = _dp
@@ -87,20 +88,23 @@ def points(ptype, n):
 class Elem:
     """Tables + operators of one (shape, nm, nq0) expansion with Nektar's default points."""
 
-    def __init__(self, shape, nm, nq0):
+    def __init__(self, shape, nm, nq0, coordim=None):
         self.L = oracle_lib()
         self.shape, self.nm, self.nq0 = shape, nm, nq0
         self.h = self.L.mfo_create(shape, nm, nq0)
         if not self.h:
             raise ValueError("unsupported shape")
         self.dim = self.L.mfo_dim(self.h)
+        self.coordim = self.dim if coordim is None else int(coordim)  # segments: 1..3 space dimensions
+        if self.coordim != self.dim:
+            self.L.mfo_set_coordim(self.h, self.coordim)
         self.nmTot = self.L.mfo_nmtot(self.h)
         self.nqTot = self.L.mfo_nqtot(self.h)
         self.nq = [self.L.mfo_nq(self.h, d) for d in range(self.dim)]
         self.ptype = [self.L.mfo_ptype(self.h, d) for d in range(self.dim)]
         self.btype = [self.L.mfo_btype(self.h, d) for d in range(self.dim)]
         self.brows = [self.L.mfo_brows(self.h, d) for d in range(self.dim)]
-        self.ndf = self.dim * self.dim
+        self.ndf = self.dim * self.coordim
 
         def tab(d, which, n):
             return np.ctypeslib.as_array(self.L.mfo_table(self.h, d, which), shape=(n,)).copy()
@@ -128,9 +132,10 @@ class Elem:
         return out
 
     def physderiv(self, nel, deformed, df, x):
-        outs = [np.zeros(nel * self.nqTot) for _ in range(self.dim)]
-        o2 = _p(outs[2]) if self.dim == 3 else None
-        self.L.mfo_physderiv(self.h, nel, int(deformed), _p(df), _p(x), _p(outs[0]), _p(outs[1]), o2)
+        outs = [np.zeros(nel * self.nqTot) for _ in range(self.coordim)]
+        o1 = _p(outs[1]) if self.coordim >= 2 else None
+        o2 = _p(outs[2]) if self.coordim == 3 else None
+        self.L.mfo_physderiv(self.h, nel, int(deformed), _p(df), _p(x), _p(outs[0]), o1, o2)
         return outs
 
     def helmholtz(self, nel, deformed, jac, df, lam, x):
@@ -140,9 +145,9 @@ class Elem:
 
     def iproductwrtderivbase(self, nel, deformed, jac, df, ins):
         out = np.zeros(nel * self.nmTot)
-        i2 = _p(ins[2]) if self.dim == 3 else None
-        rc = self.L.mfo_iproductwrtderivbase(self.h, nel, int(deformed), _p(jac), _p(df), _p(ins[0]), _p(ins[1]),
-                                             i2, _p(out))
+        i1 = _p(ins[1]) if self.coordim >= 2 else None
+        i2 = _p(ins[2]) if self.coordim == 3 else None
+        rc = self.L.mfo_iproductwrtderivbase(self.h, nel, int(deformed), _p(jac), _p(df), _p(ins[0]), i1, i2, _p(out))
         if rc != 0:
             raise NotImplementedError
         return out
@@ -186,6 +191,8 @@ class Ref:
         pp = C.POINTER(_dp)
         L.nekref_create.restype = C.c_void_p
         L.nekref_create.argtypes = [C.c_int] * 5 + [pp] * 5 + [_ip] * 3 + [C.c_int, _dp, _dp]
+        L.nekref_create2.restype = C.c_void_p
+        L.nekref_create2.argtypes = [C.c_int] * 5 + [pp] * 5 + [_ip] * 3 + [C.c_int, _dp, _dp, C.c_int]
         L.nekref_run.argtypes = [C.c_void_p] + [_dp] * 6 + [C.c_double, C.c_int]
         L.nekref_destroy.argtypes = [C.c_void_p]
         for f in ("nekref_zwglj", "nekref_zwgrjm"):
@@ -235,8 +242,8 @@ class RefOperator:
         blen = (C.c_int * 3)(*[el.bdata[d].size for d in range(dim)] + [0] * (3 - dim))
         nqd = (C.c_int * 3)(*el.nq + [1] * (3 - dim))
         pty = (C.c_int * 3)(*el.ptype + [0] * (3 - dim))
-        self.h = ref.L.nekref_create(op, el.shape, el.nm, el.nq0, int(deformed), arr(el.bdata), arr(el.dbdata),
-                                     arr(el.D), arr(el.Z), arr(el.W), blen, nqd, pty, nel, _p(jac), _p(df))
+        self.h = ref.L.nekref_create2(op, el.shape, el.nm, el.nq0, int(deformed), arr(el.bdata), arr(el.dbdata),
+                                      arr(el.D), arr(el.Z), arr(el.W), blen, nqd, pty, nel, _p(jac), _p(df), el.coordim)
         if not self.h:
             raise ValueError("reference operator not available")
 
@@ -252,7 +259,7 @@ class RefOperator:
             ins = [ins]
         nout = {OP_BWD: el.nqTot, OP_HELM: el.nmTot, OP_IPROD: el.nmTot, OP_IPWDB: el.nmTot,
                 OP_PHYSDERIV: el.nqTot}[self.op]
-        nouts = el.dim if self.op == OP_PHYSDERIV else 1
+        nouts = el.coordim if self.op == OP_PHYSDERIV else 1
         if outs is None:
             outs = [np.zeros(nel * nout) for _ in range(nouts)]
         i = list(ins) + [None] * (3 - len(ins))

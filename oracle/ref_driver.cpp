@@ -41,7 +41,7 @@ using VecVec = std::vector<vec_t, allocator<vec_t>>;
 namespace nekref
 {
 
-enum { SH_QUAD = 0, SH_TRI = 1, SH_HEX = 2, SH_PRISM = 3, SH_PYR = 4, SH_TET = 5 };
+enum { SH_QUAD = 0, SH_TRI = 1, SH_HEX = 2, SH_PRISM = 3, SH_PYR = 4, SH_TET = 5, SH_SEG = 6 };
 enum { OP_BWD = 0, OP_HELM = 1, OP_IPROD = 2, OP_IPWDB = 3, OP_PHYSDERIV = 4 };
 
 struct Ctx
@@ -1215,6 +1215,102 @@ template <int NM, int NQ, bool DEF> struct PyrOps
     }
 };
 
+// =============================================================== SEG  (coordim 1..3)
+template <int NM, int NQ, bool DEF> struct SegOps
+{
+    static constexpr int nmTot = NM, nqTot = NQ;
+    static void bwd(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        PAR_BLOCKS_BEGIN(c)
+        VecVec tmpIn(nmTot), tmpOut(nqTot);
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            load_interleave(c.in[0] + (size_t)e * nmTot * W, nmTot, tmpIn);
+            BwdTransSegKernel<NM, NQ>(tmpIn, c.bdata[0], tmpOut);
+            deinterleave_store(tmpOut, nqTot, c.out[0] + (size_t)e * nqTot * W);
+        }
+        PAR_BLOCKS_END
+    }
+    static void iprod(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        PAR_BLOCKS_BEGIN(c)
+        VecVec tmpIn(nqTot), tmpOut(nmTot);
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            const vec_t *jac_ptr = DEF ? &c.jac[(size_t)nqTot * e] : &c.jac[e];
+            load_interleave(c.in[0] + (size_t)e * nqTot * W, nqTot, tmpIn);
+            IProductSegKernel<NM, NQ, false, false, DEF>(tmpIn, c.bdata[0], c.w[0], jac_ptr, tmpOut);
+            deinterleave_store(tmpOut, nmTot, c.out[0] + (size_t)e * nmTot * W);
+        }
+        PAR_BLOCKS_END
+    }
+    // PhysDeriv.h:60-250: tensor derivative, then one product per space dimension
+    static void physderiv(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        const int ndf       = c.coordim;
+        const size_t dfSize = DEF ? (size_t)ndf * nqTot : ndf;
+        PAR_BLOCKS_BEGIN(c)
+        VecVec tmpIn(nqTot), d0(nqTot), o(nqTot);
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            const vec_t *df_ptr = &c.df[e * dfSize];
+            load_interleave(c.in[0] + (size_t)e * nqTot * W, nqTot, tmpIn);
+            PhysDerivTensor1DKernel<NQ>(tmpIn, c.D[0], d0);
+            for (int dir = 0; dir < ndf; ++dir)
+            {
+                for (int j = 0; j < NQ; ++j) o[j] = d0[j] * (DEF ? df_ptr[j * ndf + dir] : df_ptr[dir]);
+                deinterleave_store(o, nqTot, c.out[dir] + (size_t)e * nqTot * W);
+            }
+        }
+        PAR_BLOCKS_END
+    }
+    static void helm(Ctx &) {}
+    // IProductWRTDerivBase.h:182-365 (incl. the regular coordim-3 branch reading df[1] twice, :321-323)
+    static void ipwdb(Ctx &c)
+    {
+        constexpr int W = vec_t::width;
+        const int ndf       = c.coordim;
+        const size_t dfSize = DEF ? (size_t)ndf * nqTot : ndf;
+        PAR_BLOCKS_BEGIN(c)
+        VecVec i0(nqTot), i1(nqTot), i2(nqTot), t0(nqTot), tmpOut(nmTot);
+        PAR_FOR
+        for (int e = 0; e < c.nBlocks; ++e)
+        {
+            const vec_t *df_ptr  = &c.df[e * dfSize];
+            const vec_t *jac_ptr = DEF ? &c.jac[(size_t)nqTot * e] : &c.jac[e];
+            load_interleave(c.in[0] + (size_t)e * nqTot * W, nqTot, i0);
+            if (ndf >= 2) load_interleave(c.in[1] + (size_t)e * nqTot * W, nqTot, i1);
+            if (ndf == 3) load_interleave(c.in[2] + (size_t)e * nqTot * W, nqTot, i2);
+            for (int i = 0; i < nqTot; ++i)
+            {
+                vec_t df0 = DEF ? df_ptr[i * ndf] : df_ptr[0];
+                if (ndf == 1)
+                    t0[i] = df0 * i0[i];
+                else if (ndf == 2)
+                {
+                    vec_t df1 = DEF ? df_ptr[i * ndf + 1] : df_ptr[1];
+                    t0[i]     = df0 * i0[i] + df1 * i1[i];
+                }
+                else
+                {
+                    vec_t df1 = DEF ? df_ptr[i * ndf + 1] : df_ptr[1];
+                    vec_t df2 = DEF ? df_ptr[i * ndf + 2] : df_ptr[1];
+                    t0[i]     = df0 * i0[i] + df1 * i1[i] + df2 * i2[i];
+                }
+            }
+            IProductSegKernel<NM, NQ, false, false, DEF>(t0, c.dbdata[0], c.w[0], jac_ptr, tmpOut);
+            deinterleave_store(tmpOut, nmTot, c.out[0] + (size_t)e * nmTot * W);
+        }
+        PAR_BLOCKS_END
+    }
+};
+
 template <class Ops> int run_op(int op, Ctx &c)
 {
     switch (op)
@@ -1246,6 +1342,7 @@ int dispatch_hex(int nm, int nq, int op, bool def, Ctx &c);
 int dispatch_prism(int nm, int nq, int op, bool def, Ctx &c);
 int dispatch_tet(int nm, int nq, int op, bool def, Ctx &c);
 int dispatch_pyr(int nm, int nq, int op, bool def, Ctx &c);
+int dispatch_seg(int nm, int nq, int op, bool def, Ctx &c);
 
 #define X(A, B)                                                                \
     if (nm == A && nq == B) return run_def<OPS, A, B>(op, def, c);
@@ -1261,6 +1358,9 @@ int dispatch_hex(int nm, int nq, int op, bool def, Ctx &c) { REF_PAIRS_HEX(X) re
 #elif defined(REF_TU_SHAPE) && REF_TU_SHAPE == 3
 #define OPS PrismOps
 int dispatch_prism(int nm, int nq, int op, bool def, Ctx &c) { REF_PAIRS_BASE(X) return -3; }
+#elif defined(REF_TU_SHAPE) && REF_TU_SHAPE == 6
+#define OPS SegOps
+int dispatch_seg(int nm, int nq, int op, bool def, Ctx &c) { REF_PAIRS_BASE(X) return -3; }
 #elif defined(REF_TU_SHAPE) && REF_TU_SHAPE == 4
 #define OPS PyrOps
 int dispatch_pyr(int nm, int nq, int op, bool def, Ctx &c) { REF_PAIRS_BASE(X) return -3; }
@@ -1309,17 +1409,30 @@ struct RefHandle
     std::vector<double> pin[3], pout[3];
 };
 
+void *nekref_create2(int op, int shape, int nm, int nq0, int deformed, const double *const *bdata,
+                     const double *const *dbdata, const double *const *D, const double *const *Z,
+                     const double *const *w, const int *blen, const int *nqd, const int *ptype,
+                     int nElmt, const double *jac, const double *df, int coordim);
 void *nekref_create(int op, int shape, int nm, int nq0, int deformed, const double *const *bdata,
                     const double *const *dbdata, const double *const *D, const double *const *Z,
                     const double *const *w, const int *blen, const int *nqd, const int *ptype,
                     int nElmt, const double *jac, const double *df)
 {
+    const int dim = shape == SH_SEG ? 1 : ((shape == SH_QUAD || shape == SH_TRI) ? 2 : 3);
+    return nekref_create2(op, shape, nm, nq0, deformed, bdata, dbdata, D, Z, w, blen, nqd, ptype, nElmt, jac, df, dim);
+}
+// coordim: number of space dimensions (only segments may differ from the element dimension)
+void *nekref_create2(int op, int shape, int nm, int nq0, int deformed, const double *const *bdata,
+                     const double *const *dbdata, const double *const *D, const double *const *Z,
+                     const double *const *w, const int *blen, const int *nqd, const int *ptype,
+                     int nElmt, const double *jac, const double *df, int coordim)
+{
     RefHandle *h = new RefHandle;
     Ctx &c       = h->c;
     constexpr int W = vec_t::width;
     h->op = op; h->shape = shape; h->nm = nm; h->nq0 = nq0; h->deformed = deformed;
-    c.dim     = (shape == SH_QUAD || shape == SH_TRI) ? 2 : 3;
-    c.coordim = c.dim;
+    c.dim     = shape == SH_SEG ? 1 : ((shape == SH_QUAD || shape == SH_TRI) ? 2 : 3);
+    c.coordim = shape == SH_SEG ? coordim : c.dim;
     c.nqTot   = 1;
     for (int d = 0; d < c.dim; ++d) c.nqTot *= nqd[d];
     switch (shape)
@@ -1330,6 +1443,7 @@ void *nekref_create(int op, int shape, int nm, int nq0, int deformed, const doub
         case SH_PRISM: c.nmTot = nm * nm * (nm + 1) / 2; break;
         case SH_TET: c.nmTot = nm * (nm + 1) * (nm + 2) / 6; break;
         case SH_PYR: c.nmTot = nm * (nm + 1) * (2 * nm + 1) / 6; break;
+        case SH_SEG: c.nmTot = nm; break;
         default: delete h; return nullptr;
     }
     for (int d = 0; d < c.dim; ++d)
@@ -1389,8 +1503,8 @@ void *nekref_create(int op, int shape, int nm, int nq0, int deformed, const doub
         case OP_BWD: h->nin = c.nmTot; h->nout = c.nqTot; break;
         case OP_HELM: h->nin = c.nmTot; h->nout = c.nmTot; break;
         case OP_IPROD: h->nin = c.nqTot; h->nout = c.nmTot; break;
-        case OP_IPWDB: h->nin = c.nqTot; h->nout = c.nmTot; h->nins = c.dim; break;
-        case OP_PHYSDERIV: h->nin = c.nqTot; h->nout = c.nqTot; h->nouts = c.dim; break;
+        case OP_IPWDB: h->nin = c.nqTot; h->nout = c.nmTot; h->nins = c.coordim; break;
+        case OP_PHYSDERIV: h->nin = c.nqTot; h->nout = c.nqTot; h->nouts = c.coordim; break;
         default: delete h; return nullptr;
     }
     if (h->nPad != nElmt)
@@ -1427,6 +1541,7 @@ int nekref_run(void *handle, const double *in0, const double *in1, const double 
     const bool def = h->deformed != 0;
     switch (h->shape)
     {
+        case SH_SEG: rc = dispatch_seg(h->nm, h->nq0, h->op, def, c); break;
         case SH_QUAD: rc = dispatch_quad(h->nm, h->nq0, h->op, def, c); break;
         case SH_TRI: rc = dispatch_tri(h->nm, h->nq0, h->op, def, c); break;
         case SH_HEX: rc = dispatch_hex(h->nm, h->nq0, h->op, def, c); break;

@@ -60,6 +60,27 @@ def main():
                 out[key + "_pd%d" % d] = pd[d]
             out[key + "_helm"] = ref.operator(po.OP_HELM, el, NEL, deformed, jac, df)(x, lam=LAMBDA)
             out[key + "_ipwdb"] = ref.operator(po.OP_IPWDB, el, NEL, deformed, jac, df)(f)
+    # segments in 1, 2 and 3 space dimensions (appended last: the random streams above are unchanged)
+    for nm, nq0 in ((4, 5), (7, 8), (5, 8)):
+        for cd in (1, 2, 3):
+            el = po.Elem(po.SEG, nm, nq0, coordim=cd)
+            for deformed in (0, 1):
+                key = "Seg%d_%d_%d_%s" % (cd, nm, nq0, "def" if deformed else "reg")
+                npt = NEL * (el.nqTot if deformed else 1)
+                jac = rng.uniform(0.5, 1.5, npt)
+                df = rng.uniform(-1.5, 1.5, cd * npt)
+                x = rng.uniform(-1, 1, NEL * el.nmTot)
+                f = [rng.uniform(-1, 1, NEL * el.nqTot) for _ in range(cd)]
+                out[key + "_jac"], out[key + "_df"], out[key + "_x"] = jac, df, x
+                for d in range(cd):
+                    out[key + "_f%d" % d] = f[d]
+                out[key + "_bwd"] = ref.operator(po.OP_BWD, el, NEL, deformed, jac, df)(x)
+                out[key + "_iprod"] = ref.operator(po.OP_IPROD, el, NEL, deformed, jac, df)(f[0])
+                pd = ref.operator(po.OP_PHYSDERIV, el, NEL, deformed, jac, df)(f[0])
+                pd = pd if isinstance(pd, list) else [pd]
+                for d in range(cd):
+                    out[key + "_pd%d" % d] = pd[d]
+                out[key + "_ipwdb"] = ref.operator(po.OP_IPWDB, el, NEL, deformed, jac, df)(f)
     np.savez_compressed(os.path.join(HERE, "ref_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

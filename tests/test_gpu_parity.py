@@ -76,7 +76,7 @@ def test_all_shapes_runtime_kernels(shape, nm, nq0, deformed):
 
 
 def golden_cases():
-    return sorted(set(k.rsplit("_", 1)[0] for k in GOLD.files if k.endswith("_x")))
+    return sorted(set(k.rsplit("_", 1)[0] for k in GOLD.files if k.endswith("_x") and not k.startswith("Seg")))
 
 
 @pytest.mark.parametrize("key", golden_cases())
@@ -441,3 +441,42 @@ def test_host_array_pinned_and_pageable_repeated(zero_copy, monkeypatch):
         yh.zero_()
         coll.ApplyOperator(nk.eHelmholtz, xh, yh, factors={nk.eFactorLambda: 2.5})
         assert np.array_equal(yh.numpy(), y)
+
+
+@pytest.mark.parametrize("deformed", [False, True])
+@pytest.mark.parametrize("coordim", [1, 2, 3])
+@pytest.mark.parametrize("nm,nq0", [(2, 3), (4, 5), (7, 8), (11, 12), (5, 8)])
+def test_segment_operators(nm, nq0, coordim, deformed):
+    """1-D elements embedded in 1..3 space dimensions (boundary / trace expansions): every operator the reference
+    registers for eSegment, against the oracle and (where stored) the reference's golden vectors."""
+    nk = nekmf()
+    rng = np.random.default_rng(100 * nm + 10 * coordim + deformed)
+    nel = 1001
+    el = po.Elem(po.SEG, nm, nq0, coordim=coordim)
+    std = nk.StdExpansion(nk.eSegment, nm, nq0, coordim=coordim)
+    assert std.GetNcoeffs() == nm and std.GetTotPoints() == nq0
+    npt = nel * (nq0 if deformed else 1)
+    jac = rng.uniform(0.5, 1.5, npt)
+    df = rng.uniform(-1.5, 1.5, coordim * npt)
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, deformed))
+    x = rng.uniform(-1, 1, nel * nm)
+    f = [rng.uniform(-1, 1, nel * nq0) for _ in range(coordim)]
+    out = np.zeros(nel * nq0)
+    coll.ApplyOperator(nk.eBwdTrans, x, out)
+    check(out, el.bwdtrans(nel, x), "BwdTransSeg")
+    out = np.zeros(nel * nm)
+    coll.ApplyOperator(nk.eIProductWRTBase, f[0], out)
+    check(out, el.iproduct(nel, deformed, jac, f[0]), "IProductSeg")
+    outs = [np.zeros(nel * nq0) for _ in range(coordim)]
+    coll.ApplyOperator(nk.ePhysDeriv, f[0], *outs)
+    check(np.concatenate(outs), np.concatenate(el.physderiv(nel, deformed, df, f[0])), "PhysDerivSeg")
+    if coordim == 3 and not deformed:
+        # the reference multiplies the third input by df[1] here (IProductWRTDerivBase.h:321-323): refused
+        with pytest.raises(nk.NekError, match="not supported"):
+            coll.Initialise(nk.eIProductWRTDerivBase)
+    else:
+        out = np.zeros(nel * nm)
+        coll.ApplyOperator(nk.eIProductWRTDerivBase, *f, out)
+        check(out, el.iproductwrtderivbase(nel, deformed, jac, df, f), "IProductWRTDerivBaseSeg")
+    with pytest.raises(nk.NekError):
+        coll.Initialise(nk.eHelmholtz)  # no (eSegment, eHelmholtz) operator in the reference either
