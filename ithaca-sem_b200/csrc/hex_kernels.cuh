@@ -93,7 +93,11 @@ template <int OP, int NM, int NQ, bool DEF> struct HexCfg
     // work buffers actually live at the same time (the others alias them, see the kernel):
     //   BwdTrans: P1 -> sA, P2 -> sB, P3 -> sU = sA           IProductWRTBase: sU, sA, sB, sC = sA
     static constexpr int NBUF    = OP == HEX_BWD ? 2 : (OP == HEX_IPROD ? 3 : 4);
-    static constexpr bool HASCIN = HexOpTraits<OP>::COEFF_IN;
+    // the coefficient staging block is dropped only for IProductWRTBase; PhysDeriv and IProductWRTDerivBase keep it
+    // although they do not use it: with the smaller footprint more CTAs become resident and both measured
+    // SLOWER (IPWDB nm=5 0.75 -> 1.18 ms, PhysDeriv nm=9 0.58 -> 0.76 ms), the pencil passes being bound by
+    // shared-memory wavefronts, not by latency
+    static constexpr bool HASCIN = OP != HEX_IPROD;
     // doubles of shared memory per element: work buffers + coefficient staging + geometry
     static constexpr int PER_ELMT = NBUF * NQ3 + (HASCIN ? round_up(NM3, 2) : 0) + NGEO * NQ3P;
     static constexpr int SMEM_BUDGET = 100 * 1024; // aim at >= 2 CTAs per SM
@@ -111,7 +115,7 @@ template <int OP, int NM, int NQ, bool DEF> struct HexCfg
     // unrolls into >160 registers, which leaves ONE CTA per SM.  Bound the allocation so that two CTAs are
     // resident (measured: nm=5 1.25 -> 1.15 ms, nm=8 1.74 -> 1.18 ms, nm=11 2.42 -> 1.70 ms; the same bound
     // on IProductWRTDerivBase lost more than it won and is not applied).
-    static constexpr int MINB = (!DEF && OP == HEX_HELM && 2 * SMEM <= 220 * 1024) ? 2 : 1;
+    static constexpr int MINB = (!DEF && OP == HEX_HELM && 2 * SMEM <= 220 * 1024) ? 2 : 0; // 0 = no bound
 };
 
 // y[b] = sum_a M[a*NOUT+b] x[a]          (forward: basis / derivative evaluation)

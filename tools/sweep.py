@@ -31,6 +31,23 @@ def algorithmic_bytes(op, dim, nmTot, nqTot, deformed):
                 "IProductWRTDerivBase": dim * nqTot + nmTot + (ndf + 1) * g}[op]
 
 
+def algorithmic_flops(op, shape, nm, nq):
+    """per element, hexahedra and quadrilaterals with nq = nm + 1, counted on the reference's algorithm
+    (SURVEY.md 8(a)/(d)): sum-factorised passes 2*(nq nm^d-1 ... ) flops, tensor derivatives 2*d*nq^(d+1),
+    pointwise metric work.  None for the collapsed shapes (their pass lengths depend on the mode index)."""
+    if shape == "Hex":
+        sf = 2 * (nq * nm ** 3 + nq ** 2 * nm ** 2 + nq ** 3 * nm)
+        der, pts = 2 * 3 * nq ** 4, nq ** 3
+        return {"BwdTrans": sf, "IProductWRTBase": sf + 3 * pts, "PhysDeriv": der + 15 * pts,
+                "Helmholtz": 5 * sf + der + 50 * pts, "IProductWRTDerivBase": 3 * sf + 24 * pts}[op]
+    if shape == "Quad":
+        sf = 2 * (nq * nm ** 2 + nq ** 2 * nm)
+        der, pts = 2 * 2 * nq ** 3, nq ** 2
+        return {"BwdTrans": sf, "IProductWRTBase": sf + 2 * pts, "PhysDeriv": der + 6 * pts,
+                "Helmholtz": 4 * sf + der + 20 * pts, "IProductWRTDerivBase": 2 * sf + 10 * pts}[op]
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="Hex")
@@ -48,6 +65,7 @@ def main():
               "Pyr": nk.ePyramid, "Tet": nk.eTetrahedron}
     ops = list(OPS) if a.ops == "all" else a.ops.split(",")
     peak, peak_src = bench.measured_peaks()
+    fp64_peak = bench.recorded("fp64_tflops_measured")  # DFMA microbenchmark, profiles/r01_fp64_peak.jsonl
     gen = torch.Generator(device=dev).manual_seed(1234)
     out = open(a.out, "w") if a.out else None
     for sname in a.shapes.split(","):
@@ -100,6 +118,14 @@ def main():
                            "nElmt": nel, "ms": round(ms, 4), "gdof_per_s": round(nel * nmTot / (ms * 1e-3) / 1e9, 2),
                            "bytes_per_element": by, "gb_per_s": round(gbs, 1), "frac_hbm": round(gbs / peak, 3),
                            "kernel": o.kernel_name}
+                    fl = algorithmic_flops(opn, sname, nm, std.nq[0])
+                    if fl is not None and fp64_peak:
+                        tf = fl * nel / (ms * 1e-3) / 1e12
+                        # reference-algorithm flops: a kernel that does LESS work (coefficient-space Helmholtz) can
+                        # exceed 1.0 here; the bound that applies is the larger of the two fractions
+                        rec.update({"flops_per_element_reference_algorithm": fl, "tflops": round(tf, 2),
+                                    "frac_fp64": round(tf / fp64_peak, 3),
+                                    "bound": "fp64" if tf / fp64_peak > gbs / peak else "hbm"})
                     line = json.dumps(rec)
                     print(line, flush=True)
                     if out:
@@ -110,7 +136,7 @@ def main():
                 del coll, geom, jac, df
                 torch.cuda.empty_cache()
     if out:
-        out.write(json.dumps({"hbm_peak_gb_per_s": peak, "peak_source": peak_src}) + "\n")
+        out.write(json.dumps({"hbm_peak_gb_per_s": peak, "peak_source": peak_src, "fp64_peak_tflops": fp64_peak}) + "\n")
         out.close()
 
 
