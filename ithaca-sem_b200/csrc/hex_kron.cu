@@ -20,6 +20,7 @@
 #include "hex_kernels.cuh"
 #include "op_internal.h"
 #include <cmath>
+#include <stdlib.h>
 #include <string.h>
 
 namespace nekmf
@@ -338,6 +339,32 @@ __global__ void __launch_bounds__(KronCfg<NM, GATHER>::T, 1)
 #undef KNZ
 }
 
+} // namespace nekmf
+#include "hex_kron_full.cuh"
+namespace nekmf
+{
+
+// full constant metric of every element for hex_helm_kronfull_kernel
+__global__ void kron_prepare_full_kernel(const double *__restrict__ jac, const double *__restrict__ df, int nElmt,
+                                         double *__restrict__ geo8)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nElmt) return;
+    double f[9];
+#pragma unroll
+    for (int n = 0; n < 9; ++n) f[n] = df[(size_t)n * nElmt + e];
+    const double j = jac[e];
+    double *g      = geo8 + (size_t)e * 8;
+    g[0] = j;
+    g[1] = j * (f[0] * f[0] + f[3] * f[3] + f[6] * f[6]);
+    g[2] = j * (f[1] * f[1] + f[4] * f[4] + f[7] * f[7]);
+    g[3] = j * (f[2] * f[2] + f[5] * f[5] + f[8] * f[8]);
+    g[4] = j * (f[0] * f[1] + f[3] * f[4] + f[6] * f[7]);
+    g[5] = j * (f[0] * f[2] + f[3] * f[5] + f[6] * f[8]);
+    g[6] = j * (f[1] * f[2] + f[4] * f[5] + f[7] * f[8]);
+    g[7] = 0.0;
+}
+
 // G off-diagonal == 0 for every element?  (computed exactly as the quadrature-space kernel would)
 __global__ void kron_prepare_kernel(const double *__restrict__ jac, const double *__restrict__ df, int nElmt,
                                     double *__restrict__ geo4, int *__restrict__ nondiag)
@@ -364,8 +391,13 @@ __global__ void kron_prepare_kernel(const double *__restrict__ jac, const double
 struct KronState
 {
     void *tab      = nullptr;
+    void *tab_full = nullptr; // KronFullTab<NM>
     bool sparse_k  = false;
     double *d_geo4 = nullptr;
+    double *d_geo8 = nullptr; // full constant metric (non-diagonal collections)
+    bool use_full  = false;
+    bool sparse_full = false; // K, M and S all have the modified-basis sparsity patterns
+    int blocks_per_sm_full = 0;
     int blocks_per_sm = 0, blocks_per_sm_gather = 0;
     // the quadrature-space launcher this operator falls back to for non-diagonal metrics
     int (*fallback)(nekmf_op_s *, const double *const in[3], double *const out[3]) = nullptr;
@@ -404,9 +436,36 @@ template <int NM, bool GATHER> static int kron_launch_t(nekmf_op_s *op, KronStat
     return NEKMF_OK;
 }
 
+template <int NM> static int kron_full_launch(nekmf_op_s *op, KronState *st, const double *in, double *out)
+{
+    using Cfg = KronFullCfg<NM>;
+    auto kern = st->sparse_full ? hex_helm_kronfull_kernel<NM, true> : hex_helm_kronfull_kernel<NM, false>;
+    if (st->blocks_per_sm_full == 0)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int nb = 0;
+        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
+        if (nb < 1) { set_error("full-metric kron kernel does not fit on an SM"); return NEKMF_ERR_CUDA; }
+        st->blocks_per_sm_full = nb;
+    }
+    KronFullArgs a;
+    a.in = in; a.out = out; a.geo8 = st->d_geo8 + (size_t)op->run_e0 * 8; a.nElmt = op->run_ne; a.lambda = op->lambda;
+    a.io_aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
+    const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
+    int grid           = st->blocks_per_sm_full * NUM_SMS;
+    if (grid > nBatches) grid = nBatches;
+    if (grid < 1) return NEKMF_OK;
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const KronFullTab<NM> *>(st->tab_full), a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+
 template <int NM> static int kron_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
 {
     KronState *st = static_cast<KronState *>(op->kstate);
+    if (st->use_full && !op->gather_map) return kron_full_launch<NM>(op, st, in[0], out[0]);
     if (!st->use_kron)
     {
         if (op->gather_map) { set_error("fused gather requested from a kernel that does not provide it"); return NEKMF_ERR_ARG; }
@@ -441,12 +500,34 @@ template <int NM> static void kron_wrap(nekmf_op_s *op)
             if (pattern) kmax = std::fmax(kmax, std::fabs(k));
             else koff = std::fmax(koff, std::fabs(k));
         }
+    auto *tabf = new KronFullTab<NM>;
+    memcpy(tabf->Ms, tab->Ms, sizeof(tab->Ms));
+    memcpy(tabf->Ks, tab->Ks, sizeof(tab->Ks));
+    // sparsity patterns the full-metric kernel's sparse variant relies on (hex_kron_full.cuh): entries outside them
+    // must be at round-off level
+    double mmax = 0.0, moff = 0.0, smax = 0.0, soff = 0.0;
+    for (int a = 0; a < NM; ++a)
+        for (int c = 0; c < NM; ++c)
+        {
+            double sv = 0.0;
+            for (int i = 0; i < nq; ++i) sv += dB[a * nq + i] * w[i] * B[c * nq + i];
+            tabf->S[a * NM + c] = sv;
+            const int lo = a < c ? a : c, hi = a < c ? c : a;
+            const bool spat = hi < 2 || (lo < 2 && hi == 2) || (lo >= 2 && hi - lo == 1);
+            const bool mpat = hi < 2 || (lo < 2 && hi <= 3) || (lo >= 2 && (hi - lo) % 2 == 0 && hi - lo <= 2);
+            const double mv = std::fabs(tab->Ms[tri(a, c, NM)]);
+            if (spat) smax = std::fmax(smax, std::fabs(sv)); else soff = std::fmax(soff, std::fabs(sv));
+            if (mpat) mmax = std::fmax(mmax, mv); else moff = std::fmax(moff, mv);
+        }
+    const bool sparse_ms = moff <= 1e-14 * mmax && soff <= 1e-14 * smax;
     // entries outside the (vertex block + diagonal) pattern are quadrature round-off for the modified
     // basis; drop them only when they are at round-off level relative to the matrix
     const bool sparse_k = koff <= 1e-14 * kmax;
     KronState *st      = new KronState;
     st->tab            = tab;
+    st->tab_full       = tabf;
     st->sparse_k       = sparse_k;
+    st->sparse_full    = sparse_k && sparse_ms;
     st->fallback       = op->launch;
     st->fallback_state = op->kstate;
     st->fallback_free  = op->kstate_free;
@@ -456,7 +537,9 @@ template <int NM> static void kron_wrap(nekmf_op_s *op)
         KronState *s = static_cast<KronState *>(p);
         if (s->fallback_state && s->fallback_free) s->fallback_free(s->fallback_state);
         delete static_cast<KronTab<NM> *>(s->tab);
+        delete static_cast<KronFullTab<NM> *>(s->tab_full);
         cudaFree(s->d_geo4);
+        cudaFree(s->d_geo8);
         delete s;
     };
     op->launch = kron_launch<NM>;
@@ -466,6 +549,8 @@ template <int NM> static void kron_wrap(nekmf_op_s *op)
 void kron_maybe_wrap(nekmf_op_s *op)
 {
     if (op->shape != NEKMF_HEX || op->optype != NEKMF_HELMHOLTZ || op->deformed) return;
+    const char *v = getenv("NEKMF_HEX_KRON"); // NEKMF_HEX_KRON=0: quadrature-space kernel only (cross-kernel tests)
+    if (v && v[0] == '0') return;
     switch (op->nm[0])
     {
         case 2: kron_wrap<2>(op); break;
@@ -496,6 +581,20 @@ int kron_geom_changed(nekmf_op_s *op)
     int flag = 1;
     NEKMF_CUDA(cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost));
     cudaFree(d_flag);
+    st->use_full = false;
+    if (flag != 0)
+    {
+        // constant but non-diagonal metric (sheared / rotated affine elements): full-metric coefficient-space kernel
+        if (!st->d_geo8) NEKMF_CUDA(cudaMalloc(&st->d_geo8, (size_t)op->nElmt * 8 * 8));
+        kron_prepare_full_kernel<<<(op->nElmt + 255) / 256, 256>>>(op->d_jac, op->d_df, op->nElmt, st->d_geo8);
+        ++g_launches;
+        NEKMF_CUDA(cudaGetLastError());
+        st->use_full = true;
+        char name[96];
+        snprintf(name, sizeof(name), "hex_helm_kronfull_kernel<nm=%d,%s>(regular,full metric)", op->nm[0],
+                 st->sparse_full ? "sparse" : "dense");
+        op->kname = name;
+    }
     if (flag == 0)
     {
         st->use_kron  = true;

@@ -135,13 +135,17 @@ def test_hex_helmholtz_coefficient_space_kernel(nm, nel):
         coll.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
         check(out, el.helmholtz(nel, False, jac, df, lam, x), "Helmholtz(kron)")
     assert "kron" in coll.m_ops[nk.eHelmholtz].kernel_name
-    # a sheared (non-diagonal metric) collection must NOT take it
+    # a sheared (non-diagonal metric) collection
     jac2, df2 = random_geometry(rng, 3, nel, el.nqTot, False)
     coll2 = nk.Collection(std, nel, nk.CoalescedGeomData(jac2, df2, False))
     out = np.zeros(nel * el.nmTot)
     coll2.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: 1.0})
-    check(out, el.helmholtz(nel, False, jac2, df2, 1.0, x), "Helmholtz(quad-space)")
-    assert "kron" not in coll2.m_ops[nk.eHelmholtz].kernel_name
+    check(out, el.helmholtz(nel, False, jac2, df2, 1.0, x), "Helmholtz(full metric)")
+    # a sheared / rotated affine collection takes the full-metric coefficient-space kernel
+    assert "kronfull" in coll2.m_ops[nk.eHelmholtz].kernel_name
+    for lam in (0.0, 37.5):
+        coll2.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
+        check(out, el.helmholtz(nel, False, jac2, df2, lam, x), "Helmholtz(full metric, lambda %g)" % lam)
 
 
 @pytest.mark.parametrize("nm", [2, 3, 4, 5, 6, 7, 8])
@@ -284,19 +288,30 @@ def test_full_size_properties_hex_p4():
     df = torch.zeros((9, nel), dtype=torch.float64, device="cuda")
     df[0] = df[4] = df[8] = 2 / h
     coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df.reshape(-1), False))
-    # tiny shear on the LAST element only -> metric not exactly diagonal -> quadrature-space kernel
+    # the same collection through the quadrature-space kernel (coefficient-space kernels switched off at creation)
+    os.environ["NEKMF_HEX_KRON"] = "0"
+    try:
+        coll_q = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df.reshape(-1), False))
+        coll_q.Initialise(nk.eHelmholtz)
+    finally:
+        del os.environ["NEKMF_HEX_KRON"]
+    # ... and, with a tiny shear on the LAST element only, through the full-metric coefficient-space kernel
     df2 = df.clone()
     df2[1, -1] = 1e-300
-    coll_q = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df2.reshape(-1), False))
+    coll_f = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df2.reshape(-1), False))
     lam = {nk.eFactorLambda: 1.0}
     Ax, Ay, Axy, Aq = (torch.empty_like(x) for _ in range(4))
     coll.ApplyOperator(nk.eHelmholtz, x, Ax, factors=lam)
     coll.ApplyOperator(nk.eHelmholtz, y, Ay, factors=lam)
     coll.ApplyOperator(nk.eHelmholtz, (2.0 * x - 3.0 * y).contiguous(), Axy, factors=lam)
     coll_q.ApplyOperator(nk.eHelmholtz, x, Aq, factors=lam)
+    Af = torch.empty_like(x)
+    coll_f.ApplyOperator(nk.eHelmholtz, x, Af, factors=lam)
     torch.cuda.synchronize()
-    assert "kron" in coll.m_ops[nk.eHelmholtz].kernel_name
+    assert "hex_helm_kron_kernel" in coll.m_ops[nk.eHelmholtz].kernel_name
     assert "kron" not in coll_q.m_ops[nk.eHelmholtz].kernel_name
+    assert "kronfull" in coll_f.m_ops[nk.eHelmholtz].kernel_name
+    assert float(torch.linalg.vector_norm(Af - Aq)) < 1e-12 * float(torch.linalg.vector_norm(Aq))
     nrm = float(torch.linalg.vector_norm(Ax))
     assert float(torch.linalg.vector_norm(Axy - (2.0 * Ax - 3.0 * Ay))) < 1e-12 * nrm * 5
     assert float(torch.linalg.vector_norm(Ax - Aq)) < 1e-12 * nrm
