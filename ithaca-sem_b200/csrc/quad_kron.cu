@@ -1,5 +1,6 @@
-// quad_kron.cu -- Helmholtz on REGULAR (affine) quadrilaterals whose Laplacian metric is diagonal
-// (axis-aligned rectangles: every structured mesh), evaluated entirely in coefficient space.
+// quad_kron.cu -- Helmholtz on REGULAR (affine) quadrilaterals, evaluated entirely in coefficient space: diagonal
+// Laplacian metric (axis-aligned rectangles: every structured mesh) or full constant metric (sheared / rotated
+// parallelograms, one extra mixed 1-D matrix S).
 //
 // Reference semantics: MatrixFreeOps/Helmholtz.h:138-275 (HelmholtzQuadImpl, DEFORMED=false).  As for the
 // hexahedron (hex_kron.cu) the chain BwdTrans -> lambda*IProduct -> PhysDerivTensor -> G -> 2x IProduct(dbdata)
@@ -27,6 +28,7 @@ template <int NM> struct QKronTab
 {
     double Ms[NM * (NM + 1) / 2]; // upper triangles, both matrices are symmetric
     double Ks[NM * (NM + 1) / 2];
+    double S[NM * NM];            // S[a*NM+b] = sum_i w_i dB_a(i) B_b(i): cross terms of a non-diagonal metric
 };
 __host__ __device__ constexpr int qtri(int a, int b, int n)
 {
@@ -37,7 +39,7 @@ struct QKronArgs
 {
     const double *in;
     double *out;
-    const double *geo4; // [nElmt][4] = J, J*G00, J*G11, 0
+    const double *geo4; // [nElmt][4] = J, J*G00, J*G11, J*G01
     int nElmt;
     int io_aligned; // in and out 16-byte aligned
     double lambda;
@@ -58,7 +60,9 @@ template <int NM> struct QKronCfg
 };
 
 // SPARSEK: K = 2x2 vertex block + diagonal (modified C0 basis), verified numerically at creation
-template <int NM, bool SPARSEK>
+// FULL: the collection has sheared / rotated elements (G01 != 0): the cross term
+//       J G01 (S_pp' S_q'q + S_p'p S_qq') is added (reference: Helmholtz.h:205-230 with constant factors)
+template <int NM, bool SPARSEK, bool FULL>
 __global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
     quad_helm_kron_kernel(const __grid_constant__ QKronTab<NM> tab, const __grid_constant__ QKronArgs args)
 {
@@ -74,6 +78,7 @@ __global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
 #define QM(a, b) tab.Ms[qtri(a, b, NM)]
 #define QK(a, b) tab.Ks[qtri(a, b, NM)]
 #define QNZ(a, b) (!SPARSEK || (a) == (b) || ((a) < 2 && (b) < 2))
+#define QS(a, b) tab.S[(a) * NM + (b)]
 
     const int nElmt = args.nElmt;
     const int nB    = (nElmt + 31) / 32;
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
         {
             double *xe        = buf + lane * ES;
             const double *geo = sGeo + s * Cfg::GEO + lane * 4;
-            const double lamJ = args.lambda * geo[0], jg00 = geo[1], jg11 = geo[2];
+            const double lamJ = args.lambda * geo[0], jg00 = geo[1], jg11 = geo[2], jg01 = geo[3];
             double x[NM][NM]; // x[q][p]
 #pragma unroll
             for (int q = 0; q < NM; ++q)
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
 #pragma unroll
             for (int pp = 0; pp < NM; ++pp)
             {
-                double a[NM], bk[NM];
+                double a[NM], bk[NM], cS[NM], cT[NM];
 #pragma unroll
                 for (int q = 0; q < NM; ++q)
                 {
@@ -152,6 +157,18 @@ __global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
                     bool kset = false;
 #pragma unroll
                     for (int p = 1; p < NM; ++p) m = fma(QM(pp, p), x[q][p], m);
+                    if (FULL)
+                    {
+                        double sS = QS(0, pp) * x[q][0], sT = QS(pp, 0) * x[q][0];
+#pragma unroll
+                        for (int p = 1; p < NM; ++p)
+                        {
+                            sS = fma(QS(p, pp), x[q][p], sS);
+                            sT = fma(QS(pp, p), x[q][p], sT);
+                        }
+                        cS[q] = jg01 * sS;
+                        cT[q] = jg01 * sT;
+                    }
 #pragma unroll
                     for (int p = 0; p < NM; ++p)
                         if (QNZ(pp, p))
@@ -172,6 +189,11 @@ __global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
 #pragma unroll
                     for (int q = 0; q < NM; ++q)
                         if (QNZ(qq, q)) o = fma(QK(qq, q), bk[q], o);
+                    if (FULL)
+                    {
+#pragma unroll
+                        for (int q = 0; q < NM; ++q) o = fma(QS(q, qq), cT[q], fma(QS(qq, q), cS[q], o));
+                    }
                     xe[qq * NM + pp] = o; // the lane's own slot: x is in registers, nobody else reads it
                 }
             }
@@ -200,6 +222,7 @@ __global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
 #undef QM
 #undef QK
 #undef QNZ
+#undef QS
 }
 
 // G01 == 0 for every element?  (computed exactly as the quadrature-space kernel would, Helmholtz.h:205-215)
@@ -215,7 +238,7 @@ __global__ void quad_kron_prepare_kernel(const double *__restrict__ jac, const d
     geo4[(size_t)e * 4 + 0] = j;
     geo4[(size_t)e * 4 + 1] = j * m00;
     geo4[(size_t)e * 4 + 2] = j * m11;
-    geo4[(size_t)e * 4 + 3] = 0.0;
+    geo4[(size_t)e * 4 + 3] = j * m01;
 }
 
 struct QKronState
@@ -230,6 +253,8 @@ struct QKronState
     void (*fallback_free)(void *)                                                  = nullptr;
     std::string fallback_name;
     bool use_kron = false;
+    bool full     = false; // some element has G01 != 0
+    int blocks_per_sm_full = 0;
 };
 
 template <int NM> static int quad_kron_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
@@ -244,21 +269,23 @@ template <int NM> static int quad_kron_launch(nekmf_op_s *op, const double *cons
         return rc;
     }
     using Cfg = QKronCfg<NM>;
-    auto kern = st->sparse_k ? quad_helm_kron_kernel<NM, true> : quad_helm_kron_kernel<NM, false>;
-    if (st->blocks_per_sm == 0)
+    auto kern = st->full ? (st->sparse_k ? quad_helm_kron_kernel<NM, true, true> : quad_helm_kron_kernel<NM, false, true>)
+                         : (st->sparse_k ? quad_helm_kron_kernel<NM, true, false> : quad_helm_kron_kernel<NM, false, false>);
+    int &bps  = st->full ? st->blocks_per_sm_full : st->blocks_per_sm;
+    if (bps == 0)
     {
         NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int nb = 0;
         NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
         if (nb < 1) { set_error("quad kron kernel does not fit on an SM"); return NEKMF_ERR_CUDA; }
-        st->blocks_per_sm = nb;
+        bps = nb;
     }
     QKronArgs a;
     a.in = in[0]; a.out = out[0]; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
     a.io_aligned = ((((uintptr_t)in[0]) | ((uintptr_t)out[0])) & 15) == 0;
     const int nBatches = (op->run_ne + 32 * Cfg::WARPS - 1) / (32 * Cfg::WARPS);
-    int grid           = st->blocks_per_sm * NUM_SMS;
+    int grid           = bps * NUM_SMS;
     if (grid > nBatches) grid = nBatches;
     if (grid < 1) return NEKMF_OK;
     kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const QKronTab<NM> *>(st->tab), a);
@@ -287,6 +314,13 @@ template <int NM> static void quad_kron_wrap(nekmf_op_s *op)
             const bool pattern = a == c || (a < 2 && c < 2);
             if (pattern) kmax = std::fmax(kmax, std::fabs(k));
             else koff = std::fmax(koff, std::fabs(k));
+        }
+    for (int a = 0; a < NM; ++a)
+        for (int c = 0; c < NM; ++c)
+        {
+            double sv = 0.0;
+            for (int i = 0; i < nq; ++i) sv += dB[a * nq + i] * w[i] * B[c * nq + i];
+            tab->S[a * NM + c] = sv;
         }
     QKronState *st     = new QKronState;
     st->tab            = tab;
@@ -345,14 +379,12 @@ int quad_kron_geom_changed(nekmf_op_s *op)
     int flag = 1;
     NEKMF_CUDA(cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost));
     cudaFree(d_flag);
-    if (flag == 0)
-    {
-        st->use_kron = true;
-        char name[96];
-        snprintf(name, sizeof(name), "quad_helm_kron_kernel<nm=%d,%s>(regular,diagonal metric)", op->nm[0],
-                 st->sparse_k ? "sparseK" : "denseK");
-        op->kname = name;
-    }
+    st->use_kron = true;
+    st->full     = flag != 0;
+    char name[96];
+    snprintf(name, sizeof(name), "quad_helm_kron_kernel<nm=%d,%s>(regular,%s metric)", op->nm[0],
+             st->sparse_k ? "sparseK" : "denseK", st->full ? "full" : "diagonal");
+    op->kname = name;
     return NEKMF_OK;
 }
 

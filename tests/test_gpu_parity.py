@@ -153,7 +153,7 @@ def test_hex_helmholtz_coefficient_space_kernel(nm, nel):
 def test_quad_helmholtz_coefficient_space_kernel(nm, nel):
     """Axis-aligned regular quads (diagonal Laplacian metric) take quad_kron.cu: one lane per element, padded
     per-element TMA copies for even nm, one bulk copy per batch for odd nm, ragged last batch, device arrays that
-    are only 8-byte aligned; rotated / sheared elements must fall back to the quadrature-space kernel."""
+    are only 8-byte aligned; rotated / sheared elements take the full-metric variant of the same kernel."""
     torch = _torch()
     nk = nekmf()
     rng = np.random.default_rng(nm * 977 + nel)
@@ -184,8 +184,10 @@ def test_quad_helmholtz_coefficient_space_kernel(nm, nel):
     coll2 = nk.Collection(std, nel, nk.CoalescedGeomData(jac2, df2, False))
     out = np.zeros(nel * el.nmTot)
     coll2.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: 1.0})
-    check(out, el.helmholtz(nel, False, jac2, df2, 1.0, x), "Helmholtz(quad-space)")
-    assert "kron" not in coll2.m_ops[nk.eHelmholtz].kernel_name
+    check(out, el.helmholtz(nel, False, jac2, df2, 1.0, x), "Helmholtz(quad kron, full metric)")
+    assert "full metric" in coll2.m_ops[nk.eHelmholtz].kernel_name
+    coll2.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: 0.0})
+    check(out, el.helmholtz(nel, False, jac2, df2, 0.0, x), "Laplacian(quad kron, full metric)")
 
 
 @pytest.mark.parametrize("nel", [0, 1, 2, 3, 5, 8, 9])
@@ -415,7 +417,10 @@ def test_shape_fast_kernels(shape, nm, deformed):
     nel = {"Quad": 331, "Tri": 331, "Prism": 67, "Tet": 67}[shape]
     coll = run_all_ops(nk, SHAPES[shape], nm, nm + 1, nel, deformed, np.random.default_rng(31 * nm + len(shape)))
     for op in (nk.eBwdTrans, nk.eIProductWRTBase, nk.ePhysDeriv, nk.eHelmholtz):
-        assert "shape_op_kernel" in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
+        # regular quads up to nm = 8 take the coefficient-space Helmholtz kernel (quad_kron.cu, full-metric variant
+        # for this random geometry)
+        want = "quad_helm_kron" if (shape == "Quad" and not deformed and op == nk.eHelmholtz and nm <= 8) else "shape_op_kernel"
+        assert want in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
 
 
 @pytest.mark.parametrize("zero_copy", ["0", "1"])
