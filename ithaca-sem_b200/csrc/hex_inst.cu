@@ -95,12 +95,56 @@ template <int OP, int NM> static int hex_slab_launch(nekmf_op_s *op, const doubl
     NEKMF_CUDA(cudaGetLastError());
     return NEKMF_OK;
 }
+template <int NM> static int hex_pd_slab_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
+{
+    using Cfg = PdSlabCfg<NM>;
+    static int blocks_per_sm = 0;
+    auto kern                = hex_pd_slab_kernel<NM>;
+    if (blocks_per_sm == 0)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int nb = 0;
+        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
+        if (nb < 1) { set_error("hex PhysDeriv slab kernel <%d> does not fit on an SM", NM); return NEKMF_ERR_CUDA; }
+        blocks_per_sm = nb;
+    }
+    PdSlabArgs a;
+    a.in = in[0]; a.out0 = out[0]; a.out1 = out[1]; a.out2 = out[2];
+    a.df = op->d_df + (size_t)op->run_e0;
+    a.dfStride = (size_t)op->nElmt;
+    a.nElmt    = op->run_ne;
+    a.io_aligned = (((uintptr_t)in[0] | (uintptr_t)out[0] | (uintptr_t)out[1] | (uintptr_t)out[2]) & 15) == 0;
+    const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
+    int grid           = blocks_per_sm * NUM_SMS;
+    if (grid > nBatches) grid = nBatches;
+    if (grid < 1) return NEKMF_OK;
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const HexTab<NM, NM + 1> *>(op->kstate), a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
 template <int NM, int NQ> static bool hex_slab_install(nekmf_op_s *op)
 {
     if constexpr (NQ == NM + 1 && NM <= HEX_SLAB_MAX_NM)
     {
         const char *v = getenv("NEKMF_HEX_SLAB"); // NEKMF_HEX_SLAB=0: keep the pencil kernels (A/B comparisons)
         if (v && v[0] == '0') return false;
+        // PhysDeriv slab kernel: only where the quadrature slabs have odd length (even nm) and travel as ONE bulk
+        // copy per batch and output.  With even-length slabs every lane issues its own padded-slot copies (1 load +
+        // 3 stores per slab and batch), and those serialised TMA issues cost more than the pencil kernel's shared-
+        // memory traffic: measured 0.72 -> 0.51 (nm=3) and 0.77 -> 0.64 (nm=5) of the HBM peak, against
+        // 0.70 -> 0.82, 0.77 -> 0.91, 0.55 -> 0.71 for nm = 2, 4, 6.
+        if (op->optype == HEX_PD && !op->deformed && (NM % 2) == 0)
+        {
+            const char *vp = getenv("NEKMF_HEX_PD_SLAB"); // NEKMF_HEX_PD_SLAB=0: pencil kernel
+            if (vp && vp[0] == '0') return false;
+            char pname[96];
+            snprintf(pname, sizeof(pname), "hex_pd_slab_kernel<nm=%d,nq=%d,regular>", NM, NQ);
+            op->kname  = pname;
+            op->launch = hex_pd_slab_launch<NM>;
+            return true;
+        }
         if (op->optype != HEX_BWD && !(op->optype == HEX_IPROD && !op->deformed)) return false;
         char name[96];
         snprintf(name, sizeof(name), "hex_slab_kernel<%s,nm=%d,nq=%d,%s>", op->optype == HEX_BWD ? "bwd" : "iprod", NM, NQ,

@@ -298,4 +298,183 @@ __global__ void __launch_bounds__(SlabCfg<OP, NM>::T, 1)
     tma_store_wait0();
 }
 
+// ------------------------------------------------------------------------------------------------ PhysDeriv
+// PhysDeriv on REGULAR hexahedra (MatrixFreeOps/PhysDerivKernels.hpp:219-372): out_c = sum_d df[3c+d] du/dxi_d.
+// Lane (e,k) owns the quadrature slab u[k][.][.] in registers: the xi_0 and xi_1 derivatives are contractions
+// inside the slab, the xi_2 derivative reads the other slabs of the element from the shared input block (all
+// lanes of an element read the same word: a broadcast, no bank conflict) with the lane's own column D[.][k] held
+// in registers.  No exchange, no barrier; the three results are written to the lane's own slabs of three staging
+// blocks and leave by TMA bulk stores.  Deformed collections keep the pencil kernel (0.9-1.0 of the HBM peak).
+template <int NM> struct PdSlabCfg
+{
+    static constexpr int NQ = NM + 1, NQ2 = NQ * NQ, NQ3 = NQ2 * NQ;
+    static constexpr int EPW = (32 / NQ) >= 2 ? ((32 / NQ) & ~1) : 1;
+    static constexpr bool PPAD = (NQ % 2) == 0;
+    static constexpr int PS = PPAD ? NQ2 + 2 : NQ2, PE = NQ * PS, PBUF = round_up(EPW * PE, 2);
+    static constexpr int PER_WARP = 4 * PBUF + 2;
+    static constexpr int W_FIT  = (216 * 1024) / (PER_WARP * 8);
+    static constexpr int WARPS  = W_FIT >= 12 ? 12 : (W_FIT >= 8 ? 8 : (W_FIT >= 1 ? W_FIT : 1));
+    static constexpr int T      = WARPS * 32;
+    static constexpr size_t SMEM = (size_t)WARPS * PER_WARP * 8 + 16;
+};
+
+struct PdSlabArgs
+{
+    const double *in;
+    double *out0, *out1, *out2;
+    const double *df; // [9][dfStride], regular geometry: one entry per element
+    size_t dfStride;
+    int nElmt;
+    int io_aligned; // in and the three outputs 16-byte aligned
+};
+
+template <int NM>
+__global__ void __launch_bounds__(PdSlabCfg<NM>::T, 1)
+    hex_pd_slab_kernel(const __grid_constant__ HexTab<NM, NM + 1> tab, const __grid_constant__ PdSlabArgs args)
+{
+    using Cfg = PdSlabCfg<NM>;
+    constexpr int NQ = Cfg::NQ, NQ2 = Cfg::NQ2, NQ3 = Cfg::NQ3, EPW = Cfg::EPW, PS = Cfg::PS, PE = Cfg::PE;
+    constexpr bool PPAD = Cfg::PPAD;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *wbase  = reinterpret_cast<double *>(smem_raw) + (size_t)warp * Cfg::PER_WARP;
+    double *sIn    = wbase;
+    double *sO0    = sIn + Cfg::PBUF, *sO1 = sO0 + Cfg::PBUF, *sO2 = sO1 + Cfg::PBUF;
+    uint64_t *bar  = reinterpret_cast<uint64_t *>(sO2 + Cfg::PBUF);
+
+    const int nElmt = args.nElmt;
+    const int nWB   = (nElmt + EPW - 1) / EPW;
+    const int GW    = gridDim.x * Cfg::WARPS;
+    const int gw    = blockIdx.x * Cfg::WARPS + warp;
+    const int e1 = lane / NQ, k1 = lane - e1 * NQ; // lane = (element, slab)
+    const bool lane_on = lane < EPW * NQ;
+    // the lane's column of the collocation derivative matrix: D[k'][k] = dh_k'/dz(z_k)
+    double dcol[NQ];
+#pragma unroll
+    for (int m = 0; m < NQ; ++m) dcol[m] = lane_on ? tab.D[m * NQ + k1] : 0.0;
+
+    if (lane == 0)
+    {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    auto batch_ne = [&](int wb) { int r = nElmt - wb * EPW; return r < EPW ? r : EPW; };
+    auto tma_ok   = [&](int wb) { return args.io_aligned && (PPAD || (((batch_ne(wb) * NQ3) & 1) == 0 && ((wb * EPW * NQ3) & 1) == 0)); };
+    auto issue    = [&](int wb) { // whole warp; the input buffer is free
+        const int ne = batch_ne(wb);
+        if (!tma_ok(wb)) return;
+        const double *src = args.in + (size_t)wb * EPW * NQ3;
+        if (lane == 0)
+        {
+            mbar_expect_tx(bar, (uint32_t)(ne * NQ3 * 8));
+            if (!PPAD) tma_load_1d(sIn, src, (uint32_t)(ne * NQ3 * 8), bar);
+        }
+        __syncwarp();
+        if (PPAD && lane_on && e1 < ne)
+            tma_load_1d(sIn + e1 * PE + k1 * PS, src + (size_t)e1 * NQ3 + k1 * NQ2, (uint32_t)(NQ2 * 8), bar);
+    };
+
+    uint32_t phase = 0;
+    if (gw < nWB) issue(gw);
+    for (int wb = gw; wb < nWB; wb += GW)
+    {
+        const int ne = batch_ne(wb), wbnext = wb + GW;
+        const bool tma = tma_ok(wb);
+        if (!tma)
+        {
+            const double *src = args.in + (size_t)wb * EPW * NQ3;
+            for (int i = lane; i < ne * NQ3; i += 32)
+            {
+                const int e = i / NQ3, w = i - e * NQ3, s = w / NQ2;
+                sIn[e * PE + s * PS + (w - s * NQ2)] = __ldg(src + i);
+            }
+        }
+        else
+        {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        }
+        // the staging blocks must no longer be read by the previous batch's bulk stores
+        tma_store_wait_read0();
+        __syncwarp();
+
+        if (lane_on && e1 < ne)
+        {
+            const double *ue = sIn + e1 * PE; // the element's whole block (slab stride PS)
+            const double *us = ue + k1 * PS;  // the lane's slab
+            double f[9];
+#pragma unroll
+            for (int n = 0; n < 9; ++n) f[n] = __ldg(args.df + (size_t)n * args.dfStride + (size_t)wb * EPW + e1);
+            double u[NQ][NQ];
+#pragma unroll
+            for (int j = 0; j < NQ; ++j)
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) u[j][i] = us[j * NQ + i];
+            double *o0 = sO0 + e1 * PE + k1 * PS, *o1 = sO1 + e1 * PE + k1 * PS, *o2 = sO2 + e1 * PE + k1 * PS;
+#pragma unroll
+            for (int j = 0; j < NQ; ++j)
+            {
+#pragma unroll
+                for (int i = 0; i < NQ; ++i)
+                {
+                    double d0 = tab.D[i] * u[j][0], d1 = tab.D[j] * u[0][i];
+#pragma unroll
+                    for (int m = 1; m < NQ; ++m)
+                    {
+                        d0 = fma(tab.D[m * NQ + i], u[j][m], d0);
+                        d1 = fma(tab.D[m * NQ + j], u[m][i], d1);
+                    }
+                    double d2 = dcol[0] * ue[j * NQ + i];
+#pragma unroll
+                    for (int m = 1; m < NQ; ++m) d2 = fma(dcol[m], ue[m * PS + j * NQ + i], d2);
+                    o0[j * NQ + i] = f[0] * d0 + f[1] * d1 + f[2] * d2;
+                    o1[j * NQ + i] = f[3] * d0 + f[4] * d1 + f[5] * d2;
+                    o2[j * NQ + i] = f[6] * d0 + f[7] * d1 + f[8] * d2;
+                }
+            }
+        }
+        __syncwarp();
+        // every lane has read the whole input block: request the next batch, it lands during the stores
+        if (wbnext < nWB) issue(wbnext);
+        const size_t goff = (size_t)wb * EPW * NQ3;
+        if (tma)
+        {
+            fence_proxy_async();
+            __syncwarp();
+            if (PPAD)
+            {
+                if (lane_on && e1 < ne)
+                {
+                    const size_t so = (size_t)e1 * NQ3 + k1 * NQ2;
+                    const int ss    = e1 * PE + k1 * PS;
+                    tma_store_1d(args.out0 + goff + so, sO0 + ss, (uint32_t)(NQ2 * 8));
+                    tma_store_1d(args.out1 + goff + so, sO1 + ss, (uint32_t)(NQ2 * 8));
+                    tma_store_1d(args.out2 + goff + so, sO2 + ss, (uint32_t)(NQ2 * 8));
+                }
+            }
+            else if (lane == 0)
+            {
+                tma_store_1d(args.out0 + goff, sO0, (uint32_t)(ne * NQ3 * 8));
+                tma_store_1d(args.out1 + goff, sO1, (uint32_t)(ne * NQ3 * 8));
+                tma_store_1d(args.out2 + goff, sO2, (uint32_t)(ne * NQ3 * 8));
+            }
+            tma_store_commit();
+        }
+        else
+        {
+            for (int i = lane; i < ne * NQ3; i += 32)
+            {
+                const int e = i / NQ3, w = i - e * NQ3, s = w / NQ2, a = e * PE + s * PS + (w - s * NQ2);
+                args.out0[goff + i] = sO0[a];
+                args.out1[goff + i] = sO1[a];
+                args.out2[goff + i] = sO2[a];
+            }
+            __syncwarp();
+        }
+    }
+    tma_store_wait0();
+}
+
 } // namespace nekmf
