@@ -36,6 +36,7 @@ struct GenArgs
     int nmTot, nqTot, nElmt, deformed, optype;
     size_t dfStride; // df row stride (whole collection); jac/df already point at this launch's first element
     int N; // doubles per work buffer
+    int groups; // thread groups per CTA (1, 2, 4 or 8); each has 7 work buffers of N doubles
     double lambda;
 };
 
@@ -47,9 +48,17 @@ struct GenCtx
     int *offPQ; // Tet: mode offset of (p,q), running index cpq       (size nm(nm+1)/2 + 1)
                 // Pyr: mode offset of (p,q) at [p*nm+q]              (size nm*nm + 1)
     int *cpqP;  // Tet: cpq offset of p
+    int tid, tg, bar; // thread within its group, group size, named barrier of the group
 };
 
-#define GEN_FOR(idx, n) for (int idx = threadIdx.x; idx < (n); idx += blockDim.x)
+// The CTA is split into thread groups of c.tg threads; every group works on its own element with its own work
+// buffers and synchronises on its own named barrier, so small elements (a quad has 50-150 values per stage) keep
+// all 256 threads busy instead of one group's worth.
+#define GEN_FOR(idx, n) for (int idx = c.tid; idx < (n); idx += c.tg)
+__device__ __forceinline__ void gen_sync(const GenCtx &c)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(c.bar), "r"(c.tg) : "memory");
+}
 
 // ------------------------------------------------------------------------------ BwdTrans
 template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, double *out, double *w1, double *w2)
@@ -65,7 +74,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int p = 0; p < nm; ++p) s = fma(in[q * nm + p], b0[p * nq0 + i], s);
             w1[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
         GEN_FOR(t, nq0 * nq1)
         {
             const int j = t / nq0, i = t - j * nq0;
@@ -73,7 +82,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int q = 0; q < nm; ++q) s = fma(w1[i * nm + q], b1[q * nq1 + j], s);
             out[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
     }
     else if (SHAPE == NEKMF_TRI)
     {
@@ -85,7 +94,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int q = 0; q < nm - p; ++q) s = fma(b1[(m0 + q) * nq1 + e1], in[m0 + q], s);
             w1[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
         GEN_FOR(t, nq0 * nq1)
         {
             const int e1 = t / nq0, e0 = t - e1 * nq0;
@@ -94,7 +103,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             s += (in[1] * b0[nq0 + e0]) * b1[nq1 + e1]; // CORRECT: singular vertex
             out[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
     }
     else if (SHAPE == NEKMF_HEX)
     {
@@ -105,7 +114,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int p = 0; p < nm; ++p) s = fma(in[rq * nm + p], b0[p * nq0 + i], s);
             w1[t] = s; // [i][r][q]
         }
-        __syncthreads();
+        gen_sync(c);
         GEN_FOR(t, nq1 * nq0 * nm)
         {
             const int j = t / (nq0 * nm), ir = t - j * nq0 * nm;
@@ -113,7 +122,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int q = 0; q < nm; ++q) s = fma(w1[ir * nm + q], b1[q * nq1 + j], s);
             w2[t] = s; // [j][i][r]
         }
-        __syncthreads();
+        gen_sync(c);
         GEN_FOR(t, nq0 * nq1 * nq2)
         {
             const int k = t / (nq0 * nq1), ji = t - k * nq0 * nq1;
@@ -121,7 +130,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int r = 0; r < nm; ++r) s = fma(w2[ji * nm + r], b2[r * nq2 + k], s);
             out[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
     }
     else if (SHAPE == NEKMF_PRISM)
     {
@@ -135,7 +144,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int r = 0; r < nm - p; ++r) s = fma(in[m0 + r], b2[(mpr + r) * nq2 + k], s);
             w1[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
         // fp[k][j][p]
         GEN_FOR(t, nq2 * nq1 * nm)
         {
@@ -145,7 +154,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int q = 0; q < nm; ++q) s = fma(w1[(k * nm + p) * nm + q], b1[q * nq1 + j], s);
             w2[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
         GEN_FOR(t, nq0 * nq1 * nq2)
         {
             const int k = t / (nq0 * nq1), ji = t - k * nq0 * nq1;
@@ -157,7 +166,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int q = 0; q < nm; ++q) s = fma(ba2 * b1[q * nq1 + j], ba0 * in[q * nm + 1], s);
             out[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
     }
     else if (SHAPE == NEKMF_PYR)
     {
@@ -170,7 +179,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int r = 0; r < len; ++r) s = fma(in[m0 + r], b2[(m0 + r) * nq2 + k], s);
             w1[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
         // fp[k][j][p]
         GEN_FOR(t, nq2 * nq1 * nm)
         {
@@ -180,7 +189,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int q = 0; q < nm; ++q) s = fma(w1[(k * nm + p) * nm + q], b1[q * nq1 + j], s);
             w2[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
         GEN_FOR(t, nq0 * nq1 * nq2)
         {
             const int k = t / (nq0 * nq1), ji = t - k * nq0 * nq1;
@@ -192,7 +201,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             s = fma(t1 * b2[nq2 + k], in[1], s);
             out[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
     }
     else // TET
     {
@@ -206,7 +215,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int r = 0; r < len; ++r) s = fma(in[m0 + r], b2[(m0 + r) * nq2 + k], s);
             w1[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
         // fp[k][j][p]
         GEN_FOR(t, nq2 * nq1 * nm)
         {
@@ -217,7 +226,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int q = 0; q < nm - p; ++q) s = fma(w1[k * npq + c0 + q], b1[(m1 + q) * nq1 + j], s);
             w2[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
         GEN_FOR(t, nq0 * nq1 * nq2)
         {
             const int k = t / (nq0 * nq1), ji = t - k * nq0 * nq1;
@@ -233,7 +242,7 @@ template <int SHAPE> __device__ void gen_bwd(const GenCtx &c, const double *in, 
             for (int r = 1; r < nm - 1; ++r) s = fma(in[nm + r], e * b2[(r + 1) * nq2 + k], s);
             out[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
     }
 }
 
@@ -255,7 +264,7 @@ __device__ void gen_ip(const GenCtx &c, const double *f, const double *B0, const
             for (int i = 0; i < nq0; ++i) s = fma(f[j * nq0 + i], B0[p * nq0 + i], s);
             w1[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
         if (SHAPE == NEKMF_QUAD)
         {
             GEN_FOR(t, nm * nm)
@@ -283,7 +292,7 @@ __device__ void gen_ip(const GenCtx &c, const double *f, const double *B0, const
                 out[t] = append ? out[t] + s * scale : s * scale;
             }
         }
-        __syncthreads();
+        gen_sync(c);
         return;
     }
     // 3-D: s1[k][j][p]
@@ -294,7 +303,7 @@ __device__ void gen_ip(const GenCtx &c, const double *f, const double *B0, const
         for (int i = 0; i < nq0; ++i) s = fma(f[kj * nq0 + i], B0[p * nq0 + i], s);
         w1[t] = s;
     }
-    __syncthreads();
+    gen_sync(c);
     if (SHAPE == NEKMF_HEX || SHAPE == NEKMF_PRISM || SHAPE == NEKMF_PYR)
     {
         // s2[k][q][p]
@@ -306,7 +315,7 @@ __device__ void gen_ip(const GenCtx &c, const double *f, const double *B0, const
             for (int j = 0; j < nq1; ++j) s = fma(w1[(k * nq1 + j) * nm + p], B1[q * nq1 + j], s);
             w2[t] = s;
         }
-        __syncthreads();
+        gen_sync(c);
         if (SHAPE == NEKMF_HEX)
         {
             GEN_FOR(t, nm * nm * nm)
@@ -361,7 +370,7 @@ __device__ void gen_ip(const GenCtx &c, const double *f, const double *B0, const
                 out[t] = append ? out[t] + s * scale : s * scale;
             }
         }
-        __syncthreads();
+        gen_sync(c);
         return;
     }
     // TET: s2[k][cpq]
@@ -392,7 +401,7 @@ __device__ void gen_ip(const GenCtx &c, const double *f, const double *B0, const
         cc[k] = s;
         c0[k] = s0;
     }
-    __syncthreads();
+    gen_sync(c);
     GEN_FOR(t, c.nmTot)
     {
         // mode -> cpq
@@ -415,7 +424,7 @@ __device__ void gen_ip(const GenCtx &c, const double *f, const double *B0, const
         }
         out[t] = append ? out[t] + s * scale : s * scale;
     }
-    __syncthreads();
+    gen_sync(c);
 }
 
 // f[pt] = in[pt] * jac * w0 w1 w2
@@ -429,7 +438,7 @@ __device__ void gen_weight(const GenCtx &c, const double *in, double *f, const d
         if (dim == 3) w *= c.w[2][k];
         f[t] = in[t] * ((deformed ? __ldg(jac + t) : __ldg(jac)) * w);
     }
-    __syncthreads();
+    gen_sync(c);
 }
 
 // ------------------------------------------------------------------ tensor derivatives
@@ -452,7 +461,7 @@ __device__ void gen_dtensor(const GenCtx &c, int dim, const double *u, double *d
             d2[t] = s2;
         }
     }
-    __syncthreads();
+    gen_sync(c);
 }
 
 #define GDF(n) (deformed ? __ldg(df + (size_t)(n) * dfs + t) : __ldg(df + (size_t)(n) * dfs))
@@ -511,7 +520,7 @@ __device__ void gen_pd_apply(const GenCtx &c, double *d0, double *d1, double *d2
             d2[t] = a * GDF(6) + b * GDF(7) + g * GDF(8);
         }
     }
-    __syncthreads();
+    gen_sync(c);
 }
 
 // ---------------------------------------------------------------------------- Helmholtz metric
@@ -608,7 +617,7 @@ __device__ void gen_metric(const GenCtx &c, double *g0, double *g1, double *g2, 
             g2[t] = m02 * d0 + m12 * d1 + m22 * d2;
         }
     }
-    __syncthreads();
+    gen_sync(c);
 }
 
 // ---------------------------------------------------------------------------- the kernel
@@ -616,14 +625,16 @@ template <int SHAPE> __global__ void __launch_bounds__(256) gen_kernel(const __g
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sTab = reinterpret_cast<double *>(smem_raw);
-    double *buf  = sTab + a.tab_len;
-    const int N  = a.N;
+    const int N  = a.N, G = a.groups, TG = 256 / G;
+    const int grp = threadIdx.x / TG;
+    double *buf  = sTab + a.tab_len + (size_t)grp * 7 * N;
     double *sIn = buf, *sOut = buf + N, *s1 = buf + 2 * N, *s2 = buf + 3 * N, *s3 = buf + 4 * N, *s4 = buf + 5 * N,
            *s5 = buf + 6 * N;
-    int *sInt = reinterpret_cast<int *>(buf + 7 * N);
+    int *sInt = reinterpret_cast<int *>(sTab + a.tab_len + (size_t)G * 7 * N);
     constexpr int dim = (SHAPE == NEKMF_QUAD || SHAPE == NEKMF_TRI) ? 2 : 3;
 
     GenCtx c;
+    c.tid = threadIdx.x - grp * TG; c.tg = TG; c.bar = 1 + grp;
     c.nm = a.nm; c.nq0 = a.nq0; c.nq1 = a.nq1; c.nq2 = dim == 3 ? a.nq2 : 1;
     c.nmTot = a.nmTot; c.nqTot = a.nqTot;
     for (int d = 0; d < 3; ++d)
@@ -677,7 +688,7 @@ template <int SHAPE> __global__ void __launch_bounds__(256) gen_kernel(const __g
     const bool coeff_out = a.optype != NEKMF_BWDTRANS && a.optype != NEKMF_PHYSDERIV;
     const int nin = coeff_in ? nmTot : nqTot, nout = coeff_out ? nmTot : nqTot;
 
-    for (int e = blockIdx.x; e < a.nElmt; e += gridDim.x)
+    for (int e = blockIdx.x * G + grp; e < a.nElmt; e += gridDim.x * G)
     {
         const size_t goff  = deformed ? (size_t)e * nqTot : (size_t)e;
         const double *jac = a.jac ? a.jac + goff : nullptr;
@@ -691,7 +702,7 @@ template <int SHAPE> __global__ void __launch_bounds__(256) gen_kernel(const __g
                 if (dim == 3) s4[t] = __ldg(a.in2 + (size_t)e * nin + t);
             }
         }
-        __syncthreads();
+        gen_sync(c);
         switch (a.optype)
         {
             case NEKMF_BWDTRANS: gen_bwd<SHAPE>(c, sIn, sOut, s1, s2); break;
@@ -775,7 +786,7 @@ template <int SHAPE> __global__ void __launch_bounds__(256) gen_kernel(const __g
                         s3[t]  = t1;
                     }
                 }
-                __syncthreads();
+                gen_sync(c);
                 gen_weight(c, sIn, sIn, jac, deformed, dim);
                 gen_ip<SHAPE>(c, sIn, c.db[0], c.b[1], c.b[2], sOut, 1.0, false, s1, s2);
                 gen_weight(c, s3, s3, jac, deformed, dim);
@@ -797,7 +808,7 @@ template <int SHAPE> __global__ void __launch_bounds__(256) gen_kernel(const __g
                 if (dim == 3) a.out2[(size_t)e * nout + t] = s4[t];
             }
         }
-        __syncthreads();
+        gen_sync(c);
     }
 }
 
@@ -806,6 +817,7 @@ struct GenState
     int N;
     size_t smem;
     int blocks_per_sm;
+    int groups;
 };
 
 template <int SHAPE> static int gen_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
@@ -841,9 +853,10 @@ template <int SHAPE> static int gen_launch(nekmf_op_s *op, const double *const i
         for (int t = 0; t < 5; ++t) a.off[d][t] = op->tab_off[d][t];
     a.nm = op->nm[0]; a.nq0 = op->nq[0]; a.nq1 = op->nq[1]; a.nq2 = op->nq[2];
     a.nmTot = op->nmTot; a.nqTot = op->nqTot; a.nElmt = op->run_ne; a.deformed = op->deformed;
-    a.optype = op->optype; a.N = st->N; a.lambda = op->lambda;
+    a.optype = op->optype; a.N = st->N; a.groups = st->groups; a.lambda = op->lambda;
     int grid = st->blocks_per_sm * NUM_SMS;
-    if (grid > op->run_ne) grid = op->run_ne;
+    const int need = (op->run_ne + st->groups - 1) / st->groups;
+    if (grid > need) grid = need;
     if (grid < 1) return NEKMF_OK;
     kern<<<grid, 256, st->smem, op->run_stream>>>(a);
     ++g_launches;
@@ -860,9 +873,15 @@ bool select_generic(nekmf_op_s *op)
     for (int v : cands)
         if (v > N) N = v;
     N = (N + 1) & ~1;
-    const size_t smem = (size_t)(op->tab_len + 7 * N) * 8 + (size_t)(2 * (nm + 1) + nm * nm + 2) * 4 + 16;
+    // thread groups: as many as keep a group's widest stage (N outputs) busy with at least 32 threads per ~N/4
+    // outputs and fit three CTAs' worth of shared memory
+    int groups = 8;
+    while (groups > 1 && (256 / groups < 32 || N > 4 * (256 / groups) ||
+                          (size_t)(op->tab_len + groups * 7 * N) * 8 > 72 * 1024))
+        groups /= 2;
+    const size_t smem = (size_t)(op->tab_len + groups * 7 * N) * 8 + (size_t)(2 * (nm + 1) + nm * nm + 2) * 4 + 16;
     if (smem > 227 * 1024) return false;
-    GenState *st    = new GenState{N, smem, 0};
+    GenState *st    = new GenState{N, smem, 0, groups};
     op->kstate      = st;
     op->kstate_free = [](void *p) { delete static_cast<GenState *>(p); };
     const char *sn[6] = {"Quad", "Tri", "Hex", "Prism", "Pyr", "Tet"};

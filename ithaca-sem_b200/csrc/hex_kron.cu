@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(KronCfg<NM, GATHER>::T, 1)
 
 } // namespace nekmf
 #include "hex_kron_full.cuh"
+#include "hex_kron_rows.cuh"
 namespace nekmf
 {
 
@@ -397,6 +398,7 @@ struct KronState
     double *d_geo8 = nullptr; // full constant metric (non-diagonal collections)
     bool use_full  = false;
     bool sparse_full = false; // K, M and S all have the modified-basis sparsity patterns
+    bool rows_kind   = false; // nm = 7, 8: row-streaming kernel (diagonal metric only, no fused gather, no full metric)
     int blocks_per_sm_full = 0;
     int blocks_per_sm = 0, blocks_per_sm_gather = 0;
     // the quadrature-space launcher this operator falls back to for non-diagonal metrics
@@ -457,6 +459,43 @@ template <int NM> static int kron_full_launch(nekmf_op_s *op, KronState *st, con
     if (grid > nBatches) grid = nBatches;
     if (grid < 1) return NEKMF_OK;
     kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const KronFullTab<NM> *>(st->tab_full), a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+
+template <int NM> static int kron_rows_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
+{
+    KronState *st = static_cast<KronState *>(op->kstate);
+    if (!st->use_kron || op->gather_map)
+    {
+        if (op->gather_map) { set_error("fused gather requested from a kernel that does not provide it"); return NEKMF_ERR_ARG; }
+        void *saved  = op->kstate;
+        op->kstate   = st->fallback_state;
+        const int rc = st->fallback(op, in, out);
+        op->kstate   = saved;
+        return rc;
+    }
+    using Cfg = KronRowsCfg<NM>;
+    auto kern = hex_helm_kronrows_kernel<NM>;
+    if (st->blocks_per_sm == 0)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int nb = 0;
+        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
+        if (nb < 1) { set_error("row-streaming kron kernel does not fit on an SM"); return NEKMF_ERR_CUDA; }
+        st->blocks_per_sm = nb;
+    }
+    KronArgs a;
+    a.in = in[0]; a.out = out[0]; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
+    a.map = nullptr; a.sign = nullptr;
+    a.io_aligned = ((((uintptr_t)in[0]) | ((uintptr_t)out[0])) & 15) == 0;
+    const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
+    int grid           = st->blocks_per_sm * NUM_SMS;
+    if (grid > nBatches) grid = nBatches;
+    if (grid < 1) return NEKMF_OK;
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const KronTab<NM> *>(st->tab), a);
     ++g_launches;
     NEKMF_CUDA(cudaGetLastError());
     return NEKMF_OK;
@@ -545,6 +584,53 @@ template <int NM> static void kron_wrap(nekmf_op_s *op)
     op->launch = kron_launch<NM>;
 }
 
+// nm = 7, 8: hex_helm_kronrows_kernel.  The kernel has the modified-basis sparsity of M and K compiled in, so the
+// wrap is skipped (quadrature-space kernel stays) when the tables do not show it.
+template <int NM> static void kron_rows_wrap(nekmf_op_s *op)
+{
+    const int nq = op->nq[0];
+    auto *tab    = new KronTab<NM>;
+    const double *B = op->b[0].data(), *dB = op->db[0].data(), *w = op->ws[0].data();
+    double kmax = 0.0, koff = 0.0, mmax = 0.0, moff = 0.0;
+    for (int a = 0; a < NM; ++a)
+        for (int c = a; c < NM; ++c)
+        {
+            double m = 0.0, k = 0.0;
+            for (int i = 0; i < nq; ++i)
+            {
+                m += B[a * nq + i] * w[i] * B[c * nq + i];
+                k += dB[a * nq + i] * w[i] * dB[c * nq + i];
+            }
+            tab->Ms[tri(a, c, NM)] = m;
+            tab->Ks[tri(a, c, NM)] = k;
+            if (rows_knz(a, c)) kmax = std::fmax(kmax, std::fabs(k)); else koff = std::fmax(koff, std::fabs(k));
+            if (rows_mnz(a, c)) mmax = std::fmax(mmax, std::fabs(m)); else moff = std::fmax(moff, std::fabs(m));
+        }
+    if (!(koff <= 1e-14 * kmax && moff <= 1e-14 * mmax))
+    {
+        delete tab;
+        return;
+    }
+    KronState *st      = new KronState;
+    st->tab            = tab;
+    st->sparse_k       = true;
+    st->rows_kind      = true;
+    st->fallback       = op->launch;
+    st->fallback_state = op->kstate;
+    st->fallback_free  = op->kstate_free;
+    st->fallback_name  = op->kname;
+    op->kstate         = st;
+    op->kstate_free    = [](void *p) {
+        KronState *s = static_cast<KronState *>(p);
+        if (s->fallback_state && s->fallback_free) s->fallback_free(s->fallback_state);
+        delete static_cast<KronTab<NM> *>(s->tab);
+        cudaFree(s->d_geo4);
+        delete s;
+    };
+    op->launch = kron_rows_launch<NM>;
+    op->kron   = 1;
+}
+
 // called from select_hex_fast after the quadrature-space launcher is installed
 void kron_maybe_wrap(nekmf_op_s *op)
 {
@@ -558,6 +644,8 @@ void kron_maybe_wrap(nekmf_op_s *op)
         case 4: kron_wrap<4>(op); break;
         case 5: kron_wrap<5>(op); break;
         case 6: kron_wrap<6>(op); break;
+        case 7: kron_rows_wrap<7>(op); return;
+        case 8: kron_rows_wrap<8>(op); return;
         default: return;
     }
     op->kron = 1;
@@ -582,6 +670,17 @@ int kron_geom_changed(nekmf_op_s *op)
     NEKMF_CUDA(cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost));
     cudaFree(d_flag);
     st->use_full = false;
+    if (st->rows_kind)
+    {
+        if (flag == 0)
+        {
+            st->use_kron = true;
+            char name[96];
+            snprintf(name, sizeof(name), "hex_helm_kronrows_kernel<nm=%d>(regular,diagonal metric)", op->nm[0]);
+            op->kname = name;
+        }
+        return NEKMF_OK;
+    }
     if (flag != 0)
     {
         // constant but non-diagonal metric (sheared / rotated affine elements): full-metric coefficient-space kernel
