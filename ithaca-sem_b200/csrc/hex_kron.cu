@@ -398,7 +398,7 @@ struct KronState
     double *d_geo8 = nullptr; // full constant metric (non-diagonal collections)
     bool use_full  = false;
     bool sparse_full = false; // K, M and S all have the modified-basis sparsity patterns
-    bool rows_kind   = false; // nm = 7, 8: row-streaming kernel (diagonal metric only, no fused gather, no full metric)
+    bool rows_kind   = false; // nm = 7..10: row-streaming kernel (diagonal metric only, no fused gather, no full metric)
     int blocks_per_sm_full = 0;
     int blocks_per_sm = 0, blocks_per_sm_gather = 0;
     // the quadrature-space launcher this operator falls back to for non-diagonal metrics
@@ -584,7 +584,7 @@ template <int NM> static void kron_wrap(nekmf_op_s *op)
     op->launch = kron_launch<NM>;
 }
 
-// nm = 7, 8: hex_helm_kronrows_kernel.  The kernel has the modified-basis sparsity of M and K compiled in, so the
+// nm = 7..10: hex_helm_kronrows_kernel.  The kernel has the modified-basis sparsity of M and K compiled in, so the
 // wrap is skipped (quadrature-space kernel stays) when the tables do not show it.
 template <int NM> static void kron_rows_wrap(nekmf_op_s *op)
 {
@@ -646,6 +646,8 @@ void kron_maybe_wrap(nekmf_op_s *op)
         case 6: kron_wrap<6>(op); break;
         case 7: kron_rows_wrap<7>(op); return;
         case 8: kron_rows_wrap<8>(op); return;
+        case 9: kron_rows_wrap<9>(op); return;
+        case 10: kron_rows_wrap<10>(op); return; // nm = 11: two warps of 22 lanes per SM, slower than the pencil kernel
         default: return;
     }
     op->kron = 1;

@@ -1,4 +1,4 @@
-// hex_kron_rows.cuh -- coefficient-space Helmholtz for regular hexahedra with a DIAGONAL metric at nm = 7, 8,
+// hex_kron_rows.cuh -- coefficient-space Helmholtz for regular hexahedra with a DIAGONAL metric at nm = 7..10,
 // where the accumulator blocks of hex_helm_kron_kernel (3 nm^2 doubles per lane) no longer fit the register file.
 // Included by hex_kron.cu.
 //

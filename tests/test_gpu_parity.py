@@ -114,7 +114,7 @@ def box_geometry(nel, hx, hy, hz):
     return jac, df.reshape(-1).copy()
 
 
-@pytest.mark.parametrize("nm", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("nm", [2, 3, 4, 5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("nel", [1, 31, 32, 33, 1000])
 def test_hex_helmholtz_coefficient_space_kernel(nm, nel):
     """axis-aligned boxes (diagonal Laplacian metric) take the Kronecker coefficient-space kernel;
@@ -142,7 +142,7 @@ def test_hex_helmholtz_coefficient_space_kernel(nm, nel):
     coll2.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: 1.0})
     check(out, el.helmholtz(nel, False, jac2, df2, 1.0, x), "Helmholtz(full metric)")
     # a sheared / rotated affine collection takes the full-metric coefficient-space kernel (nm <= 6; above, the
-    # row-streaming kernel of nm = 7, 8 handles diagonal metrics only and the quadrature-space kernel runs)
+    # row-streaming kernel of nm = 7..10 handles diagonal metrics only and the quadrature-space kernel runs)
     assert ("kronfull" in coll2.m_ops[nk.eHelmholtz].kernel_name) == (nm <= 6)
     for lam in (0.0, 37.5):
         coll2.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
