@@ -56,8 +56,8 @@ template <int OP, int NM, int NQ, bool DEF> static int hex_launch(nekmf_op_s *op
 }
 
 // register-slab kernels (hex_slab.cuh) for BwdTrans / IProductWRTBase (regular geometry) with the default
-// quadrature.  Measured against the pencil kernels (fraction of HBM peak, nm = 2..6): BwdTrans .58->.63, .61->.70,
-// .64->.87, .73->.93, .73->.78; IProductWRTBase .50->.78, .66->.65, .69->.83, .77->.80, .64->.72.  From nm = 7 the
+// quadrature.  Measured against the pencil kernels (fraction of HBM peak, nm = 2..6): BwdTrans .58->.86, .61->.70,
+// .64->.93, .73->.93, .73->.83; IProductWRTBase .50->.88, .66->.81, .69->.85, .77->.81, .64->.70.  From nm = 7 the
 // slab (nm^2 doubles plus a line) no longer fits the register file without spilling and the pencil kernels win.
 #ifndef HEX_SLAB_MAX_NM
 #define HEX_SLAB_MAX_NM 6
@@ -130,12 +130,9 @@ template <int NM, int NQ> static bool hex_slab_install(nekmf_op_s *op)
     {
         const char *v = getenv("NEKMF_HEX_SLAB"); // NEKMF_HEX_SLAB=0: keep the pencil kernels (A/B comparisons)
         if (v && v[0] == '0') return false;
-        // PhysDeriv slab kernel: only where the quadrature slabs have odd length (even nm) and travel as ONE bulk
-        // copy per batch and output.  With even-length slabs every lane issues its own padded-slot copies (1 load +
-        // 3 stores per slab and batch), and those serialised TMA issues cost more than the pencil kernel's shared-
-        // memory traffic: measured 0.72 -> 0.51 (nm=3) and 0.77 -> 0.64 (nm=5) of the HBM peak, against
-        // 0.70 -> 0.82, 0.77 -> 0.91, 0.55 -> 0.71 for nm = 2, 4, 6.
-        if (op->optype == HEX_PD && !op->deformed && (NM % 2) == 0)
+        // PhysDeriv slab kernel.  Measured against the pencil kernel (fraction of HBM peak, nm = 2..6): 0.70 -> 0.82,
+        // 0.72 -> 0.81, 0.77 -> 0.91, 0.77 -> 0.73, 0.55 -> 0.72: the pencil kernel is kept at nm = 5.
+        if (op->optype == HEX_PD && !op->deformed && NM != 5)
         {
             const char *vp = getenv("NEKMF_HEX_PD_SLAB"); // NEKMF_HEX_PD_SLAB=0: pencil kernel
             if (vp && vp[0] == '0') return false;

@@ -13,9 +13,10 @@
 //   IProduct : lane (e,k) holds (f J w)[k][.][.], contracts i->p and j->q, scatters v[k][q][p]; lane (e,q) gathers
 //              the k-lines of its (q,.) row and contracts k->r.
 // Every warp is an independent worker (own TMA-fed input buffer, own mbarrier, own bulk stores; no CTA barrier).
-// Slabs whose length is even (coefficient slabs for even nm, quadrature slabs for odd nm) are copied by one bulk
-// copy per slab into slots padded by two doubles, odd-length slabs by one bulk copy per batch: in both cases the
-// lane-strided slab reads are at most 2-way bank conflicted.  Matrix entries are kernel-parameter constants.
+// Slabs whose length is even (coefficient slabs for even nm, quadrature slabs for odd nm) live in slots padded by
+// two doubles, filled by warp-wide 16-byte cp.async copies (inputs) and drained by per-slab bulk stores (BwdTrans)
+// or warp-wide 16-byte stores (IProduct); odd-length slabs travel as one bulk copy per batch.  In both cases the
+// lane-strided slab accesses are at most 2-way bank conflicted.  Matrix entries are kernel-parameter constants.
 #pragma once
 #include "hex_kernels.cuh"
 
@@ -28,6 +29,15 @@ constexpr int slab_pad16(int minimum, int residue) // smallest v >= minimum with
     while (v % 16 != residue % 16) ++v;
     return v;
 }
+
+// 16-byte asynchronous global -> shared copy (LDGSTS.128): one warp-wide instruction moves 512 contiguous bytes
+// into arbitrary 16-byte aligned shared-memory slots -- the way to fill PADDED slab slots without one bulk-copy
+// issue per lane (per-lane cp.async.bulk instructions serialise: ~50 cycles each, measured on the PhysDeriv kernel)
+__device__ __forceinline__ void slab_cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void slab_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int OP, int NM> struct SlabCfg
 {
@@ -99,8 +109,6 @@ __global__ void __launch_bounds__(SlabCfg<OP, NM>::T, 1)
     // stage I lane = (e1, s1): s1 < IN_SLABS ; stage II lane = (e2, s2): s2 < OUT rows
     const int e1 = lane / IN_SLABS, s1 = lane - e1 * IN_SLABS;
     const int e2 = lane / Cfg::ROWS, s2 = lane - e2 * Cfg::ROWS;
-    // bulk-store issuers: lane = (eo, so): so < OUT_SLABS
-    const int eo = lane / OUT_SLABS, so = lane - eo * OUT_SLABS;
 
     if (lane == 0)
     {
@@ -112,18 +120,24 @@ __global__ void __launch_bounds__(SlabCfg<OP, NM>::T, 1)
     auto batch_ne = [&](int wb) { int r = nElmt - wb * EPW; return r < EPW ? r : EPW; };
     auto in_tma   = [&](int wb) { return args.io_aligned && (IN_PAD || (((batch_ne(wb) * IN_EL) & 1) == 0 && ((wb * EPW * IN_EL) & 1) == 0)); };
     auto out_tma  = [&](int wb) { return args.io_aligned && (OUT_PAD || (((batch_ne(wb) * OUT_EL) & 1) == 0 && ((wb * EPW * OUT_EL) & 1) == 0)); };
+    // padded blocks (even-length slabs): shared-memory address of double pair `i2` of a batch
+    auto pad_in  = [&](int i2) { const int e = (2 * i2) / IN_EL, w = 2 * i2 - e * IN_EL, s = w / IN_SLEN; return e * IN_ES + s * IN_SS + (w - s * IN_SLEN); };
+    auto pad_out = [&](int i2) { const int e = (2 * i2) / OUT_EL, w = 2 * i2 - e * OUT_EL, s = w / OUT_SLEN; return e * OUT_ES + s * OUT_SS + (w - s * OUT_SLEN); };
     auto issue    = [&](int wb) { // whole warp; the input buffer is free
         const int ne      = batch_ne(wb);
         if (!in_tma(wb)) return;
         const double *src = args.in + (size_t)wb * EPW * IN_EL;
+        if (IN_PAD)
+        {
+            // warp-wide 16-byte asynchronous copies into the padded slots
+            for (int i2 = lane; i2 < ne * IN_EL / 2; i2 += 32) slab_cp_async16(sIn + pad_in(i2), src + 2 * i2);
+            return;
+        }
         if (lane == 0)
         {
             mbar_expect_tx(bar, (uint32_t)(ne * IN_EL * 8));
-            if (!IN_PAD) tma_load_1d(sIn, src, (uint32_t)(ne * IN_EL * 8), bar);
+            tma_load_1d(sIn, src, (uint32_t)(ne * IN_EL * 8), bar);
         }
-        __syncwarp();
-        if (IN_PAD && e1 < ne && lane < EPW * IN_SLABS)
-            tma_load_1d(sIn + e1 * IN_ES + s1 * IN_SS, src + (size_t)e1 * IN_EL + s1 * IN_SLEN, (uint32_t)(IN_SLEN * 8), bar);
     };
 
     uint32_t phase = 0;
@@ -141,6 +155,8 @@ __global__ void __launch_bounds__(SlabCfg<OP, NM>::T, 1)
                 sIn[e * IN_ES + s * IN_SS + (w - s * IN_SLEN)] = __ldg(src + i);
             }
         }
+        else if (IN_PAD)
+            slab_cp_async_wait_all();
         else
         {
             mbar_wait(bar, phase);
@@ -275,14 +291,27 @@ __global__ void __launch_bounds__(SlabCfg<OP, NM>::T, 1)
         {
             fence_proxy_async();
             __syncwarp();
-            if (OUT_PAD)
+            if (OUT_PAD && BWD)
             {
+                // padded quadrature staging block (nq^3 per element): one bulk store per slab, issued by lane (eo, so)
+                // -- measured faster than warp-wide 16-byte stores here (0.94 vs 0.85 of HBM peak at nm = 5)
+                const int eo = lane / OUT_SLABS, so = lane - eo * OUT_SLABS;
                 if (lane < EPW * OUT_SLABS && eo < ne)
                     tma_store_1d(dst + (size_t)eo * OUT_EL + so * OUT_SLEN, sOut + eo * OUT_ES + so * OUT_SS, (uint32_t)(OUT_SLEN * 8));
+                tma_store_commit();
             }
-            else if (lane == 0)
-                tma_store_1d(dst, sOut, (uint32_t)(ne * OUT_EL * 8));
-            tma_store_commit();
+            else if (OUT_PAD)
+            {
+                // padded coefficient staging block (small): coalesced 16-byte stores by the whole warp
+                for (int i2 = lane; i2 < ne * OUT_EL / 2; i2 += 32)
+                    *reinterpret_cast<double2 *>(dst + 2 * i2) = *reinterpret_cast<const double2 *>(sOut + pad_out(i2));
+                __syncwarp();
+            }
+            else
+            {
+                if (lane == 0) tma_store_1d(dst, sOut, (uint32_t)(ne * OUT_EL * 8));
+                tma_store_commit();
+            }
         }
         else
         {
@@ -362,18 +391,22 @@ __global__ void __launch_bounds__(PdSlabCfg<NM>::T, 1)
 
     auto batch_ne = [&](int wb) { int r = nElmt - wb * EPW; return r < EPW ? r : EPW; };
     auto tma_ok   = [&](int wb) { return args.io_aligned && (PPAD || (((batch_ne(wb) * NQ3) & 1) == 0 && ((wb * EPW * NQ3) & 1) == 0)); };
+    // padded slots (even-length slabs): address of double pair `i2` of a batch in a padded block
+    auto padded = [&](int i2) { const int e = (2 * i2) / NQ3, w = 2 * i2 - e * NQ3, s = w / NQ2; return e * PE + s * PS + (w - s * NQ2); };
     auto issue    = [&](int wb) { // whole warp; the input buffer is free
         const int ne = batch_ne(wb);
         if (!tma_ok(wb)) return;
         const double *src = args.in + (size_t)wb * EPW * NQ3;
+        if (PPAD)
+        {
+            for (int i2 = lane; i2 < ne * NQ3 / 2; i2 += 32) slab_cp_async16(sIn + padded(i2), src + 2 * i2);
+            return;
+        }
         if (lane == 0)
         {
             mbar_expect_tx(bar, (uint32_t)(ne * NQ3 * 8));
-            if (!PPAD) tma_load_1d(sIn, src, (uint32_t)(ne * NQ3 * 8), bar);
+            tma_load_1d(sIn, src, (uint32_t)(ne * NQ3 * 8), bar);
         }
-        __syncwarp();
-        if (PPAD && lane_on && e1 < ne)
-            tma_load_1d(sIn + e1 * PE + k1 * PS, src + (size_t)e1 * NQ3 + k1 * NQ2, (uint32_t)(NQ2 * 8), bar);
     };
 
     uint32_t phase = 0;
@@ -391,6 +424,8 @@ __global__ void __launch_bounds__(PdSlabCfg<NM>::T, 1)
                 sIn[e * PE + s * PS + (w - s * NQ2)] = __ldg(src + i);
             }
         }
+        else if (PPAD)
+            slab_cp_async_wait_all();
         else
         {
             mbar_wait(bar, phase);
@@ -445,14 +480,15 @@ __global__ void __launch_bounds__(PdSlabCfg<NM>::T, 1)
             __syncwarp();
             if (PPAD)
             {
-                if (lane_on && e1 < ne)
+                // padded staging blocks: coalesced 16-byte stores by the whole warp
+                for (int i2 = lane; i2 < ne * NQ3 / 2; i2 += 32)
                 {
-                    const size_t so = (size_t)e1 * NQ3 + k1 * NQ2;
-                    const int ss    = e1 * PE + k1 * PS;
-                    tma_store_1d(args.out0 + goff + so, sO0 + ss, (uint32_t)(NQ2 * 8));
-                    tma_store_1d(args.out1 + goff + so, sO1 + ss, (uint32_t)(NQ2 * 8));
-                    tma_store_1d(args.out2 + goff + so, sO2 + ss, (uint32_t)(NQ2 * 8));
+                    const int a = padded(i2);
+                    *reinterpret_cast<double2 *>(args.out0 + goff + 2 * i2) = *reinterpret_cast<const double2 *>(sO0 + a);
+                    *reinterpret_cast<double2 *>(args.out1 + goff + 2 * i2) = *reinterpret_cast<const double2 *>(sO1 + a);
+                    *reinterpret_cast<double2 *>(args.out2 + goff + 2 * i2) = *reinterpret_cast<const double2 *>(sO2 + a);
                 }
+                __syncwarp();
             }
             else if (lane == 0)
             {
