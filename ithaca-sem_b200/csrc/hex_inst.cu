@@ -124,6 +124,46 @@ template <int NM> static int hex_pd_slab_launch(nekmf_op_s *op, const double *co
     NEKMF_CUDA(cudaGetLastError());
     return NEKMF_OK;
 }
+// the operator's constant tables: HexTab (B, D, w) followed by dbdata for the kernels that want it
+template <int NM, int NQ> struct HexTabX : HexTab<NM, NQ>
+{
+    double dB[NM * NQ];
+};
+
+template <int NM> static int hex_ipwdb_slab_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
+{
+    using Cfg = IpwdbSlabCfg<NM>;
+    static int blocks_per_sm = 0;
+    auto kern                = hex_ipwdb_slab_kernel<NM>;
+    if (blocks_per_sm == 0)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int nb = 0;
+        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
+        if (nb < 1) { set_error("hex IProductWRTDerivBase slab kernel <%d> does not fit on an SM", NM); return NEKMF_ERR_CUDA; }
+        blocks_per_sm = nb;
+    }
+    const auto *tx = static_cast<const HexTabX<NM, NM + 1> *>(op->kstate);
+    SlabDTab<NM> dt;
+    memcpy(dt.dB, tx->dB, sizeof(dt.dB));
+    IpwdbSlabArgs a;
+    a.in0 = in[0]; a.in1 = in[1]; a.in2 = in[2]; a.out = out[0];
+    a.jac = op->d_jac + (size_t)op->run_e0;
+    a.df  = op->d_df + (size_t)op->run_e0;
+    a.dfStride = (size_t)op->nElmt;
+    a.nElmt    = op->run_ne;
+    a.io_aligned = (((uintptr_t)in[0] | (uintptr_t)in[1] | (uintptr_t)in[2] | (uintptr_t)out[0]) & 15) == 0;
+    const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
+    int grid           = blocks_per_sm * NUM_SMS;
+    if (grid > nBatches) grid = nBatches;
+    if (grid < 1) return NEKMF_OK;
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const HexTab<NM, NM + 1> *>(tx), dt, a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+
 template <int NM, int NQ> static bool hex_slab_install(nekmf_op_s *op)
 {
     if constexpr (NQ == NM + 1 && NM <= HEX_SLAB_MAX_NM)
@@ -142,6 +182,18 @@ template <int NM, int NQ> static bool hex_slab_install(nekmf_op_s *op)
             op->launch = hex_pd_slab_launch<NM>;
             return true;
         }
+        // IProductWRTDerivBase slab kernel: 0.47 -> 0.72, 0.55 -> 0.73, 0.55 -> 0.66 of the HBM peak at nm = 2, 3, 4;
+        // at nm = 5, 6 the three passes need more than 255 registers (spills: 0.51 -> 0.43, 0.34 -> 0.21), pencil kept
+        if (op->optype == HEX_IPWDB && !op->deformed && NM <= 4)
+        {
+            const char *vi = getenv("NEKMF_HEX_IPWDB_SLAB"); // NEKMF_HEX_IPWDB_SLAB=0: pencil kernel
+            if (vi && vi[0] == '0') return false;
+            char iname[96];
+            snprintf(iname, sizeof(iname), "hex_ipwdb_slab_kernel<nm=%d,nq=%d,regular>", NM, NQ);
+            op->kname  = iname;
+            op->launch = hex_ipwdb_slab_launch<NM>;
+            return true;
+        }
         if (op->optype != HEX_BWD && !(op->optype == HEX_IPROD && !op->deformed)) return false;
         char name[96];
         snprintf(name, sizeof(name), "hex_slab_kernel<%s,nm=%d,nq=%d,%s>", op->optype == HEX_BWD ? "bwd" : "iprod", NM, NQ,
@@ -155,13 +207,14 @@ template <int NM, int NQ> static bool hex_slab_install(nekmf_op_s *op)
 
 template <int NM, int NQ> static bool hex_install(nekmf_op_s *op)
 {
-    auto *tab = new HexTab<NM, NQ>;
+    auto *tab = new HexTabX<NM, NQ>;
+    memcpy(tab->dB, op->db[0].data(), sizeof(tab->dB));
     memcpy(tab->B, op->b[0].data(), sizeof(tab->B));
     memcpy(tab->D, op->D[0].data(), sizeof(tab->D));
     memcpy(tab->w, op->ws[0].data(), sizeof(tab->w));
     op->kstate      = tab;
     op->geo_pitch   = round_up(NQ * NQ * NQ, 2);
-    op->kstate_free = [](void *p) { delete static_cast<HexTab<NM, NQ> *>(p); };
+    op->kstate_free = [](void *p) { delete static_cast<HexTabX<NM, NQ> *>(p); };
     char name[96];
     const char *opn[5] = {"bwd", "helm", "iprod", "ipwdb", "physderiv"};
     snprintf(name, sizeof(name), "hex_op_kernel<%s,nm=%d,nq=%d,%s>", opn[op->optype], NM, NQ, op->deformed ? "deformed" : "regular");

@@ -514,3 +514,251 @@ __global__ void __launch_bounds__(PdSlabCfg<NM>::T, 1)
 }
 
 } // namespace nekmf
+
+namespace nekmf
+{
+// ------------------------------------------------------------------------------------- IProductWRTDerivBase
+// IProductWRTDerivBase on REGULAR hexahedra (MatrixFreeOps/IProductWRTDerivBase.h:1232-1345):
+//   t_d = sum_c df[3c+d] f_c ,   out = IP(dB,B,B)[t_0] + IP(B,dB,B)[t_1] + IP(B,B,dB)[t_2]   (each weighted by J w).
+// Lane (e,k) makes three passes over its quadrature slab, one per reference direction d: it forms t_d J w for the
+// slab in registers from the three input slabs (shared memory), contracts i->p and j->q with the matrices of that
+// direction, and accumulates into two exchange blocks -- X_B (to be contracted with B along k: d = 0, 1) and X_D
+// (with dB along k: d = 2); it only ever touches its own entries, so no barrier is needed between the passes.
+// Lane (e,q) then contracts k for its row from both blocks.  Same layouts, padding and copy scheme as the
+// IProductWRTBase slab kernel.  Deformed collections keep the pencil kernel (0.8-1.0 of the HBM peak).
+template <int NM> struct IpwdbSlabCfg
+{
+    static constexpr int NQ = NM + 1, NM2 = NM * NM, NM3 = NM2 * NM, NQ2 = NQ * NQ, NQ3 = NQ2 * NQ;
+    static constexpr int EPW = (32 / NQ) >= 2 ? ((32 / NQ) & ~1) : 1;
+    static constexpr bool CPAD = (NM % 2) == 0, PPAD = (NQ % 2) == 0;
+    static constexpr int CS = CPAD ? NM2 + 2 : NM2, CE = NM * CS, CBUF = round_up(EPW * CE, 2);
+    static constexpr int PS = PPAD ? NQ2 + 2 : NQ2, PE = NQ * PS, PBUF = round_up(EPW * PE, 2);
+    static constexpr int LS = (NM * NQ) | 1;             // row q: NM lines (p) of NQ values (k)
+    static constexpr int EX = slab_pad16(NM * LS, NQ);
+    static constexpr int XBUF = round_up(EPW * EX, 2);
+    static constexpr int PER_WARP = 3 * PBUF + 2 * XBUF + CBUF + 2;
+    static constexpr int W_FIT  = (216 * 1024) / (PER_WARP * 8);
+    static constexpr int WARPS  = W_FIT >= 12 ? 12 : (W_FIT >= 8 ? 8 : (W_FIT >= 1 ? W_FIT : 1));
+    static constexpr int T      = WARPS * 32;
+    static constexpr size_t SMEM = (size_t)WARPS * PER_WARP * 8 + 16;
+};
+
+template <int NM> struct SlabDTab
+{
+    double dB[NM * (NM + 1)]; // dbdata[m*NQ+i]
+};
+
+struct IpwdbSlabArgs
+{
+    const double *in0, *in1, *in2;
+    double *out;
+    const double *jac; // [nElmt]
+    const double *df;  // [9][dfStride]
+    size_t dfStride;
+    int nElmt;
+    int io_aligned;
+};
+
+template <int NM>
+__global__ void __launch_bounds__(IpwdbSlabCfg<NM>::T, 1)
+    hex_ipwdb_slab_kernel(const __grid_constant__ HexTab<NM, NM + 1> tab, const __grid_constant__ SlabDTab<NM> dtab,
+                          const __grid_constant__ IpwdbSlabArgs args)
+{
+    using Cfg = IpwdbSlabCfg<NM>;
+    constexpr int NQ = Cfg::NQ, NM2 = Cfg::NM2, NM3 = Cfg::NM3, NQ2 = Cfg::NQ2, NQ3 = Cfg::NQ3, EPW = Cfg::EPW;
+    constexpr int CS = Cfg::CS, CE = Cfg::CE, PS = Cfg::PS, PE = Cfg::PE, LS = Cfg::LS, EX = Cfg::EX;
+    constexpr bool CPAD = Cfg::CPAD, PPAD = Cfg::PPAD;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *wbase  = reinterpret_cast<double *>(smem_raw) + (size_t)warp * Cfg::PER_WARP;
+    double *sF0 = wbase, *sF1 = sF0 + Cfg::PBUF, *sF2 = sF1 + Cfg::PBUF;
+    double *sXB = sF2 + Cfg::PBUF, *sXD = sXB + Cfg::XBUF;
+    double *sOut = sXD + Cfg::XBUF;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sOut + Cfg::CBUF);
+
+    const int nElmt = args.nElmt;
+    const int nWB   = (nElmt + EPW - 1) / EPW;
+    const int GW    = gridDim.x * Cfg::WARPS;
+    const int gw    = blockIdx.x * Cfg::WARPS + warp;
+    const int e1 = lane / NQ, k1 = lane - e1 * NQ; // stage I lane = (element, slab k)
+    const int e2 = lane / NM, q2 = lane - e2 * NM; // stage II lane = (element, row q)
+    if (lane == 0)
+    {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    auto batch_ne = [&](int wb) { int r = nElmt - wb * EPW; return r < EPW ? r : EPW; };
+    auto in_tma   = [&](int wb) { return args.io_aligned && (PPAD || (((batch_ne(wb) * NQ3) & 1) == 0 && ((wb * EPW * NQ3) & 1) == 0)); };
+    auto out_tma  = [&](int wb) { return args.io_aligned && (CPAD || (((batch_ne(wb) * NM3) & 1) == 0 && ((wb * EPW * NM3) & 1) == 0)); };
+    auto pad_in   = [&](int i2) { const int e = (2 * i2) / NQ3, w = 2 * i2 - e * NQ3, s = w / NQ2; return e * PE + s * PS + (w - s * NQ2); };
+    auto pad_out  = [&](int i2) { const int e = (2 * i2) / NM3, w = 2 * i2 - e * NM3, s = w / NM2; return e * CE + s * CS + (w - s * NM2); };
+    auto issue    = [&](int wb) { // whole warp; the three input buffers are free
+        const int ne = batch_ne(wb);
+        if (!in_tma(wb)) return;
+        const size_t off = (size_t)wb * EPW * NQ3;
+        if (PPAD)
+        {
+            for (int i2 = lane; i2 < ne * NQ3 / 2; i2 += 32)
+            {
+                const int a = pad_in(i2);
+                slab_cp_async16(sF0 + a, args.in0 + off + 2 * i2);
+                slab_cp_async16(sF1 + a, args.in1 + off + 2 * i2);
+                slab_cp_async16(sF2 + a, args.in2 + off + 2 * i2);
+            }
+            return;
+        }
+        if (lane == 0)
+        {
+            const uint32_t bytes = (uint32_t)(ne * NQ3 * 8);
+            mbar_expect_tx(bar, 3 * bytes);
+            tma_load_1d(sF0, args.in0 + off, bytes, bar);
+            tma_load_1d(sF1, args.in1 + off, bytes, bar);
+            tma_load_1d(sF2, args.in2 + off, bytes, bar);
+        }
+    };
+
+    uint32_t phase = 0;
+    if (gw < nWB) issue(gw);
+    for (int wb = gw; wb < nWB; wb += GW)
+    {
+        const int ne = batch_ne(wb), wbnext = wb + GW;
+        const bool tin = in_tma(wb), tout = out_tma(wb);
+        if (!tin)
+        {
+            const size_t off = (size_t)wb * EPW * NQ3;
+            for (int i = lane; i < ne * NQ3; i += 32)
+            {
+                const int e = i / NQ3, w = i - e * NQ3, s = w / NQ2, a = e * PE + s * PS + (w - s * NQ2);
+                sF0[a] = __ldg(args.in0 + off + i);
+                sF1[a] = __ldg(args.in1 + off + i);
+                sF2[a] = __ldg(args.in2 + off + i);
+            }
+        }
+        else if (PPAD)
+            slab_cp_async_wait_all();
+        else
+        {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------------------ stage I: lane (e, k), three passes
+        if (lane < EPW * NQ && e1 < ne)
+        {
+            const int so     = e1 * PE + k1 * PS;
+            const size_t eg  = (size_t)wb * EPW + e1;
+            const double jwk = __ldg(args.jac + eg) * tab.w[k1];
+            double *XB = sXB + e1 * EX, *XD = sXD + e1 * EX;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+                const double c0 = __ldg(args.df + (size_t)(0 + d) * args.dfStride + eg);
+                const double c1 = __ldg(args.df + (size_t)(3 + d) * args.dfStride + eg);
+                const double c2 = __ldg(args.df + (size_t)(6 + d) * args.dfStride + eg);
+                double g[NQ][NQ];
+#pragma unroll
+                for (int j = 0; j < NQ; ++j)
+#pragma unroll
+                    for (int i = 0; i < NQ; ++i)
+                    {
+                        const int a = so + j * NQ + i;
+                        g[j][i]     = (c0 * sF0[a] + c1 * sF1[a] + c2 * sF2[a]) * ((jwk * tab.w[j]) * tab.w[i]);
+                    }
+                // matrices of this pass: direction 0 uses dB along i, direction 1 dB along j
+#pragma unroll
+                for (int p = 0; p < NM; ++p)
+                {
+                    double t[NQ];
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j)
+                    {
+                        double s = (d == 0 ? dtab.dB[p * NQ] : tab.B[p * NQ]) * g[j][0];
+#pragma unroll
+                        for (int i = 1; i < NQ; ++i) s = fma(d == 0 ? dtab.dB[p * NQ + i] : tab.B[p * NQ + i], g[j][i], s);
+                        t[j] = s;
+                    }
+#pragma unroll
+                    for (int q = 0; q < NM; ++q)
+                    {
+                        double s = (d == 1 ? dtab.dB[q * NQ] : tab.B[q * NQ]) * t[0];
+#pragma unroll
+                        for (int j = 1; j < NQ; ++j) s = fma(d == 1 ? dtab.dB[q * NQ + j] : tab.B[q * NQ + j], t[j], s);
+                        const int x = q * LS + p * NQ + k1;
+                        if (d == 0) XB[x] = s;
+                        else if (d == 1) XB[x] += s;
+                        else XD[x] = s;
+                    }
+                }
+                asm volatile("" ::: "memory"); // keep the three passes apart: one slab of registers at a time
+            }
+        }
+        __syncwarp();
+        // the input buffers are consumed: request the next batch; the staging block must be free of the previous
+        // batch's bulk store
+        if (wbnext < nWB) issue(wbnext);
+        tma_store_wait_read0();
+        __syncwarp();
+
+        // ------------------------------------------------------------------ stage II: lane (e, q)
+        if (lane < EPW * NM && e2 < ne)
+        {
+            const double *XB = sXB + e2 * EX + q2 * LS, *XD = sXD + e2 * EX + q2 * LS;
+            double *O = sOut + e2 * CE;
+#pragma unroll
+            for (int p = 0; p < NM; ++p)
+            {
+                double vb[NQ], vd[NQ];
+#pragma unroll
+                for (int k = 0; k < NQ; ++k)
+                {
+                    vb[k] = XB[p * NQ + k];
+                    vd[k] = XD[p * NQ + k];
+                }
+#pragma unroll
+                for (int r = 0; r < NM; ++r)
+                {
+                    double s = tab.B[r * NQ] * vb[0];
+#pragma unroll
+                    for (int k = 1; k < NQ; ++k) s = fma(tab.B[r * NQ + k], vb[k], s);
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k) s = fma(dtab.dB[r * NQ + k], vd[k], s);
+                    O[r * CS + q2 * NM + p] = s;
+                }
+            }
+        }
+        double *dst = args.out + (size_t)wb * EPW * NM3;
+        if (tout)
+        {
+            if (CPAD)
+            {
+                __syncwarp();
+                for (int i2 = lane; i2 < ne * NM3 / 2; i2 += 32)
+                    *reinterpret_cast<double2 *>(dst + 2 * i2) = *reinterpret_cast<const double2 *>(sOut + pad_out(i2));
+                __syncwarp();
+            }
+            else
+            {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tma_store_1d(dst, sOut, (uint32_t)(ne * NM3 * 8));
+                tma_store_commit();
+            }
+        }
+        else
+        {
+            __syncwarp();
+            for (int i = lane; i < ne * NM3; i += 32)
+            {
+                const int e = i / NM3, w = i - e * NM3, s = w / NM2;
+                dst[i] = sOut[e * CE + s * CS + (w - s * NM2)];
+            }
+            __syncwarp();
+        }
+    }
+    tma_store_wait0();
+}
+
+} // namespace nekmf
