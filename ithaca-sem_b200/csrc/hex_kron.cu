@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(KronCfg<NM, GATHER>::T, 1)
 } // namespace nekmf
 #include "hex_kron_full.cuh"
 #include "hex_kron_rows.cuh"
+#include "hex_kron_lane.cuh"
 namespace nekmf
 {
 
@@ -400,7 +401,7 @@ struct KronState
     bool sparse_full = false; // K, M and S all have the modified-basis sparsity patterns
     bool rows_kind   = false; // nm = 7..10: row-streaming kernel (diagonal metric only, no fused gather, no full metric)
     int blocks_per_sm_full = 0;
-    int blocks_per_sm = 0, blocks_per_sm_gather = 0;
+    int blocks_per_sm = 0, blocks_per_sm_gather = 0, blocks_per_sm_lane = 0;
     // the quadrature-space launcher this operator falls back to for non-diagonal metrics
     int (*fallback)(nekmf_op_s *, const double *const in[3], double *const out[3]) = nullptr;
     void *fallback_state                                                           = nullptr;
@@ -501,10 +502,44 @@ template <int NM> static int kron_rows_launch(nekmf_op_s *op, const double *cons
     return NEKMF_OK;
 }
 
+// nm <= 3: one lane per element (hex_kron_lane.cuh; 1.06 -> 1.18 and 0.87 -> 0.99 of the HBM copy peak at nm = 2, 3;
+// at nm = 4 only four warps fit an SM and it merely ties); NEKMF_HEX_KRON_LANE=0 keeps the slab-per-lane kernel
+template <int NM> static int kron_lane_launch(nekmf_op_s *op, KronState *st, const double *in, double *out)
+{
+    using Cfg = KronLaneCfg<NM>;
+    auto kern = st->sparse_k ? hex_helm_kronlane_kernel<NM, true> : hex_helm_kronlane_kernel<NM, false>;
+    if (st->blocks_per_sm_lane == 0)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int nb = 0;
+        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
+        if (nb < 1) { set_error("lane-per-element kron kernel does not fit on an SM"); return NEKMF_ERR_CUDA; }
+        st->blocks_per_sm_lane = nb;
+    }
+    KronArgs a;
+    a.in = in; a.out = out; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
+    a.map = nullptr; a.sign = nullptr;
+    a.io_aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
+    const int nBatches = (op->run_ne + 32 * Cfg::WARPS - 1) / (32 * Cfg::WARPS);
+    int grid           = st->blocks_per_sm_lane * NUM_SMS;
+    if (grid > nBatches) grid = nBatches;
+    if (grid < 1) return NEKMF_OK;
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const KronTab<NM> *>(st->tab), a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+
 template <int NM> static int kron_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
 {
     KronState *st = static_cast<KronState *>(op->kstate);
     if (st->use_full && !op->gather_map) return kron_full_launch<NM>(op, st, in[0], out[0]);
+    if constexpr (NM <= 3)
+    {
+        static const bool lane_on = [] { const char *v = getenv("NEKMF_HEX_KRON_LANE"); return !(v && v[0] == '0'); }();
+        if (lane_on && st->use_kron && !op->gather_map) return kron_lane_launch<NM>(op, st, in[0], out[0]);
+    }
     if (!st->use_kron)
     {
         if (op->gather_map) { set_error("fused gather requested from a kernel that does not provide it"); return NEKMF_ERR_ARG; }
