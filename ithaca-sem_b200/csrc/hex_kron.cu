@@ -502,8 +502,8 @@ template <int NM> static int kron_rows_launch(nekmf_op_s *op, const double *cons
     return NEKMF_OK;
 }
 
-// nm <= 3: one lane per element (hex_kron_lane.cuh; 1.06 -> 1.18 and 0.87 -> 0.99 of the HBM copy peak at nm = 2, 3;
-// at nm = 4 only four warps fit an SM and it merely ties); NEKMF_HEX_KRON_LANE=0 keeps the slab-per-lane kernel
+// nm <= 4: one lane per element (hex_kron_lane.cuh; 1.06 -> 1.18, 0.87 -> 0.99, 0.61 -> 0.79 of the HBM copy peak at
+// nm = 2, 3, 4); NEKMF_HEX_KRON_LANE=0 keeps the slab-per-lane kernel
 template <int NM> static int kron_lane_launch(nekmf_op_s *op, KronState *st, const double *in, double *out)
 {
     using Cfg = KronLaneCfg<NM>;
@@ -535,7 +535,7 @@ template <int NM> static int kron_launch(nekmf_op_s *op, const double *const in[
 {
     KronState *st = static_cast<KronState *>(op->kstate);
     if (st->use_full && !op->gather_map) return kron_full_launch<NM>(op, st, in[0], out[0]);
-    if constexpr (NM <= 3)
+    if constexpr (NM <= 4)
     {
         static const bool lane_on = [] { const char *v = getenv("NEKMF_HEX_KRON_LANE"); return !(v && v[0] == '0'); }();
         if (lane_on && st->use_kron && !op->gather_map) return kron_lane_launch<NM>(op, st, in[0], out[0]);

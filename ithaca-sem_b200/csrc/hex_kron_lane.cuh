@@ -1,10 +1,11 @@
-// hex_kron_lane.cuh -- coefficient-space Helmholtz for regular hexahedra with a diagonal metric at nm = 2, 3:
+// hex_kron_lane.cuh -- coefficient-space Helmholtz for regular hexahedra with a diagonal metric at nm = 2, 3, 4:
 // ONE LANE PER ELEMENT.  Included by hex_kron.cu.
 //
 // Same operator as hex_helm_kron_kernel (out = J [ lam MMM + G00 MMK + G11 MKM + G22 KMM ] in).  At these orders an
-// element (8, 27 coefficients; 64 at nm = 4 also compiles but only ties with the slab-per-lane kernel) fits the registers of a single lane, so the whole triple contraction happens
+// element (8, 27, 64 coefficients) fits the registers of a single lane, so the whole triple contraction happens
 // there, one output column p' at a time, with no exchange between lanes and no barrier -- the scheme of
-// quad_kron.cu.  A warp is an independent worker with two 32-element buffers; results are written back into the
+// quad_kron.cu.  A warp is an independent worker with two 32-element buffers (one at nm = 4, where eight warps with a single
+// buffer beat four with two); results are written back into the
 // lane's own slot and leave from there.  Even-sized elements (nm = 2, 4) sit in slots padded by two doubles that
 // are filled by warp-wide 16-byte cp.async copies and drained by warp-wide 16-byte stores; nm = 3 (27 doubles, odd
 // stride, conflict free) travels as one bulk TMA copy per batch each way.
@@ -20,7 +21,10 @@ template <int NM> struct KronLaneCfg
     static constexpr int ES       = PADDED ? NM3 + 2 : NM3;
     static constexpr int BUF      = round_up(32 * ES, 2);
     static constexpr int GEO      = 32 * 4;
-    static constexpr int PER_WARP = 2 * BUF + 2 * GEO + 2;
+    // two buffers (the next batch lands while this one is computed) as long as >= 8 warps still fit; at nm = 4 a
+    // single buffer and three times the warps hide the latency instead
+    static constexpr bool DBUF    = (2 * BUF + 2 * GEO + 2) * 8 * 8 <= 200 * 1024;
+    static constexpr int PER_WARP = (DBUF ? 2 : 1) * (BUF + GEO) + 2;
     static constexpr int W_FIT    = (200 * 1024) / (PER_WARP * 8);
     static constexpr int WARPS    = W_FIT >= 16 ? 16 : (W_FIT >= 12 ? 12 : (W_FIT >= 8 ? 8 : (W_FIT >= 4 ? 4 : 1)));
     static constexpr int T        = WARPS * 32;
@@ -44,9 +48,11 @@ __global__ void __launch_bounds__(KronLaneCfg<NM>::T, 1)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *wbase  = reinterpret_cast<double *>(smem_raw) + (size_t)warp * Cfg::PER_WARP;
-    double *sBuf   = wbase;               // [2][BUF]
-    double *sGeo   = wbase + 2 * BUF;     // [2][GEO]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sGeo + 2 * Cfg::GEO); // [2]
+    constexpr bool DBUF = Cfg::DBUF;
+    constexpr int NB    = DBUF ? 2 : 1;
+    double *sBuf   = wbase;                // [NB][BUF]
+    double *sGeo   = wbase + NB * BUF;     // [NB][GEO]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sGeo + NB * Cfg::GEO); // [2]
 #define LM(a, b) tab.Ms[tri(a, b, NM)]
 #define LK(a, b) tab.Ks[tri(a, b, NM)]
 #define LNZ(a, b) (!SPARSEK || (a) == (b) || ((a) < 2 && (b) < 2))
@@ -84,14 +90,22 @@ __global__ void __launch_bounds__(KronLaneCfg<NM>::T, 1)
     };
 
     uint32_t phase[2] = {0u, 0u};
-    if (gw < nB) issue(gw, 0);
+    if (DBUF && gw < nB) issue(gw, 0);
     int it = 0;
     for (int b = gw; b < nB; b += GW, ++it)
     {
-        const int s = it & 1, ne = batch_ne(b), bnext = b + GW;
+        const int s = DBUF ? (it & 1) : 0, ne = batch_ne(b), bnext = b + GW;
         const bool fast = fast_ok(b);
         double *buf     = sBuf + s * BUF;
-        if (bnext < nB)
+        if (!DBUF)
+        {
+            // single buffer: it was drained at the end of the previous iteration
+            tma_store_wait_read0();
+            __syncwarp();
+            issue(b, 0);
+            if (PADDED) lane_cp_async_wait<0>();
+        }
+        else if (bnext < nB)
         {
             // the other buffer was drained by the previous iteration (bulk store: wait until it has been read)
             tma_store_wait_read0();
