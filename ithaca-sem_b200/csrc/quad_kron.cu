@@ -12,9 +12,9 @@
 // kernel-parameter constants (uniform-register operands of every DFMA), one output column at a time is formed
 // and written back into the lane's own shared-memory slot -- no exchange between lanes, no barrier.  A warp is
 // an independent worker with two TMA-fed 32-element buffers: the next batch lands while the current one is
-// computed, results leave by TMA bulk stores.  Even nm: one bulk copy per element into a padded slot (stride
-// nm^2+2 doubles: 2-way bank conflicts instead of up to 16-way); odd nm: one bulk copy per batch (stride nm^2 is
-// odd: conflict free).
+// computed.  Even nm: padded slots (stride nm^2+2 doubles: 2-way bank conflicts instead of up to 16-way) filled by
+// warp-wide 16-byte cp.async copies and drained by warp-wide 16-byte stores; odd nm: one bulk TMA copy per batch
+// each way (stride nm^2 is odd: conflict free).
 #include "hex_kernels.cuh"
 #include "op_internal.h"
 #include <cmath>
@@ -59,6 +59,13 @@ template <int NM> struct QKronCfg
     static constexpr size_t SMEM  = (size_t)WARPS * PER_WARP * 8 + 16;
 };
 
+__device__ __forceinline__ void q_cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void q_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void q_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // SPARSEK: K = 2x2 vertex block + diagonal (modified C0 basis), verified numerically at creation
 // FULL: the collection has sheared / rotated elements (G01 != 0): the cross term
 //       J G01 (S_pp' S_q'q + S_p'p S_qq') is added (reference: Helmholtz.h:205-230 with constant factors)
@@ -95,6 +102,9 @@ __global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
     auto batch_ne = [&](int b) { int r = nElmt - b * 32; return r < 32 ? r : 32; };
     // TMA eligibility of a batch: 16-byte aligned arrays and (unpadded layout) an even number of doubles
     auto tma_ok = [&](int b) { return args.io_aligned && (PADDED || ((batch_ne(b) * NM2) & 1) == 0); };
+    // padded slots (even nm): address of double pair i2 of a batch; filled by warp-wide 16-byte cp.async copies
+    // (one cp.async.bulk per lane serialises at ~50 cycles per issue) and drained by warp-wide 16-byte stores
+    auto padded = [&](int i2) { const int e = (2 * i2) / NM2; return e * ES + (2 * i2 - e * NM2); };
     auto issue  = [&](int b, int s) { // whole warp
         const int ne    = batch_ne(b);
         const bool tma  = tma_ok(b);
@@ -102,12 +112,13 @@ __global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
         const double *g = args.in + (size_t)b * 32 * NM2;
         if (lane == 0)
         {
-            mbar_expect_tx(&bars[s], (uint32_t)(ne * 32 + (tma ? ne * NM2 * 8 : 0)));
+            mbar_expect_tx(&bars[s], (uint32_t)(ne * 32 + ((tma && !PADDED) ? ne * NM2 * 8 : 0)));
             tma_load_1d(sGeo + s * Cfg::GEO, args.geo4 + (size_t)b * 32 * 4, (uint32_t)(ne * 32), &bars[s]);
             if (tma && !PADDED) tma_load_1d(dst, g, (uint32_t)(ne * NM2 * 8), &bars[s]);
         }
-        __syncwarp();
-        if (tma && PADDED && lane < ne) tma_load_1d(dst + lane * ES, g + (size_t)lane * NM2, (uint32_t)(NM2 * 8), &bars[s]);
+        if (tma && PADDED)
+            for (int i2 = lane; i2 < ne * NM2 / 2; i2 += 32) q_cp_async16(dst + padded(i2), g + 2 * i2);
+        if (PADDED) q_cp_async_commit(); // one group per issue, even when empty
     };
 
     uint32_t phase[2] = {0u, 0u};
@@ -125,7 +136,10 @@ __global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
             tma_store_wait_read0();
             __syncwarp();
             issue(bnext, s ^ 1);
+            if (PADDED) q_cp_async_wait<1>(); // everything but the group just issued has landed
         }
+        else if (PADDED)
+            q_cp_async_wait<0>();
         if (!tma)
         {
             const double *g = args.in + (size_t)b * 32 * NM2;
@@ -205,11 +219,15 @@ __global__ void __launch_bounds__(QKronCfg<NM>::T, 1)
             __syncwarp();
             if (PADDED)
             {
-                if (lane < ne) tma_store_1d(dstg + (size_t)lane * NM2, buf + lane * ES, (uint32_t)(NM2 * 8));
+                for (int i2 = lane; i2 < ne * NM2 / 2; i2 += 32)
+                    *reinterpret_cast<double2 *>(dstg + 2 * i2) = *reinterpret_cast<const double2 *>(buf + padded(i2));
+                __syncwarp();
             }
-            else if (lane == 0)
-                tma_store_1d(dstg, buf, (uint32_t)(ne * NM2 * 8));
-            tma_store_commit();
+            else
+            {
+                if (lane == 0) tma_store_1d(dstg, buf, (uint32_t)(ne * NM2 * 8));
+                tma_store_commit();
+            }
         }
         else
         {
