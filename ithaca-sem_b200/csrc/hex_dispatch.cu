@@ -42,6 +42,7 @@ SHP_DECL(2) SHP_DECL(3) SHP_DECL(4) SHP_DECL(5) SHP_DECL(6) SHP_DECL(7) SHP_DECL
 bool select_shape_fast(nekmf_op_s *op)
 {
     if (op->shape == NEKMF_HEX || op->shape == NEKMF_PYR) return false;
+    if (select_quad_lane(op)) return true; // BwdTrans / IProductWRTBase / regular PhysDeriv on quads: one lane per element
     bool ok = false;
     switch (op->nm[0])
     {

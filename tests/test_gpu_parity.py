@@ -420,7 +420,12 @@ def test_shape_fast_kernels(shape, nm, deformed):
     for op in (nk.eBwdTrans, nk.eIProductWRTBase, nk.ePhysDeriv, nk.eHelmholtz):
         # regular quads up to nm = 8 take the coefficient-space Helmholtz kernel (quad_kron.cu, full-metric variant
         # for this random geometry)
-        want = "quad_helm_kron" if (shape == "Quad" and not deformed and op == nk.eHelmholtz and nm <= 8) else "shape_op_kernel"
+        want = "shape_op_kernel"
+        if shape == "Quad" and nm <= 8:
+            if op == nk.eHelmholtz:
+                want = "quad_helm_kron" if not deformed else "shape_op_kernel"
+            elif nm <= 7 and not (op == nk.ePhysDeriv and deformed):
+                want = "quad_lane_kernel"  # one lane per element (quad_lane.cu)
         assert want in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
 
 
