@@ -1,4 +1,5 @@
-// quad_lane.cu -- BwdTrans, IProductWRTBase and PhysDeriv on quadrilaterals with ONE LANE PER ELEMENT.
+// quad_lane.cu -- BwdTrans, IProductWRTBase, PhysDeriv and (regular) IProductWRTDerivBase on quadrilaterals with ONE
+// LANE PER ELEMENT.
 //
 // Reference semantics: MatrixFreeOps/BwdTransKernels.hpp:35-76, IProductKernels.hpp:76-133,
 // PhysDerivKernels.hpp:39-90 + PhysDeriv.h (Quad): out_0 = df0 d0 + df1 d1, out_1 = df2 d0 + df3 d1.
@@ -18,18 +19,20 @@
 namespace nekmf
 {
 
-enum { QL_BWD = 0, QL_IPROD = 1, QL_PD = 2 };
+enum { QL_BWD = 0, QL_IPROD = 1, QL_PD = 2, QL_IPWDB = 3 };
 
 template <int NM> struct QLaneTab
 {
     double B[NM * (NM + 1)];       // bdata[m*NQ+i]
     double D[(NM + 1) * (NM + 1)]; // D[k*NQ+i] = dh_k/dz(z_i)
     double w[NM + 1];
+    double dB[NM * (NM + 1)];      // dbdata[m*NQ+i] (IProductWRTDerivBase)
 };
 
 struct QLaneArgs
 {
     const double *in;
+    const double *in1; // second input (IProductWRTDerivBase)
     double *out0, *out1;
     const double *jac; // [nElmt] | [nElmt][nq^2]
     const double *df;  // [4][dfStride] (regular)
@@ -42,10 +45,10 @@ template <int OP, int NM, bool DEF> struct QLaneCfg
 {
     static constexpr int NQ = NM + 1, NM2 = NM * NM, NQ2 = NQ * NQ;
     static constexpr int INL  = OP == QL_BWD ? NM2 : NQ2; // doubles per element, input side
-    static constexpr int OUTL = OP == QL_IPROD ? NM2 : NQ2;
+    static constexpr int OUTL = (OP == QL_IPROD || OP == QL_IPWDB) ? NM2 : NQ2;
     static constexpr bool INPAD = (INL % 2) == 0, OUTPAD = (OUTL % 2) == 0;
     static constexpr int INS  = INPAD ? INL + 2 : INL, OUTS = OUTPAD ? OUTL + 2 : OUTL;
-    static constexpr int NIN  = 1 + ((OP == QL_IPROD && DEF) ? 1 : 0);
+    static constexpr int NIN  = 1 + (((OP == QL_IPROD && DEF) || OP == QL_IPWDB) ? 1 : 0);
     static constexpr int NOUT = OP == QL_PD ? 2 : 1;
     static constexpr int INB  = round_up(32 * INS, 2), OUTB = round_up(32 * OUTS, 2);
     static constexpr int PER_WARP = NIN * INB + NOUT * OUTB + 2;
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(QLaneCfg<OP, NM, DEF>::T, 1)
             {
                 const int a = pad_in(i2);
                 ql_cp_async16(sIn + a, args.in + ioff + 2 * i2);
-                if (Cfg::NIN == 2) ql_cp_async16(sJac + a, args.jac + ioff + 2 * i2);
+                if (Cfg::NIN == 2) ql_cp_async16(sJac + a, (OP == QL_IPWDB ? args.in1 : args.jac) + ioff + 2 * i2);
             }
             ql_cp_async_wait_all();
         }
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(QLaneCfg<OP, NM, DEF>::T, 1)
                 const uint32_t bytes = (uint32_t)(ne * INL * 8);
                 mbar_expect_tx(bar, bytes * Cfg::NIN);
                 tma_load_1d(sIn, args.in + ioff, bytes, bar);
-                if (Cfg::NIN == 2) tma_load_1d(sJac, args.jac + ioff, bytes, bar);
+                if (Cfg::NIN == 2) tma_load_1d(sJac, (OP == QL_IPWDB ? args.in1 : args.jac) + ioff, bytes, bar);
             }
             mbar_wait(bar, phase);
             phase ^= 1;
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(QLaneCfg<OP, NM, DEF>::T, 1)
             {
                 const int a = (i / INL) * INS + (i % INL);
                 sIn[a]      = __ldg(args.in + ioff + i);
-                if (Cfg::NIN == 2) sJac[a] = __ldg(args.jac + ioff + i);
+                if (Cfg::NIN == 2) sJac[a] = __ldg((OP == QL_IPWDB ? args.in1 : args.jac) + ioff + i);
             }
         }
         __syncwarp();
@@ -202,6 +205,49 @@ __global__ void __launch_bounds__(QLaneCfg<OP, NM, DEF>::T, 1)
 #pragma unroll
                         for (int j = 1; j < NQ; ++j) s = fma(tab.B[q * NQ + j], t[j], s);
                         o0[q * NM + p] = s;
+                    }
+                }
+            }
+            else if (OP == QL_IPWDB)
+            {
+                // IProductWRTDerivBase.h:542-660 (regular): t_d = df[d] f_0 + df[2+d] f_1, out = IP(dB,B)[t_0] + IP(B,dB)[t_1]
+                const double *ye = sJac + lane * INS; // second input
+                const double jr  = __ldg(args.jac + eg);
+                const double f0 = __ldg(args.df + eg), f1 = __ldg(args.df + args.dfStride + eg),
+                             f2 = __ldg(args.df + 2 * args.dfStride + eg), f3 = __ldg(args.df + 3 * args.dfStride + eg);
+#pragma unroll
+                for (int d = 0; d < 2; ++d)
+                {
+                    double g[NQ][NQ];
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j)
+#pragma unroll
+                        for (int i = 0; i < NQ; ++i)
+                        {
+                            const double t = (d == 0 ? f0 : f1) * xe[j * NQ + i] + (d == 0 ? f2 : f3) * ye[j * NQ + i];
+                            g[j][i]        = t * (jr * (tab.w[j] * tab.w[i]));
+                        }
+#pragma unroll
+                    for (int p = 0; p < NM; ++p)
+                    {
+                        double t[NQ];
+#pragma unroll
+                        for (int j = 0; j < NQ; ++j)
+                        {
+                            double s = (d == 0 ? tab.dB[p * NQ] : tab.B[p * NQ]) * g[j][0];
+#pragma unroll
+                            for (int i = 1; i < NQ; ++i) s = fma(d == 0 ? tab.dB[p * NQ + i] : tab.B[p * NQ + i], g[j][i], s);
+                            t[j] = s;
+                        }
+#pragma unroll
+                        for (int q = 0; q < NM; ++q)
+                        {
+                            double s = (d == 1 ? tab.dB[q * NQ] : tab.B[q * NQ]) * t[0];
+#pragma unroll
+                            for (int j = 1; j < NQ; ++j) s = fma(d == 1 ? tab.dB[q * NQ + j] : tab.B[q * NQ + j], t[j], s);
+                            if (d == 0) o0[q * NM + p] = s;
+                            else o0[q * NM + p] += s;
+                        }
                     }
                 }
             }
@@ -284,7 +330,7 @@ template <int OP, int NM, bool DEF> static int quad_lane_launch(nekmf_op_s *op, 
         blocks_per_sm = nb;
     }
     QLaneArgs a;
-    a.in = in[0]; a.out0 = out[0]; a.out1 = out[1];
+    a.in = in[0]; a.in1 = in[1]; a.out0 = out[0]; a.out1 = out[1];
     const size_t gstep = DEF ? (size_t)op->nqTot : 1;
     a.jac = op->d_jac ? op->d_jac + (size_t)op->run_e0 * gstep : nullptr;
     a.df  = op->d_df ? op->d_df + (size_t)op->run_e0 * gstep : nullptr;
@@ -293,6 +339,7 @@ template <int OP, int NM, bool DEF> static int quad_lane_launch(nekmf_op_s *op, 
     uintptr_t al = (uintptr_t)in[0] | (uintptr_t)out[0];
     if (OP == QL_PD) al |= (uintptr_t)out[1];
     if (OP == QL_IPROD && DEF) al |= (uintptr_t)a.jac;
+    if (OP == QL_IPWDB) al |= (uintptr_t)in[1];
     a.io_aligned = (al & 15) == 0;
     const int nBatches = (op->run_ne + 32 * Cfg::WARPS - 1) / (32 * Cfg::WARPS);
     int grid           = blocks_per_sm * NUM_SMS;
@@ -310,20 +357,23 @@ template <int NM> static bool quad_lane_install(nekmf_op_s *op)
     if (op->optype == NEKMF_BWDTRANS) kind = QL_BWD;
     else if (op->optype == NEKMF_IPRODUCTWRTBASE) kind = QL_IPROD;
     else if (op->optype == NEKMF_PHYSDERIV && !op->deformed) kind = QL_PD;
+    else if (op->optype == NEKMF_IPRODUCTWRTDERIVBASE && !op->deformed) kind = QL_IPWDB;
     if (kind < 0) return false;
     auto *tab = new QLaneTab<NM>;
     memcpy(tab->B, op->b[0].data(), sizeof(tab->B));
     memcpy(tab->D, op->D[0].data(), sizeof(tab->D));
     memcpy(tab->w, op->ws[0].data(), sizeof(tab->w));
+    memcpy(tab->dB, op->db[0].data(), sizeof(tab->dB));
     op->kstate      = tab;
     op->kstate_free = [](void *p) { delete static_cast<QLaneTab<NM> *>(p); };
     op->geo_pitch   = op->nqTot;
-    const char *kn[3] = {"bwd", "iprod", "physderiv"};
+    const char *kn[4] = {"bwd", "iprod", "physderiv", "ipwdb"};
     char name[96];
     snprintf(name, sizeof(name), "quad_lane_kernel<%s,nm=%d,%s>", kn[kind], NM, op->deformed ? "deformed" : "regular");
     op->kname = name;
     if (kind == QL_BWD) op->launch = quad_lane_launch<QL_BWD, NM, false>;
     else if (kind == QL_PD) op->launch = quad_lane_launch<QL_PD, NM, false>;
+    else if (kind == QL_IPWDB) op->launch = quad_lane_launch<QL_IPWDB, NM, false>;
     else op->launch = op->deformed ? quad_lane_launch<QL_IPROD, NM, true> : quad_lane_launch<QL_IPROD, NM, false>;
     return true;
 }
