@@ -43,6 +43,7 @@ bool select_shape_fast(nekmf_op_s *op)
 {
     if (op->shape == NEKMF_HEX || op->shape == NEKMF_PYR) return false;
     if (select_quad_lane(op)) return true; // BwdTrans / IProductWRTBase / regular PhysDeriv on quads: one lane per element
+    if (select_tri_lane(op)) return true;  // the same for triangles
     bool ok = false;
     switch (op->nm[0])
     {

@@ -63,6 +63,7 @@ bool select_shape_fast(nekmf_op_s *op);
 bool select_generic(nekmf_op_s *op);
 bool select_seg(nekmf_op_s *op);
 bool select_quad_lane(nekmf_op_s *op);
+bool select_tri_lane(nekmf_op_s *op);
 // called after set_geom / set_lambda so launchers can precompute (e.g. detect diagonal metrics)
 void notify_geom_changed(nekmf_op_s *op);
 void kron_maybe_wrap(nekmf_op_s *op);

@@ -47,7 +47,9 @@ template <int OP, int NM, bool DEF> struct QLaneCfg
     static constexpr int INL  = OP == QL_BWD ? NM2 : NQ2; // doubles per element, input side
     static constexpr int OUTL = (OP == QL_IPROD || OP == QL_IPWDB) ? NM2 : NQ2;
     static constexpr bool INPAD = (INL % 2) == 0, OUTPAD = (OUTL % 2) == 0;
-    static constexpr int INS  = INPAD ? INL + 2 : INL, OUTS = OUTPAD ? OUTL + 2 : OUTL;
+    // lane stride of a slot: odd lengths are conflict free as they are; even lengths must stay even (16-byte copies)
+    // and are best at 2 (mod 4) doubles -- 2-way bank conflicts; a multiple of 4 would be 4- to 16-way
+    static constexpr int INS  = (INPAD && INL % 4 == 0) ? INL + 2 : INL, OUTS = (OUTPAD && OUTL % 4 == 0) ? OUTL + 2 : OUTL;
     static constexpr int NIN  = 1 + (((OP == QL_IPROD && DEF) || OP == QL_IPWDB) ? 1 : 0);
     static constexpr int NOUT = OP == QL_PD ? 2 : 1;
     static constexpr int INB  = round_up(32 * INS, 2), OUTB = round_up(32 * OUTS, 2);

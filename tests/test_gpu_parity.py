@@ -426,6 +426,8 @@ def test_shape_fast_kernels(shape, nm, deformed):
                 want = "quad_helm_kron" if not deformed else "shape_op_kernel"
             elif nm <= 7 and not (op == nk.ePhysDeriv and deformed):
                 want = "quad_lane_kernel"  # one lane per element (quad_lane.cu)
+        if shape == "Tri" and nm <= 7 and op != nk.eHelmholtz and not (op == nk.ePhysDeriv and deformed):
+            want = "tri_lane_kernel"  # one lane per element (tri_lane.cu)
         assert want in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
 
 
