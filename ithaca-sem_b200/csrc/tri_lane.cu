@@ -1,4 +1,5 @@
-// tri_lane.cu -- BwdTrans, IProductWRTBase and (regular) PhysDeriv on triangles with ONE LANE PER ELEMENT.
+// tri_lane.cu -- BwdTrans, IProductWRTBase, (regular) PhysDeriv and (regular) IProductWRTDerivBase on triangles
+// with ONE LANE PER ELEMENT.
 //
 // Reference semantics: MatrixFreeOps/BwdTransKernels.hpp:78-126, IProductKernels.hpp:135-234 (incl. the CORRECT
 // term of the singular vertex, mode 1), PhysDerivKernels.hpp:153-217 (collapsed-coordinate chain rule
@@ -18,7 +19,7 @@
 namespace nekmf
 {
 
-enum { TL_BWD = 0, TL_IPROD = 1, TL_PD = 2 };
+enum { TL_BWD = 0, TL_IPROD = 1, TL_PD = 2, TL_IPWDB = 3 };
 
 template <int NM> struct TLaneTab
 {
@@ -29,11 +30,14 @@ template <int NM> struct TLaneTab
     double D1[NQ1 * NQ1];
     double w0[NQ0], w1[NQ1]; // w1 carries the 0.5 of the collapsed Jacobian (Operator.hpp:244-258)
     double h0[NQ0], h1[NQ1]; // 0.5 (1 + z0_i),  2 / (1 - z1_j)
+    double db0[NM * NQ0];    // dbdata of both directions (IProductWRTDerivBase)
+    double db1[NP * NQ1];
 };
 
 struct TLaneArgs
 {
     const double *in;
+    const double *in1; // second input (IProductWRTDerivBase)
     double *out0, *out1;
     const double *jac;
     const double *df;
@@ -46,12 +50,12 @@ template <int OP, int NM, bool DEF> struct TLaneCfg
 {
     static constexpr int NQ0 = NM + 1, NQ1 = NM, NQT = NQ0 * NQ1, NP = NM * (NM + 1) / 2;
     static constexpr int INL  = OP == TL_BWD ? NP : NQT;
-    static constexpr int OUTL = OP == TL_IPROD ? NP : NQT;
+    static constexpr int OUTL = (OP == TL_IPROD || OP == TL_IPWDB) ? NP : NQT;
     static constexpr bool INPAD = (INL % 2) == 0, OUTPAD = (OUTL % 2) == 0;
     // lane stride of a slot: odd lengths are conflict free as they are; even lengths must stay even (16-byte copies)
     // and are best at 2 (mod 4) doubles -- 2-way bank conflicts; a multiple of 4 would be 4- to 16-way
     static constexpr int INS  = (INPAD && INL % 4 == 0) ? INL + 2 : INL, OUTS = (OUTPAD && OUTL % 4 == 0) ? OUTL + 2 : OUTL;
-    static constexpr int NIN  = 1 + ((OP == TL_IPROD && DEF) ? 1 : 0);
+    static constexpr int NIN  = 1 + (((OP == TL_IPROD && DEF) || OP == TL_IPWDB) ? 1 : 0);
     static constexpr int NOUT = OP == TL_PD ? 2 : 1;
     static constexpr int INB  = round_up(32 * INS, 2), OUTB = round_up(32 * OUTS, 2);
     static constexpr int PER_WARP = NIN * INB + NOUT * OUTB + 2;
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(TLaneCfg<OP, NM, DEF>::T, 1)
             {
                 const int a = pad_in(i2);
                 tl_cp_async16(sIn + a, args.in + ioff + 2 * i2);
-                if (Cfg::NIN == 2) tl_cp_async16(sJac + a, args.jac + ioff + 2 * i2);
+                if (Cfg::NIN == 2) tl_cp_async16(sJac + a, (OP == TL_IPWDB ? args.in1 : args.jac) + ioff + 2 * i2);
             }
             tl_cp_async_wait_all();
         }
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(TLaneCfg<OP, NM, DEF>::T, 1)
                 const uint32_t bytes = (uint32_t)(ne * INL * 8);
                 mbar_expect_tx(bar, bytes * Cfg::NIN);
                 tma_load_1d(sIn, args.in + ioff, bytes, bar);
-                if (Cfg::NIN == 2) tma_load_1d(sJac, args.jac + ioff, bytes, bar);
+                if (Cfg::NIN == 2) tma_load_1d(sJac, (OP == TL_IPWDB ? args.in1 : args.jac) + ioff, bytes, bar);
             }
             mbar_wait(bar, phase);
             phase ^= 1;
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(TLaneCfg<OP, NM, DEF>::T, 1)
             {
                 const int a = (i / INL) * INS + (i % INL);
                 sIn[a]      = __ldg(args.in + ioff + i);
-                if (Cfg::NIN == 2) sJac[a] = __ldg(args.jac + ioff + i);
+                if (Cfg::NIN == 2) sJac[a] = __ldg((OP == TL_IPWDB ? args.in1 : args.jac) + ioff + i);
             }
         }
         __syncwarp();
@@ -216,6 +220,67 @@ __global__ void __launch_bounds__(TLaneCfg<OP, NM, DEF>::T, 1)
 #pragma unroll
                     for (int j = 0; j < NQ1; ++j) s = fma(tab.b1[NQ1 + j], t1[j], s);
                     o0[1] = s;
+                }
+            }
+            else if (OP == TL_IPWDB)
+            {
+                // IProductWRTDerivBase.h:891-1060 (regular): t_d = df[d] f_0 + df[2+d] f_1, collapsed chain rule on t_0,
+                // out = IPTri(dB0, B1)[t_0] + IPTri(B0, dB1)[t_1], each with its CORRECT term
+                const double *ye = sJac + lane * INS;
+                const double jr  = __ldg(args.jac + eg);
+                const double f0 = __ldg(args.df + eg), f1 = __ldg(args.df + args.dfStride + eg),
+                             f2 = __ldg(args.df + 2 * args.dfStride + eg), f3 = __ldg(args.df + 3 * args.dfStride + eg);
+#pragma unroll
+                for (int d = 0; d < 2; ++d)
+                {
+                    double g[NQ1][NQ0];
+#pragma unroll
+                    for (int j = 0; j < NQ1; ++j)
+#pragma unroll
+                        for (int i = 0; i < NQ0; ++i)
+                        {
+                            const double x = xe[j * NQ0 + i], y = ye[j * NQ0 + i];
+                            const double t1 = f1 * x + f3 * y;
+                            double t        = t1;
+                            if (d == 0)
+                            {
+                                const double t0 = f0 * x + f2 * y;
+                                t               = t0 * tab.h1[j] + (tab.h0[i] * t1) * tab.h1[j];
+                            }
+                            g[j][i] = t * (jr * (tab.w1[j] * tab.w0[i]));
+                        }
+                    double tl1[NQ1];
+#pragma unroll
+                    for (int p = 0; p < NM; ++p)
+                    {
+                        double t[NQ1];
+#pragma unroll
+                        for (int j = 0; j < NQ1; ++j)
+                        {
+                            double s = (d == 0 ? tab.db0[p * NQ0] : tab.b0[p * NQ0]) * g[j][0];
+#pragma unroll
+                            for (int i = 1; i < NQ0; ++i) s = fma(d == 0 ? tab.db0[p * NQ0 + i] : tab.b0[p * NQ0 + i], g[j][i], s);
+                            t[j] = s;
+                            if (p == 1) tl1[j] = s;
+                        }
+#pragma unroll
+                        for (int q = 0; q < NM - p; ++q)
+                        {
+                            const int m = tl_off(p, NM) + q;
+                            double s    = (d == 1 ? tab.db1[m * NQ1] : tab.b1[m * NQ1]) * t[0];
+#pragma unroll
+                            for (int j = 1; j < NQ1; ++j) s = fma(d == 1 ? tab.db1[m * NQ1 + j] : tab.b1[m * NQ1 + j], t[j], s);
+                            if (d == 0) o0[m] = s;
+                            else o0[m] += s;
+                        }
+                    }
+                    if (NM > 1)
+                    {
+                        double s = o0[1];
+#pragma unroll
+                        for (int j = 0; j < NQ1; ++j) s = fma(d == 1 ? tab.db1[NQ1 + j] : tab.b1[NQ1 + j], tl1[j], s);
+                        o0[1] = s;
+                    }
                 }
             }
             else
@@ -297,7 +362,7 @@ template <int OP, int NM, bool DEF> static int tri_lane_launch(nekmf_op_s *op, c
         blocks_per_sm = nb;
     }
     TLaneArgs a;
-    a.in = in[0]; a.out0 = out[0]; a.out1 = out[1];
+    a.in = in[0]; a.in1 = in[1]; a.out0 = out[0]; a.out1 = out[1];
     const size_t gstep = DEF ? (size_t)op->nqTot : 1;
     a.jac = op->d_jac ? op->d_jac + (size_t)op->run_e0 * gstep : nullptr;
     a.df  = op->d_df ? op->d_df + (size_t)op->run_e0 * gstep : nullptr;
@@ -306,6 +371,7 @@ template <int OP, int NM, bool DEF> static int tri_lane_launch(nekmf_op_s *op, c
     uintptr_t al = (uintptr_t)in[0] | (uintptr_t)out[0];
     if (OP == TL_PD) al |= (uintptr_t)out[1];
     if (OP == TL_IPROD && DEF) al |= (uintptr_t)a.jac;
+    if (OP == TL_IPWDB) al |= (uintptr_t)in[1];
     a.io_aligned = (al & 15) == 0;
     const int nBatches = (op->run_ne + 32 * Cfg::WARPS - 1) / (32 * Cfg::WARPS);
     int grid           = blocks_per_sm * NUM_SMS;
@@ -324,6 +390,7 @@ template <int NM> static bool tri_lane_install(nekmf_op_s *op)
     if (op->optype == NEKMF_BWDTRANS) kind = TL_BWD;
     else if (op->optype == NEKMF_IPRODUCTWRTBASE) kind = TL_IPROD;
     else if (op->optype == NEKMF_PHYSDERIV && !op->deformed) kind = TL_PD;
+    else if (op->optype == NEKMF_IPRODUCTWRTDERIVBASE && !op->deformed) kind = TL_IPWDB;
     if (kind < 0) return false;
     if (op->rows[1] != Tab::NP || op->nq[1] != Tab::NQ1) return false;
     auto *tab = new Tab;
@@ -333,17 +400,20 @@ template <int NM> static bool tri_lane_install(nekmf_op_s *op)
     memcpy(tab->D1, op->D[1].data(), sizeof(tab->D1));
     memcpy(tab->w0, op->ws[0].data(), sizeof(tab->w0));
     memcpy(tab->w1, op->ws[1].data(), sizeof(tab->w1));
+    memcpy(tab->db0, op->db[0].data(), sizeof(tab->db0));
+    memcpy(tab->db1, op->db[1].data(), sizeof(tab->db1));
     for (int i = 0; i < Tab::NQ0; ++i) tab->h0[i] = 0.5 * (1.0 + op->Z[0][i]);
     for (int j = 0; j < Tab::NQ1; ++j) tab->h1[j] = 2.0 / (1.0 - op->Z[1][j]);
     op->kstate      = tab;
     op->kstate_free = [](void *p) { delete static_cast<Tab *>(p); };
     op->geo_pitch   = op->nqTot;
-    const char *kn[3] = {"bwd", "iprod", "physderiv"};
+    const char *kn[4] = {"bwd", "iprod", "physderiv", "ipwdb"};
     char name[96];
     snprintf(name, sizeof(name), "tri_lane_kernel<%s,nm=%d,%s>", kn[kind], NM, op->deformed ? "deformed" : "regular");
     op->kname = name;
     if (kind == TL_BWD) op->launch = tri_lane_launch<TL_BWD, NM, false>;
     else if (kind == TL_PD) op->launch = tri_lane_launch<TL_PD, NM, false>;
+    else if (kind == TL_IPWDB) op->launch = tri_lane_launch<TL_IPWDB, NM, false>;
     else op->launch = op->deformed ? tri_lane_launch<TL_IPROD, NM, true> : tri_lane_launch<TL_IPROD, NM, false>;
     return true;
 }
