@@ -75,6 +75,49 @@ def test_all_shapes_runtime_kernels(shape, nm, nq0, deformed):
     run_all_ops(nekmf(), shape, nm, nq0, 13, deformed, np.random.default_rng(7 * nm + nq0 + shape))
 
 
+# default policy of dense_helm.cu (dense_wanted): first nm at which regular Helmholtz takes the DMMA kernel
+DENSE_FROM = {"Tri": 6, "Tet": 5, "Pyr": 2}
+
+
+@pytest.mark.parametrize("nel", [1, 15, 16, 17, 127, 128, 129, 300])
+@pytest.mark.parametrize("shape,nm", [("Tri", 2), ("Tri", 5), ("Tri", 7), ("Tri", 9),
+                                      ("Tet", 2), ("Tet", 3), ("Tet", 4), ("Tet", 5), ("Tet", 6), ("Tet", 7), ("Tet", 8),
+                                      ("Tet", 9), ("Pyr", 2), ("Pyr", 3), ("Pyr", 4), ("Pyr", 5), ("Pyr", 6), ("Pyr", 7)])
+def test_dense_dmma_helmholtz(shape, nm, nel, monkeypatch):
+    """Regular Tri / Tet / Pyr Helmholtz as a batched DMMA GEMM with the reference-element matrices (dense_helm.cu),
+    forced on at every order it is instantiated for: ragged element tiles (16 per warp, 128 per CTA), row counts that
+    are not a multiple of 8, lambda = 0, a changed lambda, a second set_geom, device arrays offset by one double."""
+    monkeypatch.setenv("NEKMF_DENSE", "1")
+    torch = _torch()
+    nk = nekmf()
+    rng = np.random.default_rng(nm * 131 + nel + len(shape))
+    el = po.Elem(SHAPES[shape], nm, nm + 1)
+    std = nk.StdExpansion(SHAPES[shape], nm, nm + 1)
+    jac, df = random_geometry(rng, el.dim, nel, el.nqTot, False)
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, False))
+    x = rng.uniform(-1, 1, nel * el.nmTot)
+    for lam in (1.3, 0.0, 37.5):
+        out = np.zeros(nel * el.nmTot)
+        coll.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
+        check(out, el.helmholtz(nel, False, jac, df, lam, x), "Helmholtz(dense, lambda=%g)" % lam)
+    assert "dense_helm_kernel" in coll.m_ops[nk.eHelmholtz].kernel_name, coll.m_ops[nk.eHelmholtz].kernel_name
+    want = el.helmholtz(nel, False, jac, df, 1.0, x)
+    xd = torch.zeros(x.size + 1, dtype=torch.float64, device="cuda")
+    xd[1:] = torch.from_numpy(x).cuda()
+    yd = torch.zeros(x.size + 1, dtype=torch.float64, device="cuda")
+    coll.ApplyOperator(nk.eHelmholtz, xd[1:], yd[1:], factors={nk.eFactorLambda: 1.0})
+    torch.cuda.synchronize()
+    check(yd[1:].cpu().numpy(), want, "Helmholtz(dense, device arrays offset by one double)")
+    # the quadrature-space kernel it replaces must agree to rounding (NEKMF_DENSE=0 is read at set_geom)
+    monkeypatch.setenv("NEKMF_DENSE", "0")
+    coll0 = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, False))
+    out0 = np.zeros(nel * el.nmTot)
+    coll0.ApplyOperator(nk.eHelmholtz, x, out0, factors={nk.eFactorLambda: 1.0})
+    assert "dense_helm_kernel" not in coll0.m_ops[nk.eHelmholtz].kernel_name
+    check(out0, want, "Helmholtz(quadrature space)")
+    check(yd[1:].cpu().numpy(), out0, "dense vs quadrature-space kernel")
+
+
 def golden_cases():
     return sorted(set(k.rsplit("_", 1)[0] for k in GOLD.files if k.endswith("_x") and not k.startswith("Seg")))
 
@@ -428,6 +471,9 @@ def test_shape_fast_kernels(shape, nm, deformed):
                 want = "quad_lane_kernel"  # one lane per element (quad_lane.cu)
         if shape == "Tri" and nm <= 7 and op != nk.eHelmholtz and not (op == nk.ePhysDeriv and deformed):
             want = "tri_lane_kernel"  # one lane per element (tri_lane.cu)
+        if op == nk.eHelmholtz and not deformed and ((shape == "Tet" and nm >= DENSE_FROM["Tet"]) or
+                                                      (shape == "Tri" and nm >= DENSE_FROM["Tri"])):
+            want = "dense_helm_kernel"  # DMMA coefficient-space kernel (dense_helm.cu)
         assert want in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
 
 

@@ -126,6 +126,14 @@ def main():
                         rec.update({"flops_per_element_reference_algorithm": fl, "tflops": round(tf, 2),
                                     "frac_fp64": round(tf / fp64_peak, 3),
                                     "bound": "fp64" if tf / fp64_peak > gbs / peak else "hbm"})
+                    if o.kernel_name.startswith("dense_helm_kernel"):
+                        # the DMMA GEMM actually issued: (8 MT) rows x (nT * 4 KS) padded columns per element,
+                        # against the measured DMMA peak (profiles/r01_fp64_peak.jsonl: 37.1 TFLOP/s)
+                        nT = 1 + dim * (dim + 1) // 2
+                        fl = 2 * (8 * ((nmTot + 7) // 8)) * nT * (4 * ((nmTot + 3) // 4))
+                        tf = fl * nel / (ms * 1e-3) / 1e12
+                        rec.update({"flops_per_element_issued": fl, "tflops": round(tf, 2),
+                                    "frac_dmma": round(tf / 37.1, 3), "bound": "fp64"})
                     line = json.dumps(rec)
                     print(line, flush=True)
                     if out:
