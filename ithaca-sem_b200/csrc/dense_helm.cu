@@ -16,11 +16,11 @@
 // The matrices are measured, not re-derived: at the first set_geom the operator's own quadrature-space kernel
 // (shape_op_kernel / gen_kernel, the pinned implementation) is applied to unit vectors on probe geometries
 // (lambda = 1, df = 0 -> M;  lambda = 0, df = e_a -> K_aa;  df = e_a + e_b -> K_aa + K_bb + K_ab + K_ba) and the
-// result is repacked in DMMA fragment order.  Kernel: one CTA = 8 warps = 128 (64) elements; a warp owns 16 (8)
+// result is repacked in DMMA fragment order.  Kernel: one CTA = 4 warps = 64 (32) elements; a warp owns 16 (8)
 // elements and ALL output rows (MT tiles of 8 rows x NT tiles of 8 elements of accumulators in registers); its
 // element coefficients live in a padded shared-memory tile (pitch = 4 mod 8: the B-fragment loads are
 // conflict-free), the per-element scale c_t(e) multiplies the B fragment, and the A fragments stream from L2
-// through a three-stage cp.async ring shared by the eight warps.
+// through a four-stage cp.async ring shared by the four warps.
 #include "common.cuh"
 #include "op_internal.h"
 #include <stdlib.h>
@@ -31,15 +31,15 @@
 namespace nekmf
 {
 
-constexpr int DW      = 8; // warps per CTA
-constexpr int DSTAGES = 3; // A-fragment ring
+constexpr int DW      = 4; // warps per CTA (two or more CTAs per SM: one's tile load / store overlaps another's DMMAs)
+constexpr int DSTAGES = 4; // A-fragment ring
 
 template <int MT> struct DenseCfg
 {
     static constexpr int NT    = MT <= 18 ? 2 : 1;          // element tiles (of 8) per warp
     static constexpr int NE    = DW * 8 * NT;               // elements per CTA
-    static constexpr int KC    = 80 / MT < 1 ? 1 : 80 / MT; // k-steps (of 4) per ring stage
-    static constexpr int CHUNK = KC * MT * 32;              // doubles per ring stage (<= 20 KB)
+    static constexpr int KC    = MT <= 4 ? 8 : (36 / MT < 1 ? 1 : 36 / MT); // k-steps (of 4) per ring stage
+    static constexpr int CHUNK = KC * MT * 32;              // doubles per ring stage (<= 9 KB)
 };
 
 struct DenseArgs
@@ -65,7 +65,7 @@ __device__ __forceinline__ void cp_async16(void *s, const void *g)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int MT> __global__ void __launch_bounds__(DW * 32, 1) dense_helm_kernel(const __grid_constant__ DenseArgs a)
+template <int MT> __global__ void __launch_bounds__(DW * 32, 2) dense_helm_kernel(const __grid_constant__ DenseArgs a)
 {
     using Cfg        = DenseCfg<MT>;
     constexpr int NT = Cfg::NT, NE = Cfg::NE, KC = Cfg::KC, CHUNK = Cfg::CHUNK;
@@ -91,6 +91,7 @@ template <int MT> __global__ void __launch_bounds__(DW * 32, 1) dense_helm_kerne
     };
     issue(0);
     issue(1);
+    issue(2);
 
     // ---- per warp: c_t(e) of its own elements (J folded in), then the coefficient rows; no CTA barrier needed
     if (lane < 8 * NT)
@@ -126,13 +127,18 @@ template <int MT> __global__ void __launch_bounds__(DW * 32, 1) dense_helm_kerne
 #pragma unroll
         for (int t = 0; t < 7; ++t) sC[t * NE + el] = c[t];
     }
-    for (int r = 0; r < 8 * NT; ++r)
+    // coefficient rows of the warp's own elements: 8 NT independent loads in flight per lane and pass
+    for (int k = lane; k < pitch; k += 32)
     {
-        const int e       = e0 + we + r;
-        double *row       = sU + (size_t)(we + r) * pitch;
-        const double *src = a.in + (size_t)e * n;
-        const bool live   = e < a.nElmt;
-        for (int k = lane; k < pitch; k += 32) row[k] = (live && k < n) ? __ldg(src + k) : 0.0;
+        double v[8 * NT];
+#pragma unroll
+        for (int r = 0; r < 8 * NT; ++r)
+        {
+            const int e = e0 + we + r;
+            v[r]        = (e < a.nElmt && k < n) ? __ldg(a.in + (size_t)e * n + k) : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8 * NT; ++r) sU[(size_t)(we + r) * pitch + k] = v[r];
     }
     __syncwarp();
 
@@ -149,34 +155,52 @@ template <int MT> __global__ void __launch_bounds__(DW * 32, 1) dense_helm_kerne
         uB[j] = sU + (size_t)(we + j * 8 + (lane >> 2)) * pitch + (lane & 3);
         cB[j] = sC + we + j * 8 + (lane >> 2);
     }
-    int t = 0, kk = 0;
-    for (int c = 0; c < NC; ++c)
-    {
-        cp_async_wait<DSTAGES - 2>(); // this thread's copies of stage c have landed
-        __syncthreads();              // everyone's have, and everyone is done with stage c-1
-        issue(c + DSTAGES - 1);       // refill the buffer stage c-1 occupied
-        const double *buf = sA + (c % DSTAGES) * CHUNK + lane;
-        const int cnt     = (a.G - c * KC < KC) ? a.G - c * KC : KC;
+    // One flat loop over the G = nT KS k-steps.  The operands of step g+1 (A fragments, scaled B fragments) are
+    // fetched while the DMMAs of step g issue: a[i] is reloaded right after its last use, so no step starts with
+    // a load-to-use bubble (the warps leave every barrier in lockstep and would all stall together).  The
+    // ring barrier for stage c+1 therefore sits at the top of the LAST step of stage c.
+    cp_async_wait<DSTAGES - 2>();
+    __syncthreads(); // stage 0 visible
+    double av[MT], b[NT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) av[i] = sA[i * 32 + lane];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) b[j] = uB[j][0] * cB[j][0];
+    int c = 0, gl = 0, t = 0, kk = 0;
+    int cnt = a.G < KC ? a.G : KC;
 #pragma unroll 1
-        for (int gl = 0; gl < cnt; ++gl)
+    for (int g = 0; g < a.G; ++g)
+    {
+        const bool last_in_stage = gl == cnt - 1;
+        if (last_in_stage && c + 1 < NC)
         {
-            double b[NT];
-#pragma unroll
-            for (int j = 0; j < NT; ++j) b[j] = uB[j][kk * 4] * cB[j][t * NE];
-            const double *ap = buf + gl * MT * 32;
-#pragma unroll
-            for (int i = 0; i < MT; ++i)
-            {
-                const double av = ap[i * 32];
-#pragma unroll
-                for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], av, b[j]);
-            }
-            if (++kk == KS)
-            {
-                kk = 0;
-                ++t;
-            }
+            cp_async_wait<DSTAGES - 3>(); // this thread's copies of stage c+1 have landed
+            __syncthreads();              // everyone's have, and everyone is done with stage c-1
+            issue(c + DSTAGES - 1);       // refill the buffer stage c-1 occupied
         }
+        int c2 = c, gl2 = gl + 1, kk2 = kk + 1, t2 = t;
+        if (last_in_stage) { c2 = c + 1; gl2 = 0; }
+        if (kk2 == KS) { kk2 = 0; t2 = t + 1; }
+        if (g + 1 == a.G) { c2 = c; gl2 = gl; kk2 = kk; t2 = t; } // nothing follows: re-read this step (unused)
+        const double *apn = sA + (c2 % DSTAGES) * CHUNK + gl2 * (MT * 32) + lane;
+        double un[NT], cn[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+        {
+            un[j] = uB[j][kk2 * 4];
+            cn[j] = cB[j][t2 * NE];
+        }
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+        {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], b[j]);
+            av[i] = apn[i * 32];
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) b[j] = un[j] * cn[j];
+        if (c2 != c) cnt = (a.G - c2 * KC < KC) ? a.G - c2 * KC : KC;
+        c = c2; gl = gl2; kk = kk2; t = t2;
     }
     cp_async_wait<0>();
 
@@ -413,11 +437,13 @@ static bool dense_wanted(const nekmf_op_s *op)
     const char *env = getenv("NEKMF_DENSE");
     if (env && env[0] == '0') return false;
     if (env && env[0] == '1') return true;
+    // measured (profiles/r01_sweep_dense_helm.jsonl): faster than the quadrature-space kernels at every order
+    // it is instantiated for (Tet nm 2..9: 2.0-4.7x, Pyr nm 2..7: 5-40x, Tri nm 3..9: 1.3-2.6x)
     switch (op->shape)
     {
-        case NEKMF_TET: return op->nm[0] >= 5;
+        case NEKMF_TET: return true;
         case NEKMF_PYR: return true;
-        case NEKMF_TRI: return op->nm[0] >= 6;
+        case NEKMF_TRI: return op->nm[0] >= 3;
         default: return false;
     }
 }

@@ -76,16 +76,16 @@ def test_all_shapes_runtime_kernels(shape, nm, nq0, deformed):
 
 
 # default policy of dense_helm.cu (dense_wanted): first nm at which regular Helmholtz takes the DMMA kernel
-DENSE_FROM = {"Tri": 6, "Tet": 5, "Pyr": 2}
+DENSE_FROM = {"Tri": 3, "Tet": 2, "Pyr": 2}
 
 
-@pytest.mark.parametrize("nel", [1, 15, 16, 17, 127, 128, 129, 300])
+@pytest.mark.parametrize("nel", [1, 15, 16, 17, 63, 64, 65, 300])
 @pytest.mark.parametrize("shape,nm", [("Tri", 2), ("Tri", 5), ("Tri", 7), ("Tri", 9),
                                       ("Tet", 2), ("Tet", 3), ("Tet", 4), ("Tet", 5), ("Tet", 6), ("Tet", 7), ("Tet", 8),
                                       ("Tet", 9), ("Pyr", 2), ("Pyr", 3), ("Pyr", 4), ("Pyr", 5), ("Pyr", 6), ("Pyr", 7)])
 def test_dense_dmma_helmholtz(shape, nm, nel, monkeypatch):
     """Regular Tri / Tet / Pyr Helmholtz as a batched DMMA GEMM with the reference-element matrices (dense_helm.cu),
-    forced on at every order it is instantiated for: ragged element tiles (16 per warp, 128 per CTA), row counts that
+    forced on at every order it is instantiated for: ragged element tiles (16 per warp, 64 per CTA), row counts that
     are not a multiple of 8, lambda = 0, a changed lambda, a second set_geom, device arrays offset by one double."""
     monkeypatch.setenv("NEKMF_DENSE", "1")
     torch = _torch()
