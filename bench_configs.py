@@ -202,6 +202,14 @@ def config4(args, torch, nk, po, peak, peak_src, ClockSampler):
         per[name] = {"elements": nel, "ncoeffs": std.GetNcoeffs(), "ms": avg, "gdof_per_s": nel * std.GetNcoeffs() / (avg * 1e-3) / 1e9,
                      "algorithmic_bytes_per_element": by, "gb_per_s": by * nel / (avg * 1e-3) / 1e9,
                      "frac_hbm": by * nel / (avg * 1e-3) / 1e9 / peak, "kernel": ops[name].kernel_name}
+        if ops[name].kernel_name.startswith("dense_helm_kernel"):
+            # the DMMA GEMM issued per element: (8 MT) rows x 7 terms x (4 KS) padded columns; peak = the DMMA
+            # microbenchmark of tools/fp64_peak.cu (profiles/r01_fp64_peak.jsonl)
+            nc = std.GetNcoeffs()
+            fl = 2 * (8 * ((nc + 7) // 8)) * 7 * (4 * ((nc + 3) // 4))
+            per[name].update({"bound": "tensor (FP64 DMMA)", "flops_per_element_issued": fl,
+                              "tflops": fl * nel / (avg * 1e-3) / 1e12, "frac_dmma": fl * nel / (avg * 1e-3) / 1e12 / 37.1,
+                              "dmma_peak_tflops": 37.1})
     clocks = sampler.stop()
     # one step = the three collections back to back (what ExpList::GeneralMatrixOp does), timed as a whole
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

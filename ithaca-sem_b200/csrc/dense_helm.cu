@@ -38,8 +38,8 @@ template <int MT> struct DenseCfg
 {
     static constexpr int NT    = MT <= 18 ? 2 : 1;          // element tiles (of 8) per warp
     static constexpr int NE    = DW * 8 * NT;               // elements per CTA
-    static constexpr int KC    = MT <= 4 ? 8 : (36 / MT < 1 ? 1 : 36 / MT); // k-steps (of 4) per ring stage
-    static constexpr int CHUNK = KC * MT * 32;              // doubles per ring stage (<= 9 KB)
+    static constexpr int KC    = MT <= 4 ? 8 : MT <= 12 ? 24 / MT : MT <= 18 ? 2 : 1; // k-steps (of 4) per ring stage
+    static constexpr int CHUNK = KC * MT * 32;              // doubles per ring stage (<= 8 KB: three CTAs per SM at n = 84)
 };
 
 struct DenseArgs
