@@ -359,7 +359,7 @@ template <int NM> static bool quad_lane_install(nekmf_op_s *op)
     if (op->optype == NEKMF_BWDTRANS) kind = QL_BWD;
     else if (op->optype == NEKMF_IPRODUCTWRTBASE) kind = QL_IPROD;
     else if (op->optype == NEKMF_PHYSDERIV && !op->deformed) kind = QL_PD;
-    else if (op->optype == NEKMF_IPRODUCTWRTDERIVBASE && !op->deformed) kind = QL_IPWDB;
+    else if (op->optype == NEKMF_IPRODUCTWRTDERIVBASE && !op->deformed && NM <= 5) kind = QL_IPWDB; // nm 6, 7: shape_op_kernel<ipwdb> is 1.2-1.8x faster
     if (kind < 0) return false;
     auto *tab = new QLaneTab<NM>;
     memcpy(tab->B, op->b[0].data(), sizeof(tab->B));

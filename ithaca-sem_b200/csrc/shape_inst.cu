@@ -42,7 +42,7 @@ template <int SHAPE, int OP, int NM, bool DEF> static int shape_launch(nekmf_op_
     }
     ShpArgs a;
     const size_t gstep = DEF ? (size_t)op->nqTot : 1;
-    a.in0 = in[0];
+    a.in0 = in[0]; a.in1 = in[1]; a.in2 = in[2];
     a.out0 = out[0]; a.out1 = out[1]; a.out2 = out[2];
     a.jac = op->d_jac ? op->d_jac + (size_t)op->run_e0 * gstep : nullptr;
     a.df  = op->d_df ? op->d_df + (size_t)op->run_e0 * gstep : nullptr;
@@ -63,7 +63,6 @@ template <int SHAPE, int OP, int NM, bool DEF> static int shape_launch(nekmf_op_
 template <int SHAPE, int NM> static bool shape_install(nekmf_op_s *op)
 {
     using Dm = ShpDims<SHAPE, NM>;
-    if (op->optype == NEKMF_IPRODUCTWRTDERIVBASE) return false;
     for (int d = 0; d < Dm::DIM; ++d)
         if (op->nm[d] != NM) return false;
     if (op->nq[0] != Dm::NQ0 || op->nq[1] != Dm::NQ1 || (Dm::DIM == 3 && op->nq[2] != Dm::NQ2)) return false;
@@ -128,6 +127,7 @@ template <int SHAPE, int NM> static bool shape_install(nekmf_op_s *op)
         SHP_CASE(NEKMF_HELMHOLTZ)
         SHP_CASE(NEKMF_IPRODUCTWRTBASE)
         SHP_CASE(NEKMF_PHYSDERIV)
+        SHP_CASE(NEKMF_IPRODUCTWRTDERIVBASE)
     }
 #undef SHP_CASE
     op->kstate_free(st);

@@ -80,6 +80,7 @@ template <int SHAPE, int NM> struct ShpTab
 struct ShpArgs
 {
     const double *in0;
+    const double *in1 = nullptr, *in2 = nullptr; // IProductWRTDerivBase: the other components of the input field
     double *out0, *out1, *out2;
     const double *jac, *df; // already offset to the first element of this launch
     const double *aux;      // packed collapsed tables, weights, collapsed-coordinate factors (ShpDims::OFF_*)
@@ -148,7 +149,12 @@ __global__ void __launch_bounds__(256)
     constexpr int NMT = Dm::NMT, NPAIR = Dm::NPAIR, E = Dm::E, T = Dm::T, NQM = Dm::NQM;
     constexpr bool IS_QUAD = Dm::IS_QUAD, IS_TRI = Dm::IS_TRI, IS_PRISM = Dm::IS_PRISM, IS_TET = Dm::IS_TET;
     constexpr bool COEFF_IN = OP == NEKMF_BWDTRANS || OP == NEKMF_HELMHOLTZ;
-    constexpr bool COEFF_OUT = OP == NEKMF_HELMHOLTZ || OP == NEKMF_IPRODUCTWRTBASE;
+    // IProductWRTDerivBase (IProductWRTDerivBase.h:542-640 Quad, 891-1040 Tri, 1630-1740 Prism, 2484-2610 Tet):
+    // dbdata = D bdata (Foundations/Basis.cpp:418-420, 506, 561), so sum_d (dB_d)^T W t_d = B^T sum_d D_d^T (W t_d):
+    // a pointwise chain-rule stage feeds the transposed-derivative + IProduct half of the fused Helmholtz kernel
+    constexpr bool IPWDB     = OP == NEKMF_IPRODUCTWRTDERIVBASE;
+    constexpr bool HELM_BACK = OP == NEKMF_HELMHOLTZ || IPWDB;
+    constexpr bool COEFF_OUT = OP == NEKMF_HELMHOLTZ || OP == NEKMF_IPRODUCTWRTBASE || IPWDB;
     constexpr int NDF = DIM * DIM;
     constexpr int LN  = NQ1 * NQ2; // (j,k) lines, ln = k*NQ1 + j; FP layout [p][ln]
 
@@ -197,6 +203,25 @@ __global__ void __launch_bounds__(256)
         {
             const double *src = args.in0 + (size_t)e0 * NMT;
             for (int i = tid; i < ne * NMT; i += T) sCin[i] = __ldg(src + i);
+        }
+        else if (IPWDB)
+        {
+            // in0 -> sA, in1 -> sB (3-D) | sU (2-D), in2 -> sU
+            const size_t goff = (size_t)e0 * NQT;
+            for (int g = tid; g < ne * NQT; g += T)
+            {
+                const int e = g / NQT, r = g - e * NQT;
+                const int line = r / NQ0, i = r - line * NQ0;
+                const int s = e * NQP + line * P1 + i;
+                sA[s] = __ldg(args.in0 + goff + g);
+                if (DIM == 3)
+                {
+                    sB[s] = __ldg(args.in1 + goff + g);
+                    sU[s] = __ldg(args.in2 + goff + g);
+                }
+                else
+                    sU[s] = __ldg(args.in1 + goff + g);
+            }
         }
         else
         {
@@ -404,7 +429,7 @@ __global__ void __launch_bounds__(256)
         if (OP == NEKMF_HELMHOLTZ || OP == NEKMF_PHYSDERIV) __syncthreads();
 
         // ------------------------------------------------------------------ column pass along the last direction
-        if (OP == NEKMF_HELMHOLTZ || OP == NEKMF_PHYSDERIV)
+        if (OP == NEKMF_HELMHOLTZ || OP == NEKMF_PHYSDERIV || IPWDB)
         {
             constexpr int NL = DIM == 3 ? NQ2 : NQ1;          // points along the column
             constexpr int LS = DIM == 3 ? NQ1 * P1 : P1;      // shared-memory stride along the column
@@ -425,16 +450,69 @@ __global__ void __launch_bounds__(256)
                 {
 #pragma unroll
                     for (int n = 0; n < NDF; ++n) rdf[n] = __ldg(args.df + (size_t)n * args.dfStride + gbase);
-                    if (OP == NEKMF_HELMHOLTZ) rjac = __ldg(args.jac + gbase);
+                    if (HELM_BACK) rjac = __ldg(args.jac + gbase);
                 }
                 const double h0i = sH0[i];
                 double u[NL], dl[NL];
 #pragma unroll
                 for (int s = 0; s < NL; ++s) u[s] = sU[col + s * LS];
-                if (DIM == 3) shp_fwd<NL, NL>(tab.D2, u, dl);
-                else shp_fwd<NL, NL>(tab.D1, u, dl);
+                if constexpr (!IPWDB)
+                {
+                    if (DIM == 3) shp_fwd<NL, NL>(tab.D2, u, dl);
+                    else shp_fwd<NL, NL>(tab.D1, u, dl);
+                }
 
-                if (OP == NEKMF_PHYSDERIV)
+                if constexpr (IPWDB)
+                {
+                    // t_d = sum_c df[c*dim+d] in_c, collapsed-coordinate factors, Jacobian and weights; the last
+                    // direction's transposed derivative is taken here, the other two by the passes below
+                    const double wij = DIM == 3 ? sW0[i] * sW1[j] : sW0[i];
+                    double vl[NL];
+#pragma unroll
+                    for (int s = 0; s < NL; ++s)
+                    {
+                        const int pt = col + s * LS;
+                        double f[NDF], jc;
+#pragma unroll
+                        for (int n = 0; n < NDF; ++n)
+                            f[n] = DEF ? (ev ? __ldg(args.df + (size_t)n * args.dfStride + gbase + s * GS) : 0.0) : rdf[n];
+                        jc = DEF ? (ev ? __ldg(args.jac + gbase + s * GS) : 0.0) : rjac;
+                        const double jw = jc * (wij * (DIM == 3 ? sW2[s] : sW1[s]));
+                        if constexpr (DIM == 2)
+                        {
+                            const double x = sA[pt], y = u[s];
+                            double t0 = fma(f[2], y, f[0] * x);
+                            const double t1 = fma(f[3], y, f[1] * x);
+                            if (IS_TRI) t0 = fma(h0i, t1, t0) * sH1[s]; // IProductWRTDerivBase.h:1006-1036
+                            sA[pt] = jw * t0;
+                            vl[s]  = jw * t1;
+                        }
+                        else
+                        {
+                            const double x = sA[pt], y = sB[pt], z = u[s];
+                            double t0 = fma(f[6], z, fma(f[3], y, f[0] * x));
+                            double t1 = fma(f[7], z, fma(f[4], y, f[1] * x));
+                            const double t2 = fma(f[8], z, fma(f[5], y, f[2] * x));
+                            if (IS_PRISM) t0 = fma(h0i, t2, t0) * sH1[s]; // IProductWRTDerivBase.h:1697-1733
+                            if (IS_TET)
+                            {
+                                // IProductWRTDerivBase.h:2551-2603
+                                const double f2 = sH3[s];
+                                t0 = fma(t1 + t2, h0i, t0) * (f2 * sH2[j]);
+                                t1 = fma(t2, sH1[j], t1) * f2;
+                            }
+                            sA[pt] = jw * t0;
+                            sB[pt] = jw * t1;
+                            vl[s]  = jw * t2;
+                        }
+                    }
+                    double t[NL];
+                    if (DIM == 3) shp_tr<NL, NL>(tab.D2, vl, t);
+                    else shp_tr<NL, NL>(tab.D1, vl, t);
+#pragma unroll
+                    for (int s = 0; s < NL; ++s) sU[col + s * LS] = t[s];
+                }
+                else if (OP == NEKMF_PHYSDERIV)
                 {
 #pragma unroll
                     for (int s = 0; s < NL; ++s)
@@ -573,7 +651,7 @@ __global__ void __launch_bounds__(256)
         }
 
         // ------------------------------------------------------------------ transposed passes (Helmholtz, IProduct)
-        if (OP == NEKMF_HELMHOLTZ && DIM == 3)
+        if (HELM_BACK && DIM == 3)
         {
             // sU += D1^T sB: lines (i,k) along j
             for (int l = tid; l < E * NQ0 * NQ2; l += T)
@@ -597,7 +675,7 @@ __global__ void __launch_bounds__(256)
             double v[NQ0], f[NM];
 #pragma unroll
             for (int i = 0; i < NQ0; ++i) v[i] = sU[e * NQP + ln * P1 + i];
-            if (OP == NEKMF_HELMHOLTZ)
+            if (HELM_BACK)
             {
                 double a[NQ0], t[NQ0];
 #pragma unroll

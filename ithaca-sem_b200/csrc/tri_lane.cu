@@ -390,7 +390,7 @@ template <int NM> static bool tri_lane_install(nekmf_op_s *op)
     if (op->optype == NEKMF_BWDTRANS) kind = TL_BWD;
     else if (op->optype == NEKMF_IPRODUCTWRTBASE) kind = TL_IPROD;
     else if (op->optype == NEKMF_PHYSDERIV && !op->deformed) kind = TL_PD;
-    else if (op->optype == NEKMF_IPRODUCTWRTDERIVBASE && !op->deformed) kind = TL_IPWDB;
+    else if (op->optype == NEKMF_IPRODUCTWRTDERIVBASE && !op->deformed && NM <= 6) kind = TL_IPWDB; // nm 7: shape_op_kernel<ipwdb> is as fast
     if (kind < 0) return false;
     if (op->rows[1] != Tab::NP || op->nq[1] != Tab::NQ1) return false;
     auto *tab = new Tab;

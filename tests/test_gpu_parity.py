@@ -475,6 +475,11 @@ def test_shape_fast_kernels(shape, nm, deformed):
                                                       (shape == "Tri" and nm >= DENSE_FROM["Tri"])):
             want = "dense_helm_kernel"  # DMMA coefficient-space kernel (dense_helm.cu)
         assert want in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
+    # IProductWRTDerivBase: lane kernels for regular quads up to nm = 5 / triangles up to nm = 6, otherwise the compile-time
+    # sized kernel (chain-rule stage + the transposed-derivative / IProduct half of the fused Helmholtz kernel)
+    lane = not deformed and ((shape == "Quad" and nm <= 5) or (shape == "Tri" and nm <= 6))
+    name = coll.m_ops[nk.eIProductWRTDerivBase].kernel_name
+    assert ("_lane_kernel<ipwdb" if lane else "shape_op_kernel") in name, name
 
 
 @pytest.mark.parametrize("zero_copy", ["0", "1"])
