@@ -301,6 +301,7 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
         nekmf_op_destroy(op);
         return NEKMF_ERR_UNSUPPORTED;
     }
+    prism_maybe_wrap(op); // regular prism Helmholtz: DMMA kernel for extruded elements on top of the selected one
     dense_maybe_wrap(op); // regular Tri / Tet / Pyr Helmholtz: DMMA coefficient-space kernel on top of the selected one
     *out = op;
     return NEKMF_OK;

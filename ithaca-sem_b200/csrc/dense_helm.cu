@@ -23,6 +23,7 @@
 // through a four-stage cp.async ring shared by the four warps.
 #include "common.cuh"
 #include "op_internal.h"
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -233,13 +234,15 @@ template <int MT> __global__ void __launch_bounds__(DW * 32, 2) dense_helm_kerne
 }
 
 // P[p][k][m]: response m of probe p to unit vector k.  afrag[t][kk][i][lane] = A_t[i*8 + lane/4][kk*4 + lane%4]
+// (kk_major: afrag[kk][t][i][lane], the order the prism kernel walks)
 __global__ void dense_pack_kernel(const double *__restrict__ P, double *__restrict__ afrag, int n, int KS, int MT, int nT,
-                                  int dim)
+                                  int dim, int kk_major = 0)
 {
     const int total = nT * KS * MT * 32;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
     {
-        const int lane = idx & 31, i = (idx >> 5) % MT, kk = (idx / (32 * MT)) % KS, t = idx / (32 * MT * KS);
+        const int lane = idx & 31, i = (idx >> 5) % MT, g = idx / (32 * MT);
+        const int kk = kk_major ? g / nT : g % KS, t = kk_major ? g % nT : g / KS;
         const int m = i * 8 + (lane >> 2), k = kk * 4 + (lane & 3);
         double v = 0.0;
         if (m < n && k < n)
@@ -494,6 +497,550 @@ int dense_geom_changed(nekmf_op_s *op)
     const char *sn[6] = {"Quad", "Tri", "Hex", "Prism", "Pyr", "Tet"};
     char name[112];
     snprintf(name, sizeof(name), "dense_helm_kernel<%s,n=%d,MT=%d>(regular,DMMA m8n8k4)", sn[op->shape], op->nmTot, st->MT);
+    op->kname = name;
+    return NEKMF_OK;
+}
+
+
+// =====================================================================================================================
+// Extruded prisms.  A prism is triangle (xi_0, xi_2) x segment (xi_1): phi_pqr = T_(p,r)(xi_0, xi_2) S_q(xi_1), the
+// collapsed-coordinate factors depend on (xi_0, xi_2) only (Helmholtz.h:1382-1430), so on a regular element
+//   H = J [ (lambda Mt + G00 Kt00 + G22 Kt22 + G02 (Kt02 + Kt20)) (x) M1  +  G11 Mt (x) K1  +  G01 (..) + G12 (..) ].
+// When the segment direction is orthogonal to the triangle plane (G01 = G12 = 0 for every element: extruded meshes,
+// prisms cut from boxes), the generalised eigen-decomposition X^T M1 X = I, X^T K1 X = diag(mu) of the SEGMENT pair
+// (nm x nm, host, once) decouples the nm segment modes:  with  u~ = (I (x) X^-1) u,
+//   v~_(q~) = J [ (lambda + G11 mu_q~) Mt + G00 Kt00 + G22 Kt22 + G02 Kt02s ] u~_(q~),     out = (I (x) X^-T) v~
+// i.e. nm independent TRIANGLE Helmholtz problems per element -- the DMMA GEMM above with n = nm(nm+1)/2, nT = 4 and
+// one column per (element, q~).  The X^-1 / X^-T transforms are fused into the tile load / store of the kernel.  The
+// triangle matrices are measured like the dense ones (probes on the modes with q = 0, divided by M1[0][0]).
+struct PrismArgs
+{
+    const double *in;
+    double *out;
+    const double *jac, *df, *afrag; // afrag[kk][t][i][lane]
+    const double *tab;              // [nm*nm] Tin = X^-1 (row q~, column q) | [nm] mu
+    const int *itab;                // [n] offset of mode (i, q=0) in the prism ordering | [n] stride between q for that i
+    size_t dfStride;
+    int nElmt;
+    double lambda;
+};
+
+template <int NM> struct PrismCfg
+{
+    static constexpr int N = NM * (NM + 1) / 2, MT = (N + 7) / 8, KS = (N + 3) / 4, K4 = KS * 4;
+    static constexpr int PITCH = (K4 % 8 == 4) ? K4 : K4 + 4;
+    static constexpr int NP = NM * N, EW = 16 / NM, USED = EW * NM; // elements / live columns per warp
+    static constexpr int KPS   = 2;                                  // kk iterations per ring stage
+    static constexpr int STEP  = 4 * MT * 32;                        // doubles per kk (four terms)
+    static constexpr int CHUNK = KPS * STEP;
+    static constexpr int NS    = (KS + KPS - 1) / KPS;
+    static constexpr int TABD  = (NM * NM + NM + 1) & ~1;            // Tin | mu
+    static constexpr int TABI  = (2 * N + 1) & ~1;                   // off | len (ints)
+    static constexpr size_t SMEM = (size_t)(DSTAGES * CHUNK + DW * 16 * PITCH + TABD + TABI / 2 + DW * EW * NP) * 8;
+};
+
+template <int NM> __global__ void __launch_bounds__(DW * 32, 2) prism_helm_kernel(const __grid_constant__ PrismArgs a)
+{
+    using Cfg = PrismCfg<NM>;
+    constexpr int N = Cfg::N, MT = Cfg::MT, KS = Cfg::KS, PITCH = Cfg::PITCH, NP = Cfg::NP, EW = Cfg::EW, USED = Cfg::USED;
+    constexpr int CHUNK = Cfg::CHUNK, STEP = Cfg::STEP, NS = Cfg::NS, KPS = Cfg::KPS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sA   = reinterpret_cast<double *>(smem_raw); // [DSTAGES][CHUNK]
+    double *sU   = sA + DSTAGES * CHUNK;                 // [DW*16][PITCH]
+    double *sTin = sU + DW * 16 * PITCH;                 // [NM*NM] | mu[NM]
+    int *sOff    = reinterpret_cast<int *>(sTin + Cfg::TABD);
+    int *sLen    = sOff + N;
+    double *sRaw = sTin + Cfg::TABD + Cfg::TABI / 2;     // [DW][EW*NP] the warp's elements in the reference ordering
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int we  = warp * 16;                           // first column of the warp
+    const int eW0 = (blockIdx.x * DW + warp) * EW;       // first real element of the warp
+    const double *sMu = sTin + NM * NM;
+
+    auto issue = [&](int st) {
+        if (st < NS)
+        {
+            const int k0 = st * KPS, k1 = (k0 + KPS < KS) ? k0 + KPS : KS;
+            const int units   = (k1 - k0) * (STEP / 2);
+            const double *src = a.afrag + (size_t)k0 * STEP;
+            double *dst       = sA + (st % DSTAGES) * CHUNK;
+            for (int i = tid; i < units; i += DW * 32) cp_async16(dst + 2 * i, src + 2 * i);
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    issue(2);
+    for (int i = tid; i < NM * NM + NM; i += DW * 32) sTin[i] = __ldg(a.tab + i);
+    for (int i = tid; i < 2 * N; i += DW * 32) sOff[i] = __ldg(a.itab + i);
+
+    int nLive = a.nElmt - eW0;
+    nLive     = nLive < 0 ? 0 : (nLive > EW ? EW : nLive);
+    double *raw = sRaw + (size_t)warp * EW * NP;
+    {
+        const double *src = a.in + (size_t)eW0 * NP;
+        for (int idx = lane; idx < nLive * NP; idx += 32) raw[idx] = __ldg(src + idx);
+    }
+    __syncthreads();
+
+    // per-lane scales of its two B-fragment columns: c_t of (element, q~)
+    double cT[4][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+    {
+        const int col = j * 8 + (lane >> 2), el = col / NM, qt = col - el * NM;
+        cT[0][j] = cT[1][j] = cT[2][j] = cT[3][j] = 0.0;
+        if (col < USED && el < nLive)
+        {
+            const int e    = eW0 + el;
+            const double J = __ldg(a.jac + e);
+            double d[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) d[q] = __ldg(a.df + q * a.dfStride + e);
+            const double g11 = d[1] * d[1] + d[4] * d[4] + d[7] * d[7];
+            cT[0][j] = J * (a.lambda + g11 * sMu[qt]);
+            cT[1][j] = J * (d[0] * d[0] + d[3] * d[3] + d[6] * d[6]);
+            cT[2][j] = J * (d[2] * d[2] + d[5] * d[5] + d[8] * d[8]);
+            cT[3][j] = J * (d[0] * d[2] + d[3] * d[5] + d[6] * d[8]);
+        }
+    }
+    // u~[(e, q~)][i] = sum_q Tin[q~][q] u[e][off_i + q len_i]; lane = i
+    for (int k = lane; k < PITCH; k += 32)
+    {
+        double x[EW][NM];
+        const bool kin = k < N;
+        const int o = kin ? sOff[k] : 0, l = kin ? sLen[k] : 0;
+#pragma unroll
+        for (int el = 0; el < EW; ++el)
+#pragma unroll
+            for (int q = 0; q < NM; ++q) x[el][q] = (kin && el < nLive) ? raw[el * NP + o + q * l] : 0.0;
+#pragma unroll
+        for (int col = 0; col < 16; ++col)
+        {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int el = col / NM, qt = col - el * NM;
+            double v = 0.0;
+            if (col < USED)
+            {
+#pragma unroll
+                for (int q = 0; q < NM; ++q) v = fma(sTin[qt * NM + q], x[el < EW ? el : 0][q], v);
+            }
+            sU[(size_t)(we + col) * PITCH + k] = v;
+        }
+    }
+    __syncwarp();
+
+    double acc[MT][2][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double *uB[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) uB[j] = sU + (size_t)(we + j * 8 + (lane >> 2)) * PITCH + (lane & 3);
+
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk)
+    {
+        if (kk % KPS == 0)
+        {
+            cp_async_wait<DSTAGES - 2>(); // this thread's copies of the stage have landed
+            __syncthreads();              // everyone's have, and everyone is done with the previous stage
+            issue(kk / KPS + DSTAGES - 1);
+        }
+        const double *st = sA + ((kk / KPS) % DSTAGES) * CHUNK + (kk % KPS) * STEP + lane;
+        const double u0 = uB[0][kk * 4], u1 = uB[1][kk * 4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+        {
+            double av[MT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) av[i] = st[(t * MT + i) * 32];
+            const double b0 = u0 * cT[t][0], b1 = u1 * cT[t][1];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+            {
+                dmma884(acc[i][0][0], acc[i][0][1], av[i], b0);
+                dmma884(acc[i][1][0], acc[i][1][1], av[i], b1);
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // v~ -> the warp's rows of sU, then out[e][off_i + q len_i] = sum_q~ Tin[q~][q] v~[(e, q~)][i]; lane = i
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+    {
+        const int m = i * 8 + (lane >> 2);
+        if (m < N)
+        {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+            {
+                double *row = sU + (size_t)(we + j * 8 + 2 * (lane & 3)) * PITCH + m;
+                row[0]      = acc[i][j][0];
+                row[PITCH]  = acc[i][j][1];
+            }
+        }
+    }
+    __syncwarp();
+    for (int k = lane; k < N; k += 32)
+    {
+        const int o = sOff[k], l = sLen[k];
+#pragma unroll
+        for (int el = 0; el < EW; ++el)
+        {
+            if (el < nLive)
+            {
+                double y[NM];
+#pragma unroll
+                for (int qt = 0; qt < NM; ++qt) y[qt] = sU[(size_t)(we + el * NM + qt) * PITCH + k];
+#pragma unroll
+                for (int q = 0; q < NM; ++q)
+                {
+                    double v = 0.0;
+#pragma unroll
+                    for (int qt = 0; qt < NM; ++qt) v = fma(sTin[qt * NM + q], y[qt], v);
+                    raw[el * NP + o + q * l] = v;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    {
+        double *dst = a.out + (size_t)eW0 * NP;
+        for (int idx = lane; idx < nLive * NP; idx += 32) dst[idx] = raw[idx];
+    }
+}
+
+// Ptri[t][k][m] = Pfull[(t n + k)][off_m] / M1[0][0]
+__global__ void prism_extract_kernel(const double *__restrict__ Pfull, double *__restrict__ Ptri, const int *__restrict__ off,
+                                     int n, int NP, double inv_m00)
+{
+    const int total = 4 * n * n;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    {
+        const int m = idx % n, tk = idx / n;
+        Ptri[idx] = Pfull[(size_t)tk * NP + off[m]] * inv_m00;
+    }
+}
+
+struct PrismState
+{
+    int (*fallback)(nekmf_op_s *, const double *const in[3], double *const out[3]) = nullptr;
+    void *fallback_state          = nullptr;
+    void (*fallback_free)(void *) = nullptr;
+    std::string fallback_name;
+    double *d_afrag = nullptr, *d_tab = nullptr;
+    int *d_itab     = nullptr;
+    int n = 0, MT = 0, KS = 0, G = 0, pitch = 0, nmq = 0, EW = 0;
+    size_t smem    = 0;
+    bool built     = false;
+    bool use_fast  = false;
+    bool attr_set  = false;
+};
+
+template <int NM> static int prism_launch_nm(nekmf_op_s *op, PrismState *st, const double *in, double *out)
+{
+    using Cfg = PrismCfg<NM>;
+    auto kern = prism_helm_kernel<NM>;
+    if (!st->attr_set)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        st->attr_set = true;
+    }
+    PrismArgs a;
+    a.in = in; a.out = out;
+    a.jac = op->d_jac + op->run_e0; a.df = op->d_df + op->run_e0; a.afrag = st->d_afrag;
+    a.tab = st->d_tab; a.itab = st->d_itab;
+    a.dfStride = (size_t)op->nElmt;
+    a.nElmt = op->run_ne; a.lambda = op->lambda;
+    const int perCta = DW * Cfg::EW;
+    const int grid   = (op->run_ne + perCta - 1) / perCta;
+    if (grid < 1) return NEKMF_OK;
+    kern<<<grid, DW * 32, Cfg::SMEM, op->run_stream>>>(a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+
+static int prism_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
+{
+    PrismState *st = static_cast<PrismState *>(op->kstate);
+    if (!st->use_fast)
+    {
+        void *saved  = op->kstate;
+        op->kstate   = st->fallback_state;
+        const int rc = st->fallback(op, in, out);
+        op->kstate   = saved;
+        return rc;
+    }
+    switch (st->nmq)
+    {
+        case 2: return prism_launch_nm<2>(op, st, in[0], out[0]);
+        case 3: return prism_launch_nm<3>(op, st, in[0], out[0]);
+        case 4: return prism_launch_nm<4>(op, st, in[0], out[0]);
+        case 5: return prism_launch_nm<5>(op, st, in[0], out[0]);
+        case 6: return prism_launch_nm<6>(op, st, in[0], out[0]);
+        case 7: return prism_launch_nm<7>(op, st, in[0], out[0]);
+        case 8: return prism_launch_nm<8>(op, st, in[0], out[0]);
+        default: set_error("prism Helmholtz: no instantiation for nm = %d", st->nmq); return NEKMF_ERR_UNSUPPORTED;
+    }
+}
+
+// generalised symmetric eigenproblem K x = mu M x of the segment matrices (nm <= 8): Cholesky + cyclic Jacobi.
+// Returns Tin = X^-1 = Q^T L^T (row q~, column q) and mu, with X^T M X = I, X^T K X = diag(mu).
+static bool seg_eigen(int nm, const std::vector<double> &M, const std::vector<double> &K, std::vector<double> &Tin,
+                      std::vector<double> &mu)
+{
+    std::vector<double> L(nm * nm, 0.0), C(nm * nm, 0.0), Q(nm * nm, 0.0), Y(nm * nm, 0.0);
+    for (int i = 0; i < nm; ++i)
+        for (int j = 0; j <= i; ++j)
+        {
+            double s = M[i * nm + j];
+            for (int k = 0; k < j; ++k) s -= L[i * nm + k] * L[j * nm + k];
+            if (i == j)
+            {
+                if (s <= 0.0) return false;
+                L[i * nm + i] = sqrt(s);
+            }
+            else L[i * nm + j] = s / L[j * nm + j];
+        }
+    // Y = L^-1 K (forward substitution on columns), C = Y L^-T = L^-1 K L^-T
+    for (int c = 0; c < nm; ++c)
+        for (int i = 0; i < nm; ++i)
+        {
+            double s = K[i * nm + c];
+            for (int k = 0; k < i; ++k) s -= L[i * nm + k] * Y[k * nm + c];
+            Y[i * nm + c] = s / L[i * nm + i];
+        }
+    for (int r = 0; r < nm; ++r)
+        for (int i = 0; i < nm; ++i)
+        {
+            double s = Y[r * nm + i];
+            for (int k = 0; k < i; ++k) s -= L[i * nm + k] * C[r * nm + k];
+            C[r * nm + i] = s / L[i * nm + i];
+        }
+    for (int i = 0; i < nm; ++i)
+        for (int j = 0; j < i; ++j) C[i * nm + j] = C[j * nm + i] = 0.5 * (C[i * nm + j] + C[j * nm + i]);
+    for (int i = 0; i < nm; ++i) Q[i * nm + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep)
+    {
+        double off = 0.0, dia = 0.0;
+        for (int i = 0; i < nm; ++i)
+            for (int j = 0; j < nm; ++j) (i == j ? dia : off) += C[i * nm + j] * C[i * nm + j];
+        if (off <= 1e-32 * dia) break;
+        for (int p = 0; p < nm; ++p)
+            for (int q = p + 1; q < nm; ++q)
+            {
+                const double apq = C[p * nm + q];
+                if (apq == 0.0) continue;
+                const double th = (C[q * nm + q] - C[p * nm + p]) / (2.0 * apq);
+                const double tt = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                const double cs = 1.0 / sqrt(tt * tt + 1.0), sn = tt * cs;
+                for (int k = 0; k < nm; ++k)
+                {
+                    const double akp = C[k * nm + p], akq = C[k * nm + q];
+                    C[k * nm + p] = cs * akp - sn * akq;
+                    C[k * nm + q] = sn * akp + cs * akq;
+                }
+                for (int k = 0; k < nm; ++k)
+                {
+                    const double apk = C[p * nm + k], aqk = C[q * nm + k];
+                    C[p * nm + k] = cs * apk - sn * aqk;
+                    C[q * nm + k] = sn * apk + cs * aqk;
+                }
+                for (int k = 0; k < nm; ++k)
+                {
+                    const double qkp = Q[k * nm + p], qkq = Q[k * nm + q];
+                    Q[k * nm + p] = cs * qkp - sn * qkq;
+                    Q[k * nm + q] = sn * qkp + cs * qkq;
+                }
+            }
+    }
+    Tin.assign(nm * nm, 0.0);
+    mu.assign(nm, 0.0);
+    for (int a = 0; a < nm; ++a)
+    {
+        mu[a] = C[a * nm + a];
+        for (int q = 0; q < nm; ++q)
+        {
+            double s = 0.0; // (Q^T L^T)[a][q] = sum_k Q[k][a] L[q][k]
+            for (int k = 0; k < nm; ++k) s += Q[k * nm + a] * L[q * nm + k];
+            Tin[a * nm + q] = s;
+        }
+    }
+    return true;
+}
+
+static int prism_build(nekmf_op_s *op, PrismState *st)
+{
+    const int nm = st->nmq, n = st->n, NP = op->nmTot, nq1 = op->nq[1];
+    // segment matrices from the direction-1 tables (Operator.hpp:244-258 weights, no collapsed factor in xi_1)
+    std::vector<double> M1(nm * nm), K1(nm * nm), Tin, mu;
+    const double *B = op->b[1].data(), *dB = op->db[1].data(), *w = op->ws[1].data();
+    for (int a = 0; a < nm; ++a)
+        for (int c = 0; c < nm; ++c)
+        {
+            double m = 0.0, k = 0.0;
+            for (int j = 0; j < nq1; ++j)
+            {
+                m += B[a * nq1 + j] * w[j] * B[c * nq1 + j];
+                k += dB[a * nq1 + j] * w[j] * dB[c * nq1 + j];
+            }
+            M1[a * nm + c] = m;
+            K1[a * nm + c] = k;
+        }
+    if (!seg_eigen(nm, M1, K1, Tin, mu)) { set_error("prism Helmholtz: segment mass matrix not positive definite"); return NEKMF_ERR_ARG; }
+    std::vector<double> tab(Tin);
+    tab.insert(tab.end(), mu.begin(), mu.end());
+    std::vector<int> itab(2 * n);
+    for (int p = 0, i = 0; p < nm; ++p)
+        for (int r = 0; r < nm - p; ++r, ++i)
+        {
+            const int tri0 = p * nm - (p * (p - 1)) / 2;
+            itab[i]     = nm * tri0 + r; // mode (p, q = 0, r): [p][q][r], nm - p values of r per (p, q)
+            itab[n + i] = nm - p;
+        }
+    // probes: 4 geometries x n unit vectors on the q = 0 modes
+    const size_t nel = (size_t)3 * n;
+    std::vector<double> h_in((size_t)4 * n * NP, 0.0), h_jac(nel, 1.0), h_df((size_t)9 * nel, 0.0);
+    for (int t = 0; t < 4; ++t)
+        for (int k = 0; k < n; ++k) h_in[((size_t)t * n + k) * NP + itab[k]] = 1.0;
+    for (int k = 0; k < n; ++k)
+    {
+        h_df[(size_t)0 * nel + 0 * n + k] = 1.0;                                       // G00
+        h_df[(size_t)2 * nel + 1 * n + k] = 1.0;                                       // G22
+        h_df[(size_t)0 * nel + 2 * n + k] = 1.0; h_df[(size_t)2 * nel + 2 * n + k] = 1.0; // G00 + G22 + 2 G02
+    }
+    double *d_in = nullptr, *d_P = nullptr, *d_Pt = nullptr, *d_pjac = nullptr, *d_pdf = nullptr, *d_zero = nullptr;
+    auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_P); cudaFree(d_Pt); cudaFree(d_pjac); cudaFree(d_pdf); cudaFree(d_zero); };
+#define PB_CUDA(call)                                                                                          \
+    do                                                                                                         \
+    {                                                                                                          \
+        cudaError_t _e = (call);                                                                               \
+        if (_e != cudaSuccess)                                                                                 \
+        {                                                                                                      \
+            set_error("prism Helmholtz setup: %s failed: %s", #call, cudaGetErrorString(_e));                  \
+            cleanup();                                                                                         \
+            return NEKMF_ERR_CUDA;                                                                             \
+        }                                                                                                      \
+    } while (0)
+    PB_CUDA(cudaMalloc(&d_in, h_in.size() * 8));
+    PB_CUDA(cudaMalloc(&d_P, h_in.size() * 8));
+    PB_CUDA(cudaMalloc(&d_Pt, (size_t)4 * n * n * 8));
+    PB_CUDA(cudaMalloc(&d_pjac, nel * 8));
+    PB_CUDA(cudaMalloc(&d_pdf, h_df.size() * 8));
+    PB_CUDA(cudaMalloc(&d_zero, h_df.size() * 8));
+    PB_CUDA(cudaMemcpy(d_in, h_in.data(), h_in.size() * 8, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(d_pjac, h_jac.data(), nel * 8, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(d_pdf, h_df.data(), h_df.size() * 8, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemset(d_zero, 0, h_df.size() * 8));
+    if (!st->d_afrag) PB_CUDA(cudaMalloc(&st->d_afrag, (size_t)st->G * st->MT * 32 * 8));
+    if (!st->d_tab) PB_CUDA(cudaMalloc(&st->d_tab, tab.size() * 8));
+    if (!st->d_itab) PB_CUDA(cudaMalloc(&st->d_itab, itab.size() * 4));
+    PB_CUDA(cudaMemcpy(st->d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(st->d_itab, itab.data(), itab.size() * 4, cudaMemcpyHostToDevice));
+
+    double *s_jac = op->d_jac, *s_df = op->d_df;
+    const int s_nel = op->nElmt, s_e0 = op->run_e0, s_ne = op->run_ne;
+    const double s_lambda = op->lambda;
+    cudaStream_t s_stream = op->run_stream;
+    void *s_state         = op->kstate;
+    op->kstate     = st->fallback_state;
+    op->nElmt      = (int)nel;
+    op->run_e0     = 0;
+    op->run_stream = op->stream;
+    op->d_jac      = d_pjac;
+    const double *in3[3] = {d_in, nullptr, nullptr};
+    double *out3[3]      = {d_P, nullptr, nullptr};
+    op->lambda = 1.0; op->d_df = d_zero; op->run_ne = n;
+    int rc = st->fallback(op, in3, out3);
+    if (rc == NEKMF_OK)
+    {
+        in3[0]     = d_in + (size_t)n * NP;
+        out3[0]    = d_P + (size_t)n * NP;
+        op->lambda = 0.0; op->d_df = d_pdf; op->run_ne = (int)nel;
+        rc         = st->fallback(op, in3, out3);
+    }
+    op->kstate = s_state; op->nElmt = s_nel; op->run_e0 = s_e0; op->run_ne = s_ne; op->run_stream = s_stream;
+    op->d_jac = s_jac; op->d_df = s_df; op->lambda = s_lambda;
+    if (rc != NEKMF_OK) { cleanup(); return rc; }
+    prism_extract_kernel<<<(4 * n * n + 255) / 256, 256, 0, op->stream>>>(d_P, d_Pt, st->d_itab, n, NP, 1.0 / M1[0]);
+    ++g_launches;
+    PB_CUDA(cudaGetLastError());
+    const int total = 4 * st->KS * st->MT * 32;
+    dense_pack_kernel<<<(total + 255) / 256, 256, 0, op->stream>>>(d_Pt, st->d_afrag, n, st->KS, st->MT, 4, 2, 1);
+    ++g_launches;
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaStreamSynchronize(op->stream));
+#undef PB_CUDA
+    cleanup();
+    st->built = true;
+    return NEKMF_OK;
+}
+
+void prism_maybe_wrap(nekmf_op_s *op)
+{
+    if (op->shape != NEKMF_PRISM || op->optype != NEKMF_HELMHOLTZ || op->deformed || op->kron) return;
+    const int nm = op->nm[0];
+    if (op->nm[1] != nm || op->nm[2] != nm || nm < 2 || nm > 8) return;
+    const int n = nm * (nm + 1) / 2;
+    if (op->nmTot != nm * n || op->coordim != 3) return;
+    const int MT = (n + 7) / 8, KS = (n + 3) / 4;
+    if (MT > 5) return;
+    PrismState *st     = new PrismState;
+    st->n = n; st->MT = MT; st->KS = KS; st->G = 4 * KS; st->nmq = nm; st->EW = 16 / nm;
+    st->fallback       = op->launch;
+    st->fallback_state = op->kstate;
+    st->fallback_free  = op->kstate_free;
+    st->fallback_name  = op->kname;
+    op->kstate         = st;
+    op->kstate_free    = [](void *p) {
+        PrismState *s = static_cast<PrismState *>(p);
+        if (s->fallback_state && s->fallback_free) s->fallback_free(s->fallback_state);
+        cudaFree(s->d_afrag);
+        cudaFree(s->d_tab);
+        cudaFree(s->d_itab);
+        delete s;
+    };
+    op->launch = prism_launch;
+    op->kron   = 4;
+}
+
+int prism_geom_changed(nekmf_op_s *op)
+{
+    if (op->kron != 4) return NEKMF_OK;
+    PrismState *st = static_cast<PrismState *>(op->kstate);
+    st->use_fast   = false;
+    op->kname      = st->fallback_name;
+    const char *env = getenv("NEKMF_DENSE");
+    if (env && env[0] == '0') return NEKMF_OK;
+    if (!op->has_jac || !op->has_df || op->nElmt == 0) return NEKMF_OK;
+    // extruded prisms only: G01 = G12 = 0 for every element
+    std::vector<double> df((size_t)9 * op->nElmt);
+    NEKMF_CUDA(cudaMemcpy(df.data(), op->d_df, df.size() * 8, cudaMemcpyDeviceToHost));
+    const size_t N = op->nElmt;
+    for (size_t e = 0; e < N; ++e)
+    {
+        double g[3][3];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                g[a][b] = df[(0 * 3 + a) * N + e] * df[(0 * 3 + b) * N + e] + df[(1 * 3 + a) * N + e] * df[(1 * 3 + b) * N + e] +
+                          df[(2 * 3 + a) * N + e] * df[(2 * 3 + b) * N + e];
+        const double tol = 1e-14 * (g[0][0] + g[1][1] + g[2][2]);
+        if (fabs(g[0][1]) > tol || fabs(g[1][2]) > tol) return NEKMF_OK;
+    }
+    if (!st->built)
+    {
+        const int rc = prism_build(op, st);
+        if (rc != NEKMF_OK) return rc;
+    }
+    st->use_fast = true;
+    char name[112];
+    snprintf(name, sizeof(name), "prism_helm_kernel<nm=%d,MT=%d>(regular,extruded,DMMA m8n8k4)", st->nmq, st->MT);
     op->kname = name;
     return NEKMF_OK;
 }

@@ -65,5 +65,6 @@ void notify_geom_changed(nekmf_op_s *op)
     kron_geom_changed(op);
     quad_kron_geom_changed(op);
     dense_geom_changed(op);
+    prism_geom_changed(op);
 }
 } // namespace nekmf

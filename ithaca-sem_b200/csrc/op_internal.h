@@ -49,7 +49,7 @@ struct nekmf_op_s
     bool gather_ok           = false;
     const int *gather_map    = nullptr;
     const double *gather_sign = nullptr;
-    int kron         = 0; // regular Helmholtz: coefficient-space kernel available (1 hex_kron.cu, 2 quad_kron.cu, 3 dense_helm.cu)
+    int kron         = 0; // regular Helmholtz: coefficient-space kernel available (1 hex_kron.cu, 2 quad_kron.cu, 3 dense_helm.cu, 4 its prism variant)
     bool timing      = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed_once = false;
@@ -72,4 +72,6 @@ void quad_kron_maybe_wrap(nekmf_op_s *op);
 int quad_kron_geom_changed(nekmf_op_s *op);
 void dense_maybe_wrap(nekmf_op_s *op); // dense_helm.cu: DMMA coefficient-space Helmholtz (regular Tri / Tet / Pyr)
 int dense_geom_changed(nekmf_op_s *op);
+void prism_maybe_wrap(nekmf_op_s *op); // dense_helm.cu: extruded prisms as nm triangle problems per element
+int prism_geom_changed(nekmf_op_s *op);
 } // namespace nekmf

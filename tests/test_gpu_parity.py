@@ -118,6 +118,42 @@ def test_dense_dmma_helmholtz(shape, nm, nel, monkeypatch):
     check(yd[1:].cpu().numpy(), out0, "dense vs quadrature-space kernel")
 
 
+@pytest.mark.parametrize("nel", [1, 2, 3, 7, 8, 9, 100])
+@pytest.mark.parametrize("nm", [2, 3, 4, 5, 6, 7, 8])
+def test_prism_extruded_dmma_helmholtz(nm, nel, monkeypatch):
+    """Regular prisms whose segment direction is orthogonal to the triangle plane (G01 = G12 = 0: extruded meshes,
+    prisms cut from boxes) take prism_helm_kernel (dense_helm.cu): the segment's generalised eigen-decomposition
+    turns the element into nm triangle Helmholtz problems for the DMMA GEMM.  The geometry is an extruded element
+    rotated by a random orthogonal matrix, so all nine derivative factors are non-zero."""
+    monkeypatch.delenv("NEKMF_DENSE", raising=False)
+    nk = nekmf()
+    rng = np.random.default_rng(nm * 53 + nel)
+    el = po.Elem(po.PRISM, nm, nm + 1)
+    std = nk.StdExpansion(po.PRISM, nm, nm + 1)
+    jac = rng.uniform(0.5, 1.5, nel)
+    df = np.zeros((3, 3, nel))  # [c][d]
+    for e in range(nel):
+        a = np.zeros((3, 3))
+        a[np.ix_([0, 2], [0, 2])] = rng.uniform(-0.3, 0.3, (2, 2)) + 1.5 * np.eye(2)
+        a[1, 1] = rng.uniform(0.8, 2.0)
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        df[:, :, e] = q @ a
+    df = np.ascontiguousarray(df.reshape(9, nel)).reshape(-1)
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, False))
+    x = rng.uniform(-1, 1, nel * el.nmTot)
+    for lam in (1.3, 0.0, 37.5):
+        out = np.zeros(nel * el.nmTot)
+        coll.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
+        check(out, el.helmholtz(nel, False, jac, df, lam, x), "Helmholtz(prism extruded, lambda=%g)" % lam)
+    assert "prism_helm_kernel" in coll.m_ops[nk.eHelmholtz].kernel_name, coll.m_ops[nk.eHelmholtz].kernel_name
+    monkeypatch.setenv("NEKMF_DENSE", "0")
+    coll0 = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, False))
+    out0 = np.zeros(nel * el.nmTot)
+    coll0.ApplyOperator(nk.eHelmholtz, x, out0, factors={nk.eFactorLambda: 37.5})
+    assert "shape_op_kernel" in coll0.m_ops[nk.eHelmholtz].kernel_name
+    check(out, out0, "prism DMMA vs quadrature-space kernel")
+
+
 def golden_cases():
     return sorted(set(k.rsplit("_", 1)[0] for k in GOLD.files if k.endswith("_x") and not k.startswith("Seg")))
 
