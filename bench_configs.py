@@ -202,6 +202,14 @@ def config4(args, torch, nk, po, peak, peak_src, ClockSampler):
         per[name] = {"elements": nel, "ncoeffs": std.GetNcoeffs(), "ms": avg, "gdof_per_s": nel * std.GetNcoeffs() / (avg * 1e-3) / 1e9,
                      "algorithmic_bytes_per_element": by, "gb_per_s": by * nel / (avg * 1e-3) / 1e9,
                      "frac_hbm": by * nel / (avg * 1e-3) / 1e9 / peak, "kernel": ops[name].kernel_name}
+        if ops[name].kernel_name.startswith("prism_helm_kernel"):
+            # nm triangle problems per element: per 16-column warp tile (16 // nm elements) 4 terms of
+            # (8 MT) x (4 KS) x 16 DMMA work, idle columns included
+            ntri = nm * (nm + 1) // 2
+            fl = 2 * (8 * ((ntri + 7) // 8)) * 4 * (4 * ((ntri + 3) // 4)) * 16 // (16 // nm)
+            per[name].update({"bound": "tensor (FP64 DMMA)", "flops_per_element_issued": fl,
+                              "tflops": fl * nel / (avg * 1e-3) / 1e12, "frac_dmma": fl * nel / (avg * 1e-3) / 1e12 / 37.1,
+                              "dmma_peak_tflops": 37.1})
         if ops[name].kernel_name.startswith("dense_helm_kernel"):
             # the DMMA GEMM issued per element: (8 MT) rows x 7 terms x (4 KS) padded columns; peak = the DMMA
             # microbenchmark of tools/fp64_peak.cu (profiles/r01_fp64_peak.jsonl)
@@ -243,11 +251,20 @@ def config4(args, torch, nk, po, peak, peak_src, ClockSampler):
                                "(BASELINE configs[3])" % n,
                    "elements": {k: v["elements"] for k, v in per.items()},
                    "l2": "coefficient arrays of the three collections total %d MB per apply, no flush" % (ndof * 16 >> 20)},
-        "roofline": {"bound": "hbm", "achieved": per[dom]["gb_per_s"], "peak": peak, "unit": "GB/s",
+        "roofline": ({"bound": "tensor", "achieved": per[dom]["tflops"], "peak": 37.1, "unit": "TFLOP/s",
+                      "frac": per[dom]["frac_dmma"], "traffic": None,
+                      "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) microbenchmark tools/fp64_peak.cu, "
+                                     "profiles/r01_fp64_peak.jsonl (MEASURED_PEAKS.json holds bf16 and HBM only)",
+                      "flops_per_element_issued": per[dom]["flops_per_element_issued"], "kernel": per[dom]["kernel"],
+                      "kernel_ms": per[dom]["ms"], "frac_hbm": per[dom]["frac_hbm"],
+                      "note": "dominant kernel of the step is an FP64 tensor-core GEMM (DESIGN.md 4.3a/4.3b)"}
+                     if "frac_dmma" in per[dom] else
+                     {"bound": "hbm", "achieved": per[dom]["gb_per_s"], "peak": peak, "unit": "GB/s",
                      "frac": per[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_element": per[dom]["algorithmic_bytes_per_element"], "kernel": per[dom]["kernel"],
                      "kernel_ms": per[dom]["ms"],
-                     "note": "regular-geometry Helmholtz at P=6 is FP64/shared-memory bound, not HBM bound"},
+                     "note": "regular-geometry Helmholtz at P=6 is FP64 bound, not HBM bound: per_shape carries the DMMA "
+                             "throughput of the tensor-core kernels (frac_dmma, against the measured 37.1 TFLOP/s)"}),
         "per_shape": per, "gpu_launches": 3 * args.steps,
         "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
         "cpu_baseline": {"value": cpu_dof / cpu_t / 1e9, "unit": "GDOF/s", "cores": threads, "kind": kind,

@@ -428,7 +428,8 @@ def test_cpp_collections_mirror():
     assert "PASSED" in r.stdout
 
 
-@pytest.mark.parametrize("case", ["hex_regular_diag", "hex_regular_sheared", "hex_deformed", "tet_deformed", "quad_regular"])
+@pytest.mark.parametrize("case", ["hex_regular_diag", "hex_regular_sheared", "hex_deformed", "tet_deformed", "quad_regular",
+                                  "tet_regular", "prism_extruded"])
 def test_host_array_pipeline_many_chunks(case):
     """NEKMF_HOST applies are cut into element chunks (2 MB ramping to 32 MB) over a 3-stream H2D/kernel/D2H pipeline
     (abi.cu): collections large enough for several chunks (ragged last one) must give exactly the
@@ -439,7 +440,8 @@ def test_host_array_pipeline_many_chunks(case):
     shape, nm, nq0, nel, deformed = {
         "hex_regular_diag": (po.HEX, 5, 6, 20001, False), "hex_regular_sheared": (po.HEX, 5, 6, 20001, False),
         "hex_deformed": (po.HEX, 4, 5, 25003, True), "tet_deformed": (po.TET, 5, 6, 40001, True),
-        "quad_regular": (po.QUAD, 6, 7, 90001, False)}[case]
+        "quad_regular": (po.QUAD, 6, 7, 90001, False), "tet_regular": (po.TET, 6, 7, 30001, False),
+        "prism_extruded": (po.PRISM, 5, 6, 30001, False)}[case]
     el = po.Elem(shape, nm, nq0)
     jac, df = random_geometry(rng, el.dim, nel, el.nqTot, deformed)
     if case == "hex_regular_diag":
@@ -447,6 +449,11 @@ def test_host_array_pipeline_many_chunks(case):
         for n in range(9):
             if n not in (0, 4, 8):
                 df[n] = 0.0
+        df = df.reshape(-1)
+    if case == "prism_extruded":  # segment direction orthogonal to the triangle plane: G01 = G12 = 0
+        df = df.reshape(9, nel).copy()
+        for n in (1, 3, 5, 7):
+            df[n] = 0.0
         df = df.reshape(-1)
     std = nk.StdExpansion(shape, nm, nq0)
     coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, deformed))
@@ -476,6 +483,10 @@ def test_host_array_pipeline_many_chunks(case):
     if case == "hex_regular_diag":
         assert "kron" in coll.m_ops[nk.eHelmholtz].kernel_name if nk.eHelmholtz in coll.m_ops else True
     h = both(nk.eHelmholtz, [x], [tx], 1, nel * el.nmTot, factors={nk.eFactorLambda: 0.7})[0]
+    if case == "tet_regular":
+        assert "dense_helm_kernel" in coll.m_ops[nk.eHelmholtz].kernel_name
+    if case == "prism_extruded":
+        assert "prism_helm_kernel" in coll.m_ops[nk.eHelmholtz].kernel_name
     both(nk.eIProductWRTDerivBase, f, tf, 1, nel * el.nmTot)
     # oracle on the last 300 elements (covers the ragged last chunk and its geometry offsets)
     ns = 300
