@@ -525,6 +525,8 @@ struct PrismArgs
     double lambda;
 };
 
+constexpr int PSTAGES = 3; // A-fragment ring of the prism kernel (four CTAs per SM at nm = 7)
+
 template <int NM> struct PrismCfg
 {
     static constexpr int N = NM * (NM + 1) / 2, MT = (N + 7) / 8, KS = (N + 3) / 4, K4 = KS * 4;
@@ -536,7 +538,7 @@ template <int NM> struct PrismCfg
     static constexpr int NS    = (KS + KPS - 1) / KPS;
     static constexpr int TABD  = (NM * NM + NM + 1) & ~1;            // Tin | mu
     static constexpr int TABI  = (2 * N + 1) & ~1;                   // off | len (ints)
-    static constexpr size_t SMEM = (size_t)(DSTAGES * CHUNK + DW * 16 * PITCH + TABD + TABI / 2 + DW * EW * NP) * 8;
+    static constexpr size_t SMEM = (size_t)(PSTAGES * CHUNK + DW * 16 * PITCH + TABD + TABI / 2 + DW * EW * NP) * 8;
 };
 
 template <int NM> __global__ void __launch_bounds__(DW * 32, 2) prism_helm_kernel(const __grid_constant__ PrismArgs a)
@@ -545,8 +547,8 @@ template <int NM> __global__ void __launch_bounds__(DW * 32, 2) prism_helm_kerne
     constexpr int N = Cfg::N, MT = Cfg::MT, KS = Cfg::KS, PITCH = Cfg::PITCH, NP = Cfg::NP, EW = Cfg::EW, USED = Cfg::USED;
     constexpr int CHUNK = Cfg::CHUNK, STEP = Cfg::STEP, NS = Cfg::NS, KPS = Cfg::KPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sA   = reinterpret_cast<double *>(smem_raw); // [DSTAGES][CHUNK]
-    double *sU   = sA + DSTAGES * CHUNK;                 // [DW*16][PITCH]
+    double *sA   = reinterpret_cast<double *>(smem_raw); // [PSTAGES][CHUNK]
+    double *sU   = sA + PSTAGES * CHUNK;                 // [DW*16][PITCH]
     double *sTin = sU + DW * 16 * PITCH;                 // [NM*NM] | mu[NM]
     int *sOff    = reinterpret_cast<int *>(sTin + Cfg::TABD);
     int *sLen    = sOff + N;
@@ -562,14 +564,13 @@ template <int NM> __global__ void __launch_bounds__(DW * 32, 2) prism_helm_kerne
             const int k0 = st * KPS, k1 = (k0 + KPS < KS) ? k0 + KPS : KS;
             const int units   = (k1 - k0) * (STEP / 2);
             const double *src = a.afrag + (size_t)k0 * STEP;
-            double *dst       = sA + (st % DSTAGES) * CHUNK;
+            double *dst       = sA + (st % PSTAGES) * CHUNK;
             for (int i = tid; i < units; i += DW * 32) cp_async16(dst + 2 * i, src + 2 * i);
         }
         cp_async_commit();
     };
-    issue(0);
-    issue(1);
-    issue(2);
+#pragma unroll
+    for (int st = 0; st < PSTAGES - 1; ++st) issue(st);
     for (int i = tid; i < NM * NM + NM; i += DW * 32) sTin[i] = __ldg(a.tab + i);
     for (int i = tid; i < 2 * N; i += DW * 32) sOff[i] = __ldg(a.itab + i);
 
@@ -644,11 +645,11 @@ template <int NM> __global__ void __launch_bounds__(DW * 32, 2) prism_helm_kerne
     {
         if (kk % KPS == 0)
         {
-            cp_async_wait<DSTAGES - 2>(); // this thread's copies of the stage have landed
+            cp_async_wait<PSTAGES - 2>(); // this thread's copies of the stage have landed
             __syncthreads();              // everyone's have, and everyone is done with the previous stage
-            issue(kk / KPS + DSTAGES - 1);
+            issue(kk / KPS + PSTAGES - 1);
         }
-        const double *st = sA + ((kk / KPS) % DSTAGES) * CHUNK + (kk % KPS) * STEP + lane;
+        const double *st = sA + ((kk / KPS) % PSTAGES) * CHUNK + (kk % KPS) * STEP + lane;
         const double u0 = uB[0][kk * 4], u1 = uB[1][kk * 4];
 #pragma unroll
         for (int t = 0; t < 4; ++t)
