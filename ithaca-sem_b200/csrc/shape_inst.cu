@@ -27,15 +27,17 @@ template <int SHAPE, int OP, int NM, bool DEF> static int shape_launch(nekmf_op_
     using Dm  = ShpDims<SHAPE, NM>;
     auto *st  = static_cast<ShpState<SHAPE, NM> *>(op->kstate);
     auto kern = shape_op_kernel<SHAPE, OP, NM, DEF>;
+    // coefficient-input operators carry a second coefficient buffer behind the common layout (next-batch prefetch)
+    constexpr size_t SMEM = Dm::SMEM + ((OP == NEKMF_BWDTRANS || OP == NEKMF_HELMHOLTZ) ? (size_t)Dm::CINSZ * 8 : 0);
     if (st->blocks_per_sm == 0)
     {
-        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Dm::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int nb = 0;
-        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Dm::T, Dm::SMEM));
+        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Dm::T, SMEM));
         if (nb < 1)
         {
-            set_error("shape kernel <%d,%d,%d,%d> does not fit on an SM (smem %zu)", SHAPE, OP, NM, (int)DEF, (size_t)Dm::SMEM);
+            set_error("shape kernel <%d,%d,%d,%d> does not fit on an SM (smem %zu)", SHAPE, OP, NM, (int)DEF, (size_t)SMEM);
             return NEKMF_ERR_CUDA;
         }
         st->blocks_per_sm = nb;
@@ -54,7 +56,7 @@ template <int SHAPE, int OP, int NM, bool DEF> static int shape_launch(nekmf_op_
     int grid           = st->blocks_per_sm * NUM_SMS;
     if (grid > nBatches) grid = nBatches;
     if (grid < 1) return NEKMF_OK;
-    kern<<<grid, Dm::T, Dm::SMEM, op->run_stream>>>(st->tab, a);
+    kern<<<grid, Dm::T, SMEM, op->run_stream>>>(st->tab, a);
     ++g_launches;
     NEKMF_CUDA(cudaGetLastError());
     return NEKMF_OK;

@@ -168,6 +168,9 @@ __global__ void __launch_bounds__(256)
     int *sPQp    = reinterpret_cast<int *>(sG + Dm::GSZ); // pair index -> p
     int *sPQq    = sPQp + NPAIR;                        // pair index -> q
     int *sPQm    = sPQq + NPAIR;                        // Tet: first mode of pair (p,q)
+    // coefficient-input operators: second coefficient buffer, filled by cp.async with the NEXT batch while this
+    // one is computed (ncu: the exposed load + barrier at the top of a batch was 20 % of the prism Helmholtz kernel)
+    double *sCinAlt = reinterpret_cast<double *>(smem_raw + Dm::SMEM);
     const double *b1c = sAux + Dm::OFF_B1C, *b2c = sAux + Dm::OFF_B2C;
     const double *sW0 = sAux + Dm::OFF_W, *sW1 = sW0 + NQM, *sW2 = sW1 + NQM;
     const double *sH0 = sAux + Dm::OFF_H, *sH1 = sH0 + NQM, *sH2 = sH1 + NQM, *sH3 = sH2 + NQM;
@@ -193,6 +196,15 @@ __global__ void __launch_bounds__(256)
     // first pair / (p,r) row of outer index p: p*NM - p(p-1)/2
     auto tri0 = [](int p) { return p * NM - (p * (p - 1)) / 2; };
 
+    auto prefetch = [&](int b, double *dst) {
+        const int e0 = b * E, ne = nElmt - e0 < E ? nElmt - e0 : E;
+        const double *src = args.in0 + (size_t)e0 * NMT;
+        for (int i = tid; i < ne * NMT; i += T)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst + i)), "l"(src + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (COEFF_IN && (int)blockIdx.x < nBatches) prefetch(blockIdx.x, sCin);
+
     for (int b = blockIdx.x; b < nBatches; b += gridDim.x)
     {
         const int e0 = b * E;
@@ -201,8 +213,9 @@ __global__ void __launch_bounds__(256)
         // ------------------------------------------------------------------ load
         if (COEFF_IN)
         {
-            const double *src = args.in0 + (size_t)e0 * NMT;
-            for (int i = tid; i < ne * NMT; i += T) sCin[i] = __ldg(src + i);
+            asm volatile("cp.async.wait_group 0;" ::: "memory"); // this batch (requested one batch ago) has landed
+            __syncthreads();                                      // for every thread; the other buffer is free
+            if (b + (int)gridDim.x < nBatches) prefetch(b + gridDim.x, sCinAlt);
         }
         else if (IPWDB)
         {
@@ -393,6 +406,9 @@ __global__ void __launch_bounds__(256)
                 dst[g] = sU[e * NQP + line * P1 + i];
             }
             __syncthreads();
+            {
+                double *t = sCin; sCin = sCinAlt; sCinAlt = t;
+            }
             continue;
         }
 
@@ -833,6 +849,10 @@ __global__ void __launch_bounds__(256)
             double *dst = args.out0 + (size_t)e0 * NMT;
             for (int i = tid; i < ne * NMT; i += T) dst[i] = sCin[i];
             __syncthreads();
+        }
+        if (COEFF_IN)
+        {
+            double *t = sCin; sCin = sCinAlt; sCinAlt = t;
         }
     }
 }
