@@ -617,8 +617,6 @@ template <int NM> __global__ void __launch_bounds__(DW * 32, 2) prism_helm_kerne
 #pragma unroll
         for (int col = 0; col < 16; ++col)
         {
-            constexpr int dummy = 0;
-            (void)dummy;
             const int el = col / NM, qt = col - el * NM;
             double v = 0.0;
             if (col < USED)
@@ -735,8 +733,7 @@ struct PrismState
     std::string fallback_name;
     double *d_afrag = nullptr, *d_tab = nullptr;
     int *d_itab     = nullptr;
-    int n = 0, MT = 0, KS = 0, G = 0, pitch = 0, nmq = 0, EW = 0;
-    size_t smem    = 0;
+    int n = 0, MT = 0, KS = 0, G = 0, nmq = 0, EW = 0;
     bool built     = false;
     bool use_fast  = false;
     bool attr_set  = false;
