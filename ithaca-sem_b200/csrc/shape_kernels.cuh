@@ -204,6 +204,22 @@ __global__ void __launch_bounds__(256)
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (COEFF_IN && (int)blockIdx.x < nBatches) prefetch(blockIdx.x, sCin);
+    // regular IProductWRTBase: the quadrature values of the NEXT batch are copied (raw) into sU as soon as the first
+    // transposed pass has consumed it; Jacobian and weights are applied when that pass reads them
+    constexpr bool IP_PREF = OP == NEKMF_IPRODUCTWRTBASE && !DEF;
+    auto prefetch_phys = [&](int b) {
+        const int e0 = b * E, ne = nElmt - e0 < E ? nElmt - e0 : E;
+        const double *src = args.in0 + (size_t)e0 * NQT;
+        for (int g = tid; g < ne * NQT; g += T)
+        {
+            const int e = g / NQT, r = g - e * NQT;
+            const int line = r / NQ0, i = r - line * NQ0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sU + e * NQP + line * P1 + i)), "l"(src + g)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (IP_PREF && (int)blockIdx.x < nBatches) prefetch_phys(blockIdx.x);
 
     for (int b = blockIdx.x; b < nBatches; b += gridDim.x)
     {
@@ -216,6 +232,10 @@ __global__ void __launch_bounds__(256)
             asm volatile("cp.async.wait_group 0;" ::: "memory"); // this batch (requested one batch ago) has landed
             __syncthreads();                                      // for every thread; the other buffer is free
             if (b + (int)gridDim.x < nBatches) prefetch(b + gridDim.x, sCinAlt);
+        }
+        else if (IP_PREF)
+        {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         else if (IPWDB)
         {
@@ -691,6 +711,14 @@ __global__ void __launch_bounds__(256)
             double v[NQ0], f[NM];
 #pragma unroll
             for (int i = 0; i < NQ0; ++i) v[i] = sU[e * NQP + ln * P1 + i];
+            if (IP_PREF)
+            {
+                const int k = ln / NQ1, j = ln - k * NQ1;
+                double jwl = (e < ne ? __ldg(args.jac + e0 + e) : 0.0) * sW1[j];
+                if (DIM == 3) jwl *= sW2[k];
+#pragma unroll
+                for (int i = 0; i < NQ0; ++i) v[i] *= jwl * sW0[i];
+            }
             if (HELM_BACK)
             {
                 double a[NQ0], t[NQ0];
@@ -705,6 +733,7 @@ __global__ void __launch_bounds__(256)
             for (int p = 0; p < NM; ++p) sB[e * NQP + p * LN + ln] = f[p];
         }
         __syncthreads();
+        if (IP_PREF && b + (int)gridDim.x < nBatches) prefetch_phys(b + gridDim.x);
         // T2: j -> q, lines (p,k)
         for (int l = tid; l < E * NM * NQ2; l += T)
         {
