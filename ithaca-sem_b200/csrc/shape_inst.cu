@@ -27,8 +27,10 @@ template <int SHAPE, int OP, int NM, bool DEF> static int shape_launch(nekmf_op_
     using Dm  = ShpDims<SHAPE, NM>;
     auto *st  = static_cast<ShpState<SHAPE, NM> *>(op->kstate);
     auto kern = shape_op_kernel<SHAPE, OP, NM, DEF>;
-    // coefficient-input operators carry a second coefficient buffer behind the common layout (next-batch prefetch)
-    constexpr size_t SMEM = Dm::SMEM + ((OP == NEKMF_BWDTRANS || OP == NEKMF_HELMHOLTZ) ? (size_t)Dm::CINSZ * 8 : 0);
+    // coefficient-input operators carry a second coefficient buffer behind the common layout, PhysDeriv a second
+    // quadrature buffer (next-batch prefetch)
+    constexpr size_t SMEM = Dm::SMEM + ((OP == NEKMF_BWDTRANS || OP == NEKMF_HELMHOLTZ) ? (size_t)Dm::CINSZ * 8 : 0) +
+                            (OP == NEKMF_PHYSDERIV ? (size_t)Dm::BUF * 8 : 0); // second input buffer (next-batch prefetch)
     if (st->blocks_per_sm == 0)
     {
         NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));

@@ -207,19 +207,22 @@ __global__ void __launch_bounds__(256)
     // regular IProductWRTBase: the quadrature values of the NEXT batch are copied (raw) into sU as soon as the first
     // transposed pass has consumed it; Jacobian and weights are applied when that pass reads them
     constexpr bool IP_PREF = OP == NEKMF_IPRODUCTWRTBASE && !DEF;
-    auto prefetch_phys = [&](int b) {
+    // PhysDeriv: a second quadrature buffer behind the common layout (same place as sCinAlt) takes the next batch
+    constexpr bool PD_PREF = OP == NEKMF_PHYSDERIV;
+    double *sUAlt          = reinterpret_cast<double *>(smem_raw + Dm::SMEM);
+    auto prefetch_phys = [&](int b, double *dstU) {
         const int e0 = b * E, ne = nElmt - e0 < E ? nElmt - e0 : E;
         const double *src = args.in0 + (size_t)e0 * NQT;
         for (int g = tid; g < ne * NQT; g += T)
         {
             const int e = g / NQT, r = g - e * NQT;
             const int line = r / NQ0, i = r - line * NQ0;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sU + e * NQP + line * P1 + i)), "l"(src + g)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dstU + e * NQP + line * P1 + i)), "l"(src + g)
                          : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (IP_PREF && (int)blockIdx.x < nBatches) prefetch_phys(blockIdx.x);
+    if ((IP_PREF || PD_PREF) && (int)blockIdx.x < nBatches) prefetch_phys(blockIdx.x, sU);
 
     for (int b = blockIdx.x; b < nBatches; b += gridDim.x)
     {
@@ -236,6 +239,12 @@ __global__ void __launch_bounds__(256)
         else if (IP_PREF)
         {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        else if (PD_PREF)
+        {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            if (b + (int)gridDim.x < nBatches) prefetch_phys(b + gridDim.x, sUAlt);
         }
         else if (IPWDB)
         {
@@ -683,6 +692,9 @@ __global__ void __launch_bounds__(256)
                     args.out1[goff + g] = sU[s];
             }
             __syncthreads();
+            {
+                double *t = sU; sU = sUAlt; sUAlt = t;
+            }
             continue;
         }
 
@@ -733,7 +745,7 @@ __global__ void __launch_bounds__(256)
             for (int p = 0; p < NM; ++p) sB[e * NQP + p * LN + ln] = f[p];
         }
         __syncthreads();
-        if (IP_PREF && b + (int)gridDim.x < nBatches) prefetch_phys(b + gridDim.x);
+        if (IP_PREF && b + (int)gridDim.x < nBatches) prefetch_phys(b + gridDim.x, sU);
         // T2: j -> q, lines (p,k)
         for (int l = tid; l < E * NM * NQ2; l += T)
         {
