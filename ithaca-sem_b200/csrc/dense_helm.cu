@@ -27,6 +27,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace nekmf
@@ -737,6 +738,9 @@ struct PrismState
     bool built     = false;
     bool use_fast  = false;
     bool attr_set  = false;
+    // general (non-extruded) regular prisms: eight-term kernel
+    double *d_afrag8 = nullptr, *d_tab8 = nullptr;
+    bool built8 = false, use_general = false, attr_set8 = false;
 };
 
 template <int NM> static int prism_launch_nm(nekmf_op_s *op, PrismState *st, const double *in, double *out)
@@ -764,6 +768,261 @@ template <int NM> static int prism_launch_nm(nekmf_op_s *op, PrismState *st, con
     return NEKMF_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// General regular prisms (G01, G12 != 0).  The mixed terms are C_a (x) S^T + C_a^T (x) S with S[q][q'] = int S'_q S_q'
+// (segment tables) and C_a the mixed triangle matrices; in the segment eigen-basis they act on two more transformed
+// copies of the input, w1 = (I (x) St^T X^-1) u and w2 = (I (x) St X^-1) u with St = X^T S X:
+//   v~ = [diagonal part as above] + (G01 C0 + G12 C2) w1 + (G01 C0^T + G12 C2^T) w2
+// i.e. eight triangle-matrix terms on three B-operand tiles (tests/test_oracle.py::
+// test_prism_general_kronecker_formulation_against_oracle restates exactly this in numpy against the oracle).
+template <int NM> struct PrismGenCfg
+{
+    using C = PrismCfg<NM>;
+    static constexpr int N = C::N, MT = C::MT, KS = C::KS, PITCH = C::PITCH, NP = C::NP, EW = C::EW, USED = C::USED;
+    static constexpr int NTERM = 8;
+    static constexpr int STEP  = NTERM * MT * 32;            // doubles per kk = one ring stage
+    static constexpr int TILE  = DW * 16 * PITCH;
+    static constexpr int TABD  = (3 * NM * NM + NM + 1) & ~1; // Tin | mu | T1 | T2
+    static constexpr int TABI  = C::TABI;
+    static constexpr size_t SMEM = (size_t)(PSTAGES * STEP + 3 * TILE + TABD + TABI / 2 + DW * EW * NP) * 8;
+};
+
+template <int NM> __global__ void __launch_bounds__(DW * 32, 2) prism_gen_kernel(const __grid_constant__ PrismArgs a)
+{
+    using Cfg = PrismGenCfg<NM>;
+    constexpr int N = Cfg::N, MT = Cfg::MT, KS = Cfg::KS, PITCH = Cfg::PITCH, NP = Cfg::NP, EW = Cfg::EW, USED = Cfg::USED;
+    constexpr int STEP = Cfg::STEP, TILE = Cfg::TILE;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sA   = reinterpret_cast<double *>(smem_raw); // [PSTAGES][STEP]
+    double *sU0  = sA + PSTAGES * STEP;                  // u~   [DW*16][PITCH]
+    double *sU1  = sU0 + TILE;                           // w1
+    double *sU2  = sU1 + TILE;                           // w2
+    double *sTin = sU2 + TILE;                           // Tin | mu | T1 | T2
+    int *sOff    = reinterpret_cast<int *>(sTin + Cfg::TABD);
+    int *sLen    = sOff + N;
+    double *sRaw = sTin + Cfg::TABD + Cfg::TABI / 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int we  = warp * 16;
+    const int eW0 = (blockIdx.x * DW + warp) * EW;
+    const double *sMu = sTin + NM * NM, *sT1 = sMu + NM, *sT2 = sT1 + NM * NM;
+
+    auto issue = [&](int st) {
+        if (st < KS)
+        {
+            const double *src = a.afrag + (size_t)st * STEP;
+            double *dst       = sA + (st % PSTAGES) * STEP;
+            for (int i = tid; i < STEP / 2; i += DW * 32) cp_async16(dst + 2 * i, src + 2 * i);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int st = 0; st < PSTAGES - 1; ++st) issue(st);
+    for (int i = tid; i < 3 * NM * NM + NM; i += DW * 32) sTin[i] = __ldg(a.tab + i);
+    for (int i = tid; i < 2 * N; i += DW * 32) sOff[i] = __ldg(a.itab + i);
+
+    int nLive = a.nElmt - eW0;
+    nLive     = nLive < 0 ? 0 : (nLive > EW ? EW : nLive);
+    double *raw = sRaw + (size_t)warp * EW * NP;
+    {
+        const double *src = a.in + (size_t)eW0 * NP;
+        for (int idx = lane; idx < nLive * NP; idx += 32) raw[idx] = __ldg(src + idx);
+    }
+    __syncthreads();
+
+    double cT[8][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+    {
+        const int col = j * 8 + (lane >> 2), el = col / NM, qt = col - el * NM;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) cT[t][j] = 0.0;
+        if (col < USED && el < nLive)
+        {
+            const int e    = eW0 + el;
+            const double J = __ldg(a.jac + e);
+            double d[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) d[q] = __ldg(a.df + q * a.dfStride + e);
+            const double g11 = d[1] * d[1] + d[4] * d[4] + d[7] * d[7];
+            const double g01 = J * (d[0] * d[1] + d[3] * d[4] + d[6] * d[7]);
+            const double g12 = J * (d[1] * d[2] + d[4] * d[5] + d[7] * d[8]);
+            cT[0][j] = J * (a.lambda + g11 * sMu[qt]);
+            cT[1][j] = J * (d[0] * d[0] + d[3] * d[3] + d[6] * d[6]);
+            cT[2][j] = J * (d[2] * d[2] + d[5] * d[5] + d[8] * d[8]);
+            cT[3][j] = J * (d[0] * d[2] + d[3] * d[5] + d[6] * d[8]);
+            cT[4][j] = g01; cT[5][j] = g12; cT[6][j] = g01; cT[7][j] = g12;
+        }
+    }
+    for (int k = lane; k < PITCH; k += 32)
+    {
+        double x[EW][NM];
+        const bool kin = k < N;
+        const int o = kin ? sOff[k] : 0, l = kin ? sLen[k] : 0;
+#pragma unroll
+        for (int el = 0; el < EW; ++el)
+#pragma unroll
+            for (int q = 0; q < NM; ++q) x[el][q] = (kin && el < nLive) ? raw[el * NP + o + q * l] : 0.0;
+#pragma unroll
+        for (int col = 0; col < 16; ++col)
+        {
+            const int el = col / NM, qt = col - el * NM;
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            if (col < USED)
+            {
+#pragma unroll
+                for (int q = 0; q < NM; ++q)
+                {
+                    const double xv = x[el < EW ? el : 0][q];
+                    v0 = fma(sTin[qt * NM + q], xv, v0);
+                    v1 = fma(sT1[qt * NM + q], xv, v1);
+                    v2 = fma(sT2[qt * NM + q], xv, v2);
+                }
+            }
+            sU0[(size_t)(we + col) * PITCH + k] = v0;
+            sU1[(size_t)(we + col) * PITCH + k] = v1;
+            sU2[(size_t)(we + col) * PITCH + k] = v2;
+        }
+    }
+    __syncwarp();
+
+    double acc[MT][2][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const size_t fo[2] = {(size_t)(we + (lane >> 2)) * PITCH + (lane & 3), (size_t)(we + 8 + (lane >> 2)) * PITCH + (lane & 3)};
+
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk)
+    {
+        cp_async_wait<PSTAGES - 2>();
+        __syncthreads();
+        issue(kk + PSTAGES - 1);
+        const double *st = sA + (kk % PSTAGES) * STEP + lane;
+        double u[3][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+        {
+            u[0][j] = sU0[fo[j] + kk * 4];
+            u[1][j] = sU1[fo[j] + kk * 4];
+            u[2][j] = sU2[fo[j] + kk * 4];
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+        {
+            const int src = t < 4 ? 0 : (t < 6 ? 1 : 2);
+            double av[MT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) av[i] = st[(t * MT + i) * 32];
+            const double b0 = u[src][0] * cT[t][0], b1 = u[src][1] * cT[t][1];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+            {
+                dmma884(acc[i][0][0], acc[i][0][1], av[i], b0);
+                dmma884(acc[i][1][0], acc[i][1][1], av[i], b1);
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+    {
+        const int m = i * 8 + (lane >> 2);
+        if (m < N)
+        {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+            {
+                double *row = sU0 + (size_t)(we + j * 8 + 2 * (lane & 3)) * PITCH + m;
+                row[0]      = acc[i][j][0];
+                row[PITCH]  = acc[i][j][1];
+            }
+        }
+    }
+    __syncwarp();
+    for (int k = lane; k < N; k += 32)
+    {
+        const int o = sOff[k], l = sLen[k];
+#pragma unroll
+        for (int el = 0; el < EW; ++el)
+        {
+            if (el < nLive)
+            {
+                double y[NM];
+#pragma unroll
+                for (int qt = 0; qt < NM; ++qt) y[qt] = sU0[(size_t)(we + el * NM + qt) * PITCH + k];
+#pragma unroll
+                for (int q = 0; q < NM; ++q)
+                {
+                    double v = 0.0;
+#pragma unroll
+                    for (int qt = 0; qt < NM; ++qt) v = fma(sTin[qt * NM + q], y[qt], v);
+                    raw[el * NP + o + q * l] = v;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    {
+        double *dst = a.out + (size_t)eW0 * NP;
+        for (int idx = lane; idx < nLive * NP; idx += 32) dst[idx] = raw[idx];
+    }
+}
+
+// Pt[t][k][m], t = Mt, Kt00, Kt22, Kt02s, C0, C2, C0^T, C2^T from the probe responses
+// Pfull[g][v][NP]: g = M, K00, K22, P02, K11, P01, P12; v = unit vector on mode (i' = v, q' = 0) for v < n, (v - n, 1) above
+__global__ void prism_extract8_kernel(const double *__restrict__ Pfull, double *__restrict__ Pt, const int *__restrict__ off,
+                                      int n, int NP, double inv_m00, double inv_s00, double inv_s10)
+{
+    const int total = 8 * n * n;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    {
+        const int m = idx % n, k = (idx / n) % n, t = idx / (n * n);
+        auto resp = [&](int g, int v, int mo) { return Pfull[((size_t)g * 2 * n + v) * NP + off[mo]]; };
+        double val;
+        if (t == 0) val = resp(0, k, m) * inv_m00;
+        else if (t == 1) val = resp(1, k, m) * inv_m00;
+        else if (t == 2) val = resp(2, k, m) * inv_m00;
+        else if (t == 3) val = (resp(3, k, m) - resp(1, k, m) - resp(2, k, m)) * inv_m00;
+        else
+        {
+            const int g = (t & 1) ? 6 : 5, gd = (t & 1) ? 2 : 1; // C2: P12 - K11 - K22;  C0: P01 - K00 - K11
+            const int kc = t < 6 ? k : m, mr = t < 6 ? m : k;    // transposed matrices swap the roles
+            const double a00 = resp(g, kc, mr) - resp(gd, kc, mr) - resp(4, kc, mr);
+            const double a01 = resp(g, n + kc, mr) - resp(gd, n + kc, mr) - resp(4, n + kc, mr);
+            val = 0.5 * (a00 * inv_s00 + a01 * inv_s10);
+        }
+        Pt[idx] = val;
+    }
+}
+
+template <int NM> static int prism_gen_launch_nm(nekmf_op_s *op, PrismState *st, const double *in, double *out)
+{
+    using Cfg = PrismGenCfg<NM>;
+    auto kern = prism_gen_kernel<NM>;
+    if (!st->attr_set8)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        st->attr_set8 = true;
+    }
+    PrismArgs a;
+    a.in = in; a.out = out;
+    a.jac = op->d_jac + op->run_e0; a.df = op->d_df + op->run_e0; a.afrag = st->d_afrag8;
+    a.tab = st->d_tab8; a.itab = st->d_itab;
+    a.dfStride = (size_t)op->nElmt;
+    a.nElmt = op->run_ne; a.lambda = op->lambda;
+    const int perCta = DW * Cfg::EW;
+    const int grid   = (op->run_ne + perCta - 1) / perCta;
+    if (grid < 1) return NEKMF_OK;
+    kern<<<grid, DW * 32, Cfg::SMEM, op->run_stream>>>(a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+
 static int prism_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
 {
     PrismState *st = static_cast<PrismState *>(op->kstate);
@@ -774,6 +1033,20 @@ static int prism_launch(nekmf_op_s *op, const double *const in[3], double *const
         const int rc = st->fallback(op, in, out);
         op->kstate   = saved;
         return rc;
+    }
+    if (st->use_general)
+    {
+        switch (st->nmq)
+        {
+            case 2: return prism_gen_launch_nm<2>(op, st, in[0], out[0]);
+            case 3: return prism_gen_launch_nm<3>(op, st, in[0], out[0]);
+            case 4: return prism_gen_launch_nm<4>(op, st, in[0], out[0]);
+            case 5: return prism_gen_launch_nm<5>(op, st, in[0], out[0]);
+            case 6: return prism_gen_launch_nm<6>(op, st, in[0], out[0]);
+            case 7: return prism_gen_launch_nm<7>(op, st, in[0], out[0]);
+            case 8: return prism_gen_launch_nm<8>(op, st, in[0], out[0]);
+            default: set_error("prism Helmholtz: no instantiation for nm = %d", st->nmq); return NEKMF_ERR_UNSUPPORTED;
+        }
     }
     switch (st->nmq)
     {
@@ -980,6 +1253,164 @@ static int prism_build(nekmf_op_s *op, PrismState *st)
     return NEKMF_OK;
 }
 
+static bool small_inverse(int n, std::vector<double> A, std::vector<double> &inv)
+{
+    inv.assign(n * n, 0.0);
+    for (int i = 0; i < n; ++i) inv[i * n + i] = 1.0;
+    for (int c = 0; c < n; ++c)
+    {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r)
+            if (fabs(A[r * n + c]) > fabs(A[piv * n + c])) piv = r;
+        if (A[piv * n + c] == 0.0) return false;
+        if (piv != c)
+            for (int k = 0; k < n; ++k)
+            {
+                std::swap(A[piv * n + k], A[c * n + k]);
+                std::swap(inv[piv * n + k], inv[c * n + k]);
+            }
+        const double d = 1.0 / A[c * n + c];
+        for (int k = 0; k < n; ++k) { A[c * n + k] *= d; inv[c * n + k] *= d; }
+        for (int r = 0; r < n; ++r)
+        {
+            if (r == c) continue;
+            const double f = A[r * n + c];
+            if (f == 0.0) continue;
+            for (int k = 0; k < n; ++k) { A[r * n + k] -= f * A[c * n + k]; inv[r * n + k] -= f * inv[c * n + k]; }
+        }
+    }
+    return true;
+}
+
+// tables and matrices of the eight-term kernel (general regular prisms)
+static int prism_build_general(nekmf_op_s *op, PrismState *st)
+{
+    const int nm = st->nmq, n = st->n, NP = op->nmTot, nq1 = op->nq[1];
+    std::vector<double> M1(nm * nm), K1(nm * nm), S(nm * nm), Tin, mu, X;
+    const double *B = op->b[1].data(), *dB = op->db[1].data(), *w = op->ws[1].data();
+    for (int a = 0; a < nm; ++a)
+        for (int c = 0; c < nm; ++c)
+        {
+            double m = 0.0, k = 0.0, sv = 0.0;
+            for (int j = 0; j < nq1; ++j)
+            {
+                m += B[a * nq1 + j] * w[j] * B[c * nq1 + j];
+                k += dB[a * nq1 + j] * w[j] * dB[c * nq1 + j];
+                sv += dB[a * nq1 + j] * w[j] * B[c * nq1 + j];
+            }
+            M1[a * nm + c] = m; K1[a * nm + c] = k; S[a * nm + c] = sv;
+        }
+    if (!seg_eigen(nm, M1, K1, Tin, mu) || !small_inverse(nm, Tin, X) || S[0] == 0.0 || S[nm] == 0.0)
+    {
+        set_error("prism Helmholtz: segment eigen-decomposition failed");
+        return NEKMF_ERR_ARG;
+    }
+    // St = X^T S X;  T1 = St^T Tin;  T2 = St Tin
+    std::vector<double> SX(nm * nm, 0.0), St(nm * nm, 0.0), T1(nm * nm, 0.0), T2(nm * nm, 0.0);
+    for (int i = 0; i < nm; ++i)
+        for (int j = 0; j < nm; ++j)
+            for (int k = 0; k < nm; ++k) SX[i * nm + j] += S[i * nm + k] * X[k * nm + j];
+    for (int i = 0; i < nm; ++i)
+        for (int j = 0; j < nm; ++j)
+            for (int k = 0; k < nm; ++k) St[i * nm + j] += X[k * nm + i] * SX[k * nm + j];
+    for (int i = 0; i < nm; ++i)
+        for (int j = 0; j < nm; ++j)
+            for (int k = 0; k < nm; ++k)
+            {
+                T1[i * nm + j] += St[k * nm + i] * Tin[k * nm + j];
+                T2[i * nm + j] += St[i * nm + k] * Tin[k * nm + j];
+            }
+    std::vector<double> tab(Tin);
+    tab.insert(tab.end(), mu.begin(), mu.end());
+    tab.insert(tab.end(), T1.begin(), T1.end());
+    tab.insert(tab.end(), T2.begin(), T2.end());
+    std::vector<int> itab(2 * n);
+    for (int p = 0, i = 0; p < nm; ++p)
+        for (int r = 0; r < nm - p; ++r, ++i)
+        {
+            itab[i]     = nm * (p * nm - (p * (p - 1)) / 2) + r;
+            itab[n + i] = nm - p;
+        }
+    // probes: 7 geometries (M | K00 K22 P02 K11 P01 P12) x 2n unit vectors (modes (i', 0) then (i', 1))
+    const int nv = 2 * n;
+    const size_t nel = (size_t)6 * nv;
+    std::vector<double> h_in((size_t)7 * nv * NP, 0.0), h_jac(nel, 1.0), h_df((size_t)9 * nel, 0.0);
+    for (int g = 0; g < 7; ++g)
+        for (int v = 0; v < nv; ++v)
+            h_in[((size_t)g * nv + v) * NP + (v < n ? itab[v] : itab[v - n] + itab[n + v - n])] = 1.0;
+    const int rows[6][3] = {{1, 0, 0}, {0, 0, 1}, {1, 0, 1}, {0, 1, 0}, {1, 1, 0}, {0, 1, 1}};
+    for (int g = 0; g < 6; ++g)
+        for (int d = 0; d < 3; ++d)
+            if (rows[g][d])
+                for (int v = 0; v < nv; ++v) h_df[(size_t)d * nel + (size_t)g * nv + v] = 1.0;
+    double *d_in = nullptr, *d_P = nullptr, *d_Pt = nullptr, *d_pjac = nullptr, *d_pdf = nullptr, *d_zero = nullptr;
+    auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_P); cudaFree(d_Pt); cudaFree(d_pjac); cudaFree(d_pdf); cudaFree(d_zero); };
+#define PG_CUDA(call)                                                                                          \
+    do                                                                                                         \
+    {                                                                                                          \
+        cudaError_t _e = (call);                                                                               \
+        if (_e != cudaSuccess)                                                                                 \
+        {                                                                                                      \
+            set_error("prism Helmholtz setup: %s failed: %s", #call, cudaGetErrorString(_e));                  \
+            cleanup();                                                                                         \
+            return NEKMF_ERR_CUDA;                                                                             \
+        }                                                                                                      \
+    } while (0)
+    PG_CUDA(cudaMalloc(&d_in, h_in.size() * 8));
+    PG_CUDA(cudaMalloc(&d_P, h_in.size() * 8));
+    PG_CUDA(cudaMalloc(&d_Pt, (size_t)8 * n * n * 8));
+    PG_CUDA(cudaMalloc(&d_pjac, nel * 8));
+    PG_CUDA(cudaMalloc(&d_pdf, h_df.size() * 8));
+    PG_CUDA(cudaMalloc(&d_zero, h_df.size() * 8));
+    PG_CUDA(cudaMemcpy(d_in, h_in.data(), h_in.size() * 8, cudaMemcpyHostToDevice));
+    PG_CUDA(cudaMemcpy(d_pjac, h_jac.data(), nel * 8, cudaMemcpyHostToDevice));
+    PG_CUDA(cudaMemcpy(d_pdf, h_df.data(), h_df.size() * 8, cudaMemcpyHostToDevice));
+    PG_CUDA(cudaMemset(d_zero, 0, h_df.size() * 8));
+    if (!st->d_afrag8) PG_CUDA(cudaMalloc(&st->d_afrag8, (size_t)8 * st->KS * st->MT * 32 * 8));
+    if (!st->d_tab8) PG_CUDA(cudaMalloc(&st->d_tab8, tab.size() * 8));
+    if (!st->d_itab) PG_CUDA(cudaMalloc(&st->d_itab, itab.size() * 4));
+    PG_CUDA(cudaMemcpy(st->d_tab8, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+    PG_CUDA(cudaMemcpy(st->d_itab, itab.data(), itab.size() * 4, cudaMemcpyHostToDevice));
+
+    double *s_jac = op->d_jac, *s_df = op->d_df;
+    const int s_nel = op->nElmt, s_e0 = op->run_e0, s_ne = op->run_ne;
+    const double s_lambda = op->lambda;
+    cudaStream_t s_stream = op->run_stream;
+    void *s_state         = op->kstate;
+    op->kstate     = st->fallback_state;
+    op->nElmt      = (int)nel;
+    op->run_e0     = 0;
+    op->run_stream = op->stream;
+    op->d_jac      = d_pjac;
+    const double *in3[3] = {d_in, nullptr, nullptr};
+    double *out3[3]      = {d_P, nullptr, nullptr};
+    op->lambda = 1.0; op->d_df = d_zero; op->run_ne = nv;
+    int rc = st->fallback(op, in3, out3);
+    if (rc == NEKMF_OK)
+    {
+        in3[0]     = d_in + (size_t)nv * NP;
+        out3[0]    = d_P + (size_t)nv * NP;
+        op->lambda = 0.0; op->d_df = d_pdf; op->run_ne = (int)nel;
+        rc         = st->fallback(op, in3, out3);
+    }
+    op->kstate = s_state; op->nElmt = s_nel; op->run_e0 = s_e0; op->run_ne = s_ne; op->run_stream = s_stream;
+    op->d_jac = s_jac; op->d_df = s_df; op->lambda = s_lambda;
+    if (rc != NEKMF_OK) { cleanup(); return rc; }
+    prism_extract8_kernel<<<(8 * n * n + 255) / 256, 256, 0, op->stream>>>(d_P, d_Pt, st->d_itab, n, NP, 1.0 / M1[0], 1.0 / S[0],
+                                                                           1.0 / S[nm]);
+    ++g_launches;
+    PG_CUDA(cudaGetLastError());
+    const int total = 8 * st->KS * st->MT * 32;
+    dense_pack_kernel<<<(total + 255) / 256, 256, 0, op->stream>>>(d_Pt, st->d_afrag8, n, st->KS, st->MT, 8, 99, 1);
+    ++g_launches;
+    PG_CUDA(cudaGetLastError());
+    PG_CUDA(cudaStreamSynchronize(op->stream));
+#undef PG_CUDA
+    cleanup();
+    st->built8 = true;
+    return NEKMF_OK;
+}
+
 void prism_maybe_wrap(nekmf_op_s *op)
 {
     if (op->shape != NEKMF_PRISM || op->optype != NEKMF_HELMHOLTZ || op->deformed || op->kron) return;
@@ -1002,6 +1433,8 @@ void prism_maybe_wrap(nekmf_op_s *op)
         cudaFree(s->d_afrag);
         cudaFree(s->d_tab);
         cudaFree(s->d_itab);
+        cudaFree(s->d_afrag8);
+        cudaFree(s->d_tab8);
         delete s;
     };
     op->launch = prism_launch;
@@ -1012,8 +1445,9 @@ int prism_geom_changed(nekmf_op_s *op)
 {
     if (op->kron != 4) return NEKMF_OK;
     PrismState *st = static_cast<PrismState *>(op->kstate);
-    st->use_fast   = false;
-    op->kname      = st->fallback_name;
+    st->use_fast    = false;
+    st->use_general = false;
+    op->kname       = st->fallback_name;
     const char *env = getenv("NEKMF_DENSE");
     if (env && env[0] == '0') return NEKMF_OK;
     if (!op->has_jac || !op->has_df || op->nElmt == 0) return NEKMF_OK;
@@ -1029,7 +1463,24 @@ int prism_geom_changed(nekmf_op_s *op)
                 g[a][b] = df[(0 * 3 + a) * N + e] * df[(0 * 3 + b) * N + e] + df[(1 * 3 + a) * N + e] * df[(1 * 3 + b) * N + e] +
                           df[(2 * 3 + a) * N + e] * df[(2 * 3 + b) * N + e];
         const double tol = 1e-14 * (g[0][0] + g[1][1] + g[2][2]);
-        if (fabs(g[0][1]) > tol || fabs(g[1][2]) > tol) return NEKMF_OK;
+        if (fabs(g[0][1]) > tol || fabs(g[1][2]) > tol)
+        {
+            // general regular prisms: the eight-term kernel where it was measured faster than the quadrature-space
+            // kernel (nm 3..5: 1.5-2.2x; equal at nm = 7, 8); NEKMF_PRISM_GENERAL=1 takes it at every order, =0 never
+            const char *eg = getenv("NEKMF_PRISM_GENERAL");
+            if (eg && eg[0] == '0') return NEKMF_OK;
+            if (!(eg && eg[0] == '1') && (st->nmq < 3 || st->nmq > 5)) return NEKMF_OK;
+            if (!st->built8)
+            {
+                const int rc = prism_build_general(op, st);
+                if (rc != NEKMF_OK) return rc;
+            }
+            st->use_fast = st->use_general = true;
+            char gname[112];
+            snprintf(gname, sizeof(gname), "prism_gen_kernel<nm=%d,MT=%d>(regular,general,DMMA m8n8k4)", st->nmq, st->MT);
+            op->kname = gname;
+            return NEKMF_OK;
+        }
     }
     if (!st->built)
     {

@@ -154,6 +154,34 @@ def test_prism_extruded_dmma_helmholtz(nm, nel, monkeypatch):
     check(out, out0, "prism DMMA vs quadrature-space kernel")
 
 
+@pytest.mark.parametrize("nel", [1, 2, 3, 9, 100])
+@pytest.mark.parametrize("nm", [2, 3, 4, 5, 6, 7, 8])
+def test_prism_general_dmma_helmholtz(nm, nel, monkeypatch):
+    """General regular prisms (G01, G12 != 0) take prism_gen_kernel (dense_helm.cu): eight triangle-matrix terms in the
+    segment eigen-basis, mixed matrices recovered from probes (the numpy restatement of the same formulation is
+    tests/test_oracle.py::test_prism_general_kronecker_formulation_against_oracle)."""
+    monkeypatch.delenv("NEKMF_DENSE", raising=False)
+    monkeypatch.setenv("NEKMF_PRISM_GENERAL", "1")  # every order (the default policy takes it at nm 3..5)
+    nk = nekmf()
+    rng = np.random.default_rng(nm * 71 + nel)
+    el = po.Elem(po.PRISM, nm, nm + 1)
+    std = nk.StdExpansion(po.PRISM, nm, nm + 1)
+    jac, df = random_geometry(rng, 3, nel, el.nqTot, False)
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, False))
+    x = rng.uniform(-1, 1, nel * el.nmTot)
+    for lam in (1.3, 0.0, 37.5):
+        out = np.zeros(nel * el.nmTot)
+        coll.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
+        check(out, el.helmholtz(nel, False, jac, df, lam, x), "Helmholtz(prism general, lambda=%g)" % lam)
+    assert "prism_gen_kernel" in coll.m_ops[nk.eHelmholtz].kernel_name, coll.m_ops[nk.eHelmholtz].kernel_name
+    monkeypatch.setenv("NEKMF_PRISM_GENERAL", "0")
+    coll0 = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, False))
+    out0 = np.zeros(nel * el.nmTot)
+    coll0.ApplyOperator(nk.eHelmholtz, x, out0, factors={nk.eFactorLambda: 37.5})
+    assert "shape_op_kernel" in coll0.m_ops[nk.eHelmholtz].kernel_name
+    check(out, out0, "prism general DMMA vs quadrature-space kernel")
+
+
 def golden_cases():
     return sorted(set(k.rsplit("_", 1)[0] for k in GOLD.files if k.endswith("_x") and not k.startswith("Seg")))
 
@@ -521,6 +549,8 @@ def test_shape_fast_kernels(shape, nm, deformed):
         if op == nk.eHelmholtz and not deformed and ((shape == "Tet" and nm >= DENSE_FROM["Tet"]) or
                                                       (shape == "Tri" and nm >= DENSE_FROM["Tri"])):
             want = "dense_helm_kernel"  # DMMA coefficient-space kernel (dense_helm.cu)
+        if op == nk.eHelmholtz and not deformed and shape == "Prism" and 3 <= nm <= 5:
+            want = "prism_gen_kernel"  # general regular prisms: eight-term DMMA kernel (dense_helm.cu), default at nm 3..5
         assert want in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
     # IProductWRTDerivBase: lane kernels for regular quads up to nm = 5 / triangles up to nm = 6, otherwise the compile-time
     # sized kernel (chain-rule stage + the transposed-derivative / IProduct half of the fused Helmholtz kernel)
