@@ -1416,6 +1416,9 @@ void prism_maybe_wrap(nekmf_op_s *op)
     if (op->shape != NEKMF_PRISM || op->optype != NEKMF_HELMHOLTZ || op->deformed || op->kron) return;
     const int nm = op->nm[0];
     if (op->nm[1] != nm || op->nm[2] != nm || nm < 2 || nm > 8) return;
+    // default quadrature only (the combinations the GPU parity tests of these kernels cover); other quadratures keep
+    // the runtime-sized kernel
+    if (op->nq[0] != nm + 1 || op->nq[1] != nm + 1 || op->nq[2] != nm) return;
     const int n = nm * (nm + 1) / 2;
     if (op->nmTot != nm * n || op->coordim != 3) return;
     const int MT = (n + 7) / 8, KS = (n + 3) / 4;
