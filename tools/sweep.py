@@ -134,6 +134,14 @@ def main():
                         tf = fl * nel / (ms * 1e-3) / 1e12
                         rec.update({"flops_per_element_issued": fl, "tflops": round(tf, 2),
                                     "frac_dmma": round(tf / 37.1, 3), "bound": "fp64"})
+                    if o.kernel_name.startswith(("prism_helm_kernel", "prism_gen_kernel")):
+                        # nm triangle problems per element, 4 (extruded) or 8 (general) terms; per 16-column warp tile
+                        # (16 // nm elements) terms x (8 MT) x (4 KS) x 16 DMMA work, idle columns included
+                        ntri, terms = nm * (nm + 1) // 2, (4 if o.kernel_name.startswith("prism_helm") else 8)
+                        fl = 2 * (8 * ((ntri + 7) // 8)) * terms * (4 * ((ntri + 3) // 4)) * 16 // (16 // nm)
+                        tf = fl * nel / (ms * 1e-3) / 1e12
+                        rec.update({"flops_per_element_issued": fl, "tflops": round(tf, 2),
+                                    "frac_dmma": round(tf / 37.1, 3), "bound": "fp64"})
                     line = json.dumps(rec)
                     print(line, flush=True)
                     if out:
