@@ -377,6 +377,117 @@ def SetFixedImpType(defaultType):
     return {op: defaultType for op in range(SIZE_OperatorType)}
 
 
+def GenerateSeqVector(text):
+    """ParseUtils::GenerateSeqVector (LibUtilities/BasicUtils/ParseUtils.cpp:108-121): "1-3,5" -> [1, 2, 3, 5]."""
+    out = []
+    for item in text.split(","):
+        item = item.strip()
+        lo, sep, hi = item.partition("-")
+        if sep:
+            if not (lo.strip().isdigit() and hi.strip().isdigit()):
+                raise NekError("cannot parse sequence '%s'" % text)
+            out.extend(range(int(lo), int(hi) + 1))
+        else:
+            if not item.isdigit():
+                raise NekError("cannot parse sequence '%s'" % text)
+            out.append(int(item))
+    return out
+
+
+class CollectionOptimisation:
+    """Collections::CollectionOptimisation (CollectionOptimisation.cpp:52-316): which ImplementationType each
+    (operator, shape, order) uses, from the constructor default and the session's
+    <COLLECTIONS DEFAULT="B200" MAXSIZE="..."><OPERATOR TYPE="Helmholtz"><ELEMENT TYPE="H" ORDER="*" IMPTYPE="B200"/>
+    block.  `session` is None (the unit tests' dummy session), XML text, a path, or an xml.etree element whose root is
+    <NEKTAR>; selection semantics, defaults and error messages follow the reference line by line.  The autotuner
+    (SetWithTimings, DEFAULT="auto") needs the reference's other implementations to time against and is not mirrored:
+    IsUsingAutotuning() reports the request, the caller decides."""
+
+    _elTypes = {"S": eSegment, "T": eTriangle, "Q": eQuadrilateral, "A": eTetrahedron, "P": ePyramid, "R": ePrism,
+                "H": eHexahedron}
+
+    def __init__(self, session=None, defaultType=eNoImpType):
+        self.m_setByXml, self.m_autotune, self.m_maxCollSize = False, False, 0
+        self.m_defaultType = eIterPerExp if defaultType == eNoImpType else defaultType
+        defaults = {(sh, -1): self.m_defaultType for sh in self._elTypes.values()}
+        defaultsPhysDeriv = dict(defaults)
+        if defaultType == eNoImpType:
+            for sh in self._elTypes.values():
+                for i in range(1, 5):
+                    defaults[(sh, i)] = eStdMat
+                defaultsPhysDeriv[(sh, -1)] = eNoCollection
+                for i in range(1, 3):
+                    defaultsPhysDeriv[(sh, i)] = eSumFac
+        self.m_global = {op: dict(defaultsPhysDeriv if op == ePhysDeriv else defaults) for op in range(SIZE_OperatorType)}
+        if session is None:
+            return
+        import xml.etree.ElementTree as ET
+        if isinstance(session, str):
+            root = ET.fromstring(session) if session.lstrip().startswith("<") else ET.parse(session).getroot()
+        else:
+            root = session
+        if root.tag != "NEKTAR":
+            raise NekError("Unable to find NEKTAR tag in file.")
+        xmlCol = root.find("COLLECTIONS")
+        if xmlCol is None:
+            return
+        self.m_maxCollSize = int(xmlCol.get("MAXSIZE", 0))
+        defaultImpl = xmlCol.get("DEFAULT")
+        self.m_defaultType = defaultType
+        if defaultType == eNoImpType and defaultImpl:
+            self.m_autotune = defaultImpl.lower() == "auto"
+            if not self.m_autotune:
+                names = [n.lower() for n in ImplementationTypeMap]
+                if defaultImpl.lower() not in names[1:]:
+                    raise NekError("Unknown default collection scheme: " + defaultImpl)
+                self.m_defaultType = names.index(defaultImpl.lower())
+                defaults = {(sh, -1): self.m_defaultType for sh in self._elTypes.values()}
+                self.m_global = {op: dict(defaults) for op in range(SIZE_OperatorType)}
+        for elmt in xmlCol:
+            self.m_setByXml = True
+            if elmt.tag.upper() != "OPERATOR":
+                raise NekError("Only OPERATOR tags are supported inside the COLLECTIONS tag.")
+            opType = elmt.get("TYPE")
+            if opType is None:
+                raise NekError("Missing TYPE in OPERATOR tag.")
+            if opType not in OperatorTypeMap:
+                raise NekError("Unknown OPERATOR type " + opType + ".")
+            ot = OperatorTypeMap.index(opType)
+            for elmt2 in elmt:
+                if elmt2.tag.upper() != "ELEMENT":
+                    raise NekError("Only ELEMENT tags are supported inside the OPERATOR tag.")
+                elType = elmt2.get("TYPE")
+                if elType is None:
+                    raise NekError("Missing TYPE in ELEMENT tag.")
+                if elType not in self._elTypes:
+                    raise NekError("Unknown element type " + elType + " in ELEMENT tag")
+                impType = elmt2.get("IMPTYPE")
+                if impType is None:
+                    raise NekError("Missing IMPTYPE in ELEMENT tag.")
+                if impType not in ImplementationTypeMap:
+                    raise NekError("Unknown IMPTYPE type " + impType + ".")
+                order = elmt2.get("ORDER")
+                if order is None:
+                    raise NekError("Missing ORDER in ELEMENT tag.")
+                imp, sh = ImplementationTypeMap.index(impType), self._elTypes[elType]
+                if order == "*":
+                    self.m_global[ot][(sh, -1)] = imp
+                else:
+                    for o in GenerateSeqVector(order):
+                        self.m_global[ot][(sh, o)] = imp
+
+    def GetOperatorImpMap(self, pExp):
+        """(shape, number of modes in direction 0) first, then the shape's default, else eNoCollection
+        (CollectionOptimisation.cpp:283-316)."""
+        shape, nm0 = pExp.DetShapeType(), pExp.GetBasis(0).GetNumModes()
+        return {op: table.get((shape, nm0), table.get((shape, -1), eNoCollection)) for op, table in self.m_global.items()}
+
+    def GetDefaultImplementationType(self): return self.m_defaultType
+    def GetMaxCollectionSize(self): return self.m_maxCollSize
+    def IsUsingAutotuning(self): return self.m_autotune
+    def SetByXml(self): return self.m_setByXml
+
+
 class Collection:
     """Collections::Collection (Collection.h:53-110, Collection.cpp:46-87): lazy Initialise(opType), then
     ApplyOperator.  Only eB200 is registered in this library; any other ImplementationType raises, as

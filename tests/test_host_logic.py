@@ -225,3 +225,58 @@ def test_config1_quad_helmholtz_solve_oracle():
     mf = el.helmholtz(mesh.nElmt, False, jac, df, lam, loc)
     sm = (loc.reshape(mesh.nElmt, n) @ A.T).reshape(-1)
     assert max(rel_errs(mf, sm)) < 1e-12
+
+
+def test_collection_optimisation_mirror(tmp_path):
+    """Collections::CollectionOptimisation (CollectionOptimisation.cpp:52-316) as mirrored in nekmf.py: constructor
+    defaults, the <COLLECTIONS> block of a session file (DEFAULT, MAXSIZE, OPERATOR / ELEMENT with ORDER "*" or a
+    sequence), the (shape, order) -> shape default -> eNoCollection lookup, and the reference's error messages.  This
+    is how ExpList selects eB200; needs no GPU."""
+    nk = nekmf()
+    hex5, tet2, tet6 = nk.StdExpansion(nk.eHexahedron, 5, 6), nk.StdExpansion(nk.eTetrahedron, 2, 3), nk.StdExpansion(nk.eTetrahedron, 6, 7)
+    # the unit tests' form: dummy session + explicit type (TestHexCollection.cpp:3699-3704)
+    opt = nk.CollectionOptimisation(None, nk.eB200)
+    assert opt.GetOperatorImpMap(hex5) == nk.SetFixedImpType(nk.eB200)
+    assert not opt.SetByXml() and not opt.IsUsingAutotuning() and opt.GetMaxCollectionSize() == 0
+    # no session, no type: IterPerExp, StdMat for orders 1..4, PhysDeriv NoCollection / SumFac for orders 1, 2
+    opt = nk.CollectionOptimisation()
+    assert opt.GetDefaultImplementationType() == nk.eIterPerExp
+    low, high = opt.GetOperatorImpMap(tet2), opt.GetOperatorImpMap(tet6)
+    assert low[nk.eBwdTrans] == nk.eStdMat and low[nk.ePhysDeriv] == nk.eSumFac
+    assert high[nk.eHelmholtz] == nk.eIterPerExp and high[nk.ePhysDeriv] == nk.eNoCollection
+    # session file: case-insensitive DEFAULT, per-operator overrides
+    xml = """<NEKTAR><COLLECTIONS DEFAULT="b200" MAXSIZE="64">
+               <OPERATOR TYPE="Helmholtz"><ELEMENT TYPE="H" ORDER="2-4,7" IMPTYPE="MatrixFree"/>
+                                          <ELEMENT TYPE="A" ORDER="*" IMPTYPE="StdMat"/></OPERATOR>
+             </COLLECTIONS></NEKTAR>"""
+    path = tmp_path / "session.xml"
+    path.write_text(xml)
+    for src in (xml, str(path)):
+        opt = nk.CollectionOptimisation(src)
+        assert opt.GetDefaultImplementationType() == nk.eB200 and opt.GetMaxCollectionSize() == 64 and opt.SetByXml()
+        assert opt.GetOperatorImpMap(hex5)[nk.eHelmholtz] == nk.eB200            # order 5 is not in 2-4,7
+        assert opt.GetOperatorImpMap(nk.StdExpansion(nk.eHexahedron, 7, 8))[nk.eHelmholtz] == nk.eMatrixFree
+        assert opt.GetOperatorImpMap(nk.StdExpansion(nk.eHexahedron, 3, 4))[nk.eBwdTrans] == nk.eB200
+        assert opt.GetOperatorImpMap(tet6)[nk.eHelmholtz] == nk.eStdMat and opt.GetOperatorImpMap(tet6)[nk.eBwdTrans] == nk.eB200
+    # an explicit constructor type wins over DEFAULT (CollectionOptimisation.cpp:150-153)
+    assert nk.CollectionOptimisation(xml, nk.eMatrixFree).GetOperatorImpMap(hex5)[nk.eBwdTrans] == nk.eMatrixFree
+    assert nk.CollectionOptimisation('<NEKTAR><COLLECTIONS DEFAULT="auto"/></NEKTAR>').IsUsingAutotuning()
+    assert nk.GenerateSeqVector("1-3, 5") == [1, 2, 3, 5]
+    for bad, msg in (('<FOO/>', "Unable to find NEKTAR tag"),
+                     ('<NEKTAR><COLLECTIONS DEFAULT="Fast"/></NEKTAR>', "Unknown default collection scheme: Fast"),
+                     ('<NEKTAR><COLLECTIONS><THING/></COLLECTIONS></NEKTAR>', "Only OPERATOR tags"),
+                     ('<NEKTAR><COLLECTIONS><OPERATOR/></COLLECTIONS></NEKTAR>', "Missing TYPE in OPERATOR tag"),
+                     ('<NEKTAR><COLLECTIONS><OPERATOR TYPE="Mass"/></COLLECTIONS></NEKTAR>', "Unknown OPERATOR type Mass"),
+                     ('<NEKTAR><COLLECTIONS><OPERATOR TYPE="BwdTrans"><ELEMENT TYPE="X" ORDER="*" IMPTYPE="B200"/></OPERATOR>'
+                      '</COLLECTIONS></NEKTAR>', "Unknown element type X"),
+                     ('<NEKTAR><COLLECTIONS><OPERATOR TYPE="BwdTrans"><ELEMENT TYPE="H" ORDER="*" IMPTYPE="Cuda"/></OPERATOR>'
+                      '</COLLECTIONS></NEKTAR>', "Unknown IMPTYPE type Cuda"),
+                     ('<NEKTAR><COLLECTIONS><OPERATOR TYPE="BwdTrans"><ELEMENT TYPE="H" IMPTYPE="B200"/></OPERATOR>'
+                      '</COLLECTIONS></NEKTAR>', "Missing ORDER in ELEMENT tag")):
+        with pytest.raises(nk.NekError, match=msg):
+            nk.CollectionOptimisation(bad)
+    # a Collection built from the map refuses implementation types that are not registered in this library
+    coll = nk.Collection(tet6, 3, nk.CoalescedGeomData(np.ones(3), np.ones(27), False),
+                         nk.CollectionOptimisation(xml).GetOperatorImpMap(tet6))
+    with pytest.raises(nk.NekError, match="no operator registered for key"):
+        coll.Initialise(nk.eHelmholtz)
