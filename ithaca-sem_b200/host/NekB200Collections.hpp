@@ -19,12 +19,15 @@
 // as the reference's NekFactory does for an unregistered key (NekFactory.hpp:145-209).
 #pragma once
 #include "../../include/nekmf_b200.h"
+#include <cctype>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
 #include <string>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 namespace Nektar
@@ -410,19 +413,284 @@ struct Registrar
 static Registrar g_registrar; // static registration, as the reference's m_typeArr[] initialisers
 } // namespace detail
 
-// CollectionOptimisation.cpp:52-281 reduced to what the unit tests use: a fixed implementation type,
-// no session file (the reference's tests pass a null session pointer, TestHexCollection.cpp:3699-3704)
+// ---- session document stand-in + the XML subset the <COLLECTIONS> block needs (the reference reads a TinyXML
+// document from LibUtilities::SessionReader; neither is available here)
+} // namespace Collections
+namespace LibUtilities
+{
+class SessionReader
+{
+public:
+    static std::shared_ptr<SessionReader> CreateInstance(const std::string &xmlText)
+    {
+        return std::shared_ptr<SessionReader>(new SessionReader(xmlText));
+    }
+    const std::string &GetDocumentText() const { return m_text; }
+
+private:
+    explicit SessionReader(const std::string &t) : m_text(t) {}
+    std::string m_text;
+};
+typedef std::shared_ptr<SessionReader> SessionReaderSharedPtr;
+} // namespace LibUtilities
+namespace Collections
+{
+namespace detail
+{
+struct XmlNode
+{
+    std::string tag;
+    std::map<std::string, std::string> attr;
+    std::vector<XmlNode> children;
+    const XmlNode *FirstChild(const std::string &t) const
+    {
+        for (const XmlNode &c : children)
+            if (c.tag == t) return &c;
+        return nullptr;
+    }
+    const char *Attribute(const std::string &k) const
+    {
+        auto it = attr.find(k);
+        return it == attr.end() ? nullptr : it->second.c_str();
+    }
+};
+// elements, attributes (single or double quotes), self-closing tags, comments, declarations; text is ignored
+inline XmlNode ParseXml(const std::string &s)
+{
+    XmlNode doc;
+    std::vector<XmlNode *> stack{&doc};
+    size_t i = 0;
+    auto skipws = [&]() { while (i < s.size() && isspace((unsigned char)s[i])) ++i; };
+    auto name = [&]() {
+        const size_t b = i;
+        while (i < s.size() && (isalnum((unsigned char)s[i]) || s[i] == '_' || s[i] == ':' || s[i] == '-' || s[i] == '.')) ++i;
+        return s.substr(b, i - b);
+    };
+    while (i < s.size())
+    {
+        if (s[i] != '<') { ++i; continue; }
+        if (s.compare(i, 4, "<!--") == 0)
+        {
+            const size_t e = s.find("-->", i);
+            if (e == std::string::npos) NEKB200_ERROR("XML: unterminated comment");
+            i = e + 3;
+            continue;
+        }
+        if (s.compare(i, 2, "<?") == 0 || s.compare(i, 2, "<!") == 0)
+        {
+            const size_t e = s.find('>', i);
+            if (e == std::string::npos) NEKB200_ERROR("XML: unterminated declaration");
+            i = e + 1;
+            continue;
+        }
+        if (s.compare(i, 2, "</") == 0)
+        {
+            i += 2;
+            const std::string t = name();
+            skipws();
+            if (i >= s.size() || s[i] != '>' || stack.size() < 2 || stack.back()->tag != t) NEKB200_ERROR("XML: mismatched </" << t << ">");
+            ++i;
+            stack.pop_back();
+            continue;
+        }
+        ++i;
+        XmlNode node;
+        node.tag = name();
+        if (node.tag.empty()) NEKB200_ERROR("XML: empty tag name");
+        bool closed = false;
+        for (;;)
+        {
+            skipws();
+            if (i >= s.size()) NEKB200_ERROR("XML: unterminated tag <" << node.tag);
+            if (s[i] == '/') { closed = true; ++i; continue; }
+            if (s[i] == '>') { ++i; break; }
+            const std::string k = name();
+            skipws();
+            if (k.empty() || i >= s.size() || s[i] != '=') NEKB200_ERROR("XML: bad attribute in <" << node.tag << ">");
+            ++i;
+            skipws();
+            if (i >= s.size() || (s[i] != '"' && s[i] != '\'')) NEKB200_ERROR("XML: unquoted attribute " << k);
+            const char q   = s[i++];
+            const size_t e = s.find(q, i);
+            if (e == std::string::npos) NEKB200_ERROR("XML: unterminated attribute " << k);
+            node.attr[k] = s.substr(i, e - i);
+            i            = e + 1;
+        }
+        // pointers into `children` stay valid only until the next push_back at that level: re-take back()
+        stack.back()->children.push_back(node);
+        if (!closed) stack.push_back(&stack.back()->children.back());
+    }
+    if (stack.size() != 1) NEKB200_ERROR("XML: unclosed <" << stack.back()->tag << ">");
+    return doc;
+}
+inline std::string Lower(std::string v)
+{
+    for (char &c : v) c = (char)tolower((unsigned char)c);
+    return v;
+}
+// ParseUtils::GenerateSeqVector (LibUtilities/BasicUtils/ParseUtils.cpp:108-121): "1-3,5" -> 1 2 3 5
+inline bool GenerateSeqVector(const std::string &str, std::vector<unsigned int> &out)
+{
+    size_t i = 0;
+    auto skipws = [&]() { while (i < str.size() && isspace((unsigned char)str[i])) ++i; };
+    auto number = [&](unsigned int &v) {
+        skipws();
+        const size_t b = i;
+        v              = 0;
+        while (i < str.size() && isdigit((unsigned char)str[i])) v = v * 10 + (unsigned int)(str[i++] - '0');
+        return i > b;
+    };
+    for (;;)
+    {
+        unsigned int a, b;
+        if (!number(a)) return false;
+        skipws();
+        if (i < str.size() && str[i] == '-')
+        {
+            ++i;
+            if (!number(b)) return false;
+            for (unsigned int v = a; v <= b; ++v) out.push_back(v);
+        }
+        else out.push_back(a);
+        skipws();
+        if (i == str.size()) return true;
+        if (str[i] != ',') return false;
+        ++i;
+    }
+}
+} // namespace detail
+
+// CollectionOptimisation.cpp:52-316: which ImplementationType each (operator, shape, order) uses, from the
+// constructor default and the session's <COLLECTIONS DEFAULT=".." MAXSIZE=".."><OPERATOR TYPE=".."><ELEMENT TYPE="H"
+// ORDER="*" IMPTYPE="B200"/> block; defaults, lookup and error messages follow the reference.  The autotuner
+// (SetWithTimings) times the reference's other implementations and is not mirrored.
 class CollectionOptimisation
 {
 public:
-    CollectionOptimisation(void *pSession, ImplementationType defaultType = eB200) : m_default(defaultType)
+    typedef std::pair<LibUtilities::ShapeType, int> ElmtOrder;
+    // the unit tests' form: a null dummy session (TestHexCollection.cpp:3699-3704)
+    CollectionOptimisation(void *pSession, ImplementationType defaultType = eB200)
     {
-        if (pSession) NEKB200_ERROR("CollectionOptimisation: session files are not supported by this mirror");
+        if (pSession) NEKB200_ERROR("CollectionOptimisation: pass a LibUtilities::SessionReaderSharedPtr");
+        Init(LibUtilities::SessionReaderSharedPtr(), defaultType);
     }
-    OperatorImpMap GetOperatorImpMap(StdRegions::StdExpansionSharedPtr) { return SetFixedImpType(m_default); }
+    CollectionOptimisation(LibUtilities::SessionReaderSharedPtr pSession, ImplementationType defaultType = eNoImpType)
+    {
+        Init(pSession, defaultType);
+    }
+    OperatorImpMap GetOperatorImpMap(StdRegions::StdExpansionSharedPtr pExp)
+    {
+        OperatorImpMap ret;
+        const ElmtOrder searchKey(pExp->DetShapeType(), pExp->GetBasis(0)->GetNumModes()), defSearch(pExp->DetShapeType(), -1);
+        for (auto &it : m_global)
+        {
+            auto it2 = it.second.find(searchKey);
+            if (it2 == it.second.end()) it2 = it.second.find(defSearch);
+            ret[it.first] = it2 == it.second.end() ? eNoCollection : it2->second;
+        }
+        return ret;
+    }
+    ImplementationType GetDefaultImplementationType() { return m_defaultType; }
+    unsigned int GetMaxCollectionSize() { return m_maxCollSize; }
+    bool IsUsingAutotuning() { return m_autotune; }
+    bool SetByXml() { return m_setByXml; }
 
 private:
-    ImplementationType m_default;
+    void Init(LibUtilities::SessionReaderSharedPtr pSession, ImplementationType defaultType)
+    {
+        using namespace LibUtilities;
+        std::map<ElmtOrder, ImplementationType> defaults, defaultsPhysDeriv;
+        m_setByXml = m_autotune = false;
+        m_maxCollSize            = 0;
+        m_defaultType            = defaultType == eNoImpType ? eIterPerExp : defaultType;
+        std::map<std::string, ShapeType> elTypes;
+        elTypes["S"] = static_cast<ShapeType>(NEKMF_SEG);
+        elTypes["T"] = eTriangle; elTypes["Q"] = eQuadrilateral; elTypes["A"] = eTetrahedron;
+        elTypes["P"] = ePyramid;  elTypes["R"] = ePrism;         elTypes["H"] = eHexahedron;
+        for (auto &it2 : elTypes) defaults[ElmtOrder(it2.second, -1)] = defaultsPhysDeriv[ElmtOrder(it2.second, -1)] = m_defaultType;
+        if (defaultType == eNoImpType)
+            for (auto &it2 : elTypes)
+            {
+                for (int i = 1; i < 5; ++i) defaults[ElmtOrder(it2.second, i)] = eStdMat;
+                defaultsPhysDeriv[ElmtOrder(it2.second, -1)] = eNoCollection;
+                for (int i = 1; i < 3; ++i) defaultsPhysDeriv[ElmtOrder(it2.second, i)] = eSumFac;
+            }
+        std::map<std::string, OperatorType> opTypes;
+        for (int i = 0; i < SIZE_OperatorType; ++i)
+        {
+            opTypes[OperatorTypeMap[i]]  = (OperatorType)i;
+            m_global[(OperatorType)i] = (OperatorType)i == ePhysDeriv ? defaultsPhysDeriv : defaults;
+        }
+        std::map<std::string, ImplementationType> impTypes;
+        for (int i = 0; i < SIZE_ImplementationType; ++i) impTypes[ImplementationTypeMap[i]] = (ImplementationType)i;
+        if (!pSession) return; // dummy session: no file reader
+        const detail::XmlNode doc    = detail::ParseXml(pSession->GetDocumentText());
+        const detail::XmlNode *master = doc.FirstChild("NEKTAR");
+        if (!master) NEKB200_ERROR("Unable to find NEKTAR tag in file.");
+        const detail::XmlNode *xmlCol = master->FirstChild("COLLECTIONS");
+        if (!xmlCol) return;
+        const char *maxSize = xmlCol->Attribute("MAXSIZE");
+        m_maxCollSize       = maxSize ? (unsigned int)atoi(maxSize) : 0;
+        const char *defaultImpl = xmlCol->Attribute("DEFAULT");
+        m_defaultType           = defaultType;
+        if (defaultType == eNoImpType && defaultImpl)
+        {
+            const std::string collinfo(defaultImpl);
+            m_autotune = detail::Lower(collinfo) == "auto";
+            if (!m_autotune)
+            {
+                bool collectionFound = false;
+                for (int i = 1; i < SIZE_ImplementationType; ++i)
+                    if (detail::Lower(collinfo) == detail::Lower(ImplementationTypeMap[i]))
+                    {
+                        m_defaultType   = (ImplementationType)i;
+                        collectionFound = true;
+                        break;
+                    }
+                if (!collectionFound) NEKB200_ERROR("Unknown default collection scheme: " + collinfo);
+                defaults.clear();
+                for (auto &it2 : elTypes) defaults[ElmtOrder(it2.second, -1)] = m_defaultType;
+                for (int i = 0; i < SIZE_OperatorType; ++i) m_global[(OperatorType)i] = defaults;
+            }
+        }
+        for (const detail::XmlNode &elmt : xmlCol->children)
+        {
+            m_setByXml = true;
+            if (detail::Lower(elmt.tag) != "operator") NEKB200_ERROR("Only OPERATOR tags are supported inside the COLLECTIONS tag.");
+            const char *attr = elmt.Attribute("TYPE");
+            if (!attr) NEKB200_ERROR("Missing TYPE in OPERATOR tag.");
+            const std::string opType(attr);
+            if (!opTypes.count(opType)) NEKB200_ERROR("Unknown OPERATOR type " + opType + ".");
+            const OperatorType ot = opTypes[opType];
+            for (const detail::XmlNode &elmt2 : elmt.children)
+            {
+                if (detail::Lower(elmt2.tag) != "element") NEKB200_ERROR("Only ELEMENT tags are supported inside the OPERATOR tag.");
+                const char *a1 = elmt2.Attribute("TYPE");
+                if (!a1) NEKB200_ERROR("Missing TYPE in ELEMENT tag.");
+                const std::string elType(a1);
+                auto it2 = elTypes.find(elType);
+                if (it2 == elTypes.end()) NEKB200_ERROR("Unknown element type " + elType + " in ELEMENT tag");
+                const char *a2 = elmt2.Attribute("IMPTYPE");
+                if (!a2) NEKB200_ERROR("Missing IMPTYPE in ELEMENT tag.");
+                const std::string impType(a2);
+                if (!impTypes.count(impType)) NEKB200_ERROR("Unknown IMPTYPE type " + impType + ".");
+                const char *a3 = elmt2.Attribute("ORDER");
+                if (!a3) NEKB200_ERROR("Missing ORDER in ELEMENT tag.");
+                const std::string order(a3);
+                if (order == "*") m_global[ot][ElmtOrder(it2->second, -1)] = impTypes[impType];
+                else
+                {
+                    std::vector<unsigned int> orders;
+                    if (!detail::GenerateSeqVector(order, orders)) NEKB200_ERROR("Unable to interpret ORDER '" + order + "'.");
+                    for (unsigned int o : orders) m_global[ot][ElmtOrder(it2->second, (int)o)] = impTypes[impType];
+                }
+            }
+        }
+    }
+    std::map<OperatorType, std::map<ElmtOrder, ImplementationType>> m_global;
+    ImplementationType m_defaultType;
+    unsigned int m_maxCollSize;
+    bool m_setByXml, m_autotune;
 };
 
 // Collection.h:53-110, Collection.cpp:46-87

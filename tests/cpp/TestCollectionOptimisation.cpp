@@ -1,0 +1,101 @@
+// TestCollectionOptimisation.cpp -- the selection logic of Collections::CollectionOptimisation
+// (/root/reference/library/Collections/CollectionOptimisation.cpp:52-316) in the C++ host mirror
+// (ithaca-sem_b200/host/NekB200Collections.hpp): constructor defaults, the <COLLECTIONS> block of a session
+// document, the (shape, order) -> shape default -> eNoCollection lookup and the reference's error messages.
+// Needs no GPU: nothing here creates an operator.
+#include "../../ithaca-sem_b200/host/NekB200Collections.hpp"
+#include <cstdio>
+#include <cstring>
+
+using namespace Nektar;
+using namespace Nektar::Collections;
+
+static int g_fail = 0;
+#define CHECK(cond, what)                                   \
+    do                                                      \
+    {                                                       \
+        if (!(cond))                                        \
+        {                                                   \
+            printf("FAILED: %s (%s)\n", what, #cond);       \
+            ++g_fail;                                       \
+        }                                                   \
+    } while (0)
+
+static bool throws(const std::string &xml, const char *msg)
+{
+    try
+    {
+        CollectionOptimisation opt(LibUtilities::SessionReader::CreateInstance(xml));
+    }
+    catch (const ErrorUtil::NekError &e)
+    {
+        return strstr(e.what(), msg) != nullptr;
+    }
+    return false;
+}
+
+int main()
+{
+    auto exp = [](LibUtilities::ShapeType s, int nm) { return std::make_shared<StdRegions::StdExpansion>(s, nm); };
+    auto hex5 = exp(LibUtilities::eHexahedron, 5), hex7 = exp(LibUtilities::eHexahedron, 7), hex3 = exp(LibUtilities::eHexahedron, 3);
+    auto tet2 = exp(LibUtilities::eTetrahedron, 2), tet6 = exp(LibUtilities::eTetrahedron, 6);
+    {
+        void *dummySession = nullptr; // TestHexCollection.cpp:3699-3704
+        CollectionOptimisation opt(dummySession, eB200);
+        OperatorImpMap m = opt.GetOperatorImpMap(hex5);
+        bool all = true;
+        for (auto &it : m) all = all && it.second == eB200;
+        CHECK(all && m.size() == SIZE_OperatorType, "dummy session, fixed type");
+        CHECK(!opt.SetByXml() && !opt.IsUsingAutotuning() && opt.GetMaxCollectionSize() == 0, "dummy session flags");
+    }
+    {
+        CollectionOptimisation opt(LibUtilities::SessionReaderSharedPtr(), eNoImpType);
+        CHECK(opt.GetDefaultImplementationType() == eIterPerExp, "default type");
+        OperatorImpMap lo = opt.GetOperatorImpMap(tet2), hi = opt.GetOperatorImpMap(tet6);
+        CHECK(lo[eBwdTrans] == eStdMat && lo[ePhysDeriv] == eSumFac, "low-order defaults");
+        CHECK(hi[eHelmholtz] == eIterPerExp && hi[ePhysDeriv] == eNoCollection, "high-order defaults");
+    }
+    const std::string xml = "<?xml version='1.0'?>\n<NEKTAR>\n <!-- selection -->\n"
+                            " <COLLECTIONS DEFAULT=\"b200\" MAXSIZE=\"64\">\n"
+                            "  <OPERATOR TYPE=\"Helmholtz\">\n"
+                            "   <ELEMENT TYPE=\"H\" ORDER=\"2-4,7\" IMPTYPE=\"MatrixFree\" />\n"
+                            "   <ELEMENT TYPE='A' ORDER='*' IMPTYPE='StdMat'/>\n"
+                            "  </OPERATOR>\n </COLLECTIONS>\n <EXPANSIONS><E COMPOSITE=\"C[0]\"/></EXPANSIONS>\n</NEKTAR>\n";
+    {
+        CollectionOptimisation opt(LibUtilities::SessionReader::CreateInstance(xml));
+        CHECK(opt.GetDefaultImplementationType() == eB200 && opt.GetMaxCollectionSize() == 64 && opt.SetByXml(), "session flags");
+        CHECK(opt.GetOperatorImpMap(hex5)[eHelmholtz] == eB200, "order 5 not in 2-4,7");
+        CHECK(opt.GetOperatorImpMap(hex7)[eHelmholtz] == eMatrixFree, "order 7 in 2-4,7");
+        CHECK(opt.GetOperatorImpMap(hex3)[eHelmholtz] == eMatrixFree && opt.GetOperatorImpMap(hex3)[eBwdTrans] == eB200, "order 3");
+        CHECK(opt.GetOperatorImpMap(tet6)[eHelmholtz] == eStdMat && opt.GetOperatorImpMap(tet6)[eBwdTrans] == eB200, "ORDER=*");
+        CollectionOptimisation fixed(LibUtilities::SessionReader::CreateInstance(xml), eMatrixFree);
+        CHECK(fixed.GetOperatorImpMap(hex5)[eBwdTrans] == eMatrixFree, "constructor type wins over DEFAULT");
+        CollectionOptimisation au(LibUtilities::SessionReader::CreateInstance("<NEKTAR><COLLECTIONS DEFAULT=\"auto\"/></NEKTAR>"));
+        CHECK(au.IsUsingAutotuning(), "DEFAULT=auto");
+    }
+    CHECK(throws("<FOO/>", "Unable to find NEKTAR tag"), "no NEKTAR tag");
+    CHECK(throws("<NEKTAR><COLLECTIONS DEFAULT=\"Fast\"/></NEKTAR>", "Unknown default collection scheme: Fast"), "unknown default");
+    CHECK(throws("<NEKTAR><COLLECTIONS><THING/></COLLECTIONS></NEKTAR>", "Only OPERATOR tags"), "non-OPERATOR child");
+    CHECK(throws("<NEKTAR><COLLECTIONS><OPERATOR/></COLLECTIONS></NEKTAR>", "Missing TYPE in OPERATOR tag"), "missing TYPE");
+    CHECK(throws("<NEKTAR><COLLECTIONS><OPERATOR TYPE=\"Mass\"/></COLLECTIONS></NEKTAR>", "Unknown OPERATOR type Mass"), "unknown operator");
+    CHECK(throws("<NEKTAR><COLLECTIONS><OPERATOR TYPE=\"BwdTrans\"><ELEMENT TYPE=\"X\" ORDER=\"*\" IMPTYPE=\"B200\"/></OPERATOR>"
+                 "</COLLECTIONS></NEKTAR>", "Unknown element type X"), "unknown element");
+    CHECK(throws("<NEKTAR><COLLECTIONS><OPERATOR TYPE=\"BwdTrans\"><ELEMENT TYPE=\"H\" ORDER=\"*\" IMPTYPE=\"Cuda\"/></OPERATOR>"
+                 "</COLLECTIONS></NEKTAR>", "Unknown IMPTYPE type Cuda"), "unknown imptype");
+    CHECK(throws("<NEKTAR><COLLECTIONS><OPERATOR TYPE=\"BwdTrans\"><ELEMENT TYPE=\"H\" IMPTYPE=\"B200\"/></OPERATOR>"
+                 "</COLLECTIONS></NEKTAR>", "Missing ORDER in ELEMENT tag"), "missing order");
+    CHECK(throws("<NEKTAR><COLLECTIONS></NEKTAR>", "XML: mismatched"), "malformed document");
+    {
+        // a Collection built from the map refuses implementation types that are not registered here (NekFactory.hpp:145-209)
+        CollectionOptimisation opt(LibUtilities::SessionReader::CreateInstance(xml));
+        std::vector<StdRegions::StdExpansionSharedPtr> v(3, tet6);
+        OperatorImpMap imp = opt.GetOperatorImpMap(tet6);
+        Collection c(v, imp);
+        bool refused = false;
+        try { c.Initialise(eHelmholtz); }
+        catch (const ErrorUtil::NekError &e) { refused = strstr(e.what(), "No such module") != nullptr; }
+        CHECK(refused, "unregistered implementation type");
+    }
+    printf(g_fail ? "%d check(s) FAILED\n" : "PASSED%.0d\n", g_fail);
+    return g_fail ? 1 : 0;
+}

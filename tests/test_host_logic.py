@@ -193,6 +193,15 @@ def test_cpp_collections_mirror_builds_and_refuses_without_gpu():
     assert r.returncode == 77 and "no CUDA device" in r.stdout
 
 
+def test_cpp_collection_optimisation_mirror():
+    """the C++ host side's CollectionOptimisation (session <COLLECTIONS> block, defaults, lookup, error messages):
+    tests/cpp/TestCollectionOptimisation.cpp, needs no GPU"""
+    import subprocess
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "TestCollectionOptimisation")], capture_output=True, text=True)
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout + r.stderr
+
+
 def test_config1_quad_helmholtz_solve_oracle():
     """BASELINE configs[0] on the CPU: 2-D Helmholtz on a structured quad mesh at P=5 (nm=6, nq=7), the
     reference's Helmholtz2D_modal set-up (lambda=1, u = sin(pi x) sin(pi y), homogeneous Dirichlet).  The
