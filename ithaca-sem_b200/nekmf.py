@@ -515,6 +515,97 @@ class Collection:
         return self.m_ops[opType](*args, **kw)
 
 
+# ----------------------------------------------------------------------------- ExpList (the callers of the path)
+class ExpList:
+    """MultiRegions::ExpList reduced to what drives the Collections: CreateCollections (ExpList.cpp:5005-5151) and the
+    four call sites that loop over the collections with coefficient / quadrature offsets -- IProductWRTBase
+    (:1262-1284), PhysDeriv (:1465-1504), BwdTrans (:1961-1989), GeneralMatrixOp for Helmholtz (:2359-2397).
+
+    `exps` lists the elements in mesh order as (StdExpansion, jac, df, deformed) with jac of 1 | nq values and df of
+    ndf x (1 | nq) values (the element's GeomFactors).  Elements are grouped exactly as the reference does: per shape
+    (in LibUtilities::ShapeType order), a collection ends where the next element is not contiguous in the coefficient /
+    quadrature arrays, differs in nCoeffs / nPhys / deformed-ness, or the collection holds collmax = MAXSIZE (else
+    2 x number of elements) members."""
+
+    _shapeOrder = {eSegment: 1, eTriangle: 2, eQuadrilateral: 3, eTetrahedron: 4, ePyramid: 5, ePrism: 6, eHexahedron: 7}
+
+    def __init__(self, exps, session=None):
+        self.m_exp, self.m_session = list(exps), session
+        self.m_coeff_offset, self.m_phys_offset = [], []
+        nc = nq = 0
+        for std, _, _, _ in self.m_exp:
+            self.m_coeff_offset.append(nc)
+            self.m_phys_offset.append(nq)
+            nc += std.GetNcoeffs()
+            nq += std.GetTotPoints()
+        self.m_ncoeffs, self.m_npoints = nc, nq
+        self.m_collections, self.m_coll_coeff_offset, self.m_coll_phys_offset = [], [], []
+
+    def GetNcoeffs(self): return self.m_ncoeffs
+    def GetTotPoints(self): return self.m_npoints
+
+    def _group(self, collmax):
+        """-> list of element-index lists, one per collection, in the reference's order"""
+        byShape = {}
+        for i, (std, _, _, _) in enumerate(self.m_exp):
+            byShape.setdefault(std.DetShapeType(), []).append(i)
+        groups = []
+        for shape in sorted(byShape, key=lambda sh: self._shapeOrder[sh]):
+            idx = byShape[shape]
+            cur = [idx[0]]
+            for prev, i in zip(idx, idx[1:]):
+                sp, si = self.m_exp[prev][0], self.m_exp[i][0]
+                split = (self.m_coeff_offset[prev] + si.GetNcoeffs() != self.m_coeff_offset[i] or
+                         sp.GetNcoeffs() != si.GetNcoeffs() or
+                         self.m_phys_offset[prev] + si.GetTotPoints() != self.m_phys_offset[i] or
+                         bool(self.m_exp[prev][3]) != bool(self.m_exp[i][3]) or
+                         sp.GetTotPoints() != si.GetTotPoints() or len(cur) >= collmax)
+                if split:
+                    groups.append(cur)
+                    cur = [i]
+                else:
+                    cur.append(i)
+            groups.append(cur)
+        return groups
+
+    def CreateCollections(self, ImpType=eNoImpType):
+        colOpt = CollectionOptimisation(self.m_session, ImpType)
+        collmax = colOpt.GetMaxCollectionSize() if colOpt.GetMaxCollectionSize() > 0 else 2 * len(self.m_exp)
+        self.m_collections, self.m_coll_coeff_offset, self.m_coll_phys_offset = [], [], []
+        for members in self._group(collmax):
+            std, _, _, deformed = self.m_exp[members[0]]
+            jac = np.concatenate([np.atleast_1d(np.asarray(self.m_exp[i][1], dtype=np.float64)) for i in members])
+            ndf = std.dim * std.coordim
+            df = np.concatenate([np.asarray(self.m_exp[i][2], dtype=np.float64).reshape(ndf, -1) for i in members], axis=1)
+            geom = CoalescedGeomData(np.ascontiguousarray(jac), np.ascontiguousarray(df).reshape(-1), bool(deformed))
+            self.m_collections.append(Collection(std, len(members), geom, colOpt.GetOperatorImpMap(std)))
+            self.m_coll_coeff_offset.append(self.m_coeff_offset[members[0]])
+            self.m_coll_phys_offset.append(self.m_phys_offset[members[0]])
+        return self
+
+    def _spans(self):
+        for c, co, po_ in zip(self.m_collections, self.m_coll_coeff_offset, self.m_coll_phys_offset):
+            yield c, co, co + c.m_nElmt * c.m_stdExp.GetNcoeffs(), po_, po_ + c.m_nElmt * c.m_stdExp.GetTotPoints()
+
+    def BwdTrans(self, inarray, outarray):
+        for c, c0, c1, p0, p1 in self._spans():
+            c.ApplyOperator(eBwdTrans, inarray[c0:c1], outarray[p0:p1])
+
+    def IProductWRTBase(self, inarray, outarray):
+        for c, c0, c1, p0, p1 in self._spans():
+            c.ApplyOperator(eIProductWRTBase, inarray[p0:p1], outarray[c0:c1])
+
+    def PhysDeriv(self, inarray, out_d0, out_d1=None, out_d2=None):
+        for c, c0, c1, p0, p1 in self._spans():
+            outs = [o[p0:p1] for o in (out_d0, out_d1, out_d2)[:c.m_stdExp.dim]]
+            c.ApplyOperator(ePhysDeriv, inarray[p0:p1], *outs)
+
+    def GeneralMatrixOp_Helmholtz(self, inarray, outarray, factors):
+        """ExpList::GeneralMatrixOp for a Helmholtz matrix key (ExpList.cpp:2359-2397): local coefficients in and out"""
+        for c, c0, c1, p0, p1 in self._spans():
+            c.ApplyOperator(eHelmholtz, inarray[c0:c1], outarray[c0:c1], factors=factors)
+
+
 # ----------------------------------------------------------------------------- AssemblyMap
 class AssemblyMap:
     """AssemblyMapCG local<->global (AssemblyMapCG.cpp:2853-2923)."""

@@ -289,3 +289,51 @@ def test_collection_optimisation_mirror(tmp_path):
                          nk.CollectionOptimisation(xml).GetOperatorImpMap(tet6))
     with pytest.raises(nk.NekError, match="no operator registered for key"):
         coll.Initialise(nk.eHelmholtz)
+
+
+def test_explist_create_collections_mirror(monkeypatch):
+    """MultiRegions::ExpList::CreateCollections (ExpList.cpp:5005-5151) as mirrored in nekmf.py: one pass per shape in
+    LibUtilities::ShapeType order; a collection ends at a gap in the coefficient / quadrature arrays, a change of
+    nCoeffs / nPhys / deformed-ness or at collmax members; the call sites hand each collection its slice of the
+    ExpList arrays.  Needs no GPU: ApplyOperator is replaced by a recorder."""
+    nk = nekmf()
+    hex4, hex5, tet4 = nk.StdExpansion(nk.eHexahedron, 4), nk.StdExpansion(nk.eHexahedron, 5), nk.StdExpansion(nk.eTetrahedron, 4)
+
+    def elem(std, deformed, tag):
+        npt = std.GetTotPoints() if deformed else 1
+        return (std, np.full(npt, float(tag)), np.full(std.dim * std.dim * npt, 10.0 + tag), deformed)
+
+    mesh = [elem(hex4, False, 0), elem(hex4, False, 1), elem(hex4, False, 2), elem(hex4, True, 3), elem(hex4, True, 4),
+            elem(tet4, False, 5), elem(tet4, False, 6), elem(hex5, False, 7), elem(hex4, False, 8), elem(hex4, False, 9)]
+    exp = nk.ExpList(mesh).CreateCollections(nk.eB200)
+    members = [(c.m_stdExp.DetShapeType(), c.m_stdExp.nm, c.m_nElmt, bool(c.m_geomData.IsDeformed())) for c in exp.m_collections]
+    # tetrahedra come before hexahedra (ShapeType order); the tets at positions 5, 6 break the contiguity of the hexes
+    assert members == [(nk.eTetrahedron, 4, 2, False), (nk.eHexahedron, 4, 3, False), (nk.eHexahedron, 4, 2, True),
+                       (nk.eHexahedron, 5, 1, False), (nk.eHexahedron, 4, 2, False)]
+    nc4, nq4, nct, nqt = hex4.GetNcoeffs(), hex4.GetTotPoints(), tet4.GetNcoeffs(), tet4.GetTotPoints()
+    assert exp.m_coll_coeff_offset == [5 * nc4, 0, 3 * nc4, 5 * nc4 + 2 * nct, 5 * nc4 + 2 * nct + hex5.GetNcoeffs()]
+    assert exp.m_coll_phys_offset == [5 * nq4, 0, 3 * nq4, 5 * nq4 + 2 * nqt, 5 * nq4 + 2 * nqt + hex5.GetTotPoints()]
+    # coalesced geometry in the reference layout: jac [nElmt(*nq)], df [ndf][nElmt(*nq)]
+    g = exp.m_collections[1].m_geomData
+    assert np.array_equal(g.GetJac(), [0.0, 1.0, 2.0]) and np.array_equal(np.asarray(g.GetDerivFactors()).reshape(9, 3)[4], [10.0, 11.0, 12.0])
+    g = exp.m_collections[2].m_geomData
+    assert g.GetJac().size == 2 * nq4 and np.array_equal(np.asarray(g.GetDerivFactors()).reshape(9, 2 * nq4)[0, nq4 - 1:nq4 + 1], [13.0, 14.0])
+    # MAXSIZE from the session caps the members of a collection
+    capped = nk.ExpList(mesh, '<NEKTAR><COLLECTIONS DEFAULT="B200" MAXSIZE="2"/></NEKTAR>').CreateCollections()
+    assert [c.m_nElmt for c in capped.m_collections] == [2, 2, 1, 2, 1, 2]
+    assert all(c.m_impTypes[nk.eHelmholtz] == nk.eB200 for c in capped.m_collections)
+    # call sites: every collection gets its own slice of the ExpList arrays
+    calls = []
+    monkeypatch.setattr(nk.Collection, "ApplyOperator", lambda self, op, *a, **kw: calls.append((op, [x.size for x in a], [x[0] for x in a], kw)))
+    coeffs, phys = np.arange(exp.GetNcoeffs(), dtype=np.float64), np.arange(exp.GetTotPoints(), dtype=np.float64)
+    exp.BwdTrans(coeffs, phys)
+    assert [c[1] for c in calls] == [[2 * nct, 2 * nqt], [3 * nc4, 3 * nq4], [2 * nc4, 2 * nq4], [hex5.GetNcoeffs(), hex5.GetTotPoints()], [2 * nc4, 2 * nq4]]
+    assert [c[2] for c in calls] == [[float(a), float(b)] for a, b in zip(exp.m_coll_coeff_offset, exp.m_coll_phys_offset)]
+    calls.clear()
+    d = [np.zeros(exp.GetTotPoints()) for _ in range(3)]
+    exp.PhysDeriv(phys, *d)
+    exp.IProductWRTBase(phys, coeffs)
+    exp.GeneralMatrixOp_Helmholtz(coeffs, np.zeros_like(coeffs), {nk.eFactorLambda: 2.0})
+    assert [c[0] for c in calls] == [nk.ePhysDeriv] * 5 + [nk.eIProductWRTBase] * 5 + [nk.eHelmholtz] * 5
+    assert all(len(c[1]) == 4 for c in calls[:5]) and calls[-1][3] == {"factors": {nk.eFactorLambda: 2.0}}
+    assert calls[5][1] == [2 * nqt, 2 * nct] and calls[10][1] == [2 * nct, 2 * nct]
