@@ -207,3 +207,43 @@ class StructuredQuadMesh:
         diag = np.zeros(self.nGlobal)
         np.add.at(diag, self.localToGlobal, np.tile(d.reshape(-1), self.nElmt))
         return diag
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# gslib set-up from universal ids: the generic form of the partition interfaces above.
+def interface_from_universal_maps(universal_maps, rank):
+    """What `Gs::Init` + `Gs::Unique` give AssemblyMapCG from `m_globalToUniversalMap` (AssemblyMapCG.h:118-126; call
+    sites AssemblyMapCG.cpp:2563-2569, 2840, 2922), restated for the pairwise exchange of comm.cu: `universal_maps[r]`
+    holds rank r's universal id of each of its rank-local global DOFs (id 0 = not taking part, gslib's convention).
+    Returns (peers, lists, ownerMask) for `rank`: the ranks it shares ids with in ascending order, for each of them
+    the rank-local indices of the shared DOFs ordered by universal id (both sides of a pair build the same order), and
+    the 0/1 mask that is 1 where `rank` is the lowest rank holding the id (so a masked dot product counts every DOF
+    once).  An id held by k ranks appears in k-1 lists of each holder: after every holder has added what the others
+    SENT (their pre-exchange values) all copies hold the sum of the k contributions -- gs_add."""
+    mine = np.asarray(universal_maps[rank], dtype=np.int64)
+    order = np.argsort(mine, kind="stable")
+    sorted_ids = mine[order]
+    if sorted_ids.size and np.any((sorted_ids[1:] == sorted_ids[:-1]) & (sorted_ids[1:] != 0)):
+        raise ValueError("universal ids must be unique within a rank")
+    peers, lists = [], []
+    owner = np.ones(mine.size)
+    for r, other in enumerate(universal_maps):
+        if r == rank:
+            continue
+        other = np.asarray(other, dtype=np.int64)
+        shared = np.intersect1d(sorted_ids[sorted_ids != 0], other[other != 0], assume_unique=True)
+        if shared.size == 0:
+            continue
+        pos = order[np.searchsorted(sorted_ids, shared)]  # rank-local indices, ascending universal id
+        peers.append(r)
+        lists.append(pos.astype(np.int32))
+        if r < rank:
+            owner[pos] = 0.0
+    return peers, lists, owner
+
+
+def interface_from_universal_map(dist, universal_map):
+    """the same for this process under torch.distributed: all-gathers the ranks' universal-id arrays"""
+    maps = [None] * dist.get_world_size()
+    dist.all_gather_object(maps, np.asarray(universal_map, dtype=np.int64))
+    return interface_from_universal_maps(maps, dist.get_rank())

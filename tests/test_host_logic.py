@@ -337,3 +337,79 @@ def test_explist_create_collections_mirror(monkeypatch):
     assert [c[0] for c in calls] == [nk.ePhysDeriv] * 5 + [nk.eIProductWRTBase] * 5 + [nk.eHelmholtz] * 5
     assert all(len(c[1]) == 4 for c in calls[:5]) and calls[-1][3] == {"factors": {nk.eFactorLambda: 2.0}}
     assert calls[5][1] == [2 * nqt, 2 * nct] and calls[10][1] == [2 * nct, 2 * nct]
+
+
+def _universal_ids(mesh):
+    """universal id of every rank-local global DOF of a z-slab mesh: 1 + global lattice index, 0 on the Dirichlet
+    boundary (those DOFs take no part in the exchange)"""
+    gz, gy, gx = np.meshgrid(np.arange(mesh.gz0, mesh.gz1 + 1), np.arange(mesh.Gy), np.arange(mesh.Gx), indexing="ij")
+    uid = 1 + gx + mesh.Gx * (gy + mesh.Gy * gz)
+    uid[mesh.dirichlet] = 0
+    out = np.zeros(mesh.nGlobal, dtype=np.int64)
+    out[mesh.lattice_ids.reshape(-1)] = uid.reshape(-1)
+    return out
+
+
+def test_interface_from_universal_maps():
+    """the gslib set-up restated (mesh.interface_from_universal_maps): against the analytic z-slab interfaces of
+    StructuredHexMesh, and on a hand-made case with a DOF shared by three ranks where the pairwise exchange-add must
+    reproduce gs_add (sum of all copies) and the owner mask must count every DOF once"""
+    mesh_mod = load_pkg_module("mesh")
+    R = 3
+    meshes = [mesh_mod.StructuredHexMesh(3, 2, 5, 4, slab=(r, R)) for r in range(R)]
+    maps = [_universal_ids(m) for m in meshes]
+    for r, m in enumerate(meshes):
+        peers, lists, owner = mesh_mod.interface_from_universal_maps(maps, r)
+        assert peers == m.peers
+        assert all(np.array_equal(a, b) for a, b in zip(lists, m.interface_lists))
+        interior = np.ones(m.nGlobal, dtype=bool)
+        interior[:m.nDir] = False
+        assert np.array_equal(owner[interior], m.ownerMask[interior])
+    # three ranks around a shared point: ids 7 (all three), 8 (ranks 0, 1), 9 (ranks 1, 2), 0 = not exchanged
+    maps = [np.array([5, 7, 8, 0]), np.array([8, 9, 7, 0, 11]), np.array([0, 9, 12, 7])]
+    vals = [np.array([1.0, 2.0, 3.0, 4.0]), np.array([10.0, 20.0, 30.0, 40.0, 50.0]), np.array([100.0, 200.0, 300.0, 400.0])]
+    setups = [mesh_mod.interface_from_universal_maps(maps, r) for r in range(3)]
+    assert setups[0][0] == [1, 2] and setups[1][0] == [0, 2] and setups[2][0] == [0, 1]
+    assert [l.tolist() for l in setups[1][1]] == [[2, 0], [2, 1]]  # ascending universal id: 7 then 8; 7 then 9
+    sent = [[vals[r][l].copy() for l in setups[r][1]] for r in range(3)]
+    out = [v.copy() for v in vals]
+    for r in range(3):
+        for k, p in enumerate(setups[r][0]):
+            out[r][setups[r][1][k]] += sent[p][setups[p][0].index(r)]
+    total = {}
+    for r in range(3):
+        for u, v in zip(maps[r], vals[r]):
+            total[u] = total.get(u, 0.0) + v
+    for r in range(3):
+        for i, u in enumerate(maps[r]):
+            assert out[r][i] == (total[u] if u != 0 else vals[r][i]), (r, i)
+    counted = {}
+    for r in range(3):
+        for u, w in zip(maps[r], setups[r][2]):
+            if u != 0:
+                counted[u] = counted.get(u, 0.0) + w
+    assert all(v == 1.0 for v in counted.values())
+    with pytest.raises(ValueError):
+        mesh_mod.interface_from_universal_maps([np.array([3, 3]), np.array([3])], 0)
+
+
+def _gloo_universal_worker(rank, world, port, outdir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mesh_mod = load_pkg_module("mesh")
+    m = mesh_mod.StructuredHexMesh(2, 2, 4, 3, slab=(rank, world))
+    peers, lists, owner = mesh_mod.interface_from_universal_map(dist, _universal_ids(m))
+    ok = peers == m.peers and all(np.array_equal(a, b) for a, b in zip(lists, m.interface_lists))
+    np.save(os.path.join(outdir, "uok_%d.npy" % rank), np.array([1.0 if ok else 0.0, owner[m.nDir:].sum()]))
+    dist.destroy_process_group()
+
+
+def test_interface_from_universal_map_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_gloo_universal_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    res = [np.load(os.path.join(str(tmp_path), "uok_%d.npy" % r)) for r in range(2)]
+    assert all(r[0] == 1.0 for r in res)
+    # every interior DOF of the full mesh is owned exactly once
+    full = load_pkg_module("mesh").StructuredHexMesh(2, 2, 4, 3)
+    assert res[0][1] + res[1][1] == full.nGlobal - full.nDir
