@@ -746,7 +746,161 @@ protected:
     CoalescedGeomDataSharedPtr m_geomData;
     std::vector<StdRegions::StdExpansionSharedPtr> m_collExp;
     OperatorImpMap m_impTypes;
+
+public:
+    size_t GetNumElmt() const { return m_collExp.size(); }
+    const StdRegions::StdExpansionSharedPtr &GetExp(size_t i) const { return m_collExp[i]; }
+    const OperatorImpMap &GetImpTypes() const { return m_impTypes; }
 };
 
 } // namespace Collections
+
+// ------------------------------------------------------------------------------------------ MultiRegions
+namespace MultiRegions
+{
+// ExpList reduced to what drives the Collections: CreateCollections (ExpList.cpp:5005-5151) and the call sites that
+// loop over the collections with their coefficient / quadrature offsets -- IProductWRTBase (:1262-1284), PhysDeriv
+// (:1465-1504), BwdTrans (:1961-1989), GeneralMatrixOp for a Helmholtz key (:2359-2397).
+class ExpList
+{
+public:
+    ExpList(const std::vector<StdRegions::StdExpansionSharedPtr> &exp,
+            LibUtilities::SessionReaderSharedPtr session = LibUtilities::SessionReaderSharedPtr())
+        : m_exp(exp), m_session(session), m_ncoeffs(0), m_npoints(0)
+    {
+        for (auto &e : m_exp)
+        {
+            m_coeff_offset.push_back(m_ncoeffs);
+            m_phys_offset.push_back(m_npoints);
+            m_ncoeffs += e->GetNcoeffs();
+            m_npoints += e->GetTotPoints();
+        }
+    }
+    int GetNcoeffs() const { return m_ncoeffs; }
+    int GetTotPoints() const { return m_npoints; }
+    std::vector<Collections::Collection> &GetCollections() { return m_collections; }
+    const std::vector<int> &GetCollCoeffOffset() const { return m_coll_coeff_offset; }
+    const std::vector<int> &GetCollPhysOffset() const { return m_coll_phys_offset; }
+
+    void CreateCollections(Collections::ImplementationType ImpType = Collections::eNoImpType)
+    {
+        // the reference iterates a map keyed by LibUtilities::ShapeType: Seg, Tri, Quad, Tet, Pyr, Prism, Hex
+        struct ShapeLess
+        {
+            static int Rank(LibUtilities::ShapeType s)
+            {
+                switch ((int)s)
+                {
+                    case NEKMF_SEG: return 1;
+                    case NEKMF_TRI: return 2;
+                    case NEKMF_QUAD: return 3;
+                    case NEKMF_TET: return 4;
+                    case NEKMF_PYR: return 5;
+                    case NEKMF_PRISM: return 6;
+                    default: return 7;
+                }
+            }
+            bool operator()(LibUtilities::ShapeType a, LibUtilities::ShapeType b) const { return Rank(a) < Rank(b); }
+        };
+        std::map<LibUtilities::ShapeType, std::vector<std::pair<StdRegions::StdExpansionSharedPtr, int>>, ShapeLess> collections;
+        Collections::CollectionOptimisation colOpt(m_session, ImpType);
+        const int collmax = colOpt.GetMaxCollectionSize() > 0 ? (int)colOpt.GetMaxCollectionSize() : 2 * (int)m_exp.size();
+        m_collections.clear();
+        m_coll_coeff_offset.clear();
+        m_coll_phys_offset.clear();
+        for (int i = 0; i < (int)m_exp.size(); ++i) collections[m_exp[i]->DetShapeType()].push_back(std::make_pair(m_exp[i], i));
+        for (auto &it : collections)
+        {
+            Collections::OperatorImpMap impTypes = colOpt.GetOperatorImpMap(it.second[0].first);
+            std::vector<StdRegions::StdExpansionSharedPtr> collExp;
+            int prevCoeffOffset = m_coeff_offset[it.second[0].second];
+            int prevPhysOffset  = m_phys_offset[it.second[0].second];
+            m_coll_coeff_offset.push_back(prevCoeffOffset);
+            m_coll_phys_offset.push_back(prevPhysOffset);
+            collExp.push_back(it.second[0].first);
+            int prevnCoeff    = it.second[0].first->GetNcoeffs();
+            int prevnPhys     = it.second[0].first->GetTotPoints();
+            bool prevDeformed = it.second[0].first->IsDeformed();
+            int collcnt       = 1;
+            for (size_t i = 1; i < it.second.size(); ++i)
+            {
+                const int nCoeffs     = it.second[i].first->GetNcoeffs();
+                const int nPhys       = it.second[i].first->GetTotPoints();
+                const bool Deformed   = it.second[i].first->IsDeformed();
+                const int coeffOffset = m_coeff_offset[it.second[i].second];
+                const int physOffset  = m_phys_offset[it.second[i].second];
+                // next element different, not contiguous, or collmax reached: end the collection, start a new one
+                if (prevCoeffOffset + nCoeffs != coeffOffset || prevnCoeff != nCoeffs || prevPhysOffset + nPhys != physOffset ||
+                    prevDeformed != Deformed || prevnPhys != nPhys || collcnt >= collmax)
+                {
+                    m_collections.push_back(Collections::Collection(collExp, impTypes));
+                    collExp.clear();
+                    m_coll_coeff_offset.push_back(coeffOffset);
+                    m_coll_phys_offset.push_back(physOffset);
+                    collExp.push_back(it.second[i].first);
+                    collcnt = 1;
+                }
+                else
+                {
+                    collExp.push_back(it.second[i].first);
+                    collcnt++;
+                }
+                prevCoeffOffset = coeffOffset;
+                prevPhysOffset  = physOffset;
+                prevDeformed    = Deformed;
+                prevnCoeff      = nCoeffs;
+                prevnPhys       = nPhys;
+            }
+            m_collections.push_back(Collections::Collection(collExp, impTypes));
+        }
+    }
+    void BwdTrans(const Array<OneD, const NekDouble> &inarray, Array<OneD, NekDouble> &outarray)
+    {
+        for (size_t i = 0; i < m_collections.size(); ++i)
+        {
+            Array<OneD, NekDouble> tmp = outarray + m_coll_phys_offset[i];
+            m_collections[i].ApplyOperator(Collections::eBwdTrans, inarray + m_coll_coeff_offset[i], tmp);
+        }
+    }
+    void IProductWRTBase(const Array<OneD, const NekDouble> &inarray, Array<OneD, NekDouble> &outarray)
+    {
+        for (size_t i = 0; i < m_collections.size(); ++i)
+        {
+            Array<OneD, NekDouble> tmp = outarray + m_coll_coeff_offset[i];
+            m_collections[i].ApplyOperator(Collections::eIProductWRTBase, inarray + m_coll_phys_offset[i], tmp);
+        }
+    }
+    void PhysDeriv(const Array<OneD, const NekDouble> &inarray, Array<OneD, NekDouble> &out_d0, Array<OneD, NekDouble> &out_d1,
+                   Array<OneD, NekDouble> &out_d2)
+    {
+        for (size_t i = 0; i < m_collections.size(); ++i)
+        {
+            const size_t o = m_coll_phys_offset[i];
+            Array<OneD, NekDouble> e0 = out_d0 + o, e1 = out_d1 + o, e2;
+            if (m_collections[i].GetExp(0)->GetShapeDimension() == 3)
+            {
+                e2 = out_d2 + o;
+                m_collections[i].ApplyOperator(Collections::ePhysDeriv, inarray + o, e0, e1, e2);
+            }
+            else m_collections[i].ApplyOperator(Collections::ePhysDeriv, inarray + o, e0, e1);
+        }
+    }
+    void GeneralMatrixOp_Helmholtz(const Array<OneD, const NekDouble> &inarray, Array<OneD, NekDouble> &outarray,
+                                   const StdRegions::ConstFactorMap &factors)
+    {
+        for (size_t i = 0; i < m_collections.size(); ++i)
+        {
+            Array<OneD, NekDouble> tmp = outarray + m_coll_coeff_offset[i];
+            m_collections[i].ApplyOperator(Collections::eHelmholtz, inarray + m_coll_coeff_offset[i], tmp, factors);
+        }
+    }
+
+private:
+    std::vector<StdRegions::StdExpansionSharedPtr> m_exp;
+    LibUtilities::SessionReaderSharedPtr m_session;
+    int m_ncoeffs, m_npoints;
+    std::vector<int> m_coeff_offset, m_phys_offset, m_coll_coeff_offset, m_coll_phys_offset;
+    std::vector<Collections::Collection> m_collections;
+};
+} // namespace MultiRegions
 } // namespace Nektar

@@ -96,6 +96,43 @@ int main()
         catch (const ErrorUtil::NekError &e) { refused = strstr(e.what(), "No such module") != nullptr; }
         CHECK(refused, "unregistered implementation type");
     }
+    {
+        // MultiRegions::ExpList::CreateCollections (ExpList.cpp:5005-5151): per-shape passes in ShapeType order, a
+        // collection ends at a gap in the arrays, a change of nCoeffs / nPhys / deformed-ness, or at collmax members
+        auto hex4 = exp(LibUtilities::eHexahedron, 4);
+        auto tet4 = exp(LibUtilities::eTetrahedron, 4);
+        auto reg = [](const StdRegions::StdExpansionSharedPtr &b) {
+            const int d = b->GetShapeDimension();
+            return std::make_shared<StdRegions::StdExpansion>(*b, false, Array<OneD, NekDouble>(1, 1.0), Array<OneD, NekDouble>(d * d, 1.0));
+        };
+        auto def = [](const StdRegions::StdExpansionSharedPtr &b) {
+            const int d = b->GetShapeDimension(), n = b->GetTotPoints();
+            return std::make_shared<StdRegions::StdExpansion>(*b, true, Array<OneD, NekDouble>(n, 1.0), Array<OneD, NekDouble>(d * d * n, 1.0));
+        };
+        std::vector<StdRegions::StdExpansionSharedPtr> mesh{reg(hex4), reg(hex4), reg(hex4), def(hex4), def(hex4), reg(tet4),
+                                                          reg(tet4), reg(hex5), reg(hex4), reg(hex4)};
+        MultiRegions::ExpList list(mesh);
+        list.CreateCollections(eB200);
+        auto &c = list.GetCollections();
+        const int nc4 = hex4->GetNcoeffs(), nq4 = hex4->GetTotPoints(), nct = tet4->GetNcoeffs(), nqt = tet4->GetTotPoints();
+        const size_t sizes[5] = {2, 3, 2, 1, 2};
+        bool ok = c.size() == 5;
+        for (size_t i = 0; ok && i < 5; ++i) ok = c[i].GetNumElmt() == sizes[i];
+        CHECK(ok, "CreateCollections group sizes");
+        CHECK(ok && c[0].GetExp(0)->DetShapeType() == LibUtilities::eTetrahedron && c[2].GetExp(0)->IsDeformed() &&
+                  c[3].GetExp(0)->GetNcoeffs() == hex5->GetNcoeffs(), "CreateCollections group contents");
+        const std::vector<int> co{5 * nc4, 0, 3 * nc4, 5 * nc4 + 2 * nct, 5 * nc4 + 2 * nct + hex5->GetNcoeffs()};
+        const std::vector<int> po{5 * nq4, 0, 3 * nq4, 5 * nq4 + 2 * nqt, 5 * nq4 + 2 * nqt + hex5->GetTotPoints()};
+        CHECK(list.GetCollCoeffOffset() == co && list.GetCollPhysOffset() == po, "CreateCollections offsets");
+        MultiRegions::ExpList capped(mesh, LibUtilities::SessionReader::CreateInstance(
+                                               "<NEKTAR><COLLECTIONS DEFAULT=\"B200\" MAXSIZE=\"2\"/></NEKTAR>"));
+        capped.CreateCollections();
+        const size_t csz[6] = {2, 2, 1, 2, 1, 2};
+        bool okc = capped.GetCollections().size() == 6;
+        for (size_t i = 0; okc && i < 6; ++i)
+            okc = capped.GetCollections()[i].GetNumElmt() == csz[i] && capped.GetCollections()[i].GetImpTypes().at(eHelmholtz) == eB200;
+        CHECK(okc, "CreateCollections with MAXSIZE");
+    }
     printf(g_fail ? "%d check(s) FAILED\n" : "PASSED%.0d\n", g_fail);
     return g_fail ? 1 : 0;
 }
