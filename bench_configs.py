@@ -106,10 +106,10 @@ def config1(args, torch, nk, po, peak, peak_src, ClockSampler):
     rhs = torch.rand(mesh.nGlobal, dtype=torch.float64, device=dev)
     rhs[:mesh.nDir] = 0.0
     xs = torch.zeros(mesh.nGlobal, dtype=torch.float64, device=dev)
-    cg.solve(rhs, xs, tol=0.0, maxiter=3)
+    cg.solve(rhs, xs, tol=0.0, maxiter=3, raise_on_maxiter=False)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    its, _ = cg.solve(rhs, xs, tol=0.0, maxiter=30)
+    its, _ = cg.solve(rhs, xs, tol=0.0, maxiter=30, raise_on_maxiter=False)
     torch.cuda.synchronize()
     cg_ms = (time.perf_counter() - t0) / its * 1e3
     bytes_el = 8 * (2 * nm * nm + 5)  # 616 B per quad at P=5, regular geometry

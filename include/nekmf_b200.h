@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define NEKMF_ABI_VERSION 1
+#define NEKMF_ABI_VERSION 2
 
 /* LibUtilities::ShapeType subset (LibUtilities/BasicUtils/ShapeType.hpp); numbering is this ABI's */
 enum nekmf_shape
@@ -96,7 +96,10 @@ enum nekmf_status
     NEKMF_ERR_UNSUPPORTED = 2, /* shape/op/order outside the registered set (reference: NEKERROR "not implemented") */
     NEKMF_ERR_CUDA        = 3, /* CUDA runtime failure or no device */
     NEKMF_ERR_STATE       = 4, /* geometry / lambda not set before apply */
-    NEKMF_ERR_COMM        = 5  /* NCCL failure */
+    NEKMF_ERR_COMM        = 5, /* NCCL failure, or a peer-memory wait that timed out */
+    NEKMF_ERR_NOCONVERGE  = 6  /* CG reached the iteration cap: the reference's NEKERROR(efatal, "Exceeded maximum
+                                  number of iterations") (NekLinSysIterCG.cpp:190-203); x, iterations and final_eps
+                                  are still filled in */
 };
 
 typedef struct nekmf_op_s *nekmf_op_t;
@@ -188,19 +191,31 @@ int nekmf_map_global_to_local(nekmf_map_t map, const double *glob, double *loc, 
 int nekmf_map_assemble(nekmf_map_t map, const double *loc, double *glob, int memkind, void *stream);
 int nekmf_map_destroy(nekmf_map_t map);
 
-/* ---- communicator (one rank per GPU, NCCL) ------------------------------------------------ */
-/* 128-byte ncclUniqueId produced on rank 0 and distributed by the host (torch.distributed, MPI ...) */
+/* ---- communicator (one rank per GPU) ------------------------------------------------------ */
+/* Replaces LibUtilities::Comm for this path (AllReduce of the CG dot products, NekLinSysIterCG.cpp:226-235, and
+ * the transport under Gs::Gather).  Bootstrapped with NCCL: 128-byte ncclUniqueId produced on rank 0 and
+ * distributed by the host (torch.distributed, MPI ...).  COLLECTIVE: every rank calls create.  On an NVLink box
+ * create also exports one small reduction window per rank with CUDA IPC and maps all of them: the data path then
+ * runs over peer memory (kernels store into / spin on the windows) without NCCL calls.  NEKMF_TRANSPORT=nccl in
+ * the environment, or a mapping failure on any rank, keeps every rank on NCCL send/recv/all-reduce instead. */
 int nekmf_comm_unique_id(unsigned char id[128]);
 int nekmf_comm_create(const unsigned char id[128], int rank, int nranks, nekmf_comm_t *comm);
+/* 1 = peer-memory transport (NVLink loads/stores), 0 = NCCL calls */
+int nekmf_comm_transport(nekmf_comm_t comm);
 int nekmf_comm_destroy(nekmf_comm_t comm);
 
 /* ---- interface-DOF exchange: the Gs::Gather(gs_add) replacement -------------------------- */
-/* For each of nNeighbours peer ranks, the (identically ordered on both sides) list of this
- * rank's global indices shared with that peer: idx[offsets[n] .. offsets[n+1]).  comm may be
- * NULL when nNeighbours == 0. */
-int nekmf_exchange_create(nekmf_comm_t comm, int nNeighbours, const int *peerRanks, const int *offsets,
+/* For each of nNeighbours (<= 255) peer ranks, the (identically ordered on both sides) list of this
+ * rank's global indices in [0,nGlobal) shared with that peer: idx[offsets[n] .. offsets[n+1]).  A DOF held by k
+ * ranks appears in k-1 lists of each holder (what Gs::Init derives from m_globalToUniversalMap,
+ * AssemblyMapCG.cpp:2563-2565).  comm may be NULL when nNeighbours == 0.  COLLECTIVE when comm has more than one
+ * rank and uses the peer-memory transport (the receive windows are exported / mapped here). */
+int nekmf_exchange_create(nekmf_comm_t comm, int nGlobal, int nNeighbours, const int *peerRanks, const int *offsets,
                           const int *idx, nekmf_exchange_t *ex);
-/* glob[idx] += peers' glob[idx]  (pack -> ncclSend/ncclRecv group -> unpack-add), device memory */
+/* Every copy of a shared DOF ends up holding the sum over all copies (gs_add), device memory.  The copies are
+ * added in ascending RANK order by one thread per DOF (no atomics): deterministic, and all holders of a DOF
+ * compute the bit-identical sum.  Peer-memory transport: deposit kernel (NVLink stores + flags) -> wait/add
+ * kernel; NCCL transport: pack -> grouped ncclSend/ncclRecv -> the same add kernel. */
 int nekmf_exchange_add(nekmf_exchange_t ex, double *glob, void *stream);
 int nekmf_exchange_destroy(nekmf_exchange_t ex);
 
@@ -213,10 +228,17 @@ int nekmf_exchange_destroy(nekmf_exchange_t ex);
 int nekmf_cg_create(nekmf_op_t op, nekmf_map_t map, nekmf_exchange_t ex, nekmf_comm_t comm, int nDir,
                     const double *invdiag, const double *ownerMask, nekmf_cg_t *cg);
 /* rhs, x: global vectors [nGlobal] (memkind as given).  Follows DoConjugateGradient: x[nDir:]
- * starts at 0, stops when r.r < tol^2 * max(rhs.rhs, 1e-6 ? ...) or maxiter.  Returns iteration
- * count and the final r.r. */
+ * starts at 0, stops when r.r < tol^2 * rhs_magnitude (rhs.rhs, or 1 when that is below 1e-6).  Returns the
+ * iteration count (m_totalIterations) and the final r.r.  When the loop counter reaches maxiter the reference
+ * raises a fatal error; here the call returns NEKMF_ERR_NOCONVERGE with x / iterations / final_eps filled.
+ * alpha, beta and the convergence test live on the device; iterations are replayed from CUDA graphs and the
+ * host reads the state one graph behind (cg.cu).  Fails with NEKMF_ERR_STATE when the operator has no geometry
+ * or lambda. */
 int nekmf_cg_solve(nekmf_cg_t cg, const double *rhs, double *x, int memkind, double tol, int maxiter,
                    int *iterations, double *final_eps);
+/* device time (CUDA events on the solver's stream) of the iteration loop of the last solve and the number of
+ * iterations launched inside it (set-up, the first mat-vec and the final copies excluded); ms < 0 if none ran */
+int nekmf_cg_last_loop(nekmf_cg_t cg, float *ms, int *iterations);
 /* one mat-vec s = A w on device global vectors (exposed for tests and the benchmark) */
 int nekmf_cg_matvec(nekmf_cg_t cg, const double *w, double *s);
 int nekmf_cg_destroy(nekmf_cg_t cg);

@@ -337,8 +337,7 @@ int nekmf_op_set_geom(nekmf_op_t op, const double *jac, const double *df, int me
         else if (rows) NEKMF_CUDA(cudaMemcpy2D(op->d_df, pitch * 8, df, width * 8, width * 8, rows * op->ndf, k));
         op->has_df = true;
     }
-    notify_geom_changed(op);
-    return NEKMF_OK;
+    return notify_geom_changed(op);
 }
 
 int nekmf_op_set_lambda(nekmf_op_t op, double lambda)
@@ -385,7 +384,10 @@ int nekmf_op_last_ms(nekmf_op_t op, float *ms)
     return NEKMF_OK;
 }
 
-static int op_check_ready(nekmf_op_t op)
+} // extern "C"
+namespace nekmf
+{
+int op_check_ready(nekmf_op_s *op)
 {
     const bool need_jac = op->optype == NEKMF_HELMHOLTZ || op->optype == NEKMF_IPRODUCTWRTBASE ||
                           op->optype == NEKMF_IPRODUCTWRTDERIVBASE;
@@ -403,6 +405,9 @@ static int op_check_ready(nekmf_op_t op)
     }
     return NEKMF_OK;
 }
+
+} // namespace nekmf
+extern "C" {
 
 // Device-side aliases of page-locked host arrays (cudaHostAlloc / cudaHostRegister); false if any array is
 // pageable or not mapped into the device address space.

@@ -69,18 +69,21 @@ __global__ void assemble_kernel(const int *__restrict__ rowptr, const int *__res
     glob[g] = s;
 }
 
-// Assemble fused with the CG dot product mu = sum_{g >= nDir} mask[g] * glob[g] * w[g] (the s.w of
+// Assemble fused with the CG dot product mu = sum_{g >= nDir} owned(g) * glob[g] * w[g] (the s.w of
 // NekLinSysIterCG.cpp:226-235): fixed grid, grid-stride, one partial sum per block -> deterministic.
+// Sharded solves (EX): the first blocks start with the partition-interface entries -- they assemble those DOFs
+// and store the values straight into the neighbours' receive windows over NVLink (peer-memory transport) or into
+// the NCCL send buffer, and the last of them raises the neighbours' flags; the transfer then overlaps the rest of
+// the assemble.  The s.w terms of shared DOFs are left to the unpack kernel (their sums are not complete yet).
+template <bool EX>
 __global__ void __launch_bounds__(256)
     assemble_dot_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ sign,
                         const double *__restrict__ loc, double *__restrict__ glob, int nGlobal,
-                        const double *__restrict__ w, const double *__restrict__ mask, int nDir,
-                        double *__restrict__ part)
+                        const double *__restrict__ w, const unsigned char *__restrict__ flags, int nDir,
+                        double *__restrict__ part, const __grid_constant__ nekmf_exdev ex, int nIfBlocks)
 {
     __shared__ double sh[8];
-    double mu = 0.0;
-    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nGlobal; g += gridDim.x * blockDim.x)
-    {
+    auto row_sum = [&](int g) {
         const int b = rowptr[g], e = rowptr[g + 1];
         double s = 0.0;
         for (int k = b; k < e; ++k)
@@ -88,11 +91,24 @@ __global__ void __launch_bounds__(256)
             const int i = col[k];
             s += sign ? sign[i] * __ldg(loc + i) : __ldg(loc + i);
         }
+        return s;
+    };
+    if (EX && (int)blockIdx.x < nIfBlocks)
+    {
+        const unsigned long long epoch = *ex.epoch + 1ull;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ex.total; i += nIfBlocks * blockDim.x)
+            exchange_put(ex, i, epoch, row_sum(ex.idx[i]));
+        exchange_signal(ex, epoch, (unsigned int)nIfBlocks);
+    }
+    double mu = 0.0;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nGlobal; g += gridDim.x * blockDim.x)
+    {
+        const double s = row_sum(g);
         glob[g] = s;
         if (g >= nDir)
         {
-            const double wg = mask ? w[g] * mask[g] : w[g];
-            mu = fma(s, wg, mu);
+            const unsigned char f = flags ? flags[g] : (unsigned char)1;
+            if ((f & 1) && !(f & 2)) mu = fma(s, w[g], mu);
         }
     }
 #pragma unroll
@@ -202,11 +218,22 @@ int map_assemble_device(nekmf_map_s *m, const double *loc, double *glob, cudaStr
     NEKMF_CUDA(cudaGetLastError());
     return NEKMF_OK;
 }
-int map_assemble_dot_device(nekmf_map_s *m, const double *loc, double *glob, const double *w, const double *mask,
-                            int nDir, double *part, int nBlocks, cudaStream_t st)
+int map_assemble_dot_device(nekmf_map_s *m, const double *loc, double *glob, const double *w,
+                            const unsigned char *flags, int nDir, double *part, const nekmf_exdev *ex, cudaStream_t st)
 {
-    assemble_dot_kernel<<<nBlocks, 256, 0, st>>>(m->d_rowptr, m->d_col, m->d_sign, loc, glob, m->nGlobal, w, mask, nDir,
-                                                 part);
+    if (ex && ex->total > 0)
+    {
+        int nIf = (ex->total + 255) / 256;
+        if (nIf > RED_BLOCKS) nIf = RED_BLOCKS;
+        assemble_dot_kernel<true><<<RED_BLOCKS, 256, 0, st>>>(m->d_rowptr, m->d_col, m->d_sign, loc, glob, m->nGlobal, w,
+                                                              flags, nDir, part, *ex, nIf);
+    }
+    else
+    {
+        nekmf_exdev none;
+        assemble_dot_kernel<false><<<RED_BLOCKS, 256, 0, st>>>(m->d_rowptr, m->d_col, m->d_sign, loc, glob, m->nGlobal,
+                                                               w, flags, nDir, part, none, 0);
+    }
     ++g_launches;
     NEKMF_CUDA(cudaGetLastError());
     return NEKMF_OK;

@@ -60,11 +60,12 @@ bool select_shape_fast(nekmf_op_s *op)
     if (ok) quad_kron_maybe_wrap(op);
     return ok;
 }
-void notify_geom_changed(nekmf_op_s *op)
+int notify_geom_changed(nekmf_op_s *op)
 {
-    kron_geom_changed(op);
-    quad_kron_geom_changed(op);
-    dense_geom_changed(op);
-    prism_geom_changed(op);
+    int rc = kron_geom_changed(op);
+    if (!rc) rc = quad_kron_geom_changed(op);
+    if (!rc) rc = dense_geom_changed(op);
+    if (!rc) rc = prism_geom_changed(op);
+    return rc;
 }
 } // namespace nekmf

@@ -57,6 +57,8 @@ struct nekmf_op_s
 
 namespace nekmf
 {
+// geometry / lambda set? (NEKMF_ERR_STATE otherwise); every entry point that launches the operator calls it
+int op_check_ready(nekmf_op_s *op);
 // each returns true if it installed a launcher for this operator
 bool select_hex_fast(nekmf_op_s *op);
 bool select_shape_fast(nekmf_op_s *op);
@@ -65,7 +67,7 @@ bool select_seg(nekmf_op_s *op);
 bool select_quad_lane(nekmf_op_s *op);
 bool select_tri_lane(nekmf_op_s *op);
 // called after set_geom / set_lambda so launchers can precompute (e.g. detect diagonal metrics)
-void notify_geom_changed(nekmf_op_s *op);
+int notify_geom_changed(nekmf_op_s *op); // status of the launchers' geometry pre-passes
 void kron_maybe_wrap(nekmf_op_s *op);
 int kron_geom_changed(nekmf_op_s *op);
 void quad_kron_maybe_wrap(nekmf_op_s *op);

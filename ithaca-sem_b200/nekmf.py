@@ -38,6 +38,7 @@ ImplementationTypeMap = ["NoImplementationType", "NoCollection", "IterPerExp", "
 eModified_A, eModified_B, eModified_C, eModifiedPyr_C = 0, 1, 2, 3
 eGaussLobattoLegendre, eGaussRadauMAlpha1Beta0, eGaussRadauMAlpha2Beta0 = 0, 1, 2
 HOST, DEVICE = 0, 1
+ERR_NOCONVERGE = 6  # nekmf_status
 eFactorLambda = "FactorLambda"
 
 _dp = C.POINTER(C.c_double)
@@ -52,9 +53,9 @@ EXPORTS = [
     "nekmf_op_create", "nekmf_op_set_geom", "nekmf_op_set_lambda", "nekmf_op_apply", "nekmf_op_set_stream",
     "nekmf_op_ncoeff", "nekmf_op_nphys", "nekmf_op_kernel_name", "nekmf_op_enable_timing", "nekmf_op_last_ms",
     "nekmf_op_destroy", "nekmf_map_create", "nekmf_map_global_to_local", "nekmf_map_assemble", "nekmf_map_destroy",
-    "nekmf_comm_unique_id", "nekmf_comm_create", "nekmf_comm_destroy", "nekmf_exchange_create",
+    "nekmf_comm_unique_id", "nekmf_comm_create", "nekmf_comm_transport", "nekmf_comm_destroy", "nekmf_exchange_create",
     "nekmf_exchange_add", "nekmf_exchange_destroy", "nekmf_cg_create", "nekmf_cg_solve", "nekmf_cg_matvec",
-    "nekmf_cg_destroy",
+    "nekmf_cg_last_loop", "nekmf_cg_destroy",
 ]
 
 
@@ -98,13 +99,15 @@ def lib():
         L.nekmf_map_destroy.argtypes = [_vp]
         L.nekmf_comm_unique_id.argtypes = [C.c_char_p]
         L.nekmf_comm_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]
+        L.nekmf_comm_transport.argtypes = [_vp]
         L.nekmf_comm_destroy.argtypes = [_vp]
-        L.nekmf_exchange_create.argtypes = [_vp, C.c_int, _ip, _ip, _ip, C.POINTER(_vp)]
+        L.nekmf_exchange_create.argtypes = [_vp, C.c_int, C.c_int, _ip, _ip, _ip, C.POINTER(_vp)]
         L.nekmf_exchange_add.argtypes = [_vp, _vp, _vp]
         L.nekmf_exchange_destroy.argtypes = [_vp]
         L.nekmf_cg_create.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _dp, _dp, C.POINTER(_vp)]
         L.nekmf_cg_solve.argtypes = [_vp, _vp, _vp, C.c_int, C.c_double, C.c_int, _ip, _dp]
         L.nekmf_cg_matvec.argtypes = [_vp, _vp, _vp]
+        L.nekmf_cg_last_loop.argtypes = [_vp, C.POINTER(C.c_float), _ip]
         L.nekmf_cg_destroy.argtypes = [_vp]
         L.nekmf_malloc_device.argtypes = [C.POINTER(_vp), C.c_size_t]
         L.nekmf_free_device.argtypes = [_vp]
@@ -647,6 +650,11 @@ class Comm:
         self.rank, self.nranks = rank, nranks
         check(lib().nekmf_comm_create(unique_id, rank, nranks, C.byref(self.h)), "nekmf_comm_create")
 
+    @property
+    def transport(self):
+        """"p2p": kernels store into / spin on CUDA-IPC mapped peer windows over NVLink; "nccl": NCCL calls"""
+        return "p2p" if lib().nekmf_comm_transport(self.h) else "nccl"
+
     @staticmethod
     def unique_id():
         buf = C.create_string_buffer(128)
@@ -674,7 +682,7 @@ class Comm:
 class Exchange:
     """Gs::Gather(gs_add) replacement for partition-interface DOFs."""
 
-    def __init__(self, comm, peers, lists):
+    def __init__(self, comm, peers, lists, nGlobal):
         self.h = _vp()
         self.comm = comm
         n = len(peers)
@@ -684,7 +692,7 @@ class Exchange:
         idx = np.ascontiguousarray(np.concatenate([np.asarray(l, dtype=np.int32) for l in lists])
                                    if n else np.zeros(0, dtype=np.int32))
         pr = np.ascontiguousarray(peers, dtype=np.int32)
-        check(lib().nekmf_exchange_create(comm.h if comm is not None else None, n, pr.ctypes.data_as(_ip),
+        check(lib().nekmf_exchange_create(comm.h if comm is not None else None, int(nGlobal), n, pr.ctypes.data_as(_ip),
                                           offs.ctypes.data_as(_ip), idx.ctypes.data_as(_ip), C.byref(self.h)),
               "nekmf_exchange_create")
 
@@ -713,15 +721,27 @@ class HelmholtzCG:
                                     _np_p(iv) if iv is not None else None, _np_p(om) if om is not None else None,
                                     C.byref(self.h)), "nekmf_cg_create")
 
-    def solve(self, rhs, x, tol=1e-9, maxiter=5000):
+    def solve(self, rhs, x, tol=1e-9, maxiter=5000, raise_on_maxiter=True):
+        """-> (m_totalIterations, final r.r).  Reaching the iteration cap raises NekError like the reference's
+        NEKERROR(efatal, "Exceeded maximum number of iterations") (NekLinSysIterCG.cpp:190-203) unless
+        raise_on_maxiter is False (fixed-iteration timing runs)."""
         its, eps = C.c_int(0), C.c_double(0.0)
         kind = _kind(rhs, x)
-        check(lib().nekmf_cg_solve(self.h, _ptr(rhs)[0], _ptr(x)[0], kind, float(tol), int(maxiter), C.byref(its),
-                                   C.byref(eps)), "nekmf_cg_solve")
+        rc = lib().nekmf_cg_solve(self.h, _ptr(rhs)[0], _ptr(x)[0], kind, float(tol), int(maxiter), C.byref(its),
+                                  C.byref(eps))
+        if rc == ERR_NOCONVERGE and not raise_on_maxiter:
+            return its.value, eps.value
+        check(rc, "nekmf_cg_solve")
         return its.value, eps.value
 
     def matvec(self, w, s):
         check(lib().nekmf_cg_matvec(self.h, _ptr(w)[0], _ptr(s)[0]), "nekmf_cg_matvec")
+
+    def last_loop(self):
+        """-> (ms, iterations): device time of the iteration loop of the last solve (CUDA events)"""
+        ms, n = C.c_float(-1.0), C.c_int(0)
+        check(lib().nekmf_cg_last_loop(self.h, C.byref(ms), C.byref(n)), "nekmf_cg_last_loop")
+        return ms.value, n.value
 
     def __del__(self):
         try:

@@ -38,7 +38,9 @@ def main():
     if dist is not None:
         dist.all_reduce(t)
     if rank == 0:
-        print("rank0 its=%d (oracle %d) err=%.2e" % (its, itso, err))
+        comm = S["keepalive"][2]
+        print("rank0 its=%d (oracle %d) err=%.2e transport=%s ranks=%d" % (
+            its, itso, err, comm.transport if comm is not None else "none", S["world"]))
         print("CHECK OK" if float(t.item()) == 0.0 else "CHECK FAILED")
     if dist is not None:
         dist.destroy_process_group()

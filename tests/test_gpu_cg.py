@@ -99,22 +99,42 @@ def test_cg_trivial_rhs_and_exchange_without_neighbours():
     helm = nk.Operator(std, mesh.nElmt, nk.CoalescedGeomData(jac, df, False), nk.eHelmholtz)
     helm.SetLambda(lam)
     amap = nk.AssemblyMap(mesh.localToGlobal, mesh.nGlobal)
-    ex = nk.Exchange(None, [], [])
+    ex = nk.Exchange(None, [], [], mesh.nGlobal)
     cg = nk.HelmholtzCG(helm, amap, mesh.nDir, None, exchange=ex)
     x = np.ones(mesh.nGlobal)
     its, eps = cg.solve(np.zeros(mesh.nGlobal), x)
     assert its == 0 and np.all(x[mesh.nDir:] == 0.0) and np.all(x[:mesh.nDir] == 1.0)
 
 
-def test_sharded_cg_two_gpus():
-    """2 ranks over NCCL (one process per GPU): same solution as the serial oracle solve"""
+def _torchrun(script, nproc, port, args=(), env=None):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", script)] + list(args)
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=e)
+
+
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_sharded_cg_two_gpus(transport):
+    """2 ranks (one process per GPU), z-slab partition, interface exchange over peer memory / NCCL: same solution
+    as the serial oracle solve"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "_cg_check.py"), "--nx", "6", "--ny", "5",
-           "--nz", "8"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = _torchrun("_cg_check.py", 2, 29611, ["--nx", "6", "--ny", "5", "--nz", "8"], {"NEKMF_TRANSPORT": transport})
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "CHECK OK" in r.stdout
+
+
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_exchange_multi_gpu(transport):
+    """every visible GPU: random universal-id maps with DOFs held by up to all ranks; the device exchange must be
+    bit-identical to the rank-ordered numpy sum (tests/_exchange_check.py)"""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun("_exchange_check.py", min(n, 8), 29613, env={"NEKMF_TRANSPORT": transport})
     assert r.returncode == 0, r.stdout + r.stderr
     assert "CHECK OK" in r.stdout
 

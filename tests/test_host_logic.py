@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, missing
     assert sorted(nk.EXPORTS) == declared
-    assert L.nekmf_abi_version() == 1
+    assert L.nekmf_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():
