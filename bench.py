@@ -28,6 +28,7 @@ NM, NQ = 5, 6
 NX = 64
 LAMBDA = 1.0
 SEED = 1234
+E2E_TOL = 1e-9  # NekConstants::kNekIterativeTol, the reference's default IterativeSolverTolerance
 
 
 def measured_peaks():
@@ -161,23 +162,26 @@ def algorithmic_bytes_per_element(deformed):
     return 8 * (2 * NM ** 3 + (10 * NQ ** 3 if deformed else 10))
 
 
-def cpu_reference_leg(seconds_target=12.0, max_threads=None):
-    """The reference's own MatrixFree Helmholtz kernels (AVX2 build, width 4) on the host cores,
-    elements split over all threads, on a bounded sample of the same workload."""
-    import numpy as np
+def _ref_engine():
     import pyoracle as po
     try:
-        ref = po.Ref("avx2")
-        kind, variant = "reference", "oracle/_ref libnekref_avx2.so (reference MatrixFreeOps kernels, AVX2 width 4)"
+        return po.Ref("avx2"), "reference", "oracle/_ref libnekref_avx2.so (reference MatrixFreeOps kernels, AVX2 width 4)"
     except Exception:
-        ref = None
-        kind, variant = "port", "oracle/libmforacle.so (plain-C restatement)"
+        return None, "port", "oracle/libmforacle.so (plain-C restatement)"
+
+
+def cpu_reference_leg(seconds_target=12.0, max_threads=None, nx=NX):
+    """The reference's own MatrixFree Helmholtz kernels (AVX2 build, width 4) on the host cores, elements split over
+    all threads, on the WHOLE nx^3 mesh of the benchmark; bounded by the number of repetitions."""
+    import numpy as np
+    import pyoracle as po
+    ref, kind, variant = _ref_engine()
     threads = max_threads or (os.cpu_count() or 1)
-    nel = 16384  # 1/16 of the 64^3 mesh
+    nel = nx ** 3
     el = po.Elem(po.HEX, NM, NQ)
     rng = np.random.default_rng(SEED)
     x = rng.uniform(-1, 1, nel * el.nmTot)
-    h = 1.0 / NX
+    h = 1.0 / nx
     jac = np.full(nel, (h / 2) ** 3)
     df = np.zeros((9, nel))
     df[0] = df[4] = df[8] = 2.0 / h
@@ -202,8 +206,42 @@ def cpu_reference_leg(seconds_target=12.0, max_threads=None):
     ts.sort()
     tmed = ts[len(ts) // 2]
     return {"value": nel * el.nmTot / tmed / 1e9, "unit": "GDOF/s", "cores": threads, "kind": kind,
-            "sample": "%d of %d elements (regular geometry), median of %d applies, %s" % (nel, NX ** 3, reps, variant),
-            "ms_per_sample": tmed * 1e3}
+            "sample": "all %d elements (regular geometry), median of %d applies, %s" % (nel, reps, variant),
+            "ms_per_step": tmed * 1e3}
+
+
+def cpu_chain_leg(max_threads=None, nx=NX, max_iters=40):
+    """The reference's ContField::v_HelmSolve chain + BwdTrans on the host cores (oracle/mf_oracle.c:
+    mfo_chain_helmsolve driving the reference's own IProductWRTBase / Helmholtz / BwdTrans kernels from oracle/_ref;
+    elements and global vector loops over all threads): the same problem as the B200 arm's `e2e` on one rank's
+    nx^3 mesh.  Bounded sample: the solve is capped at max_iters iterations (constant cost per iteration)."""
+    import numpy as np
+    import pyoracle as po
+    from _util import load_pkg_module, nekmf
+    ref, kind, variant = _ref_engine()
+    threads = max_threads or (os.cpu_count() or 1)
+    mesh = load_pkg_module("mesh").StructuredHexMesh(nx, nx, nx, NM)
+    el = po.Elem(po.HEX, NM, NQ)
+    jac, df = mesh.geometry()
+    nk = nekmf()
+    diag = mesh.helmholtz_diagonal(nk.StdExpansion(nk.eHexahedron, NM, NQ).basis[0], LAMBDA)
+    X, Y, Z = mesh.quad_coords(el.Z[0])
+    f = -(LAMBDA + 3 * np.pi ** 2) * np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z)
+    del X, Y, Z
+    ch = po.Chain(el, mesh.nElmt, False, jac, df, LAMBDA, mesh.localToGlobal, None, mesh.nGlobal, mesh.nDir,
+                  1.0 / diag[mesh.nDir:], engine=ref if ref is not None else "oracle", threads=threads)
+    coef, phys = np.zeros(mesh.nLocal), np.zeros(f.size)
+    ch.helmsolve(f, coef, phys, tol=E2E_TOL, maxiter=2)  # warm-up: page in, spin up the thread team
+    coef[:] = 0.0
+    t0 = time.perf_counter()
+    its, _ = ch.helmsolve(f, coef, phys, tol=E2E_TOL, maxiter=max_iters)
+    dt = time.perf_counter() - t0
+    po.set_threads(1)
+    applies = abs(its) + 1
+    return {"value": mesh.nLocal * applies / dt / 1e9, "unit": "GDOF/s", "cores": threads, "kind": kind,
+            "sample": "HelmSolve chain on the %d^3 mesh capped at %d of its CG iterations (%d Helmholtz applies), %s"
+                      % (nx, max_iters, applies, variant),
+            "ms_per_step": dt * 1e3, "helmholtz_applies": applies, "ms_per_apply": dt * 1e3 / applies}
 
 
 def main():
@@ -231,12 +269,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_reference_leg(seconds_target=max(10.0, min(60.0, 0.5 * (K + W))))
+        # per-apply on the whole mesh (what `value` of the B200 arm measures) and the HelmSolve chain (what its `e2e`
+        # measures): `value` below is the former, `e2e.value` the latter, so each ratio compares like with like
+        cb = cpu_reference_leg(seconds_target=max(5.0, min(30.0, 0.04 * (K + W) * 10)), nx=args.nx)
+        chain = cpu_chain_leg(nx=args.nx)
         line = {"impl": "reference", "metric": "GDOF/s FP64 Helmholtz apply (hex P=4)", "value": cb["value"],
-                "unit": "GDOF/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": cb["ms_per_sample"],
+                "unit": "GDOF/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": cb["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "cpu_baseline": cb,
-                "e2e": {"value": cb["value"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": chain["value"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "ms_per_step": chain["ms_per_step"], "helmholtz_applies": chain["helmholtz_applies"],
+                        "note": "Helmholtz-apply DOF/s delivered by the reference's ContField::HelmSolve chain "
+                                "(IProductWRTBase -> Helmholtz lift -> Assemble -> CG -> GlobalToLocal -> BwdTrans) "
+                                "on the host cores: " + chain["sample"]}}
         print(json.dumps(line))
         return
 
@@ -334,15 +379,70 @@ def main():
             tt = torch.tensor([te], dtype=torch.float64, device=dev)
             if dist is not None:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            results["e2e_s"] = float(tt.item())
+            results["e2e_apply_s"] = float(tt.item())
             chk = float(torch.linalg.vector_norm(y).item())
             chk_host = float(torch.linalg.vector_norm(y_host).item())
             results["checksum"] = (chk, chk_host)
         del coll, op
         torch.cuda.empty_cache()
 
+    del x, y, x_host, y_host
+    torch.cuda.empty_cache()
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import numpy as np
+    import bench_cg
+    import _cg_check
+    comm = nk.Comm.from_torch_distributed() if world > 1 else None
+
+    # ---- e2e: the reference's solve chain through the public host-array call (nekmf_helmsolve =
+    # ContField::v_HelmSolve + BwdTrans): forcing at the quadrature points in pinned host memory -> H2D ->
+    # IProductWRTBase -> Dirichlet lift -> Assemble (+ interface exchange) -> CG to the reference's default tolerance
+    # -> GlobalToLocal -> BwdTrans -> D2H of coefficients and physical values.  One nx^3 slab per rank of a
+    # nx x nx x (nx*N) mesh (weak scaling; N > 1 exchanges the slab interfaces every iteration).
+    ae = bench_cg.parse_args(["--nx", str(args.nx), "--ny", str(args.nx), "--nz", str(args.nx * world)])
+    S = bench_cg.setup(ae, comm=comm)
+    hs = nk.HelmSolver(S["cg"], S["ipr"], S["bwd"])
+    f_host = torch.tensor(-(LAMBDA + 3 * np.pi ** 2) * S["u_exact"]).pin_memory()
+    coef_host = torch.zeros(S["mesh"].nLocal, dtype=torch.float64).pin_memory()
+    phys_host = torch.zeros(f_host.numel(), dtype=torch.float64).pin_memory()
+    hs.HelmSolve(f_host, coef_host, phys_host, tol=E2E_TOL)  # warm-up solve (also captures the iteration graphs)
+    Ke = 2
+    barrier()
+    l0 = nk.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        coef_host.zero_()
+        its_e, eps_e = hs.HelmSolve(f_host, coef_host, phys_host, tol=E2E_TOL)  # synchronous
+    te = (time.perf_counter() - t0) / Ke
+    tt = torch.tensor([te], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    u_err = float(np.abs(phys_host.numpy() - S["u_exact"]).max())
+    e2e = {"s": float(tt.item()), "iterations": its_e, "applies": its_e + 1, "final_eps": eps_e,
+           "launches": (nk.launch_count() - l0) // Ke, "device_ms": hs.last_ms(), "u_err": u_err,
+           "h2d": (f_host.numel() + coef_host.numel()) * 8, "d2h": (coef_host.numel() + phys_host.numel()) * 8,
+           "ndof_local": S["mesh"].nLocal}
+    del hs, S, f_host, coef_host, phys_host
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4]: 2^20 hex elements at P=4 split in z-slabs over the ranks (STRONG scaling),
+    # fixed iteration count, device-event time of the iteration loop, max over ranks
+    ac = bench_cg.parse_args(["--nx", "64", "--ny", "128", "--nz", "128", "--iters", "60"])
+    S = bench_cg.setup(ac, comm=comm)
+    cg_line = bench_cg.measure(S, ac)
+    del S
+    torch.cuda.empty_cache()
+    # ---- parity of the sharded solve on a mesh the CPU oracle solves in seconds
+    ap_ = bench_cg.parse_args(["--nx", "8", "--ny", "8", "--nz", str(max(8, 4 * world))])
+    S = bench_cg.setup(ap_, comm=comm)
+    cg_parity = _cg_check.reduce_ok(S, _cg_check.run_check(S, ap_))
+    del S
+    torch.cuda.empty_cache()
+
     if rank != 0:
         if dist is not None:
+            dist.barrier()
+            del comm
             dist.destroy_process_group()
         return
 
@@ -352,10 +452,15 @@ def main():
     def roof(r, deformed):
         bytes_launch = algorithmic_bytes_per_element(deformed) * nel
         ach = bytes_launch / (r["kernel_ms_avg"] * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": recorded("traffic_bytes_deformed" if deformed else "traffic_bytes_regular"),
-                "peak_source": peak_src, "algorithmic_bytes_per_element": algorithmic_bytes_per_element(deformed),
-                "kernel": r["kernel"], "kernel_ms": r["kernel_ms_avg"]}
+        traffic = recorded("traffic_bytes_deformed" if deformed else "traffic_bytes_regular")
+        out = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+               "traffic": traffic, "peak_source": peak_src,
+               "algorithmic_bytes_per_element": algorithmic_bytes_per_element(deformed),
+               "kernel": r["kernel"], "kernel_ms": r["kernel_ms_avg"]}
+        if traffic:
+            out["frac_by_dram_bytes"] = traffic / (r["kernel_ms_avg"] * 1e-3) / 1e9 / peak
+            out["traffic_source"] = recorded("traffic_source")
+        return out
 
     value = world * ndof / (reg["ms_per_step"] * 1e-3) / 1e9
     line = {
@@ -363,15 +468,31 @@ def main():
         "steps": K, "warmup": W, "ms_per_step": reg["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "roofline": roof(reg, False),
-        "e2e": {"value": world * ndof / results["e2e_s"] / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": ndof * 8,
-                "d2h_bytes_per_step": ndof * 8, "ms_per_step": results["e2e_s"] * 1e3,
-                "note": "nekmf_op_apply(NEKMF_HOST) on pinned host arrays: H2D + kernel + D2H per step"},
+        "e2e": {"value": world * e2e["ndof_local"] * e2e["applies"] / e2e["s"] / 1e9, "unit": "GDOF/s",
+                "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["s"] * 1e3,
+                "helmholtz_applies": e2e["applies"], "cg_iterations": e2e["iterations"], "tol": E2E_TOL,
+                "device_ms": e2e["device_ms"], "gpu_launches": e2e["launches"],
+                "max_abs_error_vs_analytic_solution": e2e["u_err"],
+                "note": "Helmholtz-apply DOF/s delivered by one nekmf_helmsolve call (= ContField::HelmSolve + "
+                        "BwdTrans) on pinned host arrays: H2D forcing+coefficients, IProductWRTBase, Dirichlet lift, "
+                        "Assemble, CG to tol, GlobalToLocal, BwdTrans, D2H coefficients+physical values; one %d^3 "
+                        "slab per rank%s" % (args.nx, ", slab interfaces exchanged over NVLink every iteration"
+                                             if world > 1 else "")},
+        "e2e_apply": {"value": world * ndof / results["e2e_apply_s"] / 1e9, "unit": "GDOF/s",
+                      "h2d_bytes_per_step": ndof * 8, "d2h_bytes_per_step": ndof * 8,
+                      "ms_per_step": results["e2e_apply_s"] * 1e3,
+                      "note": "one nekmf_op_apply(NEKMF_HOST) on pinned host arrays: H2D + kernel + D2H per apply "
+                              "(PCIe-bound by construction)"},
         "gpu_launches": reg["launches"],
         "clocks": {k: reg["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if reg["clocks"] else None,
         "variants": {"deformed": {"value": world * ndof / (dfm["ms_per_step"] * 1e-3) / 1e9, "unit": "GDOF/s",
                                   "ms_per_step": dfm["ms_per_step"], "roofline": roof(dfm, True),
                                   "workload": "same mesh warped by 0.05 sin(pi x) sin(pi y) sin(pi z): geometric "
-                                              "factors per quadrature point"}},
+                                              "factors per quadrature point"},
+                     "cg": dict(cg_line, scaling="strong",
+                                workload="matrix-free CG Helmholtz solve, 2^20 hex elements P=4 in z-slabs over the "
+                                         "ranks (BASELINE configs[4]), Jacobi preconditioner, fixed 60 iterations")},
+        "cg_parity": cg_parity,
         "checksum_l2": results["checksum"][0],
     }
     fp64_peak = recorded("fp64_tflops_measured")
@@ -382,12 +503,15 @@ def main():
                                  "frac": ach / fp64_peak, "flops_per_element": flops_elt}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_reference_leg()
+            line["cpu_baseline"] = cpu_reference_leg(seconds_target=6.0, nx=args.nx)
+            line["cpu_baseline"]["chain"] = cpu_chain_leg(nx=args.nx)
         except Exception as ex:  # the baseline must never take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": "GDOF/s", "cores": 0, "kind": "reference",
                                     "sample": "failed: %r" % (ex,)}
     print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
+        del comm
         dist.destroy_process_group()
 
 

@@ -106,6 +106,7 @@ typedef struct nekmf_op_s *nekmf_op_t;
 typedef struct nekmf_map_s *nekmf_map_t;
 typedef struct nekmf_exchange_s *nekmf_exchange_t;
 typedef struct nekmf_cg_s *nekmf_cg_t;
+typedef struct nekmf_helmsolve_s *nekmf_helmsolve_t;
 typedef struct nekmf_comm_s *nekmf_comm_t;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -242,6 +243,27 @@ int nekmf_cg_last_loop(nekmf_cg_t cg, float *ms, int *iterations);
 /* one mat-vec s = A w on device global vectors (exposed for tests and the benchmark) */
 int nekmf_cg_matvec(nekmf_cg_t cg, const double *w, double *s);
 int nekmf_cg_destroy(nekmf_cg_t cg);
+
+/* ---- ContField::v_HelmSolve as one device-resident chain ---------------------------------- */
+/* Replaces the string of host-array calls under MultiRegions/ContField.cpp:878-945 (v_HelmSolve) -> GlobalSolve
+ * (:516-535) -> GlobalLinSysIterativeFull::v_Solve (GlobalLinSysIterativeFull.cpp:110-211):
+ *   wsp = -IProductWRTBase(forcing); tmp1 = wsp - Helmholtz(inout); rhs = Assemble(tmp1) (+ interface exchange);
+ *   global = CG(rhs); inout += GlobalToLocal(global)         [no Dirichlet DOF on any rank: rhs = Assemble(wsp),
+ *   inout = GlobalToLocal(global)], and, when phys_out != NULL, phys_out = BwdTrans(inout) -- the evaluation the
+ * solvers perform next.  cg carries the Helmholtz operator (lambda set), the assembly map, the exchange and the
+ * preconditioner; iprod / bwd are the IProductWRTBase / BwdTrans operators of the same collection (bwd may be
+ * NULL).  create is COLLECTIVE over cg's communicator (it sums nDir over the ranks). */
+int nekmf_helmsolve_create(nekmf_cg_t cg, nekmf_op_t iprod, nekmf_op_t bwd, nekmf_helmsolve_t *hs);
+/* forcing: f at the quadrature points [nElmt*nq]; inout: local coefficients [nLocal] holding the Dirichlet values
+ * and the initial guess on entry, the solution on return; phys_out: [nElmt*nq] or NULL.  memkind NEKMF_HOST: the
+ * three arrays are host arrays, each crosses PCIe once (forcing and inout in, inout and phys_out back);
+ * NEKMF_DEVICE: device arrays, nothing is copied.  Synchronous.  Returns what nekmf_cg_solve returns
+ * (NEKMF_ERR_NOCONVERGE leaves the capped solve's result in the outputs). */
+int nekmf_helmsolve(nekmf_helmsolve_t hs, const double *forcing, double *inout, double *phys_out, int memkind, double tol,
+                    int maxiter, int *iterations, double *final_eps);
+/* device time of the last call, copies included (CUDA events on the solver's stream); ms < 0 if none ran */
+int nekmf_helmsolve_last_ms(nekmf_helmsolve_t hs, float *ms);
+int nekmf_helmsolve_destroy(nekmf_helmsolve_t hs);
 
 #ifdef __cplusplus
 }

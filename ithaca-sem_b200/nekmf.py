@@ -55,7 +55,8 @@ EXPORTS = [
     "nekmf_op_destroy", "nekmf_map_create", "nekmf_map_global_to_local", "nekmf_map_assemble", "nekmf_map_destroy",
     "nekmf_comm_unique_id", "nekmf_comm_create", "nekmf_comm_transport", "nekmf_comm_destroy", "nekmf_exchange_create",
     "nekmf_exchange_add", "nekmf_exchange_destroy", "nekmf_cg_create", "nekmf_cg_solve", "nekmf_cg_matvec",
-    "nekmf_cg_last_loop", "nekmf_cg_destroy",
+    "nekmf_cg_last_loop", "nekmf_cg_destroy", "nekmf_helmsolve_create", "nekmf_helmsolve", "nekmf_helmsolve_last_ms",
+    "nekmf_helmsolve_destroy",
 ]
 
 
@@ -109,6 +110,10 @@ def lib():
         L.nekmf_cg_matvec.argtypes = [_vp, _vp, _vp]
         L.nekmf_cg_last_loop.argtypes = [_vp, C.POINTER(C.c_float), _ip]
         L.nekmf_cg_destroy.argtypes = [_vp]
+        L.nekmf_helmsolve_create.argtypes = [_vp, _vp, _vp, C.POINTER(_vp)]
+        L.nekmf_helmsolve.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, _ip, _dp]
+        L.nekmf_helmsolve_last_ms.argtypes = [_vp, C.POINTER(C.c_float)]
+        L.nekmf_helmsolve_destroy.argtypes = [_vp]
         L.nekmf_malloc_device.argtypes = [C.POINTER(_vp), C.c_size_t]
         L.nekmf_free_device.argtypes = [_vp]
         L.nekmf_malloc_pinned.argtypes = [C.POINTER(_vp), C.c_size_t]
@@ -747,6 +752,43 @@ class HelmholtzCG:
         try:
             if self.h:
                 lib().nekmf_cg_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class HelmSolver:
+    """ContField::v_HelmSolve (MultiRegions/ContField.cpp:878-945) + the BwdTrans the solvers run next, as one
+    device-resident chain: forcing at the quadrature points in, local coefficients (and physical values) out;
+    host arrays cross PCIe once each way.  `cg` carries the Helmholtz operator, map, exchange, preconditioner."""
+
+    def __init__(self, cg, iprod_op, bwd_op=None):
+        self.h = _vp()
+        self.cg, self.iprod, self.bwd = cg, iprod_op, bwd_op
+        check(lib().nekmf_helmsolve_create(cg.h, iprod_op.h, bwd_op.h if bwd_op is not None else None, C.byref(self.h)),
+              "nekmf_helmsolve_create")
+
+    def HelmSolve(self, forcing, inout, phys_out=None, tol=1e-9, maxiter=5000, raise_on_maxiter=True):
+        """inout: local coefficients with the Dirichlet values / initial guess on entry.  -> (iterations, final r.r)"""
+        its, eps = C.c_int(0), C.c_double(0.0)
+        arrs = [forcing, inout] + ([phys_out] if phys_out is not None else [])
+        kind = _kind(*arrs)
+        rc = lib().nekmf_helmsolve(self.h, _ptr(forcing)[0], _ptr(inout)[0],
+                                   _ptr(phys_out)[0] if phys_out is not None else None, kind, float(tol), int(maxiter),
+                                   C.byref(its), C.byref(eps))
+        if not (rc == ERR_NOCONVERGE and not raise_on_maxiter):
+            check(rc, "nekmf_helmsolve")
+        return its.value, eps.value
+
+    def last_ms(self):
+        ms = C.c_float(-1.0)
+        check(lib().nekmf_helmsolve_last_ms(self.h, C.byref(ms)), "nekmf_helmsolve_last_ms")
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().nekmf_helmsolve_destroy(self.h)
                 self.h = None
         except Exception:
             pass

@@ -1865,3 +1865,175 @@ done:
 #undef PRECON
 #undef MATVEC
 }
+
+/* ======================================================================= HelmSolve chain */
+
+/* ContField::v_HelmSolve -> GlobalSolve -> GlobalLinSysIterativeFull::v_Solve -> DoConjugateGradient, then
+ * BwdTrans of the result (ContField.cpp:878-945, 516-535; GlobalLinSysIterativeFull.cpp:110-211;
+ * NekLinSysIterCG.cpp:104-265), the elemental operators supplied as callbacks so that the same driver runs
+ * this file's operators (the checker) and the reference's own kernels from oracle/_ref (the CPU baseline).
+ * The global vector loops are OpenMP loops over g_threads threads -- the stand-in for the reference's MPI
+ * ranks each updating its own partition; one thread is the reference's sequential Vmath.  Assemble is the
+ * gather over a transposed map (ascending local index per global DOF = the order of Vmath::Assmb). */
+struct mfo_chain
+{
+    int nLocal, nGlobal, nDir, nPhys;
+    const int *map;
+    const double *sign, *invdiag;
+    int *rowptr, *col;
+    double *w, *s, *p, *r, *q, *lin, *lout, *wsp, *rhs, *glob;
+};
+
+mfo_chain *mfo_chain_create(int nLocal, int nGlobal, int nDir, int nPhys, const int *map, const double *sign,
+                            const double *invdiag)
+{
+    mfo_chain *c = (mfo_chain *)calloc(1, sizeof(mfo_chain));
+    int i, g, *cur;
+    c->nLocal = nLocal; c->nGlobal = nGlobal; c->nDir = nDir; c->nPhys = nPhys;
+    c->map = map; c->sign = sign; c->invdiag = invdiag;
+    c->rowptr = (int *)calloc((size_t)nGlobal + 1, sizeof(int));
+    c->col    = (int *)malloc(sizeof(int) * (size_t)(nLocal ? nLocal : 1));
+    for (i = 0; i < nLocal; ++i) c->rowptr[map[i] + 1]++;
+    for (g = 0; g < nGlobal; ++g) c->rowptr[g + 1] += c->rowptr[g];
+    cur = (int *)malloc(sizeof(int) * (size_t)(nGlobal ? nGlobal : 1));
+    memcpy(cur, c->rowptr, sizeof(int) * (size_t)nGlobal);
+    for (i = 0; i < nLocal; ++i) c->col[cur[map[i]]++] = i;
+    free(cur);
+#define CH_ALLOC(f, n) c->f = (double *)calloc((size_t)(n) + 1, sizeof(double))
+    CH_ALLOC(w, nGlobal); CH_ALLOC(s, nGlobal); CH_ALLOC(rhs, nGlobal); CH_ALLOC(glob, nGlobal);
+    CH_ALLOC(p, nGlobal - nDir); CH_ALLOC(r, nGlobal - nDir); CH_ALLOC(q, nGlobal - nDir);
+    CH_ALLOC(lin, nLocal); CH_ALLOC(lout, nLocal); CH_ALLOC(wsp, nLocal);
+#undef CH_ALLOC
+    return c;
+}
+
+void mfo_chain_destroy(mfo_chain *c)
+{
+    if (!c) return;
+    free(c->rowptr); free(c->col); free(c->w); free(c->s); free(c->p); free(c->r); free(c->q);
+    free(c->lin); free(c->lout); free(c->wsp); free(c->rhs); free(c->glob);
+    free(c);
+}
+
+static void ch_g2l(const mfo_chain *c, const double *glob, double *loc)
+{
+    int i;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+    for (i = 0; i < c->nLocal; ++i) loc[i] = c->sign ? c->sign[i] * glob[c->map[i]] : glob[c->map[i]];
+}
+static void ch_assemble(const mfo_chain *c, const double *loc, double *glob)
+{
+    int g;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+    for (g = 0; g < c->nGlobal; ++g)
+    {
+        double sum = 0.0;
+        int k;
+        for (k = c->rowptr[g]; k < c->rowptr[g + 1]; ++k)
+        {
+            const int i = c->col[k];
+            sum += c->sign ? c->sign[i] * loc[i] : loc[i];
+        }
+        glob[g] = sum;
+    }
+}
+static double ch_dot(int n, const double *a, const double *b)
+{
+    double sum = 0.0;
+    int i;
+#pragma omp parallel for schedule(static) reduction(+ : sum) num_threads(g_threads)
+    for (i = 0; i < n; ++i) sum += a[i] * b[i];
+    return sum;
+}
+
+/* forcing [nPhys]; inout [nLocal] (Dirichlet values + initial guess in, solution out); phys_out [nPhys] or NULL.
+ * Returns m_totalIterations, or -its when the loop counter reached maxiter (the reference's efatal). */
+int mfo_chain_helmsolve(mfo_chain *c, mfo_elop_fn iprod, void *ci, mfo_elop_fn helm, void *ch, mfo_elop_fn bwd, void *cb,
+                        const double *forcing, double *inout, double *phys_out, double tol, int maxiter,
+                        double *final_eps)
+{
+    const int nL = c->nLocal, nG = c->nGlobal, nD = c->nDir, nN = nG - nD;
+    double *w = c->w, *s = c->s, *p = c->p, *r = c->r, *q = c->q, *x = c->glob;
+    double alpha, beta, rho, rho_new, mu, eps, rhs_mag;
+    int i, k = 0, its = 0, capped = 0;
+    /* ContField.cpp:894-900 */
+    iprod(ci, forcing, c->wsp);
+    if (nD > 0)
+    {
+        /* GlobalLinSysIterativeFull.cpp:161-181 */
+        helm(ch, inout, c->lout);
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+        for (i = 0; i < nL; ++i) c->lout[i] = (-c->wsp[i]) - c->lout[i];
+    }
+    else
+    {
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+        for (i = 0; i < nL; ++i) c->lout[i] = -c->wsp[i];
+    }
+    ch_assemble(c, c->lout, c->rhs);
+    /* DoConjugateGradient */
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+    for (i = 0; i < nG; ++i) { x[i] = 0.0; w[i] = 0.0; s[i] = 0.0; }
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+    for (i = 0; i < nN; ++i) { r[i] = c->rhs[nD + i]; p[i] = 0.0; q[i] = 0.0; }
+    eps     = ch_dot(nN, r, r);
+    rhs_mag = ch_dot(nG, c->rhs, c->rhs);
+    rhs_mag = rhs_mag > 1e-6 ? rhs_mag : 1.0;
+    if (!(eps < tol * tol * rhs_mag))
+    {
+#define CH_PRECON()                                                                                          \
+    _Pragma("omp parallel for schedule(static) num_threads(g_threads)")                                      \
+    for (i = 0; i < nN; ++i) w[nD + i] = c->invdiag ? r[i] * c->invdiag[i] : r[i]
+#define CH_MATVEC()                                                                                          \
+    do                                                                                                       \
+    {                                                                                                        \
+        ch_g2l(c, w, c->lin);                                                                                \
+        helm(ch, c->lin, c->lout);                                                                           \
+        ch_assemble(c, c->lout, s);                                                                          \
+    } while (0)
+        CH_PRECON();
+        CH_MATVEC();
+        rho   = ch_dot(nN, r, w + nD);
+        mu    = ch_dot(nN, s + nD, w + nD);
+        beta  = 0.0;
+        alpha = rho / mu;
+        its   = 1;
+        for (;;)
+        {
+            if (k >= maxiter) { capped = 1; break; }
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+            for (i = 0; i < nN; ++i)
+            {
+                p[i]      = beta * p[i] + w[nD + i];
+                q[i]      = beta * q[i] + s[nD + i];
+                x[nD + i] = alpha * p[i] + x[nD + i];
+                r[i]      = -alpha * q[i] + r[i];
+            }
+            CH_PRECON();
+            CH_MATVEC();
+            rho_new = ch_dot(nN, r, w + nD);
+            mu      = ch_dot(nN, s + nD, w + nD);
+            eps     = ch_dot(nN, r, r);
+            its++;
+            if (eps < tol * tol * rhs_mag) break;
+            beta  = rho_new / rho;
+            alpha = rho_new / (mu - rho_new * beta / alpha);
+            rho   = rho_new;
+            k++;
+        }
+#undef CH_PRECON
+#undef CH_MATVEC
+    }
+    /* GlobalLinSysIterativeFull.cpp:190-193 / :204 */
+    ch_g2l(c, x, c->lin);
+    if (nD > 0)
+    {
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+        for (i = 0; i < nL; ++i) inout[i] = c->lin[i] + inout[i];
+    }
+    else
+        memcpy(inout, c->lin, sizeof(double) * (size_t)nL);
+    if (phys_out && bwd) bwd(cb, inout, phys_out);
+    if (final_eps) *final_eps = eps;
+    return capped ? -its : its;
+}

@@ -84,6 +84,15 @@ int mfo_cg_helmholtz(const mfo_elem *e, int nElmt, int deformed, const double *j
                      double *final_eps);
 
 int mfo_max_threads(void);
+/* ---- ContField::v_HelmSolve chain with the elemental operators as callbacks (see mf_oracle.c) */
+typedef void (*mfo_elop_fn)(void *ctx, const double *in, double *out);
+typedef struct mfo_chain mfo_chain;
+mfo_chain *mfo_chain_create(int nLocal, int nGlobal, int nDir, int nPhys, const int *map, const double *sign,
+                       const double *invdiag);
+void mfo_chain_destroy(mfo_chain *chain);
+int mfo_chain_helmsolve(mfo_chain *chain, mfo_elop_fn iprod, void *ci, mfo_elop_fn helm, void *ch, mfo_elop_fn bwd, void *cb,
+                        const double *forcing, double *inout, double *phys_out, double tol, int maxiter,
+                        double *final_eps);
 void mfo_set_threads(int n);
 
 #ifdef __cplusplus

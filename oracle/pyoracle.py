@@ -21,6 +21,7 @@ OP_BWD, OP_HELM, OP_IPROD, OP_IPWDB, OP_PHYSDERIV = 0, 1, 2, 3, 4
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
+ELOP = C.CFUNCTYPE(None, C.c_void_p, _dp, _dp)  # mfo_elop_fn: (ctx, in, out)
 
 
 def _p(a):
@@ -62,6 +63,12 @@ def oracle_lib():
                                        C.c_int, _ip, _dp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]
         L.mfo_cg_helmholtz.restype = C.c_int
         L.mfo_set_threads.argtypes = [C.c_int]
+        L.mfo_chain_create.restype = C.c_void_p
+        L.mfo_chain_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp]
+        L.mfo_chain_destroy.argtypes = [C.c_void_p]
+        L.mfo_chain_helmsolve.restype = C.c_int
+        L.mfo_chain_helmsolve.argtypes = [C.c_void_p, ELOP, C.c_void_p, ELOP, C.c_void_p, ELOP, C.c_void_p, _dp, _dp, _dp,
+                                          C.c_double, C.c_int, _dp]
         L.mfo_points.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp]
         L.mfo_basis.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         L.mfo_basis_rows.argtypes = [C.c_int, C.c_int]
@@ -270,3 +277,48 @@ class RefOperator:
             raise NotImplementedError("reference kernel not instantiated for nm=%d nq=%d (rc=%d)"
                                       % (el.nm, el.nq0, rc))
         return outs if nouts > 1 else outs[0]
+
+
+class Chain:
+    """ContField::v_HelmSolve -> GlobalLinSysIterativeFull::v_Solve -> DoConjugateGradient -> BwdTrans on the CPU
+    (mf_oracle.c: mfo_chain_helmsolve).  engine "oracle": this package's plain-C operators (the checker);
+    engine a Ref instance: the reference's own kernels from oracle/_ref (the CPU baseline), elements and vector loops
+    over `threads` OpenMP threads."""
+
+    def __init__(self, el, nel, deformed, jac, df, lam, l2g, sign, nglobal, ndir, invdiag, engine="oracle", threads=1):
+        self.L = oracle_lib()
+        self.el, self.nel, self.threads = el, nel, int(threads)
+        self.l2g = np.ascontiguousarray(l2g, dtype=np.int32)
+        self.sign = None if sign is None else np.ascontiguousarray(sign, dtype=np.float64)
+        self.invdiag = None if invdiag is None else np.ascontiguousarray(invdiag, dtype=np.float64)
+        self.nphys = nel * el.nqTot
+        self.h = self.L.mfo_chain_create(self.l2g.size, int(nglobal), int(ndir), self.nphys, self.l2g.ctypes.data_as(_ip),
+                                         _p(self.sign), _p(self.invdiag))
+        self._keep = (jac, df)
+        if engine == "oracle":
+            L, h, de = self.L, el.h, int(deformed)
+            self._cb = (ELOP(lambda ctx, i, o: L.mfo_iproduct(h, nel, de, _p(jac), i, o)),
+                        ELOP(lambda ctx, i, o: L.mfo_helmholtz(h, nel, de, _p(jac), _p(df), float(lam), i, o)),
+                        ELOP(lambda ctx, i, o: L.mfo_bwdtrans(h, nel, i, o)))
+            self.kind = "port"
+        else:
+            ops = [engine.operator(o, el, nel, deformed, jac, df) for o in (OP_IPROD, OP_HELM, OP_BWD)]
+            R, nt = engine.L, self.threads
+            self._ops = ops
+            self._cb = tuple(ELOP(lambda ctx, i, o, hh=op.h: R.nekref_run(hh, i, None, None, o, None, None, float(lam), nt))
+                             for op in ops)
+            self.kind = "reference"
+
+    def helmsolve(self, forcing, inout, phys_out=None, tol=1e-9, maxiter=5000):
+        """-> (iterations, final r.r); iterations < 0: the loop counter reached maxiter (the reference's efatal)"""
+        set_threads(self.threads)
+        eps = C.c_double(0.0)
+        its = self.L.mfo_chain_helmsolve(self.h, self._cb[0], None, self._cb[1], None, self._cb[2], None, _p(forcing),
+                                         _p(inout), _p(phys_out), float(tol), int(maxiter), C.byref(eps))
+        return its, eps.value
+
+    def __del__(self):
+        try:
+            self.L.mfo_chain_destroy(self.h)
+        except Exception:
+            pass

@@ -106,6 +106,56 @@ def test_cg_trivial_rhs_and_exchange_without_neighbours():
     assert its == 0 and np.all(x[mesh.nDir:] == 0.0) and np.all(x[:mesh.nDir] == 1.0)
 
 
+@pytest.mark.parametrize("memkind", ["host", "device"])
+@pytest.mark.parametrize("dirichlet", [False, True])
+def test_helmsolve_chain_matches_oracle(memkind, dirichlet):
+    """ContField::v_HelmSolve + BwdTrans as one device-resident chain (nekmf_helmsolve) against the CPU chain
+    (mfo_chain_helmsolve): homogeneous and non-zero Dirichlet values with an initial guess, host and device arrays"""
+    import torch
+    nk = nekmf()
+    nm, lam = 5, 1.3
+    mesh, el, jac, df, _, _, diag = _problem(nk, 4, 3, 3, nm, lam)
+    invdiag = 1.0 / diag[mesh.nDir:]
+    std = nk.StdExpansion(nk.eHexahedron, nm)
+    geom = nk.CoalescedGeomData(jac, df, False)
+    helm, ipr, bwd = (nk.Operator(std, mesh.nElmt, geom, o) for o in (nk.eHelmholtz, nk.eIProductWRTBase, nk.eBwdTrans))
+    helm.SetLambda(lam)
+    amap = nk.AssemblyMap(mesh.localToGlobal, mesh.nGlobal)
+    cg = nk.HelmholtzCG(helm, amap, mesh.nDir, invdiag)
+    hs = nk.HelmSolver(cg, ipr, bwd)
+    rng = np.random.default_rng(11)
+    f = rng.uniform(-1, 1, mesh.nElmt * el.nqTot)
+    start = np.zeros(mesh.nGlobal)
+    if dirichlet:
+        start[:] = rng.uniform(-1, 1, mesh.nGlobal)
+    coef0 = po.global_to_local(mesh.localToGlobal, None, start)
+    want_c, want_p = coef0.copy(), np.zeros(f.size)
+    ch = po.Chain(el, mesh.nElmt, False, jac, df, lam, mesh.localToGlobal, None, mesh.nGlobal, mesh.nDir, invdiag)
+    itso, _ = ch.helmsolve(f, want_c, want_p, tol=1e-13)
+    if memkind == "host":
+        coef, phys = coef0.copy(), np.zeros(f.size)
+        its, _ = hs.HelmSolve(f, coef, phys, tol=1e-13)
+    else:
+        fd, cd = torch.tensor(f, device="cuda"), torch.tensor(coef0, device="cuda")
+        pd = torch.zeros(f.size, dtype=torch.float64, device="cuda")
+        its, _ = hs.HelmSolve(fd, cd, pd, tol=1e-13)
+        torch.cuda.synchronize()
+        coef, phys = cd.cpu().numpy(), pd.cpu().numpy()
+    assert abs(its - itso) <= max(3, itso // 10), (its, itso)
+    assert np.abs(coef - want_c).max() < 1e-10 * np.abs(want_c).max()
+    assert np.abs(phys - want_p).max() < 1e-10 * np.abs(want_p).max()
+    assert hs.last_ms() > 0.0
+    # coefficients only (no BwdTrans operator given)
+    hs2 = nk.HelmSolver(cg, ipr)
+    coef2 = coef0.copy()
+    hs2.HelmSolve(f, coef2, tol=1e-13)
+    assert np.abs(coef2 - want_c).max() < 1e-10 * np.abs(want_c).max()
+    with pytest.raises(nk.NekError):
+        hs2.HelmSolve(f, coef2, np.zeros(f.size))
+    with pytest.raises(nk.NekError, match="Exceeded maximum number of iterations"):
+        hs.HelmSolve(f, coef0.copy(), np.zeros(f.size), tol=1e-13, maxiter=2)
+
+
 def _torchrun(script, nproc, port, args=(), env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", script)] + list(args)

@@ -31,8 +31,9 @@ def parse_args(argv=None):
     return ap.parse_args(argv)
 
 
-def setup(a):
-    """builds this rank's slab, operators, assembly map, exchange, right-hand side and the CG object"""
+def setup(a, comm=None):
+    """builds this rank's slab, operators, assembly map, exchange, right-hand side and the CG object.  The
+    process group is initialised here unless the caller already did; `comm` reuses an existing nekmf communicator."""
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -40,11 +41,12 @@ def setup(a):
     nk = nekmf()
     mesh_mod = load_pkg_module("mesh")
     dist = None
-    comm = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-        comm = nk.Comm.from_torch_distributed()
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
+        if comm is None:
+            comm = nk.Comm.from_torch_distributed()
     lam = 1.0
     mesh = mesh_mod.StructuredHexMesh(a.nx, a.ny, a.nz, a.nm, slab=(rank, world))
     std = nk.StdExpansion(nk.eHexahedron, a.nm)
@@ -53,6 +55,7 @@ def setup(a):
     helm = nk.Operator(std, mesh.nElmt, geom, nk.eHelmholtz)
     helm.SetLambda(lam)
     ipr = nk.Operator(std, mesh.nElmt, geom, nk.eIProductWRTBase)
+    bwd = nk.Operator(std, mesh.nElmt, geom, nk.eBwdTrans)
     amap = nk.AssemblyMap(mesh.localToGlobal, mesh.nGlobal)
     ex = nk.Exchange(comm, mesh.peers, mesh.interface_lists, mesh.nGlobal) if world > 1 else None
     # right-hand side  -(v, f),  f = -(lam + 3 pi^2) sin sin sin  (device IProduct + Assemble + exchange)
@@ -76,27 +79,27 @@ def setup(a):
     x = torch.zeros(mesh.nGlobal, dtype=torch.float64, device=dev)
     del f, loc
     return dict(rank=rank, world=world, dev=dev, nk=nk, mesh_mod=mesh_mod, dist=dist, mesh=mesh, std=std, lam=lam, helm=helm,
-                cg=cg, rhs=rhs, x=x, keepalive=(amap, ex, comm, geom, ipr))
+                cg=cg, rhs=rhs, x=x, ipr=ipr, bwd=bwd, u_exact=u_exact, keepalive=(amap, ex, comm, geom, ipr, bwd))
 
 
-def main():
-    a = parse_args()
-    S = setup(a)
+def measure(S, a):
+    """fixed-iteration timing of the sharded solve: -> dict (identical on every rank)"""
     rank, world, dev, nk, dist, mesh, helm, cg, rhs, x = (S[k] for k in ("rank", "world", "dev", "nk", "dist", "mesh", "helm", "cg", "rhs", "x"))
     # ---- timing: fixed iteration cap (tolerance 0 never triggers), max over ranks
-    cg.solve(rhs, x, tol=0.0, maxiter=3, raise_on_maxiter=False)
+    cg.solve(rhs, x, tol=0.0, maxiter=8, raise_on_maxiter=False)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     l0 = nk.launch_count()
     t0 = time.perf_counter()
-    its, eps = cg.solve(rhs, x, tol=0.0, maxiter=a.iters, raise_on_maxiter=False)
+    its_total, eps = cg.solve(rhs, x, tol=0.0, maxiter=a.iters, raise_on_maxiter=False)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dt_wall = time.perf_counter() - t0
+    loop_ms, its = cg.last_loop()  # CUDA events on the solver's stream around the iteration loop
+    t = torch.tensor([dt_wall, loop_ms * 1e-3], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+    dt_wall, dt = float(t[0].item()), float(t[1].item())
     nel_total = a.nx * a.ny * a.nz
     gdof = (a.nx * (a.nm - 1) + 1) * (a.ny * (a.nm - 1) + 1) * (a.nz * (a.nm - 1) + 1)
     # per-rank bytes one iteration must move with the kernels as fused (DESIGN.md 4.4): update 7 reads + 5 writes
@@ -104,23 +107,29 @@ def main():
     # (4 B) per local DOF, gathered w + rowptr + s written + w re-read for s.w per global DOF
     nN = mesh.nGlobal - mesh.nDir
     by = 12 * 8 * nN + mesh.nLocal * (4 + 16 + 4) + mesh.nGlobal * (8 + 4 + 8 + 8) + mesh.nElmt * 32
-    if world > 1:
-        by += 3 * 8 * nN  # separate masked s.w pass after the interface exchange
     sys.path.insert(0, ROOT)
     import bench
     peak, peak_src = bench.measured_peaks()
-    if rank == 0:
-        gbs = by * its / dt / 1e9
-        print(json.dumps({"metric": "matrix-free CG Helmholtz, hex P=%d" % (a.nm - 1), "n_gpus": world,
-                          "kernel": helm.kernel_name,
-                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                                       "bytes_per_iteration_per_rank": by, "peak_source": peak_src},
-                          "elements": nel_total, "global_dof": gdof, "iterations": its,
-                          "ms_per_iteration": dt / its * 1e3,
-                          "gdof_per_s_local": nel_total * a.nm ** 3 * its / dt / 1e9,
-                          "launches": nk.launch_count() - l0, "final_eps": eps}))
-    if dist is not None:
-        dist.destroy_process_group()
+    gbs = by * its / dt / 1e9
+    return {"metric": "matrix-free CG Helmholtz, hex P=%d" % (a.nm - 1), "n_gpus": world,
+            "kernel": helm.kernel_name,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "bytes_per_iteration_per_rank": by, "peak_source": peak_src},
+            "elements": nel_total, "global_dof": gdof, "iterations": its,
+            "ms_per_iteration": dt / its * 1e3, "ms_per_iteration_wall": dt_wall / its_total * 1e3,
+            "transport": S["keepalive"][2].transport if world > 1 else "none",
+            "gdof_per_s_local": nel_total * a.nm ** 3 * its / dt / 1e9,
+            "launches": nk.launch_count() - l0, "final_eps": eps}
+
+
+def main():
+    a = parse_args()
+    S = setup(a)
+    res = measure(S, a)
+    if S["rank"] == 0:
+        print(json.dumps(res))
+    if S["dist"] is not None:
+        S["dist"].destroy_process_group()
 
 
 if __name__ == "__main__":
