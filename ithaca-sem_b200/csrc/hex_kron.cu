@@ -62,7 +62,7 @@ constexpr int kron_pad(int minimum, int residue) // smallest v >= minimum with v
 
 // Every warp is an independent worker: it owns EPW elements per step, its own TMA-fed input
 // buffer, its own exchange/staging buffer and its own mbarrier -- no CTA-wide barrier in the loop.
-template <int NM, bool GATHER = false> struct KronCfg
+template <int NM, bool GATHER = false, int WSEL = 0> struct KronCfg
 {
     static constexpr int NM2 = NM * NM, NM3 = NM2 * NM;
     static constexpr int EPW   = 32 / NM;                // elements per warp step (NM lanes per element)
@@ -77,7 +77,8 @@ template <int NM, bool GATHER = false> struct KronCfg
     static constexpr int PER_WARP = INB + GEO + XB + 2 + MAPB; // doubles (+2: mbarrier, 16-byte slot)
     // one CTA per SM; warps in multiples of 4 (one FP64 pipe per SM sub-partition)
     static constexpr int W_FIT = (224 * 1024) / (PER_WARP * 8);
-    static constexpr int WARPS = W_FIT >= 12 ? 12 : (W_FIT >= 8 ? 8 : 4);
+    // WSEL != 0: explicit warp count (NM = 5 is instantiated with 8 and 12 for the A/B in tools/prof_helm.py)
+    static constexpr int WARPS = WSEL ? WSEL : (W_FIT >= 12 ? 12 : (W_FIT >= 8 ? 8 : 4));
     static constexpr int T     = WARPS * 32;
     static constexpr size_t SMEM = (size_t)WARPS * PER_WARP * 8 + 16;
 };
@@ -96,11 +97,13 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int NM, bool SPARSEK, bool GATHER = false>
-__global__ void __launch_bounds__(KronCfg<NM, GATHER>::T, 1)
+// SPARSEK == 2: the mass matrix is sparse as well (vertex block, vertex x modes {2,3}, interior |a-b| in {0,2}:
+// 17 of 25 entries at NM = 5), also verified at creation -- about a quarter of the DFMAs of the kernel go away.
+template <int NM, int SPARSEK, bool GATHER = false, int WSEL = 0>
+__global__ void __launch_bounds__(KronCfg<NM, GATHER, WSEL>::T, 1)
     hex_helm_kron_kernel(const __grid_constant__ KronTab<NM> tab, const __grid_constant__ KronArgs args)
 {
-    using Cfg = KronCfg<NM, GATHER>;
+    using Cfg = KronCfg<NM, GATHER, WSEL>;
     constexpr int NM2 = Cfg::NM2, NM3 = Cfg::NM3, EPW = Cfg::EPW, INB = Cfg::INB, PS = Cfg::PS, ES = Cfg::ES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,6 +124,9 @@ __global__ void __launch_bounds__(KronCfg<NM, GATHER>::T, 1)
 #define KM(a, b) tab.Ms[tri(a, b, NM)]
 #define KK(a, b) tab.Ks[tri(a, b, NM)]
 #define KNZ(a, b) (!SPARSEK || (a) == (b) || ((a) < 2 && (b) < 2))
+#define KLO(a, b) ((a) < (b) ? (a) : (b))
+#define KHI(a, b) ((a) < (b) ? (b) : (a))
+#define MNZ(a, b) (SPARSEK < 2 || KHI(a, b) < 2 || (KLO(a, b) < 2 && KHI(a, b) <= 3) || (KLO(a, b) >= 2 && (KHI(a, b) - KLO(a, b)) % 2 == 0 && KHI(a, b) - KLO(a, b) <= 2))
 
     if (lane == 0)
     {
@@ -212,10 +218,15 @@ __global__ void __launch_bounds__(KronCfg<NM, GATHER>::T, 1)
 #pragma unroll
                 for (int pp = 0; pp < NM; ++pp)
                 {
-                    double m = KM(pp, 0) * xr[0], k = 0.0;
-                    bool kset = false;
+                    double m = 0.0, k = 0.0;
+                    bool kset = false, mset = false;
 #pragma unroll
-                    for (int p = 1; p < NM; ++p) m = fma(KM(pp, p), xr[p], m);
+                    for (int p = 0; p < NM; ++p)
+                        if (MNZ(pp, p))
+                        {
+                            m    = mset ? fma(KM(pp, p), xr[p], m) : KM(pp, p) * xr[p];
+                            mset = true;
+                        }
 #pragma unroll
                     for (int p = 0; p < NM; ++p)
                         if (KNZ(pp, p))
@@ -232,8 +243,11 @@ __global__ void __launch_bounds__(KronCfg<NM, GATHER>::T, 1)
 #pragma unroll
                     for (int pp = 0; pp < NM; ++pp)
                     {
-                        A2[qq][pp] = fma(KM(qq, q), am[pp], A2[qq][pp]);
-                        R[qq][pp]  = fma(KM(qq, q), bk[pp], R[qq][pp]);
+                        if (MNZ(qq, q))
+                        {
+                            A2[qq][pp] = fma(KM(qq, q), am[pp], A2[qq][pp]);
+                            R[qq][pp]  = fma(KM(qq, q), bk[pp], R[qq][pp]);
+                        }
                         if (KNZ(qq, q)) R[qq][pp] = fma(KK(qq, q), a11[pp], R[qq][pp]);
                     }
             }
@@ -274,9 +288,15 @@ __global__ void __launch_bounds__(KronCfg<NM, GATHER>::T, 1)
 #pragma unroll
                 for (int rr = 0; rr < NM; ++rr)
                 {
-                    double sacc = KM(rr, 0) * col[0];
+                    double sacc = 0.0;
+                    bool sset   = false;
 #pragma unroll
-                    for (int r = 1; r < NM; ++r) sacc = fma(KM(rr, r), col[r], sacc);
+                    for (int r = 0; r < NM; ++r)
+                        if (MNZ(rr, r))
+                        {
+                            sacc = sset ? fma(KM(rr, r), col[r], sacc) : KM(rr, r) * col[r];
+                            sset = true;
+                        }
                     acc[rr][qq] = sacc;
                 }
             }
@@ -337,6 +357,9 @@ __global__ void __launch_bounds__(KronCfg<NM, GATHER>::T, 1)
 #undef KM
 #undef KK
 #undef KNZ
+#undef MNZ
+#undef KLO
+#undef KHI
 }
 
 } // namespace nekmf
@@ -401,7 +424,8 @@ struct KronState
     bool sparse_full = false; // K, M and S all have the modified-basis sparsity patterns
     bool rows_kind   = false; // nm = 7..10: row-streaming kernel (diagonal metric only, no fused gather, no full metric)
     int blocks_per_sm_full = 0;
-    int blocks_per_sm = 0, blocks_per_sm_gather = 0, blocks_per_sm_lane = 0;
+    int blocks_per_sm = 0, blocks_per_sm_lane = 0;
+    int bps_slot[2][2] = {{0, 0}, {0, 0}}; // [gather][8-warp variant]
     // the quadrature-space launcher this operator falls back to for non-diagonal metrics
     int (*fallback)(nekmf_op_s *, const double *const in[3], double *const out[3]) = nullptr;
     void *fallback_state                                                           = nullptr;
@@ -410,11 +434,12 @@ struct KronState
     bool use_kron = false;
 };
 
-template <int NM, bool GATHER> static int kron_launch_t(nekmf_op_s *op, KronState *st, const double *in, double *out)
+template <int NM, bool GATHER, int WSEL = 0> static int kron_launch_t(nekmf_op_s *op, KronState *st, const double *in, double *out)
 {
-    using Cfg = KronCfg<NM, GATHER>;
-    auto kern = st->sparse_k ? hex_helm_kron_kernel<NM, true, GATHER> : hex_helm_kron_kernel<NM, false, GATHER>;
-    int &bps  = GATHER ? st->blocks_per_sm_gather : st->blocks_per_sm;
+    using Cfg = KronCfg<NM, GATHER, WSEL>;
+    auto kern = st->sparse_full ? hex_helm_kron_kernel<NM, 2, GATHER, WSEL>
+                                : (st->sparse_k ? hex_helm_kron_kernel<NM, 1, GATHER, WSEL> : hex_helm_kron_kernel<NM, 0, GATHER, WSEL>);
+    int &bps  = st->bps_slot[GATHER ? 1 : 0][WSEL == 8 ? 1 : 0];
     if (bps == 0)
     {
         NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -548,6 +573,12 @@ template <int NM> static int kron_launch(nekmf_op_s *op, const double *const in[
         const int rc = st->fallback(op, in, out);
         op->kstate  = saved;
         return rc;
+    }
+    if constexpr (NM == 5)
+    {
+        const char *v = getenv("NEKMF_KRON_WARPS"); // A/B knob, read per launch
+        if (v && atoi(v) == 8)
+            return op->gather_map ? kron_launch_t<NM, true, 8>(op, st, in[0], out[0]) : kron_launch_t<NM, false, 8>(op, st, in[0], out[0]);
     }
     return op->gather_map ? kron_launch_t<NM, true>(op, st, in[0], out[0]) : kron_launch_t<NM, false>(op, st, in[0], out[0]);
 }
@@ -737,7 +768,7 @@ int kron_geom_changed(nekmf_op_s *op)
         op->gather_ok = true;
         char name[96];
         snprintf(name, sizeof(name), "hex_helm_kron_kernel<nm=%d,%s>(regular,diagonal metric)", op->nm[0],
-                 st->sparse_k ? "sparseK" : "denseK");
+                 st->sparse_full ? "sparseKM" : (st->sparse_k ? "sparseK" : "denseK"));
         op->kname = name;
     }
     return NEKMF_OK;

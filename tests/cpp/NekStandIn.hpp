@@ -1,24 +1,33 @@
-// NekB200Collections.hpp -- C++ host side above the C ABI: a self-contained mirror of the part of
-// library/Collections that selects and drives the matrix-free operators, with the new
-// ImplementationType eB200 registered in the operator factory.
+// NekStandIn.hpp -- TEST DOUBLE, not product code.
 //
-// The reference's own headers cannot be compiled here (they include Boost), so the few types the
-// Collections interface exchanges are re-declared with the same names, argument meaning and error
-// behaviour:
+// A stand-in for the handful of ITHACA-SEM / Nektar++ headers that integration/B200Operators.cpp (the adapter a
+// maintainer drops into library/Collections) and its callers need.  The reference's own headers cannot be compiled
+// here (they include Boost and the build's generated config), so the types the Collections interface exchanges are
+// re-declared with the same names, argument meaning and error behaviour, and the selection logic around the
+// operator factory is RESTATED from the reference so that the adapter can be compiled, linked and run on the GPU
+// without Nektar++ (tests/cpp/*.cpp, -DNEKB200_STANDIN):
 //
-//   Array<OneD, T>                 LibUtilities/BasicUtils/SharedArray.hpp  (ref-counted pointer + offset)
-//   LibUtilities::Basis            LibUtilities/Foundations/Basis.h         (GetBdata/GetDbdata/GetD/GetZ/GetW ...)
-//   StdRegions::StdExpansion       StdRegions/StdExpansion.h                (GetBasis, DetShapeType, GetNcoeffs ...)
-//                                  + the per-element geometric factors a LocalRegions::Expansion would own
+//   Array<OneD, T>, Array<TwoD, T>  LibUtilities/BasicUtils/SharedArray.hpp  (ref-counted pointer + offset)
+//   MemoryManager<T>                LibUtilities/Memory/NekMemoryManager.hpp (AllocateSharedPtr only)
+//   NEKERROR / ASSERTL0             LibUtilities/BasicUtils/ErrorUtil.hpp
+//   Vmath::Vcopy                    LibUtilities/BasicUtils/Vmath.hpp
+//   LibUtilities::Basis             LibUtilities/Foundations/Basis.h         (GetBdata/GetDbdata/GetD/GetZ/GetW ...)
+//   StdRegions::StdExpansion        StdRegions/StdExpansion.h                (GetBasis, DetShapeType, GetNcoeffs ...)
+//                                   + the per-element geometric factors a LocalRegions::Expansion would own
 //   Collections::OperatorType / ImplementationType / OperatorKey / Operator / OperatorFactory /
 //   GetOperatorFactory / CoalescedGeomData / Collection / CollectionOptimisation / SetFixedImpType
-//                                  Collections/Operator.h:65-191, Collection.h:53-110,
-//                                  CoalescedGeomData.cpp:53-424, CollectionOptimisation.cpp:52-281
+//                                   Collections/Operator.h:45-191, Collection.h:53-110,
+//                                   CoalescedGeomData.cpp:53-424, CollectionOptimisation.cpp:52-281  (restated)
+//   MultiRegions::ExpList           MultiRegions/ExpList.cpp:5005-5151 (CreateCollections) + the four call sites
+//                                   (restated)
 //
-// Only eB200 operators are registered; asking the factory for any other key throws NekError exactly
-// as the reference's NekFactory does for an unregistered key (NekFactory.hpp:145-209).
+// No operator is registered here: the eB200 operators register themselves from integration/B200Operators.cpp's
+// static m_typeArr[] initialisers, exactly as the reference's *_MatrixFree classes do.  Asking the factory for any
+// other key throws NekError as the reference's NekFactory does for an unregistered key (NekFactory.hpp:145-209).
 #pragma once
 #include "../../include/nekmf_b200.h"
+#include <cstring>
+#include <type_traits>
 #include <cctype>
 #include <cstdlib>
 #include <map>
@@ -49,8 +58,30 @@ struct NekError : public std::runtime_error
         throw ::Nektar::ErrorUtil::NekError(_s.str());                                  \
     } while (0)
 
+// ErrorUtil.hpp:88-186, 246-262
+namespace ErrorUtil
+{
+enum ErrType { efatal, ewarning };
+}
+#define NEKERROR(type, msg) NEKB200_ERROR(msg)
+#define ASSERTL0(cond, msg)                                                             \
+    do                                                                                  \
+    {                                                                                   \
+        if (!(cond)) NEKB200_ERROR(msg);                                                \
+    } while (0)
+
+// NekMemoryManager.hpp: only the call the OPERATOR_CREATE macro makes
+template <typename T> struct MemoryManager
+{
+    template <typename... A> static std::shared_ptr<T> AllocateSharedPtr(A &&...a)
+    {
+        return std::shared_ptr<T>(new T(std::forward<A>(a)...));
+    }
+};
+
 // ------------------------------------------------------------------------------------------ Array<OneD>
 struct OneD {};
+struct TwoD {};
 template <typename Dim, typename T> class Array;
 template <typename T> class Array<OneD, T>
 {
@@ -79,19 +110,55 @@ public:
     std::shared_ptr<V> m_data;
     size_t m_size, m_off;
 };
-static const Array<OneD, NekDouble> NullNekDouble1DArray;
+static Array<OneD, NekDouble> NullNekDouble1DArray;
+// rows x columns over one block; operator[] gives the row pointer (what `&df[r][0]` needs)
+template <typename T> class Array<TwoD, T>
+{
+public:
+    typedef typename std::remove_const<T>::type V;
+    Array() : m_rows(0), m_cols(0) {}
+    Array(size_t rows, size_t cols) : m_data(rows * cols), m_rows(rows), m_cols(cols) {}
+    template <typename U> Array(const Array<TwoD, U> &o) : m_data(o.m_data), m_rows(o.m_rows), m_cols(o.m_cols) {}
+    size_t GetRows() const { return m_rows; }
+    size_t GetColumns() const { return m_cols; }
+    T *operator[](size_t r) const { return m_data.get() + r * m_cols; }
+    T *get() const { return m_data.get(); }
+    size_t num_elements() const { return m_rows * m_cols; }
+
+    Array<OneD, V> m_data;
+    size_t m_rows, m_cols;
+};
+} // namespace Nektar
+namespace Vmath
+{
+template <class T> inline void Vcopy(int n, const T *x, int incx, T *y, int incy) // Vmath.hpp:1098-1108
+{
+    if (incx == 1 && incy == 1) memcpy(y, x, n * sizeof(T));
+    else
+        for (int i = 0; i < n; ++i) y[i * incy] = x[i * incx];
+}
+} // namespace Vmath
+namespace Nektar
+{
 
 // ------------------------------------------------------------------------------------------ LibUtilities
 namespace LibUtilities
 {
 enum ShapeType { eQuadrilateral = NEKMF_QUAD, eTriangle = NEKMF_TRI, eHexahedron = NEKMF_HEX, ePrism = NEKMF_PRISM,
-                 ePyramid = NEKMF_PYR, eTetrahedron = NEKMF_TET };
+                 ePyramid = NEKMF_PYR, eTetrahedron = NEKMF_TET, eSegment = NEKMF_SEG };
 enum BasisType { eModified_A = NEKMF_MODIFIED_A, eModified_B = NEKMF_MODIFIED_B, eModified_C = NEKMF_MODIFIED_C,
                  eModifiedPyr_C = NEKMF_MODIFIEDPYR_C };
 enum PointsType { eGaussLobattoLegendre = NEKMF_GLL, eGaussRadauMAlpha1Beta0 = NEKMF_GRJM_A1B0,
                   eGaussRadauMAlpha2Beta0 = NEKMF_GRJM_A2B0 };
-static const char *const ShapeTypeMap[] = {"Quadrilateral", "Triangle", "Hexahedron", "Prism", "Pyramid", "Tetrahedron"};
+static const char *const ShapeTypeMap[] = {"Quadrilateral", "Triangle", "Hexahedron", "Prism", "Pyramid", "Tetrahedron", "Segment"};
 
+// the piece of NekMatrix<NekDouble> the Helper reads: basis->GetD()->GetPtr() (MatrixFreeOps/Operator.hpp:262)
+struct DMat
+{
+    Array<OneD, NekDouble> m_v;
+    const Array<OneD, NekDouble> &GetPtr() const { return m_v; }
+    const NekDouble *GetRawPtr() const { return m_v.get(); }
+};
 class Basis
 {
 public:
@@ -105,7 +172,12 @@ public:
     }
     const Array<OneD, NekDouble> &GetBdata() const { return m_b; }
     const Array<OneD, NekDouble> &GetDbdata() const { return m_db; }
-    const Array<OneD, NekDouble> &GetD() const { return m_D; }
+    std::shared_ptr<DMat> GetD() const
+    {
+        auto d = std::make_shared<DMat>();
+        d->m_v = m_D;
+        return d;
+    }
     const Array<OneD, NekDouble> &GetZ() const { return m_z; }
     const Array<OneD, NekDouble> &GetW() const { return m_w; }
     int GetNumModes() const { return m_nm; }
@@ -131,9 +203,13 @@ static const ConstFactorMap NullConstFactorMap;
 
 // the expansion of ONE element: reference-element bases + that element's geometric factors
 // (jac: 1 or nq values; df: ndf x (1 or nq), df[c*dim+d] = d xi_d / d x_c -- GeomFactors.cpp:399-474)
-class StdExpansion
+class StdExpansion : public std::enable_shared_from_this<StdExpansion>
 {
 public:
+    // a LocalRegions::Expansion hands out its reference-element part and its coordinate dimension
+    // (StdExpansion.h:381-384, 682-685); the stand-in is both at once
+    std::shared_ptr<StdExpansion> GetStdExp() { return shared_from_this(); }
+    int GetCoordim() const { return m_dim; }
     StdExpansion(LibUtilities::ShapeType shape, int nummodes, int numpoints0 = -1) : m_shape(shape), m_deformed(false)
     {
         using namespace LibUtilities;
@@ -224,25 +300,38 @@ public:
         }
         return m_jac;
     }
-    // [ndf][nElmt(*nq)] stored row after row (the reference returns Array<TwoD>)
-    const Array<OneD, NekDouble> &GetDerivFactors(const std::vector<StdRegions::StdExpansionSharedPtr> &e)
+    // Array<TwoD>[ndf][nElmt(*nq)] (CoalescedGeomData.h:75)
+    const Array<TwoD, const NekDouble> &GetDerivFactors(const std::vector<StdRegions::StdExpansionSharedPtr> &e)
     {
         if (m_df.num_elements() == 0 && !e.empty())
         {
             const int dim = e[0]->GetShapeDimension(), ndf = dim * dim;
             const size_t n = e[0]->GetJac().num_elements(), cols = n * e.size();
-            m_df = Array<OneD, NekDouble>(ndf * cols);
+            Array<TwoD, NekDouble> df(ndf, cols);
             for (size_t i = 0; i < e.size(); ++i)
                 for (int r = 0; r < ndf; ++r)
-                    for (size_t q = 0; q < n; ++q) m_df[r * cols + i * n + q] = e[i]->GetDerivFactors()[r * n + q];
+                    for (size_t q = 0; q < n; ++q) df[r][i * n + q] = e[i]->GetDerivFactors()[r * n + q];
+            m_df = df;
         }
         return m_df;
     }
 
 private:
-    Array<OneD, NekDouble> m_jac, m_df;
+    Array<OneD, NekDouble> m_jac;
+    Array<TwoD, const NekDouble> m_df;
 };
 typedef std::shared_ptr<CoalescedGeomData> CoalescedGeomDataSharedPtr;
+
+// Operator.h:45-55
+#define OPERATOR_CREATE(cname)                                                          \
+    static OperatorKey m_type;                                                          \
+    static OperatorKey m_typeArr[];                                                     \
+    friend struct MemoryManager<cname>;                                                 \
+    static OperatorSharedPtr create(std::vector<StdRegions::StdExpansionSharedPtr> pCollExp, \
+                                    std::shared_ptr<CoalescedGeomData> GeomData)        \
+    {                                                                                   \
+        return MemoryManager<cname>::AllocateSharedPtr(pCollExp, GeomData);             \
+    }
 
 // Operator.h:113-165
 class Operator
@@ -301,117 +390,6 @@ inline OperatorFactory &GetOperatorFactory()
     static OperatorFactory f;
     return f;
 }
-
-// ---- the eB200 operators: one class, five registrations per operator type
-class Operator_B200 : public Operator
-{
-public:
-    template <OperatorType OP>
-    static OperatorSharedPtr create(std::vector<StdRegions::StdExpansionSharedPtr> e, CoalescedGeomDataSharedPtr g)
-    {
-        return OperatorSharedPtr(new Operator_B200(OP, e, g));
-    }
-    ~Operator_B200() override { nekmf_op_destroy(m_op); }
-
-    void operator()(const Array<OneD, const NekDouble> &input, Array<OneD, NekDouble> &output0,
-                    Array<OneD, NekDouble> &output1, Array<OneD, NekDouble> &output2, Array<OneD, NekDouble> &,
-                    const StdRegions::ConstFactorMap &factors) override
-    {
-        if (m_type == eHelmholtz)
-        {
-            auto it = factors.find(StdRegions::eFactorLambda);
-            if (it == factors.end()) NEKB200_ERROR("Helmholtz_B200: eFactorLambda missing from the factor map");
-            Check(nekmf_op_set_lambda(m_op, it->second));
-        }
-        if (m_type == eIProductWRTDerivBase)
-        {
-            // reference convention (IProductWRTDerivBase.cpp:285-330): 2-D (in0, in1, out), 3-D (in0, in1, in2, out)
-            const bool d3 = m_stdExp->GetShapeDimension() == 3;
-            Check(nekmf_op_apply(m_op, input.get(), output0.get(), d3 ? output1.get() : nullptr,
-                                 d3 ? output2.get() : output1.get(), nullptr, nullptr, NEKMF_HOST));
-            return;
-        }
-        Check(nekmf_op_apply(m_op, input.get(), nullptr, nullptr, output0.get(), output1.get(), output2.get(), NEKMF_HOST));
-    }
-    void operator()(int dir, const Array<OneD, const NekDouble> &input, Array<OneD, NekDouble> &output,
-                    Array<OneD, NekDouble> &) override
-    {
-        if (m_type != ePhysDeriv)
-            NEKB200_ERROR(OperatorTypeMap[m_type] << "_B200: operator()(dir, ...) is not valid for this operator.");
-        // PhysDeriv.cpp:323-341: compute every direction, keep one
-        const int dim = m_stdExp->GetShapeDimension();
-        if (dir < 0 || dir >= dim) NEKB200_ERROR("PhysDeriv_B200: direction out of range");
-        Array<OneD, NekDouble> t[3];
-        for (int d = 0; d < dim; ++d) t[d] = d == dir ? output : Array<OneD, NekDouble>(m_numElmt * m_nqe);
-        Check(nekmf_op_apply(m_op, input.get(), nullptr, nullptr, t[0].get(), t[1].get(), dim == 3 ? t[2].get() : nullptr,
-                             NEKMF_HOST));
-    }
-    const char *KernelName() const { return nekmf_op_kernel_name(m_op); }
-
-private:
-    static void Check(int rc)
-    {
-        if (rc != NEKMF_OK) NEKB200_ERROR(nekmf_last_error());
-    }
-    Operator_B200(OperatorType type, std::vector<StdRegions::StdExpansionSharedPtr> pCollExp, CoalescedGeomDataSharedPtr pGeomData)
-        : Operator(pCollExp, pGeomData), m_type(type), m_op(nullptr)
-    {
-        const auto &exp = pCollExp[0];
-        const int dim   = exp->GetShapeDimension();
-        int nm[3] = {1, 1, 1}, nq[3] = {1, 1, 1}, bt[3] = {0, 0, 0}, pt[3] = {0, 0, 0};
-        const double *b[3] = {nullptr, nullptr, nullptr}, *db[3] = {nullptr, nullptr, nullptr}, *D[3] = {nullptr, nullptr, nullptr},
-                     *Z[3] = {nullptr, nullptr, nullptr}, *W[3] = {nullptr, nullptr, nullptr};
-        for (int d = 0; d < dim; ++d) // MatrixFreeOps/Operator.hpp:223-273
-        {
-            const auto &bas = exp->GetBasis(d);
-            nm[d] = bas->GetNumModes(); nq[d] = bas->GetNumPoints();
-            bt[d] = bas->GetBasisType(); pt[d] = bas->GetPointsType();
-            b[d] = bas->GetBdata().get(); db[d] = bas->GetDbdata().get(); D[d] = bas->GetD().get();
-            Z[d] = bas->GetZ().get(); W[d] = bas->GetW().get();
-        }
-        static const int abiop[] = {NEKMF_BWDTRANS, NEKMF_HELMHOLTZ, NEKMF_IPRODUCTWRTBASE, NEKMF_IPRODUCTWRTDERIVBASE, NEKMF_PHYSDERIV};
-        Check(nekmf_op_create(exp->DetShapeType(), abiop[type], nm, nq, bt, pt, b, db, D, Z, W, (int)pCollExp.size(),
-                              m_isDeformed, dim, &m_op));
-        const bool needJac = type == eHelmholtz || type == eIProductWRTBase || type == eIProductWRTDerivBase;
-        const bool needDF  = type == eHelmholtz || type == ePhysDeriv || type == eIProductWRTDerivBase;
-        if (needJac || needDF)
-            Check(nekmf_op_set_geom(m_op, needJac ? pGeomData->GetJac(pCollExp).get() : nullptr,
-                                    needDF ? pGeomData->GetDerivFactors(pCollExp).get() : nullptr, NEKMF_HOST));
-    }
-    OperatorType m_type;
-    nekmf_op_t m_op;
-};
-
-namespace detail
-{
-template <OperatorType OP> inline void RegisterB200(bool withCollapsed)
-{
-    using namespace LibUtilities;
-    auto &f = GetOperatorFactory();
-    const std::string n = std::string(OperatorTypeMap[OP]) + "_B200_";
-    f.RegisterCreatorFunction(OperatorKey(eQuadrilateral, OP, eB200, false), Operator_B200::create<OP>, n + "Quad");
-    f.RegisterCreatorFunction(OperatorKey(eHexahedron, OP, eB200, false), Operator_B200::create<OP>, n + "Hex");
-    if (withCollapsed)
-    {
-        f.RegisterCreatorFunction(OperatorKey(eTriangle, OP, eB200, false), Operator_B200::create<OP>, n + "Tri");
-        f.RegisterCreatorFunction(OperatorKey(ePrism, OP, eB200, false), Operator_B200::create<OP>, n + "Prism");
-        f.RegisterCreatorFunction(OperatorKey(ePyramid, OP, eB200, false), Operator_B200::create<OP>, n + "Pyr");
-        f.RegisterCreatorFunction(OperatorKey(eTetrahedron, OP, eB200, false), Operator_B200::create<OP>, n + "Tet");
-    }
-}
-struct Registrar
-{
-    Registrar()
-    {
-        RegisterB200<eBwdTrans>(true);
-        RegisterB200<eHelmholtz>(true);
-        RegisterB200<eIProductWRTBase>(true);
-        RegisterB200<ePhysDeriv>(true);
-        RegisterB200<eIProductWRTDerivBase>(true);
-    }
-};
-static Registrar g_registrar; // static registration, as the reference's m_typeArr[] initialisers
-} // namespace detail
 
 // ---- session document stand-in + the XML subset the <COLLECTIONS> block needs (the reference reads a TinyXML
 // document from LibUtilities::SessionReader; neither is available here)

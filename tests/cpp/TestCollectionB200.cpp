@@ -5,7 +5,7 @@
 // implementation of the same operator -- here the CPU oracle (oracle/mf_oracle.h; test
 // infrastructure) instead of the LocalRegions routines.  Tolerance 1e-12 relative (the reference
 // tests use BOOST_CHECK_CLOSE 1e-8 percent = 1e-10).
-#include "../../ithaca-sem_b200/host/NekB200Collections.hpp"
+#include "NekStandIn.hpp"
 #include "../../oracle/mf_oracle.h"
 #include <cmath>
 #include <cstdio>

@@ -3,7 +3,7 @@
 // (ithaca-sem_b200/host/NekB200Collections.hpp): constructor defaults, the <COLLECTIONS> block of a session
 // document, the (shape, order) -> shape default -> eNoCollection lookup and the reference's error messages.
 // Needs no GPU: nothing here creates an operator.
-#include "../../ithaca-sem_b200/host/NekB200Collections.hpp"
+#include "NekStandIn.hpp"
 #include <cstdio>
 #include <cstring>
 

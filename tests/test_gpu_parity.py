@@ -444,13 +444,13 @@ def test_full_size_properties_hex_p4():
 
 
 def test_cpp_collections_mirror():
-    """the C++ host side (ithaca-sem_b200/host/NekB200Collections.hpp: Collection / OperatorFactory /
-    eB200 operators over the C ABI) through tests/cpp/TestCollectionB200.cpp, the analogue of
+    """the adapter source a maintainer drops into library/Collections (integration/B200Operators.cpp: the five
+    *_B200 operator classes over the C ABI, registered in the operator factory) compiled against the stand-in headers
+    of tests/cpp/ and driven by tests/cpp/TestCollectionB200.cpp, the analogue of
     library/UnitTests/Collections/TestHexCollection.cpp"""
     import subprocess
     exe = os.path.join(ROOT, "tests", "cpp", "TestCollectionB200")
-    if not os.path.exists(exe):
-        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "PASSED" in r.stdout

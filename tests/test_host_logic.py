@@ -10,6 +10,7 @@ import pytest
 
 import pyoracle as po
 from _util import ROOT, load_pkg_module, nekmf, rel_errs
+import _nek_standin as si
 
 
 def test_library_exports_every_declared_symbol():
@@ -244,11 +245,11 @@ def test_collection_optimisation_mirror(tmp_path):
     nk = nekmf()
     hex5, tet2, tet6 = nk.StdExpansion(nk.eHexahedron, 5, 6), nk.StdExpansion(nk.eTetrahedron, 2, 3), nk.StdExpansion(nk.eTetrahedron, 6, 7)
     # the unit tests' form: dummy session + explicit type (TestHexCollection.cpp:3699-3704)
-    opt = nk.CollectionOptimisation(None, nk.eB200)
+    opt = si.CollectionOptimisation(None, nk.eB200)
     assert opt.GetOperatorImpMap(hex5) == nk.SetFixedImpType(nk.eB200)
     assert not opt.SetByXml() and not opt.IsUsingAutotuning() and opt.GetMaxCollectionSize() == 0
     # no session, no type: IterPerExp, StdMat for orders 1..4, PhysDeriv NoCollection / SumFac for orders 1, 2
-    opt = nk.CollectionOptimisation()
+    opt = si.CollectionOptimisation()
     assert opt.GetDefaultImplementationType() == nk.eIterPerExp
     low, high = opt.GetOperatorImpMap(tet2), opt.GetOperatorImpMap(tet6)
     assert low[nk.eBwdTrans] == nk.eStdMat and low[nk.ePhysDeriv] == nk.eSumFac
@@ -261,16 +262,16 @@ def test_collection_optimisation_mirror(tmp_path):
     path = tmp_path / "session.xml"
     path.write_text(xml)
     for src in (xml, str(path)):
-        opt = nk.CollectionOptimisation(src)
+        opt = si.CollectionOptimisation(src)
         assert opt.GetDefaultImplementationType() == nk.eB200 and opt.GetMaxCollectionSize() == 64 and opt.SetByXml()
         assert opt.GetOperatorImpMap(hex5)[nk.eHelmholtz] == nk.eB200            # order 5 is not in 2-4,7
         assert opt.GetOperatorImpMap(nk.StdExpansion(nk.eHexahedron, 7, 8))[nk.eHelmholtz] == nk.eMatrixFree
         assert opt.GetOperatorImpMap(nk.StdExpansion(nk.eHexahedron, 3, 4))[nk.eBwdTrans] == nk.eB200
         assert opt.GetOperatorImpMap(tet6)[nk.eHelmholtz] == nk.eStdMat and opt.GetOperatorImpMap(tet6)[nk.eBwdTrans] == nk.eB200
     # an explicit constructor type wins over DEFAULT (CollectionOptimisation.cpp:150-153)
-    assert nk.CollectionOptimisation(xml, nk.eMatrixFree).GetOperatorImpMap(hex5)[nk.eBwdTrans] == nk.eMatrixFree
-    assert nk.CollectionOptimisation('<NEKTAR><COLLECTIONS DEFAULT="auto"/></NEKTAR>').IsUsingAutotuning()
-    assert nk.GenerateSeqVector("1-3, 5") == [1, 2, 3, 5]
+    assert si.CollectionOptimisation(xml, nk.eMatrixFree).GetOperatorImpMap(hex5)[nk.eBwdTrans] == nk.eMatrixFree
+    assert si.CollectionOptimisation('<NEKTAR><COLLECTIONS DEFAULT="auto"/></NEKTAR>').IsUsingAutotuning()
+    assert si.GenerateSeqVector("1-3, 5") == [1, 2, 3, 5]
     for bad, msg in (('<FOO/>', "Unable to find NEKTAR tag"),
                      ('<NEKTAR><COLLECTIONS DEFAULT="Fast"/></NEKTAR>', "Unknown default collection scheme: Fast"),
                      ('<NEKTAR><COLLECTIONS><THING/></COLLECTIONS></NEKTAR>', "Only OPERATOR tags"),
@@ -283,10 +284,10 @@ def test_collection_optimisation_mirror(tmp_path):
                      ('<NEKTAR><COLLECTIONS><OPERATOR TYPE="BwdTrans"><ELEMENT TYPE="H" IMPTYPE="B200"/></OPERATOR>'
                       '</COLLECTIONS></NEKTAR>', "Missing ORDER in ELEMENT tag")):
         with pytest.raises(nk.NekError, match=msg):
-            nk.CollectionOptimisation(bad)
+            si.CollectionOptimisation(bad)
     # a Collection built from the map refuses implementation types that are not registered in this library
     coll = nk.Collection(tet6, 3, nk.CoalescedGeomData(np.ones(3), np.ones(27), False),
-                         nk.CollectionOptimisation(xml).GetOperatorImpMap(tet6))
+                         si.CollectionOptimisation(xml).GetOperatorImpMap(tet6))
     with pytest.raises(nk.NekError, match="no operator registered for key"):
         coll.Initialise(nk.eHelmholtz)
 
@@ -305,7 +306,7 @@ def test_explist_create_collections_mirror(monkeypatch):
 
     mesh = [elem(hex4, False, 0), elem(hex4, False, 1), elem(hex4, False, 2), elem(hex4, True, 3), elem(hex4, True, 4),
             elem(tet4, False, 5), elem(tet4, False, 6), elem(hex5, False, 7), elem(hex4, False, 8), elem(hex4, False, 9)]
-    exp = nk.ExpList(mesh).CreateCollections(nk.eB200)
+    exp = si.ExpList(mesh).CreateCollections(nk.eB200)
     members = [(c.m_stdExp.DetShapeType(), c.m_stdExp.nm, c.m_nElmt, bool(c.m_geomData.IsDeformed())) for c in exp.m_collections]
     # tetrahedra come before hexahedra (ShapeType order); the tets at positions 5, 6 break the contiguity of the hexes
     assert members == [(nk.eTetrahedron, 4, 2, False), (nk.eHexahedron, 4, 3, False), (nk.eHexahedron, 4, 2, True),
@@ -319,7 +320,7 @@ def test_explist_create_collections_mirror(monkeypatch):
     g = exp.m_collections[2].m_geomData
     assert g.GetJac().size == 2 * nq4 and np.array_equal(np.asarray(g.GetDerivFactors()).reshape(9, 2 * nq4)[0, nq4 - 1:nq4 + 1], [13.0, 14.0])
     # MAXSIZE from the session caps the members of a collection
-    capped = nk.ExpList(mesh, '<NEKTAR><COLLECTIONS DEFAULT="B200" MAXSIZE="2"/></NEKTAR>').CreateCollections()
+    capped = si.ExpList(mesh, '<NEKTAR><COLLECTIONS DEFAULT="B200" MAXSIZE="2"/></NEKTAR>').CreateCollections()
     assert [c.m_nElmt for c in capped.m_collections] == [2, 2, 1, 2, 1, 2]
     assert all(c.m_impTypes[nk.eHelmholtz] == nk.eB200 for c in capped.m_collections)
     # call sites: every collection gets its own slice of the ExpList arrays

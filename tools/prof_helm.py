@@ -17,6 +17,7 @@ ap.add_argument("--variant", default="regular")
 ap.add_argument("--nx", type=int, default=64)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--op", default="helm")
+ap.add_argument("--ab", default=None, help="ENVVAR=v1,v2: alternate the knob between rounds of `reps` applies (same process, same buffers)")
 a = ap.parse_args()
 nk = nekmf()
 dev = torch.device("cuda", 0)
@@ -32,6 +33,24 @@ y = torch.empty_like(x)
 coll.Initialise(nk.eHelmholtz)
 op = coll.m_ops[nk.eHelmholtz]
 op.SetLambda(1.0)
+if a.ab:
+    name, vals = a.ab.split("=")
+    for rnd in range(4):
+        for v in vals.split(","):
+            if v == "-":
+                os.environ.pop(name, None)
+            else:
+                os.environ[name] = v
+            for _ in range(3):
+                op.apply([x], [y])
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            evs[0].record()
+            for i in range(a.reps):
+                op.apply([x], [y])
+            evs[1].record()
+            torch.cuda.synchronize()
+            print("round %d %s=%s: %.4f ms per apply" % (rnd, name, v, evs[0].elapsed_time(evs[1]) / a.reps))
+    sys.exit(0)
 evs = [torch.cuda.Event(enable_timing=True) for _ in range(a.reps + 1)]
 evs[0].record()
 for i in range(a.reps):
