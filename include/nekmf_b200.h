@@ -244,6 +244,16 @@ int nekmf_cg_last_loop(nekmf_cg_t cg, float *ms, int *iterations);
 int nekmf_cg_matvec(nekmf_cg_t cg, const double *w, double *s);
 int nekmf_cg_destroy(nekmf_cg_t cg);
 
+/* ---- matrix-free Jacobi preconditioner ---------------------------------------------------- */
+/* Replaces PreconditionerDiagonal::DiagonalPreconditionerSum (MultiRegions/PreconditionerDiagonal.cpp:98-162), which
+ * sums loc_mat(i,i) of the assembled elemental matrices.  nekmf_op_diagonal: the diagonal of every elemental
+ * Helmholtz matrix, diag[nElmt*ncoeff], obtained from the operator itself (ncoeff applies to unit vectors: any
+ * shape, regular or deformed, the kernel the mat-vec uses).  nekmf_cg_set_jacobi: that diagonal assembled with the
+ * solver's map, summed across the partition interfaces and inverted on the device, installed as the solver's
+ * preconditioner (replacing the invdiag given at create, if any).  COLLECTIVE over the solver's communicator. */
+int nekmf_op_diagonal(nekmf_op_t op, double *diag, int memkind);
+int nekmf_cg_set_jacobi(nekmf_cg_t cg);
+
 /* ---- ContField::v_HelmSolve as one device-resident chain ---------------------------------- */
 /* Replaces the string of host-array calls under MultiRegions/ContField.cpp:878-945 (v_HelmSolve) -> GlobalSolve
  * (:516-535) -> GlobalLinSysIterativeFull::v_Solve (GlobalLinSysIterativeFull.cpp:110-211):

@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256)
             exchange_put(ex, i, epoch, row_sum(ex.idx[i]));
         exchange_signal(ex, epoch, (unsigned int)nIfBlocks);
     }
+    // (measured alternative: four rows per thread with interleaved rowptr -> col -> loc chains: 0.73 -> 1.25 ms on
+    // 2^20 hex elements -- the four row windows thrash the L2 lines the neighbouring rows share)
     double mu = 0.0;
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nGlobal; g += gridDim.x * blockDim.x)
     {

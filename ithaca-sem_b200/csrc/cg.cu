@@ -181,12 +181,16 @@ __global__ void __launch_bounds__(RED_T)
     if (sc->done) return;
     const double alpha = sc->alpha, beta = sc->beta;
     double rho = 0.0, eps = 0.0;
+    // w is not read: the previous iteration stored w = r * invdiag (or r), which is recomputed from the r and invdiag
+    // values this pass loads anyway -- the same product, bit for bit, one vector stream less
     for (int i = blockIdx.x * RED_T + threadIdx.x; i < n; i += RED_BLOCKS * RED_T)
     {
-        const double pi = fma(beta, p[i], w[i]);
+        const double ro = r[i], dinv = invdiag ? invdiag[i] : 1.0;
+        const double wo = invdiag ? ro * dinv : ro;
+        const double pi = fma(beta, p[i], wo);
         const double qi = fma(beta, q[i], s[i]);
-        const double ri = fma(-alpha, qi, r[i]);
-        const double wi = invdiag ? ri * invdiag[i] : ri;
+        const double ri = fma(-alpha, qi, ro);
+        const double wi = invdiag ? ri * dinv : ri;
         p[i] = pi;
         q[i] = qi;
         x[i] = fma(alpha, pi, x[i]);
@@ -317,6 +321,12 @@ static void cg_drop_graphs(nekmf_cg_s *cg)
             cudaGraphExecDestroy(cg->graph[g]);
             cg->graph[g] = nullptr;
         }
+}
+
+void cg_invalidate_graphs(nekmf_cg_s *cg)
+{
+    cg_drop_graphs(cg);
+    cg->graph_x = nullptr;
 }
 
 // capture nIter iterations into an executable graph

@@ -45,3 +45,8 @@ struct nekmf_cg_s
     std::string graph_kernel;
 };
 
+namespace nekmf
+{
+void cg_invalidate_graphs(nekmf_cg_s *cg); // cg.cu: drop the captured iterations (a pointer they bake in changed)
+int op_diagonal_device(nekmf_op_s *op, double *d_diag, double *x, double *y, cudaStream_t st); // jacobi.cu
+} // namespace nekmf

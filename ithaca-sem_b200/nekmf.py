@@ -56,7 +56,7 @@ EXPORTS = [
     "nekmf_comm_unique_id", "nekmf_comm_create", "nekmf_comm_transport", "nekmf_comm_destroy", "nekmf_exchange_create",
     "nekmf_exchange_add", "nekmf_exchange_destroy", "nekmf_cg_create", "nekmf_cg_solve", "nekmf_cg_matvec",
     "nekmf_cg_last_loop", "nekmf_cg_destroy", "nekmf_helmsolve_create", "nekmf_helmsolve", "nekmf_helmsolve_last_ms",
-    "nekmf_helmsolve_destroy",
+    "nekmf_helmsolve_destroy", "nekmf_op_diagonal", "nekmf_cg_set_jacobi",
 ]
 
 
@@ -110,6 +110,8 @@ def lib():
         L.nekmf_cg_matvec.argtypes = [_vp, _vp, _vp]
         L.nekmf_cg_last_loop.argtypes = [_vp, C.POINTER(C.c_float), _ip]
         L.nekmf_cg_destroy.argtypes = [_vp]
+        L.nekmf_op_diagonal.argtypes = [_vp, _vp, C.c_int]
+        L.nekmf_cg_set_jacobi.argtypes = [_vp]
         L.nekmf_helmsolve_create.argtypes = [_vp, _vp, _vp, C.POINTER(_vp)]
         L.nekmf_helmsolve.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, _ip, _dp]
         L.nekmf_helmsolve_last_ms.argtypes = [_vp, C.POINTER(C.c_float)]
@@ -309,6 +311,14 @@ class Operator:
 
     def SetLambda(self, lam):
         check(lib().nekmf_op_set_lambda(self.h, float(lam)), "nekmf_op_set_lambda")
+
+    def diagonal(self, out=None):
+        """diagonal of every elemental Helmholtz matrix [nElmt*ncoeff] (nekmf_op_diagonal); numpy unless `out` given"""
+        if out is None:
+            out = np.zeros(self.nElmt * self.ncoeff)
+        p, kind, _ = _ptr(out)
+        check(lib().nekmf_op_diagonal(self.h, p, kind), "nekmf_op_diagonal")
+        return out
 
     def enable_timing(self, on=True):
         check(lib().nekmf_op_enable_timing(self.h, int(on)), "nekmf_op_enable_timing")
@@ -536,6 +546,10 @@ class HelmholtzCG:
             return its.value, eps.value
         check(rc, "nekmf_cg_solve")
         return its.value, eps.value
+
+    def set_jacobi(self):
+        """matrix-free diagonal preconditioner computed, assembled, exchanged and inverted on the device"""
+        check(lib().nekmf_cg_set_jacobi(self.h), "nekmf_cg_set_jacobi")
 
     def matvec(self, w, s):
         check(lib().nekmf_cg_matvec(self.h, _ptr(w)[0], _ptr(s)[0]), "nekmf_cg_matvec")

@@ -68,14 +68,14 @@ def setup(a, comm=None):
     ipr.apply([f], [loc])
     rhs = torch.empty(mesh.nGlobal, dtype=torch.float64, device=dev)
     amap.Assemble(loc, rhs)
-    diag = torch.tensor(mesh.helmholtz_diagonal(std.basis[0], lam), device=dev)
     if ex is not None:
         ex.add(rhs)
-        ex.add(diag)
     rhs[:mesh.nDir] = 0.0
     torch.cuda.synchronize()
-    invdiag = (1.0 / diag[mesh.nDir:]).cpu().numpy()
-    cg = nk.HelmholtzCG(helm, amap, mesh.nDir, invdiag, exchange=ex, comm=comm, ownerMask=mesh.ownerMask)
+    # Jacobi preconditioner: elemental diagonals from the operator itself, assembled / exchanged / inverted on the
+    # device (nekmf_cg_set_jacobi, the PreconditionerDiagonal replacement)
+    cg = nk.HelmholtzCG(helm, amap, mesh.nDir, None, exchange=ex, comm=comm, ownerMask=mesh.ownerMask)
+    cg.set_jacobi()
     x = torch.zeros(mesh.nGlobal, dtype=torch.float64, device=dev)
     del f, loc
     return dict(rank=rank, world=world, dev=dev, nk=nk, mesh_mod=mesh_mod, dist=dist, mesh=mesh, std=std, lam=lam, helm=helm,
