@@ -252,6 +252,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=NX, help="elements per direction (default 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the compact config 1 / 3 / 4 legs (N=1 only)")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4],
                     help="BASELINE.json configuration, 1-based: 2 (default) = configs[1], the metric's workload; "
                          "1 = 2-D quad Helmholtz P=5; 4 = mixed Hex/Prism/Tet Helmholtz P=6 (bench_configs.py)")
@@ -500,6 +501,39 @@ def main():
         ach = flops_elt * nel / (reg["kernel_ms_avg"] * 1e-3) / 1e12
         line["roofline_fp64"] = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
                                  "frac": ach / fp64_peak, "flops_per_element": flops_elt}
+    if world == 1 and not args.no_variants:
+        # the other BASELINE.json configurations, compact, so that they are on the driver's record:
+        # configs[0] (quad P=5 Helmholtz), configs[2] (hex operator sweep points), configs[3] (mixed mesh P=6)
+        import bench_configs
+        import pyoracle as po
+        import sweep
+
+        def compact(d):
+            r = d.get("roofline", {})
+            return {"value": d.get("value"), "unit": d.get("unit"), "ms_per_step": d.get("ms_per_step"),
+                    "workload": d.get("config", {}).get("workload"),
+                    "roofline": {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "kernel") if k in r},
+                    "e2e": d.get("e2e", {}).get("value"), "cpu_baseline": (d.get("cpu_baseline") or {}).get("value")}
+
+        class _A:
+            nx, steps, warmup = 64, 20, 3
+        for name, fn in (("config1_quad_p5", bench_configs.config1), ("config4_mixed_p6", bench_configs.config4)):
+            try:
+                line["variants"][name] = compact(fn(_A, torch, nk, po, peak, peak_src, ClockSampler))
+            except Exception as ex:
+                line["variants"][name] = {"failed": repr(ex)}
+            torch.cuda.empty_cache()
+        try:
+            pts = []
+            for nm_ in (3, 5, 8, 11):
+                for rec in sweep.iter_points("Hex", nm_, nm_, "regular,deformed", ["BwdTrans", "IProductWRTBase", "PhysDeriv"],
+                                             5, 1 << 26):
+                    pts.append({k: rec[k] for k in ("op", "nm", "geometry", "ms", "gdof_per_s", "gb_per_s", "frac_hbm",
+                                                    "kernel")})
+            line["variants"]["config3_hex_sweep_points"] = pts
+        except Exception as ex:
+            line["variants"]["config3_hex_sweep_points"] = {"failed": repr(ex)}
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_reference_leg(seconds_target=6.0, nx=args.nx)

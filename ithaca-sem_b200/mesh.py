@@ -26,72 +26,100 @@ def _gi(e, p, nm):
 
 
 class StructuredHexMesh:
-    """nx x ny x nz hexahedra on [0,Lx]x[0,Ly]x[0,Lz], nm modes per direction.  `slab=(rank, nranks)`
-    restricts the mesh to this rank's z-slab of elements; numbering is then rank-local."""
+    """nx x ny x nz hexahedra on [0,Lx]x[0,Ly]x[0,Lz], nm modes per direction.  `slab=(rank, nranks)` restricts the
+    mesh to this rank's z-slab of elements; `part=(px, py, pz)` with `rank` to its box of a px x py x pz partition
+    (rank = rx + px (ry + py rz); up to 26 neighbours, edge / corner DOFs held by 4 / 8 ranks).  Numbering is then
+    rank-local; `universal` holds the cross-rank id of every local DOF, from which the
+    interface lists and the ownership mask are derived exactly as Gs::Init / Gs::Unique derive them
+    (interface_from_universal_maps below)."""
 
-    def __init__(self, nx, ny, nz, nm, lengths=(1.0, 1.0, 1.0), slab=(0, 1)):
+    def __init__(self, nx, ny, nz, nm, lengths=(1.0, 1.0, 1.0), slab=(0, 1), part=None, rank=None):
         self.nx, self.ny, self.nz, self.nm = nx, ny, nz, nm
         self.L = tuple(float(v) for v in lengths)
-        self.rank, self.nranks = slab
-        if not 0 <= self.rank < self.nranks or self.nranks > nz:
-            raise ValueError("bad slab partition")
-        # contiguous z ranges, remainder spread over the first ranks
-        base, rem = divmod(nz, self.nranks)
-        counts = [base + (1 if r < rem else 0) for r in range(self.nranks)]
-        self.ez0 = sum(counts[:self.rank])
-        self.ez1 = self.ez0 + counts[self.rank]
-        self.nzl = self.ez1 - self.ez0
-        self.nElmt = nx * ny * self.nzl
+        if part is None:
+            self.rank, self.nranks = slab
+            part = (1, 1, self.nranks)
+        else:
+            self.rank, self.nranks = int(rank), part[0] * part[1] * part[2]
+        self.part = tuple(int(v) for v in part)
+        if not 0 <= self.rank < self.nranks or self.part[0] > nx or self.part[1] > ny or self.part[2] > nz:
+            raise ValueError("bad partition")
         self.h = (self.L[0] / nx, self.L[1] / ny, self.L[2] / nz)
         m1 = nm - 1
         self.Gx, self.Gy, self.Gz = nx * m1 + 1, ny * m1 + 1, nz * m1 + 1
-        self.gz0, self.gz1 = self.ez0 * m1, self.ez1 * m1  # inclusive global lattice planes of this slab
-        self.Gzl = self.gz1 - self.gz0 + 1
+        (self.ex0, self.ex1), (self.ey0, self.ey1), (self.ez0, self.ez1) = self._ranges(self.rank)
+        self.nxl, self.nyl, self.nzl = self.ex1 - self.ex0, self.ey1 - self.ey0, self.ez1 - self.ez0
+        self.nElmt = self.nxl * self.nyl * self.nzl
+        # inclusive global lattice ranges of this rank's box
+        self.gx0, self.gx1 = self.ex0 * m1, self.ex1 * m1
+        self.gy0, self.gy1 = self.ey0 * m1, self.ey1 * m1
+        self.gz0, self.gz1 = self.ez0 * m1, self.ez1 * m1
+        self.Gxl, self.Gyl, self.Gzl = self.gx1 - self.gx0 + 1, self.gy1 - self.gy0 + 1, self.gz1 - self.gz0 + 1
         self._number()
+
+    def _ranges(self, rank):
+        """element ranges [e0, e1) per axis of `rank`: contiguous, remainder spread over the first boxes"""
+        px, py, pz = self.part
+        r3 = (rank % px, (rank // px) % py, rank // (px * py))
+        out = []
+        for n, p, r in zip((self.nx, self.ny, self.nz), self.part, r3):
+            base, rem = divmod(n, p)
+            counts = [base + (1 if i < rem else 0) for i in range(p)]
+            out.append((sum(counts[:r]), sum(counts[:r]) + counts[r]))
+        return out
+
+    def _universal_of(self, rank):
+        """universal ids (1 + global lattice index) of `rank`'s local lattice [Gzl,Gyl,Gxl], and the Dirichlet flags.
+        Dirichlet DOFs take part in the exchange like any other, as they do in AssemblyMapCG's universal map."""
+        m1 = self.nm - 1
+        (x0, x1), (y0, y1), (z0, z1) = self._ranges(rank)
+        gx, gy, gz = np.arange(x0 * m1, x1 * m1 + 1), np.arange(y0 * m1, y1 * m1 + 1), np.arange(z0 * m1, z1 * m1 + 1)
+        uid = 1 + gx[None, None, :] + self.Gx * (gy[None, :, None] + self.Gy * gz[:, None, None]).astype(np.int64)
+        bnd = ((gx == 0) | (gx == self.Gx - 1))[None, None, :] | ((gy == 0) | (gy == self.Gy - 1))[None, :, None] | \
+              ((gz == 0) | (gz == self.Gz - 1))[:, None, None]
+        return uid, bnd
 
     # ------------------------------------------------------------------ numbering
     def _number(self):
-        Gx, Gy, Gzl = self.Gx, self.Gy, self.Gzl
-        gz = np.arange(self.gz0, self.gz1 + 1)
-        on_bnd = np.zeros((Gzl, Gy, Gx), dtype=bool)
-        on_bnd[:, :, 0] = on_bnd[:, :, -1] = True
-        on_bnd[:, 0, :] = on_bnd[:, -1, :] = True
-        on_bnd[gz == 0] = True
-        on_bnd[gz == self.Gz - 1] = True
+        uid, on_bnd = self._universal_of(self.rank)
         flat = on_bnd.reshape(-1)
         self.nGlobal = flat.size
         self.nDir = int(flat.sum())
         ids = np.empty(flat.size, dtype=np.int64)
         ids[flat] = np.arange(self.nDir)
         ids[~flat] = self.nDir + np.arange(flat.size - self.nDir)
-        self.lattice_ids = ids.reshape(Gzl, Gy, Gx)  # rank-local global id of every lattice point
+        self.lattice_ids = ids.reshape(self.Gzl, self.Gyl, self.Gxl)  # rank-local global id of every lattice point
         self.dirichlet = on_bnd
         nm = self.nm
         p = np.arange(nm)
-        ex, ey, ez = np.arange(self.nx), np.arange(self.ny), np.arange(self.nzl)
-        gx = _gi(ex[:, None], p[None, :], nm)                       # [nx, nm]
+        ex, ey, ez = np.arange(self.nxl), np.arange(self.nyl), np.arange(self.nzl)
+        gx = _gi(ex[:, None], p[None, :], nm)                       # [nxl, nm] box-local lattice column
         gy = _gi(ey[:, None], p[None, :], nm)
-        gzl = _gi(ez[:, None], p[None, :], nm)                      # slab-local lattice plane
-        # local index: e = ex + nx*(ey + ny*ez), mode = p + nm*(q + nm*r)
+        gzl = _gi(ez[:, None], p[None, :], nm)
+        # local index: e = ex + nxl*(ey + nyl*ez), mode = p + nm*(q + nm*r)
         l2g = self.lattice_ids[gzl[:, None, None, :, None, None], gy[None, :, None, None, :, None],
                                gx[None, None, :, None, None, :]]   # [ez, ey, ex, r, q, p]
         self.localToGlobal = np.ascontiguousarray(l2g.reshape(-1), dtype=np.int32)
         self.nLocal = self.localToGlobal.size
-        # ---- partition interfaces (z-slabs: at most two neighbours)
-        self.peers, self.interface_lists = [], []
-        mask = np.ones((Gzl, Gy, Gx))
-        if self.rank > 0:
-            plane = self.lattice_ids[0]
-            self.peers.append(self.rank - 1)
-            self.interface_lists.append(plane[~on_bnd[0]].astype(np.int32))
-            mask[0] = 0.0  # the lower rank owns the shared plane
-        if self.rank < self.nranks - 1:
-            plane = self.lattice_ids[-1]
-            self.peers.append(self.rank + 1)
-            self.interface_lists.append(plane[~on_bnd[-1]].astype(np.int32))
-        om = np.empty(self.nGlobal)
-        om[self.lattice_ids.reshape(-1)] = mask.reshape(-1)
-        self.ownerMask = om
+        # index of every local element in the unpartitioned mesh (e = ex + nx*(ey + ny*ez))
+        self.element_ids = ((self.ex0 + ex)[None, None, :] + self.nx * ((self.ey0 + ey)[None, :, None] +
+                            self.ny * (self.ez0 + ez)[:, None, None])).reshape(-1)
+        # universal id of every rank-local global DOF
+        self.universal = np.zeros(self.nGlobal, dtype=np.int64)
+        self.universal[self.lattice_ids.reshape(-1)] = uid.reshape(-1)
+        # ---- partition interfaces from the universal ids of the (at most 26) adjacent boxes
+        px, py, pz = self.part
+        rx, ry, rz = self.rank % px, (self.rank // px) % py, self.rank // (px * py)
+        maps = [None] * self.nranks
+        maps[self.rank] = self.universal
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    qx, qy, qz = rx + dx, ry + dy, rz + dz
+                    if (dx, dy, dz) != (0, 0, 0) and 0 <= qx < px and 0 <= qy < py and 0 <= qz < pz:
+                        q = qx + px * (qy + py * qz)
+                        maps[q] = self._universal_of(q)[0].reshape(-1)
+        self.peers, self.interface_lists, self.ownerMask = interface_from_universal_maps(maps, self.rank)
 
     # ------------------------------------------------------------------ geometry (regular boxes)
     def geometry(self):
@@ -107,10 +135,10 @@ class StructuredHexMesh:
         [elmt][k][j][i] order; z = 1-D quadrature nodes on [-1,1]."""
         nq = len(z)
         hx, hy, hz = self.h
-        X1 = (np.arange(self.nx)[:, None] + 0.5 * (z[None, :] + 1.0)) * hx
-        Y1 = (np.arange(self.ny)[:, None] + 0.5 * (z[None, :] + 1.0)) * hy
+        X1 = (self.ex0 + np.arange(self.nxl)[:, None] + 0.5 * (z[None, :] + 1.0)) * hx
+        Y1 = (self.ey0 + np.arange(self.nyl)[:, None] + 0.5 * (z[None, :] + 1.0)) * hy
         Z1 = (self.ez0 + np.arange(self.nzl)[:, None] + 0.5 * (z[None, :] + 1.0)) * hz
-        shape = (self.nzl, self.ny, self.nx, nq, nq, nq)
+        shape = (self.nzl, self.nyl, self.nxl, nq, nq, nq)
         X = np.broadcast_to(X1[None, None, :, None, None, :], shape).reshape(-1)
         Y = np.broadcast_to(Y1[None, :, None, None, :, None], shape).reshape(-1)
         Z = np.broadcast_to(Z1[:, None, None, :, None, None], shape).reshape(-1)
@@ -228,7 +256,7 @@ def interface_from_universal_maps(universal_maps, rank):
     peers, lists = [], []
     owner = np.ones(mine.size)
     for r, other in enumerate(universal_maps):
-        if r == rank:
+        if r == rank or other is None:  # None: a rank known to share nothing (not adjacent)
             continue
         other = np.asarray(other, dtype=np.int64)
         shared = np.intersect1d(sorted_ids[sorted_ids != 0], other[other != 0], assume_unique=True)

@@ -1,6 +1,6 @@
 """Sharded device CG / HelmSolve chain against the serial CPU oracle (test infrastructure; launched under torchrun by
 tests/test_gpu_cg.py::test_sharded_cg_two_gpus, and called by bench.py for its `cg_parity` field).  Builds the
-problem with tools/bench_cg.setup() on this rank's z-slab and compares, on the FULL mesh, with the oracle:
+problem with tools/bench_cg.setup() on this rank's z-slab (or box of a --part px,py,pz partition) and compares, on the FULL mesh, with the oracle:
 
   * one mat-vec s = Assemble(Helmholtz(GlobalToLocal(w))) + interface exchange on a random global vector
     (well-posed: relative Linf <= 1e-12, the north-star tolerance);
@@ -33,7 +33,8 @@ def run_check(S, a):
     el = po.Elem(po.HEX, a.nm, a.nm + 1)
     jf, dff = full.geometry()
     mine_ids = mesh.lattice_ids                                  # [Gzl, Gy, Gx] rank-local global ids
-    full_ids = full.lattice_ids[mesh.gz0:mesh.gz1 + 1]           # the same lattice points in the full numbering
+    # the same lattice points in the numbering of the unpartitioned mesh
+    full_ids = full.lattice_ids[mesh.gz0:mesh.gz1 + 1, mesh.gy0:mesh.gy1 + 1, mesh.gx0:mesh.gx1 + 1]
     # ---- mat-vec
     wf = np.random.default_rng(17).uniform(-1, 1, full.nGlobal)
     want_s = po.assemble(full.localToGlobal, None, el.helmholtz(full.nElmt, False, jf, dff, lam, po.global_to_local(
@@ -63,17 +64,21 @@ def run_check(S, a):
                   1.0 / dg[full.nDir:])
     want_c, want_p = np.zeros(full.nLocal), np.zeros(f_full.size)
     its_ho, _ = ch.helmsolve(f_full, want_c, want_p, tol=TOL_SOLVE)
-    e0, e1 = mesh.ez0 * a.nx * a.ny, mesh.ez1 * a.nx * a.ny
-    err_c = np.abs(coef - want_c[e0 * el.nmTot:e1 * el.nmTot]).max() / np.abs(want_c).max()
-    err_p = np.abs(phys - want_p[e0 * el.nqTot:e1 * el.nqTot]).max() / np.abs(want_p).max()
+    mine_c = want_c.reshape(full.nElmt, el.nmTot)[mesh.element_ids].reshape(-1)
+    mine_p = want_p.reshape(full.nElmt, el.nqTot)[mesh.element_ids].reshape(-1)
+    err_c = np.abs(coef - mine_c).max() / np.abs(want_c).max()
+    err_p = np.abs(phys - mine_p).max() / np.abs(want_p).max()
     del hs
+    # iteration counts: a sanity bound only -- at tol = 1e-12 the residual sits on its round-off plateau and the
+    # crossing iteration moves by 10-15 % with the summation order of the dot products
     ok = (err_mv < 1e-12 and err_x < 1e-9 and err_c < 1e-9 and err_p < 1e-9 and
-          abs(its - itso) <= max(3, 0.1 * itso) and abs(its_h - its_ho) <= max(3, 0.1 * its_ho))
+          abs(its - itso) <= max(3, 0.25 * itso) and abs(its_h - its_ho) <= max(3, 0.25 * its_ho))
     comm = S["keepalive"][2]
     return {"ok": bool(ok), "matvec_rel_linf": float(err_mv), "solution_rel_linf": float(err_x),
             "chain_coeff_rel_linf": float(err_c), "chain_phys_rel_linf": float(err_p),
             "iterations": [int(its), int(itso)], "chain_iterations": [int(its_h), int(its_ho)],
-            "tol": TOL_SOLVE, "mesh": [a.nx, a.ny, a.nz], "ranks": S["world"],
+            "tol": TOL_SOLVE, "mesh": [a.nx, a.ny, a.nz], "ranks": S["world"], "partition": list(mesh.part),
+            "neighbours_of_this_rank": len(mesh.peers),
             "transport": comm.transport if comm is not None else "none",
             "oracle": "oracle/libmforacle.so (mfo_cg_helmholtz, mfo_chain_helmsolve) on the unpartitioned mesh"}
 

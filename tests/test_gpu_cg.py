@@ -227,6 +227,23 @@ def test_sharded_cg_two_gpus(transport):
 
 
 @pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_sharded_cg_box_partition(transport):
+    """box partition over all visible GPUs (2 x 2 x 2 on eight: 7 neighbours per rank, edge DOFs held by 4 ranks, the
+    centre DOF by 8; 2 x 2 x 1 on four; 2 x 1 x 1 on two), interfaces derived from universal ids: mat-vec, converged
+    solve and HelmSolve chain against the serial oracle"""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    part = {2: "2,1,1", 3: "2,1,1", 4: "2,2,1", 5: "2,2,1", 6: "2,2,1", 7: "2,2,1"}.get(n, "2,2,2")
+    nr = int(np.prod([int(v) for v in part.split(",")]))
+    r = _torchrun("_cg_check.py", nr, 29615, ["--nx", "6", "--ny", "6", "--nz", "6", "--part", part],
+                  {"NEKMF_TRANSPORT": transport})
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "CHECK OK" in r.stdout
+
+
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
 def test_exchange_multi_gpu(transport):
     """every visible GPU: random universal-id maps with DOFs held by up to all ranks; the device exchange must be
     bit-identical to the rank-ordered numpy sum (tests/_exchange_check.py)"""

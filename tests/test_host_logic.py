@@ -93,7 +93,7 @@ def test_structured_mesh_numbering():
     a = mesh_mod.StructuredHexMesh(3, 2, 4, nm, slab=(0, 2))
     b = mesh_mod.StructuredHexMesh(3, 2, 4, nm, slab=(1, 2))
     assert a.peers == [1] and b.peers == [0]
-    assert a.interface_lists[0].size == b.interface_lists[0].size == (3 * 3 - 1) * (2 * 3 - 1)
+    assert a.interface_lists[0].size == b.interface_lists[0].size == (3 * 3 + 1) * (2 * 3 + 1)
     assert a.nElmt + b.nElmt == m.nElmt
     # ownership: every DOF of the global problem is owned exactly once
     assert int(a.ownerMask.sum() + b.ownerMask.sum()) == G
@@ -139,7 +139,7 @@ def _free_port():
     return p
 
 
-def _gloo_worker(rank, world, port, nm, lam, out):
+def _gloo_worker(rank, world, port, nm, lam, out, part=None):
     import torch.distributed as dist
     import _sharded_ref as sr
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -147,7 +147,8 @@ def _gloo_worker(rank, world, port, nm, lam, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     mesh_mod = load_pkg_module("mesh")
     nk = nekmf()
-    mesh = mesh_mod.StructuredHexMesh(3, 2, 4, nm, slab=(rank, world))
+    mesh = (mesh_mod.StructuredHexMesh(3, 2, 4, nm, slab=(rank, world)) if part is None else
+            mesh_mod.StructuredHexMesh(3, 2, 4, nm, part=part, rank=rank))
     el = po.Elem(po.HEX, nm, nm + 1)
     jac, df = mesh.geometry()
     rhs, _ = sr.helmholtz_rhs(dist, mesh, el, jac, lam)
@@ -156,17 +157,19 @@ def _gloo_worker(rank, world, port, nm, lam, out):
     x, its, eps = sr.sharded_cg(dist, mesh, el, jac, df, lam, rhs, 1.0 / diag[mesh.nDir:], tol=1e-13)
     # return the solution on the global lattice for comparison
     np.save(os.path.join(out, "x_%d.npy" % rank), x[mesh.lattice_ids])
-    np.save(os.path.join(out, "meta_%d.npy" % rank), np.array([its, eps, mesh.gz0, mesh.gz1]))
+    np.save(os.path.join(out, "meta_%d.npy" % rank), np.array([its, eps, mesh.gz0, mesh.gz1, mesh.gy0, mesh.gy1, mesh.gx0,
+                                                                mesh.gx1]))
     dist.destroy_process_group()
 
 
-def test_sharded_cg_world_size_2_gloo(tmp_path):
-    """two ranks (z-slabs), gloo: interface exchange + masked dots + all-reduce reproduce the serial
-    solve (same iteration count, same solution)."""
+@pytest.mark.parametrize("world,part", [(2, None), (4, (1, 2, 2))])
+def test_sharded_cg_gloo(tmp_path, world, part):
+    """two ranks in z-slabs / four ranks in a 1 x 2 x 2 box partition (the middle line of DOFs is held by all four),
+    gloo: interface exchange + masked dots + all-reduce reproduce the serial solve (iteration count, solution)."""
     import torch.multiprocessing as mp
     import _sharded_ref as sr
     nm, lam = 4, 1.0
-    mp.spawn(_gloo_worker, args=(2, _free_port(), nm, lam, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_gloo_worker, args=(world, _free_port(), nm, lam, str(tmp_path), part), nprocs=world, join=True)
     mesh_mod = load_pkg_module("mesh")
     nk = nekmf()
     mesh = mesh_mod.StructuredHexMesh(3, 2, 4, nm)
@@ -176,12 +179,12 @@ def test_sharded_cg_world_size_2_gloo(tmp_path):
     diag = mesh.helmholtz_diagonal(nk.StdExpansion(nk.eHexahedron, nm).basis[0], lam)
     x, its, eps = sr.sharded_cg(None, mesh, el, jac, df, lam, rhs, 1.0 / diag[mesh.nDir:], tol=1e-13)
     xs = x[mesh.lattice_ids]
-    for r in range(2):
+    for r in range(world):
         xr = np.load(os.path.join(str(tmp_path), "x_%d.npy" % r))
         meta = np.load(os.path.join(str(tmp_path), "meta_%d.npy" % r))
-        assert abs(int(meta[0]) - its) <= 1
-        g0, g1 = int(meta[2]), int(meta[3])
-        assert np.abs(xr - xs[g0:g1 + 1]).max() < 1e-10 * np.abs(xs).max()
+        assert abs(int(meta[0]) - its) <= 2
+        z0, z1, y0, y1, x0, x1 = (int(v) for v in meta[2:8])
+        assert np.abs(xr - xs[z0:z1 + 1, y0:y1 + 1, x0:x1 + 1]).max() < 1e-10 * np.abs(xs).max()
 
 
 def test_cpp_collections_mirror_builds_and_refuses_without_gpu():
@@ -340,32 +343,54 @@ def test_explist_create_collections_mirror(monkeypatch):
     assert calls[5][1] == [2 * nqt, 2 * nct] and calls[10][1] == [2 * nct, 2 * nct]
 
 
-def _universal_ids(mesh):
-    """universal id of every rank-local global DOF of a z-slab mesh: 1 + global lattice index, 0 on the Dirichlet
-    boundary (those DOFs take no part in the exchange)"""
-    gz, gy, gx = np.meshgrid(np.arange(mesh.gz0, mesh.gz1 + 1), np.arange(mesh.Gy), np.arange(mesh.Gx), indexing="ij")
-    uid = 1 + gx + mesh.Gx * (gy + mesh.Gy * gz)
-    uid[mesh.dirichlet] = 0
-    out = np.zeros(mesh.nGlobal, dtype=np.int64)
-    out[mesh.lattice_ids.reshape(-1)] = uid.reshape(-1)
-    return out
-
-
 def test_interface_from_universal_maps():
-    """the gslib set-up restated (mesh.interface_from_universal_maps): against the analytic z-slab interfaces of
-    StructuredHexMesh, and on a hand-made case with a DOF shared by three ranks where the pairwise exchange-add must
-    reproduce gs_add (sum of all copies) and the owner mask must count every DOF once"""
+    """the gslib set-up restated (mesh.interface_from_universal_maps): against the analytic z-slab interfaces (the
+    whole shared lattice plane in lattice order, the lower rank owning it), on a 2 x 2 x 2 box partition (7 neighbours,
+    edge DOFs on 4 ranks, the centre DOF on 8) where the pairwise exchange-add must reproduce the unpartitioned
+    assembly, and on a hand-made case with a DOF shared by three ranks"""
     mesh_mod = load_pkg_module("mesh")
     R = 3
     meshes = [mesh_mod.StructuredHexMesh(3, 2, 5, 4, slab=(r, R)) for r in range(R)]
-    maps = [_universal_ids(m) for m in meshes]
     for r, m in enumerate(meshes):
-        peers, lists, owner = mesh_mod.interface_from_universal_maps(maps, r)
-        assert peers == m.peers
-        assert all(np.array_equal(a, b) for a, b in zip(lists, m.interface_lists))
-        interior = np.ones(m.nGlobal, dtype=bool)
-        interior[:m.nDir] = False
-        assert np.array_equal(owner[interior], m.ownerMask[interior])
+        want_peers = [q for q in (r - 1, r + 1) if 0 <= q < R]
+        assert m.peers == want_peers
+        for q, lst in zip(m.peers, m.interface_lists):
+            plane = m.lattice_ids[0 if q < r else -1].reshape(-1)
+            assert np.array_equal(lst, plane)
+        mask = np.ones((m.Gzl, m.Gyl, m.Gxl))
+        if r > 0:
+            mask[0] = 0.0
+        want = np.empty(m.nGlobal)
+        want[m.lattice_ids.reshape(-1)] = mask.reshape(-1)
+        assert np.array_equal(m.ownerMask, want)
+    # ---- box partition: exchange-add of the rank-local assemblies == the unpartitioned assembly
+    nm = 3
+    full = mesh_mod.StructuredHexMesh(4, 4, 4, nm)
+    rng = np.random.default_rng(3)
+    loc_full = rng.uniform(-1, 1, full.nLocal)
+    want = po.assemble(full.localToGlobal, None, loc_full, full.nGlobal)
+    boxes = [mesh_mod.StructuredHexMesh(4, 4, 4, nm, part=(2, 2, 2), rank=r) for r in range(8)]
+    assert all(len(b.peers) == 7 for b in boxes)
+    glob = []
+    for b in boxes:
+        mine = loc_full.reshape(full.nElmt, nm ** 3)[b.element_ids].reshape(-1)
+        glob.append(po.assemble(b.localToGlobal, None, mine, b.nGlobal))
+    sent = [[g[l].copy() for l in b.interface_lists] for b, g in zip(boxes, glob)]
+    for r, b in enumerate(boxes):
+        for k, q in enumerate(b.peers):
+            back = boxes[q].peers.index(r)
+            assert np.array_equal(b.universal[b.interface_lists[k]], boxes[q].universal[boxes[q].interface_lists[back]])
+            glob[r][b.interface_lists[k]] += sent[q][back]
+    owned = 0
+    for b, g in zip(boxes, glob):
+        ids = full.lattice_ids[b.gz0:b.gz1 + 1, b.gy0:b.gy1 + 1, b.gx0:b.gx1 + 1]
+        assert np.abs(g[b.lattice_ids] - want[ids]).max() < 1e-13
+        owned += int(b.ownerMask.sum())
+    assert owned == full.nGlobal
+    multiplicity = np.zeros(full.nGlobal + 1, dtype=int)
+    for b in boxes:
+        np.add.at(multiplicity, b.universal, 1)
+    assert multiplicity.max() == 8 and (multiplicity == 4).sum() > 0
     # three ranks around a shared point: ids 7 (all three), 8 (ranks 0, 1), 9 (ranks 1, 2), 0 = not exchanged
     maps = [np.array([5, 7, 8, 0]), np.array([8, 9, 7, 0, 11]), np.array([0, 9, 12, 7])]
     vals = [np.array([1.0, 2.0, 3.0, 4.0]), np.array([10.0, 20.0, 30.0, 40.0, 50.0]), np.array([100.0, 200.0, 300.0, 400.0])]
@@ -400,7 +425,7 @@ def _gloo_universal_worker(rank, world, port, outdir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     mesh_mod = load_pkg_module("mesh")
     m = mesh_mod.StructuredHexMesh(2, 2, 4, 3, slab=(rank, world))
-    peers, lists, owner = mesh_mod.interface_from_universal_map(dist, _universal_ids(m))
+    peers, lists, owner = mesh_mod.interface_from_universal_map(dist, m.universal)
     ok = peers == m.peers and all(np.array_equal(a, b) for a, b in zip(lists, m.interface_lists))
     np.save(os.path.join(outdir, "uok_%d.npy" % rank), np.array([1.0 if ok else 0.0, owner[m.nDir:].sum()]))
     dist.destroy_process_group()

@@ -28,6 +28,7 @@ def parse_args(argv=None):
     ap.add_argument("--nz", type=int, default=128)
     ap.add_argument("--nm", type=int, default=5)
     ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--part", default=None, help="px,py,pz box partition over the ranks (default: z-slabs)")
     return ap.parse_args(argv)
 
 
@@ -48,7 +49,13 @@ def setup(a, comm=None):
         if comm is None:
             comm = nk.Comm.from_torch_distributed()
     lam = 1.0
-    mesh = mesh_mod.StructuredHexMesh(a.nx, a.ny, a.nz, a.nm, slab=(rank, world))
+    if getattr(a, "part", None):
+        part = tuple(int(v) for v in a.part.split(","))
+        if part[0] * part[1] * part[2] != world:
+            raise SystemExit("--part %s does not match %d ranks" % (a.part, world))
+        mesh = mesh_mod.StructuredHexMesh(a.nx, a.ny, a.nz, a.nm, part=part, rank=rank)
+    else:
+        mesh = mesh_mod.StructuredHexMesh(a.nx, a.ny, a.nz, a.nm, slab=(rank, world))
     std = nk.StdExpansion(nk.eHexahedron, a.nm)
     jac, df = mesh.geometry()
     geom = nk.CoalescedGeomData(jac, df, False)

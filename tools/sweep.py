@@ -48,34 +48,23 @@ def algorithmic_flops(op, shape, nm, nq):
     return None
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--shapes", default="Hex")
-    ap.add_argument("--nm", default="3..11")
-    ap.add_argument("--ops", default="all")
-    ap.add_argument("--geom", default="regular,deformed")
-    ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--words", type=int, default=1 << 27, help="in+out doubles per apply (sets nElmt)")
-    ap.add_argument("--out", default=None)
-    a = ap.parse_args()
+def iter_points(shapes_arg, lo, hi, geom_arg, ops, reps, words):
+    """yields one record per (shape, order, geometry, operator); device-resident arrays, CUDA-event timing"""
     nk = nekmf()
-    dev = torch.device("cuda", 0)
-    lo, hi = (a.nm.split("..") + [a.nm])[:2] if ".." in a.nm else (a.nm, a.nm)
+    dev = torch.device("cuda", torch.cuda.current_device())
     shapes = {"Quad": nk.eQuadrilateral, "Tri": nk.eTriangle, "Hex": nk.eHexahedron, "Prism": nk.ePrism,
               "Pyr": nk.ePyramid, "Tet": nk.eTetrahedron}
-    ops = list(OPS) if a.ops == "all" else a.ops.split(",")
     peak, peak_src = bench.measured_peaks()
     fp64_peak = bench.recorded("fp64_tflops_measured")  # DFMA microbenchmark, profiles/r01_fp64_peak.jsonl
     gen = torch.Generator(device=dev).manual_seed(1234)
-    out = open(a.out, "w") if a.out else None
-    for sname in a.shapes.split(","):
+    for sname in shapes_arg.split(","):
         shape = shapes[sname]
         for nm in range(int(lo), int(hi) + 1):
             std = nk.StdExpansion(shape, nm)
             dim, nmTot, nqTot = std.dim, std.GetNcoeffs(), std.GetTotPoints()
-            nel = a.words // (nmTot + nqTot)
+            nel = words // (nmTot + nqTot)
             nel = min(nel, int(24e9 / (8 * (dim * dim + 1) * nqTot)))
-            for gname in a.geom.split(","):
+            for gname in geom_arg.split(","):
                 deformed = gname == "deformed"
                 npt = nel * (nqTot if deformed else 1)
                 jac = torch.rand(npt, dtype=torch.float64, device=dev, generator=gen) + 0.5
@@ -104,13 +93,13 @@ def main():
                         o.SetLambda(1.0)
                     for _ in range(3):
                         o.apply(ins, outs)
-                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.reps + 1)]
+                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
                     ev[0].record()
-                    for i in range(a.reps):
+                    for i in range(reps):
                         o.apply(ins, outs)
                         ev[i + 1].record()
                     torch.cuda.synchronize()
-                    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(a.reps))
+                    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
                     ms = ts[len(ts) // 2]
                     by = algorithmic_bytes(opn, dim, nmTot, nqTot, deformed)
                     gbs = by * nel / (ms * 1e-3) / 1e9
@@ -121,10 +110,12 @@ def main():
                     fl = algorithmic_flops(opn, sname, nm, std.nq[0])
                     if fl is not None and fp64_peak:
                         tf = fl * nel / (ms * 1e-3) / 1e12
-                        # reference-algorithm flops: a kernel that does LESS work (coefficient-space Helmholtz) can
-                        # exceed 1.0 here; the bound that applies is the larger of the two fractions
+                        # flops of the REFERENCE's algorithm per second over the DFMA peak: a throughput ratio in the
+                        # reference's currency, NOT a pipe utilisation -- a kernel that needs fewer flops
+                        # (coefficient-space Helmholtz) exceeds 1.0 here.  Issued-flop fractions (frac_dmma below,
+                        # bench.py's roofline_fp64) are the roofline numbers.
                         rec.update({"flops_per_element_reference_algorithm": fl, "tflops": round(tf, 2),
-                                    "frac_fp64": round(tf / fp64_peak, 3),
+                                    "frac_fp64_of_reference_flops": round(tf / fp64_peak, 3),
                                     "bound": "fp64" if tf / fp64_peak > gbs / peak else "hbm"})
                     if o.kernel_name.startswith("dense_helm_kernel"):
                         # the DMMA GEMM actually issued: (8 MT) rows x (nT * 4 KS) padded columns per element,
@@ -142,17 +133,36 @@ def main():
                         tf = fl * nel / (ms * 1e-3) / 1e12
                         rec.update({"flops_per_element_issued": fl, "tflops": round(tf, 2),
                                     "frac_dmma": round(tf / 37.1, 3), "bound": "fp64"})
-                    line = json.dumps(rec)
-                    print(line, flush=True)
-                    if out:
-                        out.write(line + "\n")
-                        out.flush()
+                    yield rec
                     del ins, outs, o
                     coll.m_ops.pop(op)
                 del coll, geom, jac, df
                 torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shapes", default="Hex")
+    ap.add_argument("--nm", default="3..11")
+    ap.add_argument("--ops", default="all")
+    ap.add_argument("--geom", default="regular,deformed")
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--words", type=int, default=1 << 27, help="in+out doubles per apply (sets nElmt)")
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    lo, hi = (a.nm.split("..") + [a.nm])[:2] if ".." in a.nm else (a.nm, a.nm)
+    ops = list(OPS) if a.ops == "all" else a.ops.split(",")
+    out = open(a.out, "w") if a.out else None
+    for rec in iter_points(a.shapes, lo, hi, a.geom, ops, a.reps, a.words):
+        line = json.dumps(rec)
+        print(line, flush=True)
+        if out:
+            out.write(line + "\n")
+            out.flush()
     if out:
-        out.write(json.dumps({"hbm_peak_gb_per_s": peak, "peak_source": peak_src, "fp64_peak_tflops": fp64_peak}) + "\n")
+        peak, peak_src = bench.measured_peaks()
+        out.write(json.dumps({"hbm_peak_gb_per_s": peak, "peak_source": peak_src,
+                              "fp64_peak_tflops": bench.recorded("fp64_tflops_measured")}) + "\n")
         out.close()
 
 
