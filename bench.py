@@ -513,7 +513,13 @@ def main():
             return {"value": d.get("value"), "unit": d.get("unit"), "ms_per_step": d.get("ms_per_step"),
                     "workload": d.get("config", {}).get("workload"),
                     "roofline": {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "kernel") if k in r},
-                    "e2e": d.get("e2e", {}).get("value"), "cpu_baseline": (d.get("cpu_baseline") or {}).get("value")}
+                    "e2e": d.get("e2e", {}).get("value"), "cpu_baseline": (d.get("cpu_baseline") or {}).get("value"),
+                    **({"geometry_variants": {k: {kk: v[kk] for kk in ("workload", "value", "unit", "ms_per_step",
+                                                                       "frac_hbm_of_step")} |
+                                                  {"kernels": {sh: [ps["kernel"], round(ps["ms"], 4), round(ps["frac_hbm"], 3)]
+                                                               for sh, ps in v["per_shape"].items()}}
+                                              for k, v in d["geometry_variants"].items()}}
+                       if "geometry_variants" in d else {})}
 
         class _A:
             nx, steps, warmup = 64, 20, 3

@@ -6,8 +6,10 @@ itself), the per-order sweep (configs[2], tools/sweep.py) nor the sharded CG (co
             device CG iteration on the assembled problem.
   config 4  Tet and Prism (plus the hexahedra they are mixed with) Helmholtz apply at P=6 on a synthetic mixed
             mesh: an n^3 structured grid of cubes, 60 % kept as hexahedra, 30 % cut into 2 prisms, 10 % into 6
-            tetrahedra (equal element counts per shape), one collection per shape as CreateCollections forms
-            them (MultiRegions/ExpList.cpp:5005-5151).  All elements are affine (regular geometry).
+            tetrahedra, one collection per shape as CreateCollections forms them (MultiRegions/ExpList.cpp:
+            5005-5151).  Headline: the box-cut mesh (axis-aligned affine elements, extruded prisms -- the best
+            case of three special-case kernels); `geometry_variants` repeats the step on the same mesh under a
+            global rotation + shear (general affine elements) and under a smooth warp (deformed elements).
 
 Every line carries `roofline` (dominant kernel, algorithmic bytes of SURVEY.md 8(d)) and `cpu_baseline` (the
 reference's own kernels from oracle/_ref on a bounded sample, all host threads).  Imported by bench.py only."""
@@ -147,34 +149,141 @@ def affine_factors(edges):
     return float(np.linalg.det(J)), df
 
 
-def mixed_mesh(n, h):
-    """element geometry of the synthetic mixed mesh: returns {shape: (nElmt, jac[nElmt], df[9*nElmt])}.
-    Cube c (lexicographic) keeps its type by c mod 10: 0-5 hex, 6-8 two prisms, 9 six tetrahedra."""
-    ex, ey, ez = np.eye(3) * h
-    hexf = [affine_factors([ex, ey, ez])]
-    # prism reference: triangle in (xi_0, xi_2) extruded along xi_1; second prism is the point-reflected half
-    prf = [affine_factors([ex, ey, ez]), affine_factors([-ex, ey, -ez])]
-    tetf = []
-    for perm in itertools.permutations(range(3)):
-        e = [ex, ey, ez]
-        a, b, c = e[perm[0]], e[perm[1]], e[perm[2]]
-        v1, v2, v3 = a, a + b, a + b + c          # Kuhn simplex of this permutation
-        E = [v1, v2, v3]
-        if np.linalg.det(np.stack(E, axis=1)) < 0:
-            E = [v2, v1, v3]
-        tetf.append(affine_factors(E))
-    ncube = n ** 3
-    kinds = np.arange(ncube) % 10
-    counts = {"Hex": int((kinds < 6).sum()), "Prism": int(((kinds >= 6) & (kinds < 9)).sum()) * 2,
-              "Tet": int((kinds == 9).sum()) * 6}
+# a fixed global linear map (rotation about z by 0.3 rad, then a shear): turns the box-cut mesh into GENERAL affine
+# elements -- parallelepipeds with a full Laplacian metric, non-extruded prisms, skewed tetrahedra
+_c, _s = np.cos(0.3), np.sin(0.3)
+GENERAL_MAP = np.array([[1.0, 0.25, 0.10], [0.0, 1.0, 0.20], [0.15, 0.0, 1.0]]) @ np.array([[_c, -_s, 0.0], [_s, _c, 0.0], [0.0, 0.0, 1.0]])
+
+
+def element_frames(n, h, A=None):
+    """origin x0 [nel,3] and edge vectors E [nel,3(d),3(c)] of every element of the synthetic mixed mesh, per shape:
+    x = x0 + sum_d (xi_d + 1)/2 E_d.  Cube c (lexicographic) keeps its type by c mod 10: 0-5 hex, 6-8 two prisms,
+    9 six tetrahedra (Kuhn simplices).  A: optional global linear map applied to the whole mesh."""
+    c = np.arange(n ** 3)
+    corner = np.stack([c % n, (c // n) % n, c // (n * n)], axis=1) * h
+    kinds = c % 10
+    I3 = np.eye(3) * h
+    ex, ey, ez = I3
     out = {}
-    for name, fac in (("Hex", hexf), ("Prism", prf), ("Tet", tetf)):
-        nel = counts[name]
-        k = len(fac)
-        jac = np.tile(np.array([f[0] for f in fac]), nel // k)
-        df = np.tile(np.stack([f[1] for f in fac], axis=1), (1, nel // k))  # [9][nel]
-        out[name] = (nel, jac, np.ascontiguousarray(df).reshape(-1))
+    hx = corner[kinds < 6]
+    out["Hex"] = (hx, np.broadcast_to(np.stack([ex, ey, ez]), (hx.shape[0], 3, 3)).copy())
+    pc = corner[(kinds >= 6) & (kinds < 9)]
+    # prism reference: triangle in (xi_0, xi_2) extruded along xi_1; the second prism is the point-reflected half
+    px0 = np.stack([pc, pc + ex + ez], axis=1).reshape(-1, 3)
+    pE = np.broadcast_to(np.stack([np.stack([ex, ey, ez]), np.stack([-ex, ey, -ez])]), (pc.shape[0], 2, 3, 3)).reshape(-1, 3, 3).copy()
+    out["Prism"] = (px0, pE)
+    tc = corner[kinds == 9]
+    tE = []
+    for perm in itertools.permutations(range(3)):
+        a_, b_, c_ = I3[perm[0]], I3[perm[1]], I3[perm[2]]
+        E = [a_, a_ + b_, a_ + b_ + c_]          # Kuhn simplex of this permutation: vertices 0, E0, E1, E2
+        if np.linalg.det(np.stack(E, axis=1)) < 0:
+            E = [E[1], E[0], E[2]]
+        tE.append(np.stack(E))
+    out["Tet"] = (np.repeat(tc, 6, axis=0), np.broadcast_to(np.stack(tE), (tc.shape[0], 6, 3, 3)).reshape(-1, 3, 3).copy())
+    if A is not None:
+        out = {k: (x0 @ A.T, E @ A.T) for k, (x0, E) in out.items()}
     return out
+
+
+def mixed_mesh(n, h, A=None):
+    """regular (affine) geometric factors of the mixed mesh: {shape: (nElmt, jac[nElmt], df[9*nElmt])}
+    (GeomFactors.cpp:399-474: df[c*3+d] = d xi_d / d x_c, jac = det(dx/dxi))"""
+    out = {}
+    for name, (x0, E) in element_frames(n, h, A).items():
+        J = np.transpose(E, (0, 2, 1)) / 2.0        # J[e][c][d] = dx_c / dxi_d
+        Ji = np.linalg.inv(J)                        # Ji[e][d][c] = dxi_d / dx_c
+        df = np.stack([Ji[:, d, c_] for c_ in range(3) for d in range(3)])
+        out[name] = (x0.shape[0], np.linalg.det(J), np.ascontiguousarray(df).reshape(-1))
+    return out
+
+
+def mixed_mesh_deformed(n, h, std_of, torch, dev, A=None, amp=0.05):
+    """the same mesh warped by X = x + amp sin(pi x) sin(pi y) sin(pi z) (1,1,1): per-quadrature-point factors
+    {shape: (nElmt, jac[nElmt*nq], df[9*nElmt*nq])} w.r.t. the Cartesian reference coordinates xi (the collapsed
+    shapes' quadrature points are mapped eta -> xi first), computed on the device.  dX/dxi = (I + 1 g^T) J_e with
+    g = grad w, inverted with Sherman-Morrison."""
+    import math
+    out = {}
+    for name, (x0, E) in element_frames(n, h, A).items():
+        std = std_of[name]
+        z = [torch.tensor(std.basis[d].Z, dtype=torch.float64, device=dev) for d in range(3)]
+        e0, e1, e2 = torch.meshgrid(z[2], z[1], z[0], indexing="ij")[::-1]   # eta_0 fastest: [k][j][i]
+        if name == "Prism":
+            xi = [(1 + e0) * (1 - e2) / 2 - 1, e1, e2]
+        elif name == "Tet":
+            xi = [(1 + e0) * (1 - e1) * (1 - e2) / 4 - 1, (1 + e1) * (1 - e2) / 2 - 1, e2]
+        else:
+            xi = [e0, e1, e2]
+        T = torch.stack([(v.reshape(-1) + 1) / 2 for v in xi], dim=1)        # [nq, 3(d)]
+        x0t, Et = torch.tensor(x0, device=dev), torch.tensor(E, device=dev)   # [nel,3], [nel,3(d),3(c)]
+        X = x0t[:, None, :] + torch.einsum("qd,edc->eqc", T, Et)            # [nel, nq, 3]
+        sn, cs = torch.sin(math.pi * X), math.pi * torch.cos(math.pi * X)
+        g = amp * torch.stack([cs[..., 0] * sn[..., 1] * sn[..., 2], sn[..., 0] * cs[..., 1] * sn[..., 2],
+                               sn[..., 0] * sn[..., 1] * cs[..., 2]], dim=-1)  # grad w, [nel, nq, 3]
+        J = torch.transpose(Et, 1, 2) / 2.0                                   # [nel, c, d]
+        Ji = torch.linalg.inv(J)                                              # [nel, d, c]
+        sg = 1.0 + g.sum(-1)                                                  # det(I + 1 g^T)
+        jac = torch.linalg.det(J)[:, None] * sg
+        # inv(dX/dxi) = Ji (I - 1 g^T / (1 + sum g)):  inv[d][c] = Ji[d][c] - (sum_c' Ji[d][c']) g_c / sg
+        rs = Ji.sum(-1)                                                       # [nel, d]
+        inv = Ji[:, None, :, :] - rs[:, None, :, None] * (g / sg[..., None])[:, :, None, :]   # [nel, nq, d, c]
+        df = torch.stack([inv[:, :, d, c_] for c_ in range(3) for d in range(3)])             # [9, nel, nq]
+        out[name] = (x0.shape[0], jac.reshape(-1).contiguous(), df.reshape(-1).contiguous())
+    return out
+
+
+SHAPES4 = ("Hex", "Prism", "Tet")
+
+
+def _mixed_operators(torch, nk, mesh, nm, deformed, gen, dev):
+    shp = {"Hex": nk.eHexahedron, "Prism": nk.ePrism, "Tet": nk.eTetrahedron}
+    ops, bufs = {}, {}
+    for name in SHAPES4:
+        nel, jac, df = mesh[name]
+        std = nk.StdExpansion(shp[name], nm)
+        op = nk.Operator(std, nel, nk.CoalescedGeomData(jac, df, deformed), nk.eHelmholtz)
+        op.SetLambda(LAMBDA)
+        x = torch.rand(nel * std.GetNcoeffs(), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+        ops[name], bufs[name] = op, (x, torch.empty_like(x), std)
+    return ops, bufs
+
+
+def _mixed_step_ms(torch, ops, bufs, steps):
+    """one step = the three collections back to back (what ExpList::GeneralMatrixOp does), timed as a whole"""
+    for name in SHAPES4:
+        for _ in range(3):
+            ops[name].apply([bufs[name][0]], [bufs[name][1]])
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        for name in SHAPES4:
+            x, y, _ = bufs[name]
+            ops[name].apply([x], [y])
+    ev1.record()
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1) / steps
+
+
+def _geometry_variant(torch, nk, peak, mesh, nm, deformed, gen, dev, steps, workload):
+    """the mixed-mesh step on another geometry: per-shape kernels and times, aggregate GDOF/s, HBM fraction of the step"""
+    ops, bufs = _mixed_operators(torch, nk, mesh, nm, deformed, gen, dev)
+    per = {}
+    for name in SHAPES4:
+        x, y, std = bufs[name]
+        _, avg = _time_apply(torch, ops[name], [x], [y], max(3, steps // 2))
+        nq = std.GetTotPoints()
+        by = 8 * (2 * std.GetNcoeffs() + 10 * (nq if deformed else 1))
+        nel = mesh[name][0]
+        per[name] = {"elements": nel, "ms": avg, "gdof_per_s": nel * std.GetNcoeffs() / (avg * 1e-3) / 1e9,
+                     "algorithmic_bytes_per_element": by, "frac_hbm": by * nel / (avg * 1e-3) / 1e9 / peak,
+                     "kernel": ops[name].kernel_name}
+    step_ms = _mixed_step_ms(torch, ops, bufs, steps)
+    ndof = sum(mesh[n_][0] * bufs[n_][2].GetNcoeffs() for n_ in SHAPES4)
+    by_step = sum(per[n_]["algorithmic_bytes_per_element"] * per[n_]["elements"] for n_ in SHAPES4)
+    return {"workload": workload, "value": ndof / (step_ms * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_step": step_ms,
+            "frac_hbm_of_step": by_step / (step_ms * 1e-3) / 1e9 / peak, "per_shape": per}
 
 
 def config4(args, torch, nk, po, peak, peak_src, ClockSampler):
@@ -182,16 +291,9 @@ def config4(args, torch, nk, po, peak, peak_src, ClockSampler):
     nm, n = 7, args.nx if args.nx != 64 else 60
     mesh = mixed_mesh(n, 1.0 / n)
     shapes = {"Hex": (nk.eHexahedron, po.HEX), "Prism": (nk.ePrism, po.PRISM), "Tet": (nk.eTetrahedron, po.TET)}
-    per, ops, bufs = {}, {}, {}
+    per = {}
     gen = torch.Generator(device=dev).manual_seed(1234)
-    for name, (nshape, _) in shapes.items():
-        nel, jac, df = mesh[name]
-        std = nk.StdExpansion(nshape, nm)
-        op = nk.Operator(std, nel, nk.CoalescedGeomData(jac, df, False), nk.eHelmholtz)
-        op.SetLambda(LAMBDA)
-        x = torch.rand(nel * std.GetNcoeffs(), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
-        y = torch.empty_like(x)
-        ops[name], bufs[name] = op, (x, y, std)
+    ops, bufs = _mixed_operators(torch, nk, mesh, nm, False, gen, dev)
     sampler = ClockSampler(0)
     sampler.start()
     for name in shapes:
@@ -219,17 +321,7 @@ def config4(args, torch, nk, po, peak, peak_src, ClockSampler):
                               "tflops": fl * nel / (avg * 1e-3) / 1e12, "frac_dmma": fl * nel / (avg * 1e-3) / 1e12 / 37.1,
                               "dmma_peak_tflops": 37.1})
     clocks = sampler.stop()
-    # one step = the three collections back to back (what ExpList::GeneralMatrixOp does), timed as a whole
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(args.steps):
-        for name in shapes:
-            x, y, _ = bufs[name]
-            ops[name].apply([x], [y])
-    ev1.record()
-    torch.cuda.synchronize()
-    step_ms = ev0.elapsed_time(ev1) / args.steps
+    step_ms = _mixed_step_ms(torch, ops, bufs, args.steps)
     ndof = sum(p["elements"] * p["ncoeffs"] for p in per.values())
     dom = max(per, key=lambda k: per[k]["ms"])
     # CPU baseline: the same three collections, a bounded sample of each, aggregated by DOF / time
@@ -242,7 +334,25 @@ def config4(args, torch, nk, po, peak, peak_src, ClockSampler):
                                                 df.reshape(9, -1)[:, :ns].reshape(-1).copy(), seconds=3.0)
         cpu_dof += ns * per[name]["ncoeffs"] * (nel / ns)
         cpu_t += t * (nel / ns)
+    # the same mesh with GENERAL geometry: (i) a global rotation + shear (full metric, non-extruded prisms, skewed
+    # tetrahedra), (ii) warped by a smooth displacement (per-quadrature-point factors) on a smaller grid
+    del ops, bufs
+    torch.cuda.empty_cache()
+    geo = {}
+    geo["general_affine"] = _geometry_variant(
+        torch, nk, peak, mixed_mesh(n, 1.0 / n, GENERAL_MAP), nm, False, gen, dev, args.steps,
+        "same %d^3 mixed mesh under a global rotation + shear: general affine elements (full Laplacian metric)" % n)
+    torch.cuda.empty_cache()
+    nd = min(n, 40)
+    shp = {"Hex": nk.eHexahedron, "Prism": nk.ePrism, "Tet": nk.eTetrahedron}
+    std_of = {k: nk.StdExpansion(v, nm) for k, v in shp.items()}
+    geo["deformed"] = _geometry_variant(
+        torch, nk, peak, mixed_mesh_deformed(nd, 1.0 / nd, std_of, torch, dev, GENERAL_MAP), nm, True, gen, dev,
+        max(3, args.steps // 2),
+        "%d^3 mixed mesh, rotation + shear + smooth warp 0.05 sin sin sin: factors per quadrature point" % nd)
+    torch.cuda.empty_cache()
     return {
+        "geometry_variants": geo,
         "metric": "GDOF/s FP64 Helmholtz apply (mixed Hex/Prism/Tet mesh, P=6)", "value": ndof / (step_ms * 1e-3) / 1e9,
         "unit": "GDOF/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

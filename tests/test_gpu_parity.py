@@ -636,3 +636,46 @@ def test_segment_operators(nm, nq0, coordim, deformed):
         check(out, el.iproductwrtderivbase(nel, deformed, jac, df, f), "IProductWRTDerivBaseSeg")
     with pytest.raises(nk.NekError):
         coll.Initialise(nk.eHelmholtz)  # no (eSegment, eHelmholtz) operator in the reference either
+
+
+@pytest.mark.parametrize("geometry", ["box_cut", "general_affine", "deformed"])
+def test_config4_mixed_mesh_against_oracle(geometry):
+    """BASELINE configs[3] on the ACTUAL synthetic mixed mesh of bench_configs.py (3^3 cubes: 18 hexahedra, 14 prisms,
+    12 tetrahedra, P=6): box-cut (axis-aligned affine elements, extruded prisms), under a global rotation + shear
+    (general affine: full metric, non-extruded prisms) and warped (per-point factors); every collection against the
+    oracle, all five operators' worth of geometry exercised through Helmholtz + IProductWRTBase + PhysDeriv"""
+    import bench_configs as bc
+    torch = _torch()
+    nk = nekmf()
+    nm, n, lam = 7, 3, 1.0
+    shp = {"Hex": (nk.eHexahedron, po.HEX), "Prism": (nk.ePrism, po.PRISM), "Tet": (nk.eTetrahedron, po.TET)}
+    std_of = {k: nk.StdExpansion(v[0], nm) for k, v in shp.items()}
+    deformed = geometry == "deformed"
+    if geometry == "box_cut":
+        mesh = bc.mixed_mesh(n, 1.0 / n)
+    elif geometry == "general_affine":
+        mesh = bc.mixed_mesh(n, 1.0 / n, bc.GENERAL_MAP)
+    else:
+        mesh = {k: (v[0], v[1].cpu().numpy(), v[2].cpu().numpy()) for k, v in
+                bc.mixed_mesh_deformed(n, 1.0 / n, std_of, torch, torch.device("cuda"), bc.GENERAL_MAP).items()}
+    rng = np.random.default_rng(5)
+    kernels = set()
+    for name, (nshape, pshape) in shp.items():
+        nel, jac, df = mesh[name]
+        el = po.Elem(pshape, nm, nm + 1)
+        geom = nk.CoalescedGeomData(jac, df, deformed)
+        x = rng.uniform(-1, 1, nel * el.nmTot)
+        f = rng.uniform(-1, 1, nel * el.nqTot)
+        coll = nk.Collection(std_of[name], nel, geom)
+        out = np.zeros(nel * el.nmTot)
+        coll.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
+        assert max(rel_errs(out, el.helmholtz(nel, deformed, jac, df, lam, x))) < 1e-12, (name, geometry)
+        kernels.add(coll.m_ops[nk.eHelmholtz].kernel_name)
+        out2 = np.zeros(nel * el.nmTot)
+        coll.ApplyOperator(nk.eIProductWRTBase, f, out2)
+        assert max(rel_errs(out2, el.iproduct(nel, deformed, jac, f))) < 1e-12
+        d = [np.zeros(nel * el.nqTot) for _ in range(3)]
+        coll.ApplyOperator(nk.ePhysDeriv, f, *d)
+        for g, w in zip(d, el.physderiv(nel, deformed, df, f)):
+            assert max(rel_errs(g, w)) < 1e-12
+    assert len(kernels) == 3
