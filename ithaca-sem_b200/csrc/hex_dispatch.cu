@@ -31,6 +31,7 @@ bool select_hex_fast(nekmf_op_s *op)
     }
     // regular Helmholtz: add the coefficient-space kernel (used when the metric is diagonal)
     if (ok) kron_maybe_wrap(op);
+    if (ok) hex_dmma_maybe_wrap(op); // nm = 7 BwdTrans / IProductWRTBase: tensor-core tiles
     return ok;
 }
 

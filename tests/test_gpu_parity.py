@@ -679,3 +679,45 @@ def test_config4_mixed_mesh_against_oracle(geometry):
         for g, w in zip(d, el.physderiv(nel, deformed, df, f)):
             assert max(rel_errs(g, w)) < 1e-12
     assert len(kernels) == 3
+
+
+@pytest.mark.parametrize("nel", [1, 2, 37, 4096 + 3])
+@pytest.mark.parametrize("deformed", [False, True])
+def test_hex_dmma_nm7_bwd_iprod(nel, deformed, monkeypatch):
+    """the tensor-core (DMMA m8n8k4, two contractions chained in registers) BwdTrans / IProductWRTBase at nm = 7,
+    nq = 8 (hex_dmma.cu): against the oracle and against the DFMA kernel it replaces (NEKMF_HEX_DMMA=0), odd element
+    counts (the single-element tail), caller arrays that are only 8-byte aligned"""
+    torch = _torch()
+    nk = nekmf()
+    rng = np.random.default_rng(nel)
+    nm, nq = 7, 8
+    el = po.Elem(po.HEX, nm, nq)
+    std = nk.StdExpansion(nk.eHexahedron, nm, nq)
+    jac, df = random_geometry(rng, 3, nel, el.nqTot, deformed)
+    geom = nk.CoalescedGeomData(jac, df, deformed)
+    c = rng.uniform(-1, 1, nel * el.nmTot)
+    f = rng.uniform(-1, 1, nel * el.nqTot)
+    want_b, want_i = el.bwdtrans(nel, c), el.iproduct(nel, deformed, jac, f)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NEKMF_HEX_DMMA", mode)
+        bwd, ipr = nk.Operator(std, nel, geom, nk.eBwdTrans), nk.Operator(std, nel, geom, nk.eIProductWRTBase)
+        assert ("hex_dmma_kernel" in bwd.kernel_name) == (mode == "1"), bwd.kernel_name
+        assert ("hex_dmma_kernel" in ipr.kernel_name) == (mode == "1"), ipr.kernel_name
+        ob, oi = np.zeros(nel * el.nqTot), np.zeros(nel * el.nmTot)
+        bwd.apply([c], [ob])
+        ipr.apply([f], [oi])
+        assert max(rel_errs(ob, want_b)) < 1e-12 and max(rel_errs(oi, want_i)) < 1e-12
+        # device arrays at an odd offset (8-byte aligned only)
+        cd = torch.zeros(c.size + 1, dtype=torch.float64, device="cuda")
+        cd[1:] = torch.tensor(c, device="cuda")
+        od = torch.zeros(ob.size + 1, dtype=torch.float64, device="cuda")
+        bwd.apply([cd[1:]], [od[1:]])
+        fd = torch.zeros(f.size + 1, dtype=torch.float64, device="cuda")
+        fd[1:] = torch.tensor(f, device="cuda")
+        oid = torch.zeros(oi.size + 1, dtype=torch.float64, device="cuda")
+        ipr.apply([fd[1:]], [oid[1:]])
+        torch.cuda.synchronize()
+        assert np.array_equal(od[1:].cpu().numpy(), ob) and np.array_equal(oid[1:].cpu().numpy(), oi)
+        res[mode] = (ob, oi)
+    assert max(rel_errs(res["1"][0], res["0"][0])) < 1e-13 and max(rel_errs(res["1"][1], res["0"][1])) < 1e-13
