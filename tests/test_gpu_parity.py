@@ -681,16 +681,17 @@ def test_config4_mixed_mesh_against_oracle(geometry):
     assert len(kernels) == 3
 
 
-@pytest.mark.parametrize("nel", [1, 2, 37, 4096 + 3])
+@pytest.mark.parametrize("nm,nel", [(7, 1), (7, 2), (7, 37), (7, 4096 + 3), (8, 37), (9, 1), (9, 38), (10, 37), (11, 2),
+                                    (11, 1001)])
 @pytest.mark.parametrize("deformed", [False, True])
-def test_hex_dmma_nm7_bwd_iprod(nel, deformed, monkeypatch):
-    """the tensor-core (DMMA m8n8k4, two contractions chained in registers) BwdTrans / IProductWRTBase at nm = 7,
-    nq = 8 (hex_dmma.cu): against the oracle and against the DFMA kernel it replaces (NEKMF_HEX_DMMA=0), odd element
-    counts (the single-element tail), caller arrays that are only 8-byte aligned"""
+def test_hex_dmma_bwd_iprod(nm, nel, deformed, monkeypatch):
+    """the tensor-core (DMMA m8n8k4, two contractions chained in registers) BwdTrans / IProductWRTBase at nm = 7..11,
+    nq = nm + 1 (hex_dmma.cu): against the oracle and against the DFMA kernel it replaces (NEKMF_HEX_DMMA=0), odd
+    element counts (the single-element tail), caller arrays that are only 8-byte aligned"""
     torch = _torch()
     nk = nekmf()
     rng = np.random.default_rng(nel)
-    nm, nq = 7, 8
+    nq = nm + 1
     el = po.Elem(po.HEX, nm, nq)
     std = nk.StdExpansion(nk.eHexahedron, nm, nq)
     jac, df = random_geometry(rng, 3, nel, el.nqTot, deformed)
@@ -699,11 +700,11 @@ def test_hex_dmma_nm7_bwd_iprod(nel, deformed, monkeypatch):
     f = rng.uniform(-1, 1, nel * el.nqTot)
     want_b, want_i = el.bwdtrans(nel, c), el.iproduct(nel, deformed, jac, f)
     res = {}
-    for mode in ("1", "0"):
+    for mode in ("all", "0"):
         monkeypatch.setenv("NEKMF_HEX_DMMA", mode)
         bwd, ipr = nk.Operator(std, nel, geom, nk.eBwdTrans), nk.Operator(std, nel, geom, nk.eIProductWRTBase)
-        assert ("hex_dmma_kernel" in bwd.kernel_name) == (mode == "1"), bwd.kernel_name
-        assert ("hex_dmma_kernel" in ipr.kernel_name) == (mode == "1"), ipr.kernel_name
+        assert ("hex_dmma_kernel" in bwd.kernel_name) == (mode == "all"), bwd.kernel_name
+        assert ("hex_dmma_kernel" in ipr.kernel_name) == (mode == "all"), ipr.kernel_name
         ob, oi = np.zeros(nel * el.nqTot), np.zeros(nel * el.nmTot)
         bwd.apply([c], [ob])
         ipr.apply([f], [oi])
@@ -720,4 +721,4 @@ def test_hex_dmma_nm7_bwd_iprod(nel, deformed, monkeypatch):
         torch.cuda.synchronize()
         assert np.array_equal(od[1:].cpu().numpy(), ob) and np.array_equal(oid[1:].cpu().numpy(), oi)
         res[mode] = (ob, oi)
-    assert max(rel_errs(res["1"][0], res["0"][0])) < 1e-13 and max(rel_errs(res["1"][1], res["0"][1])) < 1e-13
+    assert max(rel_errs(res["all"][0], res["0"][0])) < 1e-13 and max(rel_errs(res["all"][1], res["0"][1])) < 1e-13
