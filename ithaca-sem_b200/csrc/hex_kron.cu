@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(KronCfg<NM, GATHER, WSEL>::T, 1)
 } // namespace nekmf
 #include "hex_kron_full.cuh"
 #include "hex_kron_rows.cuh"
+#include "hex_kron_fullrows.cuh"
 #include "hex_kron_lane.cuh"
 namespace nekmf
 {
@@ -432,7 +433,7 @@ struct KronState
     double *d_geo8 = nullptr; // full constant metric (non-diagonal collections)
     bool use_full  = false;
     bool sparse_full = false; // K, M and S all have the modified-basis sparsity patterns
-    bool rows_kind   = false; // nm = 7..10: row-streaming kernel (diagonal metric only, no fused gather, no full metric)
+    bool rows_kind   = false; // nm = 7..10: row-streaming kernels (diagonal metric: hex_kron_rows.cuh, full metric: hex_kron_fullrows.cuh; no fused gather)
     int blocks_per_sm_full = 0;
     int blocks_per_sm = 0, blocks_per_sm_lane = 0;
     int bps_slot[2][2] = {{0, 0}, {0, 0}}; // [gather][8-warp variant]
@@ -500,9 +501,37 @@ template <int NM> static int kron_full_launch(nekmf_op_s *op, KronState *st, con
     return NEKMF_OK;
 }
 
+template <int NM, bool DIAG> static int kron_fullrows_launch(nekmf_op_s *op, KronState *st, const double *in, double *out)
+{
+    using Cfg = KronFullRowsCfg<NM>;
+    auto kern = hex_helm_kronfullrows_kernel<NM, DIAG>;
+    if (st->blocks_per_sm_full == 0)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int nb = 0;
+        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
+        if (nb < 1) { set_error("full-metric row-streaming kron kernel does not fit on an SM"); return NEKMF_ERR_CUDA; }
+        st->blocks_per_sm_full = nb;
+    }
+    KronFullArgs a;
+    a.in = in; a.out = out; a.geo8 = st->d_geo8 + (size_t)op->run_e0 * 8; a.nElmt = op->run_ne; a.lambda = op->lambda;
+    a.io_aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
+    const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
+    int grid           = st->blocks_per_sm_full * NUM_SMS;
+    if (grid > nBatches) grid = nBatches;
+    if (grid < 1) return NEKMF_OK;
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(*static_cast<const KronFullTab<NM> *>(st->tab_full), a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+
 template <int NM> static int kron_rows_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
 {
     KronState *st = static_cast<KronState *>(op->kstate);
+    if (st->use_full && !op->gather_map)
+        return st->use_kron ? kron_fullrows_launch<NM, true>(op, st, in[0], out[0]) : kron_fullrows_launch<NM, false>(op, st, in[0], out[0]);
     if (!st->use_kron || op->gather_map)
     {
         if (op->gather_map) { set_error("fused gather requested from a kernel that does not provide it"); return NEKMF_ERR_ARG; }
@@ -687,8 +716,29 @@ template <int NM> static void kron_rows_wrap(nekmf_op_s *op)
         delete tab;
         return;
     }
+    // full-metric kernel (hex_kron_fullrows.cuh): the mixed matrix S and its sparsity pattern
+    auto *tabf = new KronFullTab<NM>;
+    memcpy(tabf->Ms, tab->Ms, sizeof(tab->Ms));
+    memcpy(tabf->Ks, tab->Ks, sizeof(tab->Ks));
+    double smax = 0.0, soff = 0.0;
+    for (int a = 0; a < NM; ++a)
+        for (int c = 0; c < NM; ++c)
+        {
+            double sv = 0.0;
+            for (int i = 0; i < nq; ++i) sv += dB[a * nq + i] * w[i] * B[c * nq + i];
+            tabf->S[a * NM + c] = sv;
+            if (fr_snz(a, c)) smax = std::fmax(smax, std::fabs(sv)); else soff = std::fmax(soff, std::fabs(sv));
+        }
+    const char *vfr = getenv("NEKMF_HEX_KRON_FULLROWS"); // =0: sheared elements stay on the quadrature-space kernel (A/B)
+    if (!(soff <= 1e-14 * smax) || (vfr && vfr[0] == '0'))
+    {
+        delete tabf;
+        tabf = nullptr;
+    }
     KronState *st      = new KronState;
     st->tab            = tab;
+    st->tab_full       = tabf;
+    st->sparse_full    = tabf != nullptr;
     st->sparse_k       = true;
     st->rows_kind      = true;
     st->fallback       = op->launch;
@@ -700,7 +750,9 @@ template <int NM> static void kron_rows_wrap(nekmf_op_s *op)
         KronState *s = static_cast<KronState *>(p);
         if (s->fallback_state && s->fallback_free) s->fallback_free(s->fallback_state);
         delete static_cast<KronTab<NM> *>(s->tab);
+        delete static_cast<KronFullTab<NM> *>(s->tab_full);
         cudaFree(s->d_geo4);
+        cudaFree(s->d_geo8);
         delete s;
     };
     op->launch = kron_rows_launch<NM>;
@@ -748,13 +800,34 @@ int kron_geom_changed(nekmf_op_s *op)
     NEKMF_CUDA(cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost));
     cudaFree(d_flag);
     st->use_full = false;
+    st->blocks_per_sm_full = 0; // the full-metric kernel variant may change with the geometry
     if (st->rows_kind)
     {
+        char name[96];
         if (flag == 0)
         {
             st->use_kron = true;
-            char name[96];
             snprintf(name, sizeof(name), "hex_helm_kronrows_kernel<nm=%d>(regular,diagonal metric)", op->nm[0]);
+            op->kname = name;
+        }
+        // the one-intermediate-at-a-time kernel (hex_kron_fullrows.cuh): sheared elements, and -- with the S terms
+        // compiled out -- axis-aligned ones where it measured faster than hex_kron_rows.cuh
+        const char *vd     = getenv("NEKMF_HEX_KRON_DIAGROWS"); // =1 / =0: force / forbid it for diagonal metrics (A/B)
+        // diagonal metric, measured against hex_kron_rows.cuh (profiles/r02_sweep_hex_diagrows_*.jsonl, fraction of the
+        // HBM peak): nm = 7: 0.72 / 0.46, 8: 0.30 / 0.30, 9: 0.25 / 0.19, 10: 0.41 / 0.29
+        const bool diag_fr = vd ? vd[0] == '1' : op->nm[0] != 8;
+        // full metric, measured against the quadrature-space kernel (profiles/r02_sweep_hex_fullrows_*.jsonl):
+        // 3.1x / 1.3x / 1.2x faster at nm = 7 / 8 / 9, 0.87x at nm = 10 (kept on the quadrature-space kernel)
+        const bool full_fr = flag != 0 && op->nm[0] <= 9;
+        if (st->tab_full && (full_fr || (flag == 0 && diag_fr)))
+        {
+            if (!st->d_geo8) NEKMF_CUDA(cudaMalloc(&st->d_geo8, (size_t)op->nElmt * 8 * 8));
+            kron_prepare_full_kernel<<<(op->nElmt + 255) / 256, 256>>>(op->d_jac, op->d_df, op->nElmt, st->d_geo8);
+            ++g_launches;
+            NEKMF_CUDA(cudaGetLastError());
+            st->use_full = true;
+            snprintf(name, sizeof(name), "hex_helm_kronfullrows_kernel<nm=%d,%s>(regular,%s metric)", op->nm[0],
+                     flag == 0 ? "diag" : "full", flag == 0 ? "diagonal" : "full");
             op->kname = name;
         }
         return NEKMF_OK;

@@ -248,9 +248,10 @@ def test_hex_helmholtz_coefficient_space_kernel(nm, nel):
     out = np.zeros(nel * el.nmTot)
     coll2.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: 1.0})
     check(out, el.helmholtz(nel, False, jac2, df2, 1.0, x), "Helmholtz(full metric)")
-    # a sheared / rotated affine collection takes the full-metric coefficient-space kernel (nm <= 6; above, the
-    # row-streaming kernel of nm = 7..10 handles diagonal metrics only and the quadrature-space kernel runs)
-    assert ("kronfull" in coll2.m_ops[nk.eHelmholtz].kernel_name) == (nm <= 6)
+    # a sheared / rotated affine collection takes the full-metric coefficient-space kernels (hex_kron_full.cuh up to
+    # nm = 6, hex_kron_fullrows.cuh at nm = 7..9; at nm = 10 the quadrature-space kernel measured faster)
+    kn = coll2.m_ops[nk.eHelmholtz].kernel_name
+    assert ("kronfull" in kn) == (nm <= 9) and ("kronfullrows" in kn) == (7 <= nm <= 9), kn
     for lam in (0.0, 37.5):
         coll2.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
         check(out, el.helmholtz(nel, False, jac2, df2, lam, x), "Helmholtz(full metric, lambda %g)" % lam)
