@@ -388,16 +388,206 @@ template <int NM> static void hex_dmma_wrap(nekmf_op_s *op)
     op->kname = name;
 }
 
+// ------------------------------------------------------------------------------------------------ PhysDeriv, nq = 8
+// PhysDeriv on REGULAR hexahedra at nm = 7 (MatrixFreeOps/PhysDerivKernels.hpp:219-372): out_c = sum_d df[3c+d] du/dxi_d.
+// Lane (g, t) reads the element's values in the C-fragment layout, u[k][j = g][i = 2t, 2t+1] for all eight planes k
+// (one 16-byte shared-memory load per plane).  Per plane:
+//   d/dxi_0 (contract i): the lane's two values ARE the A operand of two k-steps whose contracted index is ordered
+//            i = (2t | 2t + 1); the B operand is the matching pair of rows of D, fixed registers.  No extra load.
+//   d/dxi_1 (contract j): A = D^T (fixed registers), B = the plane in the fragment layout u[j = 4s + t][i = g]
+//            (two 8-byte loads, 32 consecutive doubles per k-step: conflict-free).
+//   d/dxi_2 (contract k): the whole k-line of the lane's two points is in its registers: plain DFMA.
+// All three results come out in the SAME layout (j = g, i = 2t, 2t+1), so the 3 x 3 constant factors are applied in
+// registers and the three outputs leave as 16-byte stores, 512 contiguous bytes per warp instruction.  Shared memory
+// is touched to read the input only (3 loads per plane and lane; the pencil kernel makes three passes).
+struct HexDmmaPdTab
+{
+    double D[64]; // D[a*8 + b] = dh_a/dz(z_b)
+};
+struct HexDmmaPdArgs
+{
+    const double *in;
+    double *out0, *out1, *out2;
+    const double *df; // [9][dfStride]
+    size_t dfStride;
+    int nElmt;
+    int in_aligned, out_aligned; // 16-byte aligned
+};
+struct HexDmmaPdCfg
+{
+    static constexpr int NQ = 8, NQ3 = 512, BUF = 2 * NQ3, PER_WARP = 2 * BUF + 2, WARPS = 12, T = WARPS * 32;
+    static constexpr size_t SMEM = (size_t)WARPS * PER_WARP * 8 + 16;
+};
+
+__global__ void __launch_bounds__(HexDmmaPdCfg::T, 1)
+    hex_dmma_pd_kernel(const __grid_constant__ HexDmmaPdTab tab, const __grid_constant__ HexDmmaPdArgs args)
+{
+    using Cfg = HexDmmaPdCfg;
+    constexpr int NQ = Cfg::NQ, NQ3 = Cfg::NQ3, BUF = Cfg::BUF;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = lane & 3, g = lane >> 2;
+    double *wbase = reinterpret_cast<double *>(smem_raw) + (size_t)warp * Cfg::PER_WARP;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wbase + 2 * BUF);
+
+    const int nPairs = (args.nElmt + 1) / 2;
+    const int GW = gridDim.x * Cfg::WARPS, gw = blockIdx.x * Cfg::WARPS + warp;
+    if (lane == 0)
+    {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    auto pair_ne = [&](int pr) { return args.nElmt - 2 * pr >= 2 ? 2 : 1; };
+    auto tma_ok  = [&](int pr) { return args.in_aligned && pair_ne(pr) == 2; };
+    auto issue   = [&](int pr, int slot) { // lane 0
+        if (!tma_ok(pr)) return;
+        mbar_expect_tx(bar + slot, (uint32_t)(BUF * 8));
+        tma_load_1d(wbase + slot * BUF, args.in + (size_t)pr * BUF, (uint32_t)(BUF * 8), bar + slot);
+    };
+    // fixed fragments of the collocation derivative matrix
+    const double b00 = tab.D[(2 * t) * NQ + g], b01 = tab.D[(2 * t + 1) * NQ + g]; // d/dxi_0: B[kk = t][n = g], i = 2t | 2t+1
+    const double a10 = tab.D[t * NQ + g], a11 = tab.D[(4 + t) * NQ + g];           // d/dxi_1: A[m = g][kk = t], j = t | 4+t
+
+    uint32_t phase[2] = {0, 0};
+    int slot          = 0;
+    if (lane == 0 && gw < nPairs) issue(gw, 0);
+    for (int pr = gw; pr < nPairs; pr += GW, slot ^= 1)
+    {
+        const int ne = pair_ne(pr);
+        double *sIn  = wbase + slot * BUF;
+        if (lane == 0 && pr + GW < nPairs) issue(pr + GW, slot ^ 1); // the other buffer was consumed one trip ago
+        if (tma_ok(pr))
+        {
+            mbar_wait(bar + slot, phase[slot]);
+            phase[slot] ^= 1;
+        }
+        else
+        {
+            const double *src = args.in + (size_t)pr * BUF;
+            for (int i = lane; i < ne * NQ3; i += 32) sIn[i] = __ldg(src + i);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int e = 0; e < ne; ++e)
+        {
+            const size_t el = (size_t)pr * 2 + e;
+            const double *U = sIn + e * NQ3;
+            double f[9];
+#pragma unroll
+            for (int n = 0; n < 9; ++n) f[n] = __ldg(args.df + (size_t)n * args.dfStride + el);
+            double2 u[NQ];
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) u[k] = *reinterpret_cast<const double2 *>(U + k * (NQ * NQ) + g * NQ + 2 * t);
+            const size_t o = el * NQ3 + g * NQ + 2 * t;
+#pragma unroll
+            for (int k = 0; k < NQ; ++k)
+            {
+                double d0x = 0.0, d0y = 0.0, d1x = 0.0, d1y = 0.0;
+                dm_mma(d0x, d0y, u[k].x, b00);
+                dm_mma(d0x, d0y, u[k].y, b01);
+                const double q0 = U[k * (NQ * NQ) + t * NQ + g], q1 = U[k * (NQ * NQ) + (4 + t) * NQ + g];
+                dm_mma(d1x, d1y, a10, q0);
+                dm_mma(d1x, d1y, a11, q1);
+                double d2x = tab.D[k] * u[0].x, d2y = tab.D[k] * u[0].y;
+#pragma unroll
+                for (int m = 1; m < NQ; ++m)
+                {
+                    d2x = fma(tab.D[m * NQ + k], u[m].x, d2x);
+                    d2y = fma(tab.D[m * NQ + k], u[m].y, d2y);
+                }
+                const double2 r0 = make_double2(fma(f[2], d2x, fma(f[1], d1x, f[0] * d0x)), fma(f[2], d2y, fma(f[1], d1y, f[0] * d0y)));
+                const double2 r1 = make_double2(fma(f[5], d2x, fma(f[4], d1x, f[3] * d0x)), fma(f[5], d2y, fma(f[4], d1y, f[3] * d0y)));
+                const double2 r2 = make_double2(fma(f[8], d2x, fma(f[7], d1x, f[6] * d0x)), fma(f[8], d2y, fma(f[7], d1y, f[6] * d0y)));
+                const size_t ok = o + k * (NQ * NQ);
+                if (args.out_aligned)
+                {
+                    *reinterpret_cast<double2 *>(args.out0 + ok) = r0;
+                    *reinterpret_cast<double2 *>(args.out1 + ok) = r1;
+                    *reinterpret_cast<double2 *>(args.out2 + ok) = r2;
+                }
+                else
+                {
+                    args.out0[ok] = r0.x; args.out0[ok + 1] = r0.y;
+                    args.out1[ok] = r1.x; args.out1[ok + 1] = r1.y;
+                    args.out2[ok] = r2.x; args.out2[ok + 1] = r2.y;
+                }
+            }
+        }
+        __syncwarp(); // every lane is done with this buffer before lane 0 refills it
+    }
+}
+
+struct HexDmmaPdState
+{
+    HexDmmaPdTab tab;
+    void *fallback_state          = nullptr;
+    void (*fallback_free)(void *) = nullptr;
+    int bps                       = 0;
+};
+
+static int hex_dmma_pd_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
+{
+    auto *st  = static_cast<HexDmmaPdState *>(op->kstate);
+    using Cfg = HexDmmaPdCfg;
+    auto kern = hex_dmma_pd_kernel;
+    if (st->bps == 0)
+    {
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int nb = 0;
+        NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
+        if (nb < 1) { set_error("hex DMMA PhysDeriv kernel does not fit on an SM"); return NEKMF_ERR_CUDA; }
+        st->bps = nb;
+    }
+    HexDmmaPdArgs a;
+    a.in = in[0]; a.out0 = out[0]; a.out1 = out[1]; a.out2 = out[2];
+    a.df = op->d_df + (size_t)op->run_e0; a.dfStride = (size_t)op->nElmt; a.nElmt = op->run_ne;
+    a.in_aligned  = (((uintptr_t)in[0]) & 15) == 0;
+    a.out_aligned = (((uintptr_t)out[0] | (uintptr_t)out[1] | (uintptr_t)out[2]) & 15) == 0;
+    const int nPairs = (op->run_ne + 1) / 2;
+    int grid         = st->bps * NUM_SMS;
+    const int need   = (nPairs + Cfg::WARPS - 1) / Cfg::WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) return NEKMF_OK;
+    kern<<<grid, Cfg::T, Cfg::SMEM, op->run_stream>>>(st->tab, a);
+    ++g_launches;
+    NEKMF_CUDA(cudaGetLastError());
+    return NEKMF_OK;
+}
+
+static void hex_dmma_pd_wrap(nekmf_op_s *op)
+{
+    auto *st = new HexDmmaPdState;
+    memcpy(st->tab.D, op->D[0].data(), sizeof(st->tab.D));
+    st->fallback_state = op->kstate;
+    st->fallback_free  = op->kstate_free;
+    op->kstate         = st;
+    op->kstate_free    = [](void *p) {
+        auto *s = static_cast<HexDmmaPdState *>(p);
+        if (s->fallback_state && s->fallback_free) s->fallback_free(s->fallback_state);
+        delete s;
+    };
+    op->launch = hex_dmma_pd_launch;
+    op->kname  = "hex_dmma_pd_kernel<nm=7,nq=8,regular>(DMMA m8n8k4: xi_0 / xi_1 on tensor tiles, xi_2 in the owning lane)";
+}
+
 // called from select_hex_fast after the DFMA launcher is installed: default quadrature, BwdTrans or IProductWRTBase.
 // NEKMF_HEX_DMMA=0 keeps the DFMA kernels (the other arm of the A/B), NEKMF_HEX_DMMA=all takes the tensor-core
 // kernel at every instantiated order; the default is the set of (operator, order) cells where it measured faster.
 void hex_dmma_maybe_wrap(nekmf_op_s *op)
 {
     if (op->shape != NEKMF_HEX || op->nq[0] != op->nm[0] + 1) return;
-    if (op->optype != NEKMF_BWDTRANS && op->optype != NEKMF_IPRODUCTWRTBASE) return;
     const int nm  = op->nm[0];
     const char *v = getenv("NEKMF_HEX_DMMA");
     if (v && v[0] == '0') return;
+    if (op->optype == NEKMF_PHYSDERIV && !op->deformed && nm == 7)
+    {
+        hex_dmma_pd_wrap(op); // nq = 8 fills the tiles exactly; deformed collections stream geometry at the HBM peak already
+        return;
+    }
+    if (op->optype != NEKMF_BWDTRANS && op->optype != NEKMF_IPRODUCTWRTBASE) return;
     const bool all = v && v[0] == 'a';
     // measured A/B (profiles/r02_sweep_hex_dmma_{all,0}.jsonl): every nm = 7 cell (0.77-0.90 against 0.47-0.78 of the
     // HBM peak) and regular IProductWRTBase at nm = 11 (0.39 against 0.36); the half-empty second row tile loses to

@@ -723,3 +723,39 @@ def test_hex_dmma_bwd_iprod(nm, nel, deformed, monkeypatch):
         assert np.array_equal(od[1:].cpu().numpy(), ob) and np.array_equal(oid[1:].cpu().numpy(), oi)
         res[mode] = (ob, oi)
     assert max(rel_errs(res["all"][0], res["0"][0])) < 1e-13 and max(rel_errs(res["all"][1], res["0"][1])) < 1e-13
+
+
+@pytest.mark.parametrize("nel", [1, 2, 37, 4096 + 3])
+def test_hex_dmma_physderiv_nm7(nel, monkeypatch):
+    """regular PhysDeriv at nm = 7, nq = 8 on FP64 tensor-core tiles (hex_dmma.cu: xi_0 with the lane's own values as the
+    A operand, xi_1 from fragment loads, xi_2 as DFMA in the owning lane): against the oracle and against the pencil kernel
+    it replaces (NEKMF_HEX_DMMA=0), odd element counts, caller arrays that are only 8-byte aligned"""
+    torch = _torch()
+    nk = nekmf()
+    rng = np.random.default_rng(100 + nel)
+    nm, nq = 7, 8
+    el = po.Elem(po.HEX, nm, nq)
+    std = nk.StdExpansion(nk.eHexahedron, nm, nq)
+    jac, df = random_geometry(rng, 3, nel, el.nqTot, False)
+    geom = nk.CoalescedGeomData(jac, df, False)
+    f = rng.uniform(-1, 1, nel * el.nqTot)
+    want = el.physderiv(nel, False, df, f)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NEKMF_HEX_DMMA", mode)
+        pd = nk.Operator(std, nel, geom, nk.ePhysDeriv)
+        assert ("hex_dmma_pd_kernel" in pd.kernel_name) == (mode == "1"), pd.kernel_name
+        outs = [np.zeros(nel * el.nqTot) for _ in range(3)]
+        pd.apply([f], outs)
+        for g, w in zip(outs, want):
+            assert max(rel_errs(g, w)) < 1e-12
+        fd = torch.zeros(f.size + 1, dtype=torch.float64, device="cuda")
+        fd[1:] = torch.tensor(f, device="cuda")
+        od = [torch.zeros(f.size + 1, dtype=torch.float64, device="cuda") for _ in range(3)]
+        pd.apply([fd[1:]], [o[1:] for o in od])
+        torch.cuda.synchronize()
+        for o, g in zip(od, outs):
+            assert np.array_equal(o[1:].cpu().numpy(), g)
+        res[mode] = outs
+    for a, b in zip(res["1"], res["0"]):
+        assert max(rel_errs(a, b)) < 1e-13
