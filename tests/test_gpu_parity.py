@@ -552,6 +552,12 @@ def test_shape_fast_kernels(shape, nm, deformed):
             want = "dense_helm_kernel"  # DMMA coefficient-space kernel (dense_helm.cu)
         if op == nk.eHelmholtz and not deformed and shape == "Prism" and 3 <= nm <= 5:
             want = "prism_gen_kernel"  # general regular prisms: eight-term DMMA kernel (dense_helm.cu), default at nm 3..5
+        if op in (nk.eBwdTrans, nk.eIProductWRTBase):
+            # tensor-core kernels where they measured faster (prism_dmma.cu, tet_dmma.cu)
+            if shape == "Prism" and 5 <= nm <= 7:
+                want = "prism_dmma_kernel"
+            if shape == "Tet" and (nm == 7 or (nm in (5, 6) and op == nk.eBwdTrans)):
+                want = "tet_dmma_kernel"
         assert want in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
     # IProductWRTDerivBase: lane kernels for regular quads up to nm = 5 / triangles up to nm = 6, otherwise the compile-time
     # sized kernel (chain-rule stage + the transposed-derivative / IProduct half of the fused Helmholtz kernel)
