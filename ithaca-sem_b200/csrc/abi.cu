@@ -303,6 +303,7 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
     }
     prism_maybe_wrap(op); // regular prism Helmholtz: DMMA kernel for extruded elements on top of the selected one
     dense_maybe_wrap(op); // regular Tri / Tet / Pyr Helmholtz: DMMA coefficient-space kernel on top of the selected one
+    pyr_dmma_maybe_wrap(op); // pyramid BwdTrans / IProductWRTBase: tensor-core kernels on top of the runtime-sized one
     *out = op;
     return NEKMF_OK;
 }

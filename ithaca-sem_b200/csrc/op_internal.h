@@ -70,6 +70,7 @@ bool select_tri_lane(nekmf_op_s *op);
 int notify_geom_changed(nekmf_op_s *op); // status of the launchers' geometry pre-passes
 void hex_dmma_maybe_wrap(nekmf_op_s *op); // hex_dmma.cu: DMMA BwdTrans / IProductWRTBase at nm = 7
 void prism_dmma_maybe_wrap(nekmf_op_s *op); // prism_dmma.cu: DMMA BwdTrans / IProductWRTBase on prisms, nm = 3..7
+void pyr_dmma_maybe_wrap(nekmf_op_s *op);   // the same kernel family on pyramids
 void tet_dmma_maybe_wrap(nekmf_op_s *op);   // tet_dmma.cu: DMMA + lane-per-mode-pair BwdTrans / IProductWRTBase on tetrahedra, nm = 5..7
 void kron_maybe_wrap(nekmf_op_s *op);
 int kron_geom_changed(nekmf_op_s *op);

@@ -1,9 +1,9 @@
-// prism_dmma.cu -- BwdTrans and IProductWRTBase on prisms at nm = 3..7 (default quadrature nq = (nm+1, nm+1, nm)) with
-// FP64 tensor-core tiles (DMMA, mma.sync.m8n8k4.f64).
+// prism_dmma.cu -- BwdTrans and IProductWRTBase on prisms and pyramids at nm = 3..7 (default quadrature
+// nq = (nm+1, nm+1, nm)) with FP64 tensor-core tiles (DMMA, mma.sync.m8n8k4.f64).
 //
 // Reference semantics: MatrixFreeOps/BwdTransKernels.hpp:128-300 (BwdTransPrismKernel, CORRECT = true for the
-// modified basis), IProductKernels.hpp:316-450 (IProductPrismKernel); results differ from shape_kernels.cuh by
-// summation order only.
+// modified basis) and its pyramid sibling, IProductKernels.hpp:316-450 (IProductPrismKernel) and the pyramid one;
+// results differ from shape_kernels.cuh / generic_kernels.cu by summation order only.
 //
 // A prism is (triangle in xi_0, xi_2) x (segment in xi_1): phi_pqr = A_p(xi_0) A_q(xi_1) B_pr(xi_2).  Only the xi_2
 // contraction is collapsed (its basis rows depend on p); for a fixed quadrature plane k the other two are the same
@@ -16,7 +16,10 @@
 //   IProduct:  the transposed chain: two chained DMMA passes per plane k (i -> p, j -> q), then the collapsed xi_2
 //              contraction accumulated on the fly by the lane that owns (p, q).
 // The singular-edge correction of the modified basis (mode (0, q, 1) also acts as (1, q, .) with the B_01 row) is one
-// extra FMA in the lane that holds p = 1.  Shared memory is touched to read the input only.  Every warp is an
+// extra FMA in the lane that holds p = 1.  A PYRAMID has the same two tensor directions; its xi_2 rows depend on
+// (p, q) (mode lines of length nm - max(p, q)) and its one correction is the top vertex: mode (0,0,1) also acts through
+// the entries (0,1), (1,0), (1,1) with the table row 1 -- the `PYR` variant of the same kernel.
+// Shared memory is touched to read the input only.  Every warp is an
 // independent worker: elements (pairs where one block is an odd number of doubles) arrive by TMA bulk copies into the
 // warp's own double buffer.
 #include "op_internal.h"
@@ -26,12 +29,19 @@
 namespace nekmf
 {
 
-template <int NM> struct PrismDmmaTab
+// rows of the xi_2 table: prism (p, r) pairs, pyramid all modes (p, q, r)
+template <bool PYR, int NM> constexpr int prdm_rows() { return PYR ? NM * (NM + 1) * (2 * NM + 1) / 6 : NM * (NM + 1) / 2; }
+template <bool PYR, int NM> constexpr int prdm_nmt() { return PYR ? NM * (NM + 1) * (2 * NM + 1) / 6 : NM * NM * (NM + 1) / 2; }
+
+template <bool PYR, int NM> struct PrismDmmaTab
 {
-    static constexpr int NQ0 = NM + 1, NQ2 = NM, NPAIR = NM * (NM + 1) / 2;
+    static constexpr int NQ0 = NM + 1, NQ2 = NM, NROWS = prdm_rows<PYR, NM>();
     double b0[NM * NQ0];    // bdata of direction 0 (and 1: same basis and points), [p][i]
-    double b2[NPAIR * NQ2]; // bdata of direction 2, rows (p, r)
+    double b2[NROWS * NQ2]; // bdata of direction 2
     double w0[NQ0], w2[NQ2]; // weights (collapsed-coordinate factor folded into w2)
+    int start[NM * NM];     // first coefficient of the mode line (p, q)
+    int row[NM * NM];       // its first row of the xi_2 table
+    int len[NM * NM];       // its length: nm - p (prism), nm - max(p, q) (pyramid)
 };
 
 struct PrismDmmaArgs
@@ -49,28 +59,28 @@ __device__ __forceinline__ void pr_mma(double &c0, double &c1, double a, double 
 }
 
 // OP 0: BwdTrans, 1: IProductWRTBase
-template <int OP, int NM, bool DEF> struct PrismDmmaCfg
+template <bool PYR, int OP, int NM, bool DEF> struct PrismDmmaCfg
 {
-    static constexpr int NQ0 = NM + 1, NQ1 = NM + 1, NQ2 = NM, NPAIR = NM * (NM + 1) / 2;
-    static constexpr int NMT = NM * NPAIR, NQT = NQ0 * NQ1 * NQ2;
+    static constexpr int NQ0 = NM + 1, NQ1 = NM + 1, NQ2 = NM, NROWS = prdm_rows<PYR, NM>();
+    static constexpr int NMT = prdm_nmt<PYR, NM>(), NQT = NQ0 * NQ1 * NQ2;
     static constexpr int IN_EL = OP == 0 ? NMT : NQT;
     static constexpr int EPB   = (IN_EL % 2) ? 2 : 1;                  // elements per buffer: a whole number of 16-byte units
     static constexpr int BUF   = EPB * IN_EL;
     static constexpr int SLOT  = BUF + ((OP == 1 && DEF) ? EPB * NQT : 0); // input block (+ its Jacobians)
     static constexpr int STG   = OP == 1 ? ((NMT + 1) & ~1) : 0;       // IProduct: output staging (coalesced stores)
     static constexpr int PER_WARP = 2 * SLOT + STG + 2;                // double buffer + staging + two mbarriers
-    static constexpr int B2S   = (NPAIR * NQ2 + 1) & ~1;               // shared copy of the collapsed table
+    static constexpr int B2S   = (NROWS * NQ2 + 1) & ~1;               // shared copy of the collapsed table
     static constexpr int WARPS = (B2S + 8 * PER_WARP) * 8 + 16 <= 224 * 1024 ? 8 : 6, T = WARPS * 32;
     static constexpr size_t SMEM = (size_t)(B2S + WARPS * PER_WARP) * 8 + 16;
 };
 
 // MINB: resident CTAs per SM the register allocation aims at (2: 128 registers, 3: 80, 4: 64)
-template <int OP, int NM, bool DEF, int MINB>
-__global__ void __launch_bounds__(PrismDmmaCfg<OP, NM, DEF>::T, MINB)
-    prism_dmma_kernel(const __grid_constant__ PrismDmmaTab<NM> tab, const __grid_constant__ PrismDmmaArgs args)
+template <bool PYR, int OP, int NM, bool DEF, int MINB>
+__global__ void __launch_bounds__(PrismDmmaCfg<PYR, OP, NM, DEF>::T, MINB)
+    prism_dmma_kernel(const __grid_constant__ PrismDmmaTab<PYR, NM> tab, const __grid_constant__ PrismDmmaArgs args)
 {
-    using Cfg = PrismDmmaCfg<OP, NM, DEF>;
-    constexpr int NQ0 = Cfg::NQ0, NQ1 = Cfg::NQ1, NQ2 = Cfg::NQ2, NPAIR = Cfg::NPAIR, NMT = Cfg::NMT, NQT = Cfg::NQT;
+    using Cfg = PrismDmmaCfg<PYR, OP, NM, DEF>;
+    constexpr int NQ0 = Cfg::NQ0, NQ1 = Cfg::NQ1, NQ2 = Cfg::NQ2, NROWS = Cfg::NROWS, NMT = Cfg::NMT, NQT = Cfg::NQT;
     constexpr int IN_EL = Cfg::IN_EL, BUF = Cfg::BUF, SLOT = Cfg::SLOT, EPB = Cfg::EPB;
     constexpr bool JSM = OP == 1 && DEF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -82,7 +92,7 @@ __global__ void __launch_bounds__(PrismDmmaCfg<OP, NM, DEF>::T, MINB)
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase + 2 * SLOT + Cfg::STG);
 
     // collapsed table, with the xi_2 weights folded in for IProduct
-    for (int i = threadIdx.x; i < NPAIR * NQ2; i += Cfg::T) sB2[i] = OP == 0 ? tab.b2[i] : tab.b2[i] * tab.w2[i % NQ2];
+    for (int i = threadIdx.x; i < NROWS * NQ2; i += Cfg::T) sB2[i] = OP == 0 ? tab.b2[i] : tab.b2[i] * tab.w2[i % NQ2];
     if (lane == 0)
     {
         mbar_init(bar, 1);
@@ -116,7 +126,6 @@ __global__ void __launch_bounds__(PrismDmmaCfg<OP, NM, DEF>::T, MINB)
     }
     // tile column g of pass 1 <-> second index (q resp. j) = g/2 for even g, 4 + g/2 for odd g
     const int col0 = (g & 1) ? 4 + (g >> 1) : (g >> 1);
-    auto mpr = [](int p) { return p * NM - p * (p - 1) / 2; }; // first row of the (p, .) block of the collapsed table
 
     uint32_t phase[2] = {0, 0};
     int slot          = 0;
@@ -161,27 +170,28 @@ __global__ void __launch_bounds__(PrismDmmaCfg<OP, NM, DEF>::T, MINB)
                 const int p0 = t, p1 = 4 + t;
                 const bool v0 = q < NM && p0 < NM, v1 = q < NM && p1 < NM;
                 double c0[NM], c1[NM > 4 ? NM - 4 : 1];
-                const int base0 = v0 ? NM * mpr(p0) + q * (NM - p0) : 0;
-                const int base1 = v1 ? NM * mpr(p1) + q * (NM - p1) : 0;
+                const int base0 = v0 ? tab.start[p0 * NM + q] : 0, len0 = v0 ? tab.len[p0 * NM + q] : 0;
+                const int base1 = v1 ? tab.start[p1 * NM + q] : 0, len1 = v1 ? tab.len[p1 * NM + q] : 0;
 #pragma unroll
                 for (int r = 0; r < NM; ++r)
                 {
-                    const bool ok = v0 && r < NM - p0;
+                    const bool ok = r < len0;
                     const double x = U[ok ? base0 + r : 0];
                     c0[r] = ok ? x : 0.0;
                 }
 #pragma unroll
                 for (int r = 0; r < NM - 4; ++r)
                 {
-                    const bool ok = v1 && r < NM - p1;
+                    const bool ok = r < len1;
                     const double x = U[ok ? base1 + r : 0];
                     c1[r] = ok ? x : 0.0;
                 }
-                // singular edge: mode (0, q, 1) also contributes to f[1][q] through the row (0, 1) of the table
-                const bool cor  = p0 == 1 && v0;
-                const double xc = U[cor ? q * NM + 1 : 0];
+                // prism, singular edge: mode (0, q, 1) also contributes to f[1][q] through the row (0, 1) of the table;
+                // pyramid, top vertex: mode (0, 0, 1) contributes to f[0][1], f[1][0], f[1][1] through the row 1
+                const bool cor  = v0 && (PYR ? ((p0 == 0 && q == 1) || (p0 == 1 && q <= 1)) : p0 == 1);
+                const double xc = U[cor ? (PYR ? 1 : q * NM + 1) : 0];
                 const double cc = cor ? xc : 0.0;
-                const int row0 = v0 ? mpr(p0) : 0, row1 = v1 ? mpr(p1) : 0;
+                const int row0 = v0 ? tab.row[p0 * NM + q] : 0, row1 = v1 ? tab.row[p1 * NM + q] : 0;
                 const int i0 = 2 * t;
                 double *o = args.out + el * NQT + g * NQ0 + i0;
 #pragma unroll
@@ -191,13 +201,13 @@ __global__ void __launch_bounds__(PrismDmmaCfg<OP, NM, DEF>::T, MINB)
 #pragma unroll
                     for (int r = 0; r < NM; ++r)
                     {
-                        const int row = row0 + r < NPAIR ? row0 + r : NPAIR - 1; // clamped: c0[r] is zero there
+                        const int row = row0 + r < NROWS ? row0 + r : NROWS - 1; // clamped: c0[r] is zero there
                         f0 = fma(c0[r], sB2[row * NQ2 + k], f0);
                     }
 #pragma unroll
                     for (int r = 0; r < NM - 4; ++r)
                     {
-                        const int row = row1 + r < NPAIR ? row1 + r : NPAIR - 1;
+                        const int row = row1 + r < NROWS ? row1 + r : NROWS - 1;
                         f1 = fma(c1[r], sB2[row * NQ2 + k], f1);
                     }
                     double x0 = 0.0, x1 = 0.0, d0 = 0.0, d1 = 0.0;
@@ -230,7 +240,14 @@ __global__ void __launch_bounds__(PrismDmmaCfg<OP, NM, DEF>::T, MINB)
                 const double w00 = v0 ? tab.w0[t] * wj : 0.0, w01 = v1 ? tab.w0[(4 + t) < NQ0 ? 4 + t : 0] * wj : 0.0;
                 // the lane owns (p, q) = (2t, g) and (2t + 1, g) of the result
                 const int p0 = 2 * t, p1 = 2 * t + 1;
-                const int row0 = p0 < NM ? mpr(p0) : 0, row1 = p1 < NM ? mpr(p1) : 0;
+                const bool o0 = g < NM && p0 < NM, o1 = g < NM && p1 < NM;
+                const int row0 = o0 ? tab.row[p0 * NM + g] : 0, row1 = o1 ? tab.row[p1 * NM + g] : 0;
+                // corrections: prism, singular edge: the (1, q) value also feeds mode (0, q, 1) through the row (0, 1);
+                // pyramid, top vertex: the (0,1), (1,0), (1,1) values feed mode (0,0,1) through the row 1 (lane (g,t) = (1,0)
+                // adds its share to the staged result afterwards)
+                const bool own1 = PYR ? (t == 0 && g == 0) : t == 0;
+                const bool ext1 = PYR && t == 0 && g == 1;
+                double ext = 0.0;
                 double acc0[NM], acc1[NM > 1 ? NM - 1 : 1];
 #pragma unroll
                 for (int r = 0; r < NM; ++r) acc0[r] = 0.0;
@@ -254,37 +271,41 @@ __global__ void __launch_bounds__(PrismDmmaCfg<OP, NM, DEF>::T, MINB)
 #pragma unroll
                     for (int r = 0; r < NM; ++r)
                     {
-                        const int row = row0 + r < NPAIR ? row0 + r : NPAIR - 1;
+                        const int row = row0 + r < NROWS ? row0 + r : NROWS - 1;
                         acc0[r]       = fma(sB2[row * NQ2 + k], d0, acc0[r]);
                     }
 #pragma unroll
                     for (int r = 0; r < NM - 1; ++r)
                     {
-                        const int row = row1 + r < NPAIR ? row1 + r : NPAIR - 1;
+                        const int row = row1 + r < NROWS ? row1 + r : NROWS - 1;
                         acc1[r]       = fma(sB2[row * NQ2 + k], d1, acc1[r]);
                     }
-                    // singular edge: the (1, q) value also feeds mode (0, q, 1) through the row (0, 1)
-                    if (NM > 1) acc0[1] = fma(t == 0 ? sB2[NQ2 + k] : 0.0, d1, acc0[1]);
+                    if (NM > 1) acc0[1] = fma(own1 ? sB2[NQ2 + k] : 0.0, d1, acc0[1]);
+                    if (PYR) ext = fma(ext1 ? sB2[NQ2 + k] : 0.0, d0 + d1, ext);
                 }
-                // the (p, q) owners write r-lines of length nm - p: staged in shared memory, stored coalesced
-                if (g < NM)
+                // the (p, q) owners write their mode lines: staged in shared memory, stored coalesced
+                if (o0)
                 {
-                    if (p0 < NM)
-                    {
-                        double *o = sStg + NM * mpr(p0) + g * (NM - p0);
+                    double *o    = sStg + tab.start[p0 * NM + g];
+                    const int ln = tab.len[p0 * NM + g];
 #pragma unroll
-                        for (int r = 0; r < NM; ++r)
-                            if (r < NM - p0) o[r] = acc0[r];
-                    }
-                    if (p1 < NM)
-                    {
-                        double *o = sStg + NM * mpr(p1) + g * (NM - p1);
+                    for (int r = 0; r < NM; ++r)
+                        if (r < ln) o[r] = acc0[r];
+                }
+                if (o1)
+                {
+                    double *o    = sStg + tab.start[p1 * NM + g];
+                    const int ln = tab.len[p1 * NM + g];
 #pragma unroll
-                        for (int r = 0; r < NM - 1; ++r)
-                            if (r < NM - p1) o[r] = acc1[r];
-                    }
+                    for (int r = 0; r < NM - 1; ++r)
+                        if (r < ln) o[r] = acc1[r];
                 }
                 __syncwarp();
+                if (PYR)
+                {
+                    if (ext1) sStg[1] += ext;
+                    __syncwarp();
+                }
                 {
                     double *o = args.out + el * NMT;
                     if ((NMT % 2 == 0) && args.out_aligned)
@@ -300,20 +321,20 @@ __global__ void __launch_bounds__(PrismDmmaCfg<OP, NM, DEF>::T, MINB)
     }
 }
 
-template <int NM> struct PrismDmmaState
+template <bool PYR, int NM> struct PrismDmmaState
 {
-    PrismDmmaTab<NM> tab;
+    PrismDmmaTab<PYR, NM> tab;
     void *fallback_state          = nullptr;
     void (*fallback_free)(void *) = nullptr;
     int bps[2][2]                 = {{0, 0}, {0, 0}};
     int minb                      = 2;
 };
 
-template <int OP, int NM, bool DEF> static int prism_dmma_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
+template <bool PYR, int OP, int NM, bool DEF> static int prism_dmma_launch(nekmf_op_s *op, const double *const in[3], double *const out[3])
 {
-    auto *st  = static_cast<PrismDmmaState<NM> *>(op->kstate);
-    using Cfg = PrismDmmaCfg<OP, NM, DEF>;
-    auto kern = st->minb == 3 ? prism_dmma_kernel<OP, NM, DEF, 3> : (st->minb == 4 ? prism_dmma_kernel<OP, NM, DEF, 4> : prism_dmma_kernel<OP, NM, DEF, 2>);
+    auto *st  = static_cast<PrismDmmaState<PYR, NM> *>(op->kstate);
+    using Cfg = PrismDmmaCfg<PYR, OP, NM, DEF>;
+    auto kern = st->minb == 3 ? prism_dmma_kernel<PYR, OP, NM, DEF, 3> : (st->minb == 4 ? prism_dmma_kernel<PYR, OP, NM, DEF, 4> : prism_dmma_kernel<PYR, OP, NM, DEF, 2>);
     int &bps  = st->bps[OP][DEF ? 1 : 0];
     if (bps == 0)
     {
@@ -321,7 +342,7 @@ template <int OP, int NM, bool DEF> static int prism_dmma_launch(nekmf_op_s *op,
         NEKMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         int nb = 0;
         NEKMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::T, Cfg::SMEM));
-        if (nb < 1) { set_error("prism DMMA kernel <%d> does not fit on an SM", NM); return NEKMF_ERR_CUDA; }
+        if (nb < 1) { set_error("prism / pyramid DMMA kernel <%d> does not fit on an SM", NM); return NEKMF_ERR_CUDA; }
         bps = nb;
     }
     PrismDmmaArgs a;
@@ -341,37 +362,53 @@ template <int OP, int NM, bool DEF> static int prism_dmma_launch(nekmf_op_s *op,
     return NEKMF_OK;
 }
 
-template <int NM> static void prism_dmma_wrap(nekmf_op_s *op)
+template <bool PYR, int NM> static bool prism_dmma_wrap(nekmf_op_s *op)
 {
-    using Tab = PrismDmmaTab<NM>;
-    auto *st  = new PrismDmmaState<NM>;
+    using Tab = PrismDmmaTab<PYR, NM>;
+    if (op->b[0].size() != sizeof(Tab::b0) / 8 || op->b[2].size() != sizeof(Tab::b2) / 8 || op->ws[0].size() != sizeof(Tab::w0) / 8 ||
+        op->ws[2].size() != sizeof(Tab::w2) / 8 || op->nmTot != prdm_nmt<PYR, NM>())
+        return false; // tables of another size than the kernel is compiled for: keep the installed kernel
+    auto *st  = new PrismDmmaState<PYR, NM>;
     memcpy(st->tab.b0, op->b[0].data(), sizeof(st->tab.b0));
     memcpy(st->tab.b2, op->b[2].data(), sizeof(st->tab.b2));
     memcpy(st->tab.w0, op->ws[0].data(), sizeof(st->tab.w0));
     memcpy(st->tab.w2, op->ws[2].data(), sizeof(st->tab.w2));
-    (void)sizeof(Tab);
+    {
+        // mode lines in the reference's order: p outer, q, r inner
+        int mode = 0;
+        for (int p = 0; p < NM; ++p)
+            for (int q = 0; q < NM; ++q)
+            {
+                const int ln          = PYR ? NM - (p > q ? p : q) : NM - p;
+                st->tab.start[p * NM + q] = mode;
+                st->tab.len[p * NM + q]   = ln;
+                st->tab.row[p * NM + q]   = PYR ? mode : p * NM - p * (p - 1) / 2;
+                mode += ln;
+            }
+    }
     if (const char *vb = getenv("NEKMF_PRISM_DMMA_MINB")) // A/B knob: register budget (resident CTAs per SM aimed at)
         if (vb[0] == '3' || vb[0] == '4') st->minb = vb[0] - '0'; // measured: 2 is the fastest from nm = 5 on
     st->fallback_state = op->kstate;
     st->fallback_free  = op->kstate_free;
     op->kstate         = st;
     op->kstate_free    = [](void *p) {
-        auto *s = static_cast<PrismDmmaState<NM> *>(p);
+        auto *s = static_cast<PrismDmmaState<PYR, NM> *>(p);
         if (s->fallback_state && s->fallback_free) s->fallback_free(s->fallback_state);
         delete s;
     };
     char name[128];
     if (op->optype == NEKMF_BWDTRANS)
     {
-        op->launch = prism_dmma_launch<0, NM, false>;
-        snprintf(name, sizeof(name), "prism_dmma_kernel<bwd,nm=%d>(DMMA m8n8k4, collapsed direction in the owning lane)", NM);
+        op->launch = prism_dmma_launch<PYR, 0, NM, false>;
+        snprintf(name, sizeof(name), "%s_dmma_kernel<bwd,nm=%d>(DMMA m8n8k4, collapsed direction in the owning lane)", PYR ? "pyr" : "prism", NM);
     }
     else
     {
-        op->launch = op->deformed ? prism_dmma_launch<1, NM, true> : prism_dmma_launch<1, NM, false>;
-        snprintf(name, sizeof(name), "prism_dmma_kernel<iprod,nm=%d,%s>(DMMA m8n8k4)", NM, op->deformed ? "deformed" : "regular");
+        op->launch = op->deformed ? prism_dmma_launch<PYR, 1, NM, true> : prism_dmma_launch<PYR, 1, NM, false>;
+        snprintf(name, sizeof(name), "%s_dmma_kernel<iprod,nm=%d,%s>(DMMA m8n8k4)", PYR ? "pyr" : "prism", NM, op->deformed ? "deformed" : "regular");
     }
     op->kname = name;
+    return true;
 }
 
 // called from select_shape_fast after the pencil launcher is installed: default quadrature, BwdTrans or
@@ -393,11 +430,35 @@ void prism_dmma_maybe_wrap(nekmf_op_s *op)
     if (!(v && v[0] == 'a') && nm < 5) return;
     switch (nm)
     {
-        case 3: prism_dmma_wrap<3>(op); break;
-        case 4: prism_dmma_wrap<4>(op); break;
-        case 5: prism_dmma_wrap<5>(op); break;
-        case 6: prism_dmma_wrap<6>(op); break;
-        case 7: prism_dmma_wrap<7>(op); break;
+        case 3: prism_dmma_wrap<false, 3>(op); break;
+        case 4: prism_dmma_wrap<false, 4>(op); break;
+        case 5: prism_dmma_wrap<false, 5>(op); break;
+        case 6: prism_dmma_wrap<false, 6>(op); break;
+        case 7: prism_dmma_wrap<false, 7>(op); break;
+        default: break;
+    }
+}
+
+// the same for pyramids (called from nekmf_op_create after the runtime-sized kernel is installed: there is no
+// compile-time sized pencil family for pyramids, so the tensor-core kernels are taken at every instantiated order).
+// NEKMF_PYR_DMMA=0 keeps the runtime-sized kernel.
+void pyr_dmma_maybe_wrap(nekmf_op_s *op)
+{
+    if (op->shape != NEKMF_PYR) return;
+    if (op->optype != NEKMF_BWDTRANS && op->optype != NEKMF_IPRODUCTWRTBASE) return;
+    const int nm = op->nm[0];
+    if (op->nm[1] != nm || op->nm[2] != nm || op->nq[0] != nm + 1 || op->nq[1] != nm + 1 || op->nq[2] != nm) return;
+    if (op->b[1] != op->b[0] || op->ws[1] != op->ws[0]) return;
+    if (op->deformed && op->geo_pitch != op->nqTot) return;
+    const char *v = getenv("NEKMF_PYR_DMMA");
+    if (v && v[0] == '0') return;
+    switch (nm)
+    {
+        case 3: prism_dmma_wrap<true, 3>(op); break;
+        case 4: prism_dmma_wrap<true, 4>(op); break;
+        case 5: prism_dmma_wrap<true, 5>(op); break;
+        case 6: prism_dmma_wrap<true, 6>(op); break;
+        case 7: prism_dmma_wrap<true, 7>(op); break;
         default: break;
     }
 }

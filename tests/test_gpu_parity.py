@@ -849,3 +849,44 @@ def test_tet_dmma_bwd_iprod(nm, nel, deformed, monkeypatch):
         assert np.array_equal(od[1:].cpu().numpy(), ob) and np.array_equal(oid[1:].cpu().numpy(), oi)
         res[mode] = (ob, oi)
     assert max(rel_errs(res["all"][0], res["0"][0])) < 1e-13 and max(rel_errs(res["all"][1], res["0"][1])) < 1e-13
+
+
+@pytest.mark.parametrize("nm,nel", [(3, 5), (4, 1), (4, 38), (5, 37), (6, 2), (6, 1001), (7, 1), (7, 2), (7, 37), (7, 4099)])
+@pytest.mark.parametrize("deformed", [False, True])
+def test_pyr_dmma_bwd_iprod(nm, nel, deformed, monkeypatch):
+    """BwdTrans / IProductWRTBase on pyramids at nm = 3..7 on FP64 tensor-core tiles (the PYR variant of prism_dmma.cu:
+    mode lines of length nm - max(p, q), top-vertex correction through the entries (0,1), (1,0), (1,1)): against the oracle
+    and against the runtime-sized kernel they replace (NEKMF_PYR_DMMA=0), odd element counts, caller arrays that are only
+    8-byte aligned"""
+    torch = _torch()
+    nk = nekmf()
+    rng = np.random.default_rng(13 * nm + nel)
+    el = po.Elem(po.PYR, nm, nm + 1)
+    std = nk.StdExpansion(nk.ePyramid, nm)
+    jac, df = random_geometry(rng, 3, nel, el.nqTot, deformed)
+    geom = nk.CoalescedGeomData(jac, df, deformed)
+    c = rng.uniform(-1, 1, nel * el.nmTot)
+    f = rng.uniform(-1, 1, nel * el.nqTot)
+    want_b, want_i = el.bwdtrans(nel, c), el.iproduct(nel, deformed, jac, f)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NEKMF_PYR_DMMA", mode)
+        bwd, ipr = nk.Operator(std, nel, geom, nk.eBwdTrans), nk.Operator(std, nel, geom, nk.eIProductWRTBase)
+        assert ("pyr_dmma_kernel" in bwd.kernel_name) == (mode == "1"), bwd.kernel_name
+        assert ("pyr_dmma_kernel" in ipr.kernel_name) == (mode == "1"), ipr.kernel_name
+        ob, oi = np.zeros(nel * el.nqTot), np.zeros(nel * el.nmTot)
+        bwd.apply([c], [ob])
+        ipr.apply([f], [oi])
+        assert max(rel_errs(ob, want_b)) < 1e-12 and max(rel_errs(oi, want_i)) < 1e-12
+        cd = torch.zeros(c.size + 1, dtype=torch.float64, device="cuda")
+        cd[1:] = torch.tensor(c, device="cuda")
+        od = torch.zeros(ob.size + 1, dtype=torch.float64, device="cuda")
+        bwd.apply([cd[1:]], [od[1:]])
+        fd = torch.zeros(f.size + 1, dtype=torch.float64, device="cuda")
+        fd[1:] = torch.tensor(f, device="cuda")
+        oid = torch.zeros(oi.size + 1, dtype=torch.float64, device="cuda")
+        ipr.apply([fd[1:]], [oid[1:]])
+        torch.cuda.synchronize()
+        assert np.array_equal(od[1:].cpu().numpy(), ob) and np.array_equal(oid[1:].cpu().numpy(), oi)
+        res[mode] = (ob, oi)
+    assert max(rel_errs(res["1"][0], res["0"][0])) < 1e-13 and max(rel_errs(res["1"][1], res["0"][1])) < 1e-13
