@@ -293,7 +293,7 @@ int nekmf_op_create(int shape, int optype, const int nm[3], const int nq[3], con
     op->geo_pitch = op->nqTot;
     if (shape == NEKMF_SEG) ok = select_seg(op);
     if (!ok && shape == NEKMF_HEX) ok = select_hex_fast(op);
-    if (!ok && shape != NEKMF_HEX && shape != NEKMF_PYR && shape != NEKMF_SEG) ok = select_shape_fast(op);
+    if (!ok && shape != NEKMF_HEX && shape != NEKMF_SEG) ok = select_shape_fast(op);
     if (!ok && shape != NEKMF_SEG) ok = select_generic(op);
     if (!ok)
     {

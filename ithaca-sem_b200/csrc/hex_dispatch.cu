@@ -39,10 +39,11 @@ bool select_hex_fast(nekmf_op_s *op)
 SHP_DECL(2) SHP_DECL(3) SHP_DECL(4) SHP_DECL(5) SHP_DECL(6) SHP_DECL(7) SHP_DECL(8) SHP_DECL(9)
 #undef SHP_DECL
 
-// Quad / Tri / Prism / Tet with the default quadrature: compile-time sized kernels (shape_kernels.cuh)
+// Quad / Tri / Prism / Tet (and pyramid PhysDeriv) with the default quadrature: compile-time sized kernels (shape_kernels.cuh)
 bool select_shape_fast(nekmf_op_s *op)
 {
-    if (op->shape == NEKMF_HEX || op->shape == NEKMF_PYR) return false;
+    if (op->shape == NEKMF_HEX) return false;
+    if (op->shape == NEKMF_PYR && op->optype != NEKMF_PHYSDERIV) return false; // pyramids: PhysDeriv only in this family
     if (select_quad_lane(op)) return true; // BwdTrans / IProductWRTBase / regular PhysDeriv on quads: one lane per element
     if (select_tri_lane(op)) return true;  // the same for triangles
     bool ok = false;

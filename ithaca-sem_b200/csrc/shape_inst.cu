@@ -67,6 +67,7 @@ template <int SHAPE, int OP, int NM, bool DEF> static int shape_launch(nekmf_op_
 template <int SHAPE, int NM> static bool shape_install(nekmf_op_s *op)
 {
     using Dm = ShpDims<SHAPE, NM>;
+    if (SHAPE == NEKMF_PYR && op->optype != NEKMF_PHYSDERIV) return false; // pyramids: quadrature-space operator only
     for (int d = 0; d < Dm::DIM; ++d)
         if (op->nm[d] != NM) return false;
     if (op->nq[0] != Dm::NQ0 || op->nq[1] != Dm::NQ1 || (Dm::DIM == 3 && op->nq[2] != Dm::NQ2)) return false;
@@ -91,8 +92,10 @@ template <int SHAPE, int NM> static bool shape_install(nekmf_op_s *op)
     for (int i = 0; i < Dm::NQ0; ++i) h0[i] = 0.5 * (1.0 + op->Z[0][i]);
     if (SHAPE == NEKMF_TRI)
         for (int j = 0; j < Dm::NQ1; ++j) h1[j] = 2.0 / (1.0 - op->Z[1][j]);
-    if (SHAPE == NEKMF_PRISM)
+    if (SHAPE == NEKMF_PRISM || SHAPE == NEKMF_PYR)
         for (int k = 0; k < Dm::NQ2; ++k) h1[k] = 2.0 / (1.0 - op->Z[2][k]);
+    if (SHAPE == NEKMF_PYR)
+        for (int j = 0; j < Dm::NQ1; ++j) h2[j] = 0.5 * (1.0 + op->Z[1][j]);
     if (SHAPE == NEKMF_TET)
     {
         for (int j = 0; j < Dm::NQ1; ++j)
@@ -125,13 +128,23 @@ template <int SHAPE, int NM> static bool shape_install(nekmf_op_s *op)
     case OPC:                                                                                                   \
         op->launch = op->deformed ? shape_launch<SHAPE, OPC, NM, true> : shape_launch<SHAPE, OPC, NM, false>;   \
         return true;
-    switch (op->optype)
+    if constexpr (SHAPE == NEKMF_PYR)
     {
-        SHP_CASE(NEKMF_BWDTRANS)
-        SHP_CASE(NEKMF_HELMHOLTZ)
-        SHP_CASE(NEKMF_IPRODUCTWRTBASE)
-        SHP_CASE(NEKMF_PHYSDERIV)
-        SHP_CASE(NEKMF_IPRODUCTWRTDERIVBASE)
+        switch (op->optype)
+        {
+            SHP_CASE(NEKMF_PHYSDERIV)
+        }
+    }
+    else
+    {
+        switch (op->optype)
+        {
+            SHP_CASE(NEKMF_BWDTRANS)
+            SHP_CASE(NEKMF_HELMHOLTZ)
+            SHP_CASE(NEKMF_IPRODUCTWRTBASE)
+            SHP_CASE(NEKMF_PHYSDERIV)
+            SHP_CASE(NEKMF_IPRODUCTWRTDERIVBASE)
+        }
     }
 #undef SHP_CASE
     op->kstate_free(st);
@@ -149,6 +162,7 @@ bool SHP_CAT(shape_try_nm, SHAPE_NM)(nekmf_op_s *op)
         case NEKMF_TRI: return shape_install<NEKMF_TRI, SHAPE_NM>(op);
         case NEKMF_PRISM: return shape_install<NEKMF_PRISM, SHAPE_NM>(op);
         case NEKMF_TET: return shape_install<NEKMF_TET, SHAPE_NM>(op);
+        case NEKMF_PYR: return shape_install<NEKMF_PYR, SHAPE_NM>(op);
         default: return false;
     }
 }

@@ -31,7 +31,7 @@ constexpr int shp_round2(int a) { return (a + 1) & ~1; }
 template <int SHAPE, int NM> struct ShpDims
 {
     static constexpr bool IS_QUAD = SHAPE == NEKMF_QUAD, IS_TRI = SHAPE == NEKMF_TRI, IS_PRISM = SHAPE == NEKMF_PRISM,
-                          IS_TET = SHAPE == NEKMF_TET;
+                          IS_TET = SHAPE == NEKMF_TET, IS_PYR = SHAPE == NEKMF_PYR; // pyramids: PhysDeriv only
     static constexpr int DIM = (IS_QUAD || IS_TRI) ? 2 : 3;
     static constexpr int NQ0 = NM + 1;
     static constexpr int NQ1 = (IS_TRI || IS_TET) ? NM : NM + 1;
@@ -40,7 +40,7 @@ template <int SHAPE, int NM> struct ShpDims
     static constexpr int P1  = NQ0 | 1; // odd pitch of an i-line in shared memory
     static constexpr int NQP = P1 * NQ1 * NQ2;
     static constexpr int NPAIR = NM * (NM + 1) / 2;
-    static constexpr int NMT   = IS_QUAD ? NM * NM : (IS_TRI ? NPAIR : (IS_PRISM ? NM * NPAIR : NM * (NM + 1) * (NM + 2) / 6));
+    static constexpr int NMT   = IS_QUAD ? NM * NM : (IS_TRI ? NPAIR : (IS_PRISM ? NM * NPAIR : (IS_PYR ? NM * (NM + 1) * (2 * NM + 1) / 6 : NM * (NM + 1) * (NM + 2) / 6)));
     static constexpr int B1C_ROWS = (IS_TRI || IS_TET) ? NPAIR : 0;         // collapsed rows of direction 1
     static constexpr int B2C_ROWS = IS_PRISM ? NPAIR : (IS_TET ? NMT : 0);  // collapsed rows of direction 2
     // aux table (global -> shared): [b1c | b2c | w0 w1 w2 | h0 h1 h2 h3]
@@ -585,6 +585,14 @@ __global__ void __launch_bounds__(256)
                             {
                                 d0 = d0 * sH1[s];      // 2/(1-z2_k), s == k
                                 d2 = fma(h0i, d0, d2);
+                            }
+                            if (Dm::IS_PYR)
+                            {
+                                // PhysDerivKernels.hpp:505-527: both base directions collapse towards the apex
+                                d0 = d0 * sH1[s];      // 2/(1-z2_k)
+                                d1 = d1 * sH1[s];
+                                d2 = fma(h0i, d0, d2);   // + d0 (1+z0_i)/2
+                                d2 = fma(sH2[j], d1, d2); // + d1 (1+z1_j)/2
                             }
                             if (IS_TET)
                             {

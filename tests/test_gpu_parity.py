@@ -890,3 +890,24 @@ def test_pyr_dmma_bwd_iprod(nm, nel, deformed, monkeypatch):
         assert np.array_equal(od[1:].cpu().numpy(), ob) and np.array_equal(oid[1:].cpu().numpy(), oi)
         res[mode] = (ob, oi)
     assert max(rel_errs(res["1"][0], res["0"][0])) < 1e-13 and max(rel_errs(res["1"][1], res["0"][1])) < 1e-13
+
+
+@pytest.mark.parametrize("deformed", [False, True])
+@pytest.mark.parametrize("nm", list(range(2, 10)))
+def test_pyr_physderiv_shape_kernel(nm, deformed):
+    """pyramid PhysDeriv runs the compile-time sized quadrature-space kernel (shape_kernels.cuh, prism tensor structure
+    with both base directions collapsing towards the apex, PhysDerivKernels.hpp:505-527): several batches plus a ragged
+    last one, against the oracle; the direction overload too"""
+    nk = nekmf()
+    rng = np.random.default_rng(17 * nm + deformed)
+    nel = 67
+    el = po.Elem(po.PYR, nm, nm + 1)
+    std = nk.StdExpansion(nk.ePyramid, nm)
+    jac, df = random_geometry(rng, 3, nel, el.nqTot, deformed)
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, deformed))
+    f = rng.uniform(-1, 1, nel * el.nqTot)
+    outs = [np.zeros(nel * el.nqTot) for _ in range(3)]
+    coll.ApplyOperator(nk.ePhysDeriv, f, *outs)
+    assert "shape_op_kernel<Pyr,physderiv" in coll.m_ops[nk.ePhysDeriv].kernel_name, coll.m_ops[nk.ePhysDeriv].kernel_name
+    for g, w in zip(outs, el.physderiv(nel, deformed, df, f)):
+        assert max(rel_errs(g, w)) < 1e-12
