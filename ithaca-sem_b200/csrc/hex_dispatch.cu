@@ -61,7 +61,7 @@ bool select_shape_fast(nekmf_op_s *op)
     // regular quad Helmholtz: add the coefficient-space kernel (used when the metric is diagonal)
     if (ok) quad_kron_maybe_wrap(op);
     if (ok) prism_dmma_maybe_wrap(op); // prisms, BwdTrans / IProductWRTBase: tensor-core tiles
-    if (ok) tet_dmma_maybe_wrap(op);   // tetrahedra, the same
+    if (ok && !tet_gemm_maybe_wrap(op)) tet_dmma_maybe_wrap(op); // tetrahedra: GEMM over eight elements (BwdTrans), else tiles + lane per mode pair
     return ok;
 }
 int notify_geom_changed(nekmf_op_s *op)

@@ -72,6 +72,7 @@ void hex_dmma_maybe_wrap(nekmf_op_s *op); // hex_dmma.cu: DMMA BwdTrans / IProdu
 void prism_dmma_maybe_wrap(nekmf_op_s *op); // prism_dmma.cu: DMMA BwdTrans / IProductWRTBase on prisms, nm = 3..7
 void pyr_dmma_maybe_wrap(nekmf_op_s *op);   // the same kernel family on pyramids
 void tet_dmma_maybe_wrap(nekmf_op_s *op);   // tet_dmma.cu: DMMA + lane-per-mode-pair BwdTrans / IProductWRTBase on tetrahedra, nm = 5..7
+bool tet_gemm_maybe_wrap(nekmf_op_s *op);  // tet_gemm.cu: BwdTrans on tetrahedra as DMMA GEMMs over eight elements, nm = 5..7
 void kron_maybe_wrap(nekmf_op_s *op);
 int kron_geom_changed(nekmf_op_s *op);
 void quad_kron_maybe_wrap(nekmf_op_s *op);

@@ -429,7 +429,9 @@ void tet_dmma_maybe_wrap(nekmf_op_s *op)
     //   nm = 7: BwdTrans 0.37 / 0.28, IProductWRTBase 0.28 / 0.25 (regular), 0.41 / 0.33 (deformed)
     //   nm = 5, 6: BwdTrans 0.34 / 0.28, 0.37 / 0.35; IProductWRTBase within 5 % either way (pencil kept)
     // both are bound by shared-memory wavefronts of the collapsed contractions, not by the tensor pipe
-    const bool faster = nm == 7 || ((nm == 5 || nm == 6) && op->optype == NEKMF_BWDTRANS);
+    // (tet_gemm.cu takes over where it is instantiated and faster; this policy covers what it leaves: deformed
+    // IProductWRTBase at nm = 6, and everything when NEKMF_TET_GEMM=0)
+    const bool faster = nm == 7 || ((nm == 5 || nm == 6) && op->optype == NEKMF_BWDTRANS) || (nm == 6 && op->deformed);
     if (!(v && v[0] == 'a') && !faster) return;
     switch (nm)
     {

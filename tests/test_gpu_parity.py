@@ -556,8 +556,8 @@ def test_shape_fast_kernels(shape, nm, deformed):
             # tensor-core kernels where they measured faster (prism_dmma.cu, tet_dmma.cu)
             if shape == "Prism" and 5 <= nm <= 7:
                 want = "prism_dmma_kernel"
-            if shape == "Tet" and (nm == 7 or (nm in (5, 6) and op == nk.eBwdTrans)):
-                want = "tet_dmma_kernel"
+            if shape == "Tet" and nm in (5, 6, 7):
+                want = "tet_bwd_gemm_kernel" if op == nk.eBwdTrans else ("tet_dmma_kernel" if (nm == 6 and deformed) else "tet_ip_gemm_kernel")
         assert want in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
     # IProductWRTDerivBase: lane kernels for regular quads up to nm = 5 / triangles up to nm = 6, otherwise the compile-time
     # sized kernel (chain-rule stage + the transposed-derivative / IProduct half of the fused Helmholtz kernel)
@@ -827,6 +827,7 @@ def test_tet_dmma_bwd_iprod(nm, nel, deformed, monkeypatch):
     f = rng.uniform(-1, 1, nel * el.nqTot)
     want_b, want_i = el.bwdtrans(nel, c), el.iproduct(nel, deformed, jac, f)
     res = {}
+    monkeypatch.setenv("NEKMF_TET_GEMM", "0")  # the GEMM kernel of tet_gemm.cu has its own test
     for mode in ("all", "0"):
         monkeypatch.setenv("NEKMF_TET_DMMA", mode)
         bwd, ipr = nk.Operator(std, nel, geom, nk.eBwdTrans), nk.Operator(std, nel, geom, nk.eIProductWRTBase)
@@ -911,3 +912,72 @@ def test_pyr_physderiv_shape_kernel(nm, deformed):
     assert "shape_op_kernel<Pyr,physderiv" in coll.m_ops[nk.ePhysDeriv].kernel_name, coll.m_ops[nk.ePhysDeriv].kernel_name
     for g, w in zip(outs, el.physderiv(nel, deformed, df, f)):
         assert max(rel_errs(g, w)) < 1e-12
+
+
+@pytest.mark.parametrize("nm,nel", [(5, 1), (5, 37), (6, 8), (6, 1001), (7, 1), (7, 7), (7, 8), (7, 9), (7, 37), (7, 4099)])
+def test_tet_gemm_bwdtrans(nm, nel, monkeypatch):
+    """BwdTrans on tetrahedra at nm = 5..7 as FP64 tensor-core GEMMs over eight elements (tet_gemm.cu: the two collapsed
+    contractions pre-combined into per-p tables with the vertex / edge corrections folded in on the host, last contraction
+    in the owning lane): against the oracle and against the pencil kernel (NEKMF_TET_GEMM=0, NEKMF_TET_DMMA=0), ragged
+    last batches, caller arrays that are only 8-byte aligned"""
+    torch = _torch()
+    nk = nekmf()
+    rng = np.random.default_rng(19 * nm + nel)
+    el = po.Elem(po.TET, nm, nm + 1)
+    std = nk.StdExpansion(nk.eTetrahedron, nm)
+    jac, df = random_geometry(rng, 3, nel, el.nqTot, False)
+    geom = nk.CoalescedGeomData(jac, df, False)
+    c = rng.uniform(-1, 1, nel * el.nmTot)
+    want = el.bwdtrans(nel, c)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NEKMF_TET_GEMM", mode)
+        monkeypatch.setenv("NEKMF_TET_DMMA", "0")
+        bwd = nk.Operator(std, nel, geom, nk.eBwdTrans)
+        assert ("tet_bwd_gemm_kernel" in bwd.kernel_name) == (mode == "1"), bwd.kernel_name
+        ob = np.zeros(nel * el.nqTot)
+        bwd.apply([c], [ob])
+        assert max(rel_errs(ob, want)) < 1e-12
+        cd = torch.zeros(c.size + 1, dtype=torch.float64, device="cuda")
+        cd[1:] = torch.tensor(c, device="cuda")
+        od = torch.zeros(ob.size + 1, dtype=torch.float64, device="cuda")
+        bwd.apply([cd[1:]], [od[1:]])
+        torch.cuda.synchronize()
+        assert np.array_equal(od[1:].cpu().numpy(), ob)
+        res[mode] = ob
+    assert max(rel_errs(res["1"], res["0"])) < 1e-13
+
+
+@pytest.mark.parametrize("nm,nel", [(5, 1), (5, 37), (6, 8), (6, 1001), (7, 1), (7, 7), (7, 8), (7, 9), (7, 37), (7, 4099)])
+@pytest.mark.parametrize("deformed", [False, True])
+def test_tet_gemm_iproduct(nm, nel, deformed, monkeypatch):
+    """IProductWRTBase on tetrahedra at nm = 5..7 as FP64 tensor-core GEMMs over eight elements (tet_gemm.cu: input lines
+    read straight from global memory and contracted with A_p in the loading lane, the two collapsed contractions as one
+    table per p with the vertex / edge corrections as extra rows): against the oracle and against the pencil kernel,
+    ragged last batches, caller arrays that are only 8-byte aligned"""
+    torch = _torch()
+    nk = nekmf()
+    rng = np.random.default_rng(23 * nm + nel)
+    el = po.Elem(po.TET, nm, nm + 1)
+    std = nk.StdExpansion(nk.eTetrahedron, nm)
+    jac, df = random_geometry(rng, 3, nel, el.nqTot, deformed)
+    geom = nk.CoalescedGeomData(jac, df, deformed)
+    f = rng.uniform(-1, 1, nel * el.nqTot)
+    want = el.iproduct(nel, deformed, jac, f)
+    res = {}
+    for mode in ("all", "0"):
+        monkeypatch.setenv("NEKMF_TET_GEMM", mode)
+        monkeypatch.setenv("NEKMF_TET_DMMA", "0")
+        ipr = nk.Operator(std, nel, geom, nk.eIProductWRTBase)
+        assert ("tet_ip_gemm_kernel" in ipr.kernel_name) == (mode == "all"), ipr.kernel_name
+        oi = np.zeros(nel * el.nmTot)
+        ipr.apply([f], [oi])
+        assert max(rel_errs(oi, want)) < 1e-12
+        fd = torch.zeros(f.size + 1, dtype=torch.float64, device="cuda")
+        fd[1:] = torch.tensor(f, device="cuda")
+        oid = torch.zeros(oi.size + 1, dtype=torch.float64, device="cuda")
+        ipr.apply([fd[1:]], [oid[1:]])
+        torch.cuda.synchronize()
+        assert np.array_equal(oid[1:].cpu().numpy(), oi)
+        res[mode] = oi
+    assert max(rel_errs(res["all"], res["0"])) < 1e-13
