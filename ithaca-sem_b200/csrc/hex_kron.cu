@@ -775,7 +775,8 @@ void kron_maybe_wrap(nekmf_op_s *op)
         case 7: kron_rows_wrap<7>(op); return;
         case 8: kron_rows_wrap<8>(op); return;
         case 9: kron_rows_wrap<9>(op); return;
-        case 10: kron_rows_wrap<10>(op); return; // nm = 11: two warps of 22 lanes per SM, slower than the pencil kernel
+        case 10: kron_rows_wrap<10>(op); return;
+        case 11: kron_rows_wrap<11>(op); return; // axis-aligned elements only, through hex_kron_fullrows.cuh<DIAG> (kron_geom_changed)
         default: return;
     }
     op->kron = 1;
@@ -815,10 +816,18 @@ int kron_geom_changed(nekmf_op_s *op)
         const char *vd     = getenv("NEKMF_HEX_KRON_DIAGROWS"); // =1 / =0: force / forbid it for diagonal metrics (A/B)
         // diagonal metric, measured against hex_kron_rows.cuh (profiles/r02_sweep_hex_diagrows_*.jsonl, fraction of the
         // HBM peak): nm = 7: 0.72 / 0.46, 8: 0.30 / 0.30, 9: 0.25 / 0.19, 10: 0.41 / 0.29
+        // nm = 11: only the DIAG variant of hex_kron_fullrows.cuh is used (hex_kron_rows.cuh fits two warps of 22 lanes per
+        // SM there and loses to the quadrature-space kernel)
         const bool diag_fr = vd ? vd[0] == '1' : op->nm[0] != 8;
+        if (op->nm[0] == 11 && !(st->tab_full && diag_fr))
+        {
+            st->use_kron = false;
+            op->kname    = st->fallback_name;
+        }
         // full metric, measured against the quadrature-space kernel (profiles/r02_sweep_hex_fullrows_*.jsonl):
         // 3.1x / 1.3x / 1.2x faster at nm = 7 / 8 / 9, 0.87x at nm = 10 (kept on the quadrature-space kernel)
-        const bool full_fr = flag != 0 && op->nm[0] <= 9;
+        const char *vf     = getenv("NEKMF_HEX_KRON_FULLROWS"); // =all: at every instantiated order (A/B)
+        const bool full_fr = flag != 0 && (op->nm[0] <= 9 || (vf && vf[0] == 'a'));
         if (st->tab_full && (full_fr || (flag == 0 && diag_fr)))
         {
             if (!st->d_geo8) NEKMF_CUDA(cudaMalloc(&st->d_geo8, (size_t)op->nElmt * 8 * 8));

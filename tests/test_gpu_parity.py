@@ -221,7 +221,7 @@ def box_geometry(nel, hx, hy, hz):
     return jac, df.reshape(-1).copy()
 
 
-@pytest.mark.parametrize("nm", [2, 3, 4, 5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize("nm", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
 @pytest.mark.parametrize("nel", [1, 31, 32, 33, 1000])
 def test_hex_helmholtz_coefficient_space_kernel(nm, nel):
     """axis-aligned boxes (diagonal Laplacian metric) take the Kronecker coefficient-space kernel;
