@@ -741,6 +741,9 @@ struct PrismState
     // general (non-extruded) regular prisms: eight-term kernel
     double *d_afrag8 = nullptr, *d_tab8 = nullptr;
     bool built8 = false, use_general = false, attr_set8 = false;
+    // general regular prisms at nm = 5..7: fused quadrature-space kernel on tensor tiles (prism_helm_dmma.cu)
+    void *fused    = nullptr;
+    bool use_fused = false;
 };
 
 template <int NM> static int prism_launch_nm(nekmf_op_s *op, PrismState *st, const double *in, double *out)
@@ -1034,6 +1037,7 @@ static int prism_launch(nekmf_op_s *op, const double *const in[3], double *const
         op->kstate   = saved;
         return rc;
     }
+    if (st->use_fused) return prism_helm_fused_launch(st->fused, op, in[0], out[0]);
     if (st->use_general)
     {
         switch (st->nmq)
@@ -1438,6 +1442,7 @@ void prism_maybe_wrap(nekmf_op_s *op)
         cudaFree(s->d_itab);
         cudaFree(s->d_afrag8);
         cudaFree(s->d_tab8);
+        if (s->fused) prism_helm_fused_free(s->fused, s->nmq);
         delete s;
     };
     op->launch = prism_launch;
@@ -1450,6 +1455,7 @@ int prism_geom_changed(nekmf_op_s *op)
     PrismState *st = static_cast<PrismState *>(op->kstate);
     st->use_fast    = false;
     st->use_general = false;
+    st->use_fused   = false;
     op->kname       = st->fallback_name;
     const char *env = getenv("NEKMF_DENSE");
     if (env && env[0] == '0') return NEKMF_OK;
@@ -1470,6 +1476,25 @@ int prism_geom_changed(nekmf_op_s *op)
         {
             // general regular prisms: the eight-term kernel where it was measured faster than the quadrature-space
             // kernel (nm 3..5: 1.5-2.2x; equal at nm = 7, 8); NEKMF_PRISM_GENERAL=1 takes it at every order, =0 never
+            // nm = 6, 7 (and nm = 5 with NEKMF_PRISM_FUSED=1): the fused quadrature-space kernel on tensor tiles
+            // (prism_helm_dmma.cu); NEKMF_PRISM_FUSED=0 never
+            // (an explicit NEKMF_PRISM_GENERAL selects between the eight-term and the quadrature-space kernel and leaves this
+            // one out unless NEKMF_PRISM_FUSED=1)
+            const char *ef   = getenv("NEKMF_PRISM_FUSED");
+            const bool fon   = ef && ef[0] == '1';
+            const bool fauto = !ef && !getenv("NEKMF_PRISM_GENERAL") && (st->nmq == 6 || st->nmq == 7);
+            if ((fon && st->nmq >= 5 && st->nmq <= 7) || fauto)
+            {
+                if (!st->fused) st->fused = prism_helm_fused_create(op);
+                if (st->fused)
+                {
+                    st->use_fast = st->use_fused = true;
+                    char fname[112];
+                    snprintf(fname, sizeof(fname), "prism_helm_dmma_kernel<nm=%d>(regular,general,fused quadrature space,DMMA m8n8k4)", st->nmq);
+                    op->kname = fname;
+                    return NEKMF_OK;
+                }
+            }
             const char *eg = getenv("NEKMF_PRISM_GENERAL");
             if (eg && eg[0] == '0') return NEKMF_OK;
             if (!(eg && eg[0] == '1') && (st->nmq < 3 || st->nmq > 5)) return NEKMF_OK;

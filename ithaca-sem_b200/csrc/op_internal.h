@@ -81,4 +81,8 @@ void dense_maybe_wrap(nekmf_op_s *op); // dense_helm.cu: DMMA coefficient-space 
 int dense_geom_changed(nekmf_op_s *op);
 void prism_maybe_wrap(nekmf_op_s *op); // dense_helm.cu: extruded prisms as nm triangle problems per element
 int prism_geom_changed(nekmf_op_s *op);
+// prism_helm_dmma.cu: fused quadrature-space Helmholtz for general regular prisms on tensor tiles (nm = 5..7)
+void *prism_helm_fused_create(nekmf_op_s *op);
+int prism_helm_fused_launch(void *state, nekmf_op_s *op, const double *in, double *out);
+void prism_helm_fused_free(void *state, int nm);
 } // namespace nekmf

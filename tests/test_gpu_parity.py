@@ -552,6 +552,8 @@ def test_shape_fast_kernels(shape, nm, deformed):
             want = "dense_helm_kernel"  # DMMA coefficient-space kernel (dense_helm.cu)
         if op == nk.eHelmholtz and not deformed and shape == "Prism" and 3 <= nm <= 5:
             want = "prism_gen_kernel"  # general regular prisms: eight-term DMMA kernel (dense_helm.cu), default at nm 3..5
+        if op == nk.eHelmholtz and not deformed and shape == "Prism" and nm in (6, 7):
+            want = "prism_helm_dmma_kernel"  # general regular prisms: fused quadrature-space kernel on tensor tiles
         if op in (nk.eBwdTrans, nk.eIProductWRTBase):
             # tensor-core kernels where they measured faster (prism_dmma.cu, tet_dmma.cu)
             if shape == "Prism" and 5 <= nm <= 7:
@@ -981,3 +983,41 @@ def test_tet_gemm_iproduct(nm, nel, deformed, monkeypatch):
         assert np.array_equal(oid[1:].cpu().numpy(), oi)
         res[mode] = oi
     assert max(rel_errs(res["all"], res["0"])) < 1e-13
+
+
+@pytest.mark.parametrize("nel", [1, 2, 3, 9, 100, 1001])
+@pytest.mark.parametrize("nm", [5, 6, 7])
+def test_prism_fused_dmma_helmholtz(nm, nel, monkeypatch):
+    """General regular prisms at nm = 5..7: the whole Helmholtz chain fused in quadrature space on FP64 tensor-core tiles
+    (prism_helm_dmma.cu: BwdTrans tiles, xi_0 / xi_1 derivatives and their transposes as tiles, xi_2 in the owning lane,
+    IProduct tiles fed from the accumulator fragments): against the oracle for several lambda, against the quadrature-space
+    pencil kernel, device arrays offset by one double"""
+    monkeypatch.delenv("NEKMF_DENSE", raising=False)
+    monkeypatch.delenv("NEKMF_PRISM_GENERAL", raising=False)
+    monkeypatch.setenv("NEKMF_PRISM_FUSED", "1")
+    torch = _torch()
+    nk = nekmf()
+    rng = np.random.default_rng(nm * 73 + nel)
+    el = po.Elem(po.PRISM, nm, nm + 1)
+    std = nk.StdExpansion(po.PRISM, nm, nm + 1)
+    jac, df = random_geometry(rng, 3, nel, el.nqTot, False)
+    coll = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, False))
+    x = rng.uniform(-1, 1, nel * el.nmTot)
+    for lam in (1.3, 0.0, 37.5):
+        out = np.zeros(nel * el.nmTot)
+        coll.ApplyOperator(nk.eHelmholtz, x, out, factors={nk.eFactorLambda: lam})
+        check(out, el.helmholtz(nel, False, jac, df, lam, x), "Helmholtz(prism fused, lambda=%g)" % lam)
+    assert "prism_helm_dmma_kernel" in coll.m_ops[nk.eHelmholtz].kernel_name, coll.m_ops[nk.eHelmholtz].kernel_name
+    xd = torch.zeros(x.size + 1, dtype=torch.float64, device="cuda")
+    xd[1:] = torch.from_numpy(x).cuda()
+    yd = torch.zeros(x.size + 1, dtype=torch.float64, device="cuda")
+    coll.ApplyOperator(nk.eHelmholtz, xd[1:], yd[1:], factors={nk.eFactorLambda: 37.5})
+    torch.cuda.synchronize()
+    assert np.array_equal(yd[1:].cpu().numpy(), out)
+    monkeypatch.setenv("NEKMF_PRISM_FUSED", "0")
+    monkeypatch.setenv("NEKMF_PRISM_GENERAL", "0")
+    coll0 = nk.Collection(std, nel, nk.CoalescedGeomData(jac, df, False))
+    out0 = np.zeros(nel * el.nmTot)
+    coll0.ApplyOperator(nk.eHelmholtz, x, out0, factors={nk.eFactorLambda: 37.5})
+    assert "shape_op_kernel" in coll0.m_ops[nk.eHelmholtz].kernel_name
+    check(out, out0, "prism fused DMMA vs quadrature-space kernel")
