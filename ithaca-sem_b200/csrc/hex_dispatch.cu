@@ -1,5 +1,6 @@
 // hex_dispatch.cu -- picks the compile-time specialised hexahedral kernel for an operator.
 #include "op_internal.h"
+#include <stdlib.h>
 
 namespace nekmf
 {
@@ -39,11 +40,15 @@ bool select_hex_fast(nekmf_op_s *op)
 SHP_DECL(2) SHP_DECL(3) SHP_DECL(4) SHP_DECL(5) SHP_DECL(6) SHP_DECL(7) SHP_DECL(8) SHP_DECL(9)
 #undef SHP_DECL
 
-// Quad / Tri / Prism / Tet (and pyramid PhysDeriv) with the default quadrature: compile-time sized kernels (shape_kernels.cuh)
+// Quad / Tri / Prism / Pyr / Tet with the default quadrature: compile-time sized kernels (shape_kernels.cuh)
 bool select_shape_fast(nekmf_op_s *op)
 {
     if (op->shape == NEKMF_HEX) return false;
-    if (op->shape == NEKMF_PYR && op->optype != NEKMF_PHYSDERIV) return false; // pyramids: PhysDeriv only in this family
+    if (op->shape == NEKMF_PYR && op->optype != NEKMF_PHYSDERIV)
+    {
+        const char *v = getenv("NEKMF_PYR_SHAPE"); // NEKMF_PYR_SHAPE=0: runtime-sized kernels (A/B comparisons)
+        if (v && v[0] == '0') return false;
+    }
     if (select_quad_lane(op)) return true; // BwdTrans / IProductWRTBase / regular PhysDeriv on quads: one lane per element
     if (select_tri_lane(op)) return true;  // the same for triangles
     bool ok = false;

@@ -1,4 +1,4 @@
-// shape_inst.cu -- instantiates the Quad / Tri / Prism / Tet kernels of shape_kernels.cuh for one polynomial
+// shape_inst.cu -- instantiates the Quad / Tri / Prism / Pyr / Tet kernels of shape_kernels.cuh for one polynomial
 // order (NM = SHAPE_NM modes per direction, default quadrature) and provides their launchers.  Compiled once
 // per order so the orders build in parallel.
 #include "shape_kernels.cuh"
@@ -67,7 +67,6 @@ template <int SHAPE, int OP, int NM, bool DEF> static int shape_launch(nekmf_op_
 template <int SHAPE, int NM> static bool shape_install(nekmf_op_s *op)
 {
     using Dm = ShpDims<SHAPE, NM>;
-    if (SHAPE == NEKMF_PYR && op->optype != NEKMF_PHYSDERIV) return false; // pyramids: quadrature-space operator only
     for (int d = 0; d < Dm::DIM; ++d)
         if (op->nm[d] != NM) return false;
     if (op->nq[0] != Dm::NQ0 || op->nq[1] != Dm::NQ1 || (Dm::DIM == 3 && op->nq[2] != Dm::NQ2)) return false;
@@ -87,7 +86,7 @@ template <int SHAPE, int NM> static bool shape_install(nekmf_op_s *op)
     if (Dm::B2C_ROWS) memcpy(aux.data() + Dm::OFF_B2C, op->b[2].data(), sizeof(double) * Dm::B2C_ROWS * Dm::NQ2);
     for (int d = 0; d < Dm::DIM; ++d)
         for (int i = 0; i < op->nq[d]; ++i) aux[Dm::OFF_W + d * Dm::NQM + i] = op->ws[d][i];
-    // collapsed-coordinate factors: Helmholtz.h:304-315 (Tri), 1017-1028 (Prism), 1985-2004 (Tet)
+    // collapsed-coordinate factors: Helmholtz.h:304-315 (Tri), 1017-1028 (Prism), 1490-1508 (Pyr), 1985-2004 (Tet)
     double *h0 = aux.data() + Dm::OFF_H, *h1 = h0 + Dm::NQM, *h2 = h1 + Dm::NQM, *h3 = h2 + Dm::NQM;
     for (int i = 0; i < Dm::NQ0; ++i) h0[i] = 0.5 * (1.0 + op->Z[0][i]);
     if (SHAPE == NEKMF_TRI)
@@ -128,23 +127,13 @@ template <int SHAPE, int NM> static bool shape_install(nekmf_op_s *op)
     case OPC:                                                                                                   \
         op->launch = op->deformed ? shape_launch<SHAPE, OPC, NM, true> : shape_launch<SHAPE, OPC, NM, false>;   \
         return true;
-    if constexpr (SHAPE == NEKMF_PYR)
+    switch (op->optype)
     {
-        switch (op->optype)
-        {
-            SHP_CASE(NEKMF_PHYSDERIV)
-        }
-    }
-    else
-    {
-        switch (op->optype)
-        {
-            SHP_CASE(NEKMF_BWDTRANS)
-            SHP_CASE(NEKMF_HELMHOLTZ)
-            SHP_CASE(NEKMF_IPRODUCTWRTBASE)
-            SHP_CASE(NEKMF_PHYSDERIV)
-            SHP_CASE(NEKMF_IPRODUCTWRTDERIVBASE)
-        }
+        SHP_CASE(NEKMF_BWDTRANS)
+        SHP_CASE(NEKMF_HELMHOLTZ)
+        SHP_CASE(NEKMF_IPRODUCTWRTBASE)
+        SHP_CASE(NEKMF_PHYSDERIV)
+        SHP_CASE(NEKMF_IPRODUCTWRTDERIVBASE)
     }
 #undef SHP_CASE
     op->kstate_free(st);

@@ -1,11 +1,11 @@
-// shape_kernels.cuh -- compile-time sized sum-factorised operators for Quad, Tri, Prism and Tet
+// shape_kernels.cuh -- compile-time sized sum-factorised operators for Quad, Tri, Prism, Pyr and Tet
 // (default quadrature nq0 = nm+1; Gauss-Radau directions nq = nm) on sm_100a.
 //
 // Reference semantics (what is computed, not how):
-//   BwdTrans         MatrixFreeOps/BwdTransKernels.hpp:35-76 (Quad) 78-126 (Tri) 128-300 (Prism) 374-484 (Tet)
-//   IProductWRTBase  MatrixFreeOps/IProductKernels.hpp:76-133 (Quad) 135-234 (Tri) 316-450 (Prism) 600-761 (Tet)
-//   PhysDeriv        MatrixFreeOps/PhysDerivKernels.hpp:39-90,186 (2-D) 374-430 (Prism) 555-696 (Tet)
-//   Helmholtz        MatrixFreeOps/Helmholtz.h:138-275 (Quad) 506-635 (Tri) 1291-1458 (Prism) 2266-2448 (Tet)
+//   BwdTrans         MatrixFreeOps/BwdTransKernels.hpp:35-76 (Quad) 78-126 (Tri) 128-224 (Pyr) 226-300 (Prism) 374-484 (Tet)
+//   IProductWRTBase  MatrixFreeOps/IProductKernels.hpp:76-133 (Quad) 135-234 (Tri) 316-450 (Prism) 452-598 (Pyr) 600-761 (Tet)
+//   PhysDeriv        MatrixFreeOps/PhysDerivKernels.hpp:39-90,186 (2-D) 374-430 (Prism) 505-527 (Pyr) 555-696 (Tet)
+//   Helmholtz        MatrixFreeOps/Helmholtz.h:138-275 (Quad) 506-635 (Tri) 1291-1458 (Prism) 1773-1950 (Pyr) 2266-2448 (Tet)
 //
 // Design: a persistent CTA works on batches of E elements held in shared memory.  Every 1-D contraction
 // is a pencil pass: one thread owns one line of the (collapsed) tensor along the contracted direction,
@@ -31,7 +31,7 @@ constexpr int shp_round2(int a) { return (a + 1) & ~1; }
 template <int SHAPE, int NM> struct ShpDims
 {
     static constexpr bool IS_QUAD = SHAPE == NEKMF_QUAD, IS_TRI = SHAPE == NEKMF_TRI, IS_PRISM = SHAPE == NEKMF_PRISM,
-                          IS_TET = SHAPE == NEKMF_TET, IS_PYR = SHAPE == NEKMF_PYR; // pyramids: PhysDeriv only
+                          IS_TET = SHAPE == NEKMF_TET, IS_PYR = SHAPE == NEKMF_PYR;
     static constexpr int DIM = (IS_QUAD || IS_TRI) ? 2 : 3;
     static constexpr int NQ0 = NM + 1;
     static constexpr int NQ1 = (IS_TRI || IS_TET) ? NM : NM + 1;
@@ -42,7 +42,7 @@ template <int SHAPE, int NM> struct ShpDims
     static constexpr int NPAIR = NM * (NM + 1) / 2;
     static constexpr int NMT   = IS_QUAD ? NM * NM : (IS_TRI ? NPAIR : (IS_PRISM ? NM * NPAIR : (IS_PYR ? NM * (NM + 1) * (2 * NM + 1) / 6 : NM * (NM + 1) * (NM + 2) / 6)));
     static constexpr int B1C_ROWS = (IS_TRI || IS_TET) ? NPAIR : 0;         // collapsed rows of direction 1
-    static constexpr int B2C_ROWS = IS_PRISM ? NPAIR : (IS_TET ? NMT : 0);  // collapsed rows of direction 2
+    static constexpr int B2C_ROWS = IS_PRISM ? NPAIR : ((IS_TET || IS_PYR) ? NMT : 0); // collapsed rows of direction 2
     // aux table (global -> shared): [b1c | b2c | w0 w1 w2 | h0 h1 h2 h3]
     static constexpr int NQM     = NQ0; // every per-direction helper array is padded to NQ0 entries
     static constexpr int OFF_B1C = 0;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256)
     using Dm = ShpDims<SHAPE, NM>;
     constexpr int DIM = Dm::DIM, NQ0 = Dm::NQ0, NQ1 = Dm::NQ1, NQ2 = Dm::NQ2, NQT = Dm::NQT, P1 = Dm::P1, NQP = Dm::NQP;
     constexpr int NMT = Dm::NMT, NPAIR = Dm::NPAIR, E = Dm::E, T = Dm::T, NQM = Dm::NQM;
-    constexpr bool IS_QUAD = Dm::IS_QUAD, IS_TRI = Dm::IS_TRI, IS_PRISM = Dm::IS_PRISM, IS_TET = Dm::IS_TET;
+    constexpr bool IS_QUAD = Dm::IS_QUAD, IS_TRI = Dm::IS_TRI, IS_PRISM = Dm::IS_PRISM, IS_TET = Dm::IS_TET, IS_PYR = Dm::IS_PYR;
     constexpr bool COEFF_IN = OP == NEKMF_BWDTRANS || OP == NEKMF_HELMHOLTZ;
     // IProductWRTDerivBase (IProductWRTDerivBase.h:542-640 Quad, 891-1040 Tri, 1630-1740 Prism, 2484-2610 Tet):
     // dbdata = D bdata (Foundations/Basis.cpp:418-420, 506, 561), so sum_d (dB_d)^T W t_d = B^T sum_d D_d^T (W t_d):
@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256)
     int *sPQp    = reinterpret_cast<int *>(sG + Dm::GSZ); // pair index -> p
     int *sPQq    = sPQp + NPAIR;                        // pair index -> q
     int *sPQm    = sPQq + NPAIR;                        // Tet: first mode of pair (p,q)
+    int *sM0     = sPQp;                                // Pyr: first mode of (p,q), NM*NM <= 3*NPAIR entries over the three arrays
     // coefficient-input operators: second coefficient buffer, filled by cp.async with the NEXT batch while this
     // one is computed (ncu: the exposed load + barrier at the top of a batch was 20 % of the prism Helmholtz kernel)
     double *sCinAlt = reinterpret_cast<double *>(smem_raw + Dm::SMEM);
@@ -179,15 +180,29 @@ __global__ void __launch_bounds__(256)
     for (int i = tid; i < Dm::AUX_LEN; i += T) sAux[i] = __ldg(args.aux + i);
     if (tid == 0)
     {
-        int c = 0, m = 0;
-        for (int p = 0; p < NM; ++p)
-            for (int q = 0; q < NM - p; ++q, ++c)
-            {
-                sPQp[c] = p;
-                sPQq[c] = q;
-                sPQm[c] = m;
-                m += NM - p - q;
-            }
+        if (IS_PYR)
+        {
+            // mode order of the pyramid (BwdTransKernels.hpp:146-177): p outer, q, then r < NM - max(p,q)
+            int m = 0;
+            for (int p = 0; p < NM; ++p)
+                for (int q = 0; q < NM; ++q)
+                {
+                    sM0[p * NM + q] = m;
+                    m += NM - (p > q ? p : q);
+                }
+        }
+        else
+        {
+            int c = 0, m = 0;
+            for (int p = 0; p < NM; ++p)
+                for (int q = 0; q < NM - p; ++q, ++c)
+                {
+                    sPQp[c] = p;
+                    sPQq[c] = q;
+                    sPQm[c] = m;
+                    m += NM - p - q;
+                }
+        }
     }
     __syncthreads();
 
@@ -342,6 +357,38 @@ __global__ void __launch_bounds__(256)
                 }
                 __syncthreads();
             }
+            if (IS_PYR)
+            {
+                // lines (e, p, q): FPQ[p][q][k] = sum_{r < NM - max(p,q)} in[m0+r] b2[m0+r][k]; the top-vertex term of
+                // BwdTransKernels.hpp:204-221 is in[1] b2[1][k] (b0[0] b1[1] + b0[1] b1[0] + b0[1] b1[1]): added to the
+                // entries (0,1), (1,0), (1,1) it passes through the two tensor contractions below
+                for (int l = tid; l < E * NM * NM; l += T)
+                {
+                    const int e = l / (NM * NM), pq = l - e * (NM * NM);
+                    const int p = pq / NM, q = pq - p * NM;
+                    const int m0 = sM0[pq], len = NM - (p > q ? p : q);
+                    const double *cin = sCin + e * NMT + m0;
+                    const double *row = b2c + m0 * NQ2;
+                    double y[NQ2];
+#pragma unroll
+                    for (int k = 0; k < NQ2; ++k) y[k] = 0.0;
+                    for (int r = 0; r < len; ++r)
+                    {
+                        const double x = cin[r];
+#pragma unroll
+                        for (int k = 0; k < NQ2; ++k) y[k] = fma(row[r * NQ2 + k], x, y[k]);
+                    }
+                    if (p < 2 && q < 2 && p + q > 0)
+                    {
+                        const double x = sCin[e * NMT + 1];
+#pragma unroll
+                        for (int k = 0; k < NQ2; ++k) y[k] = fma(b2c[NQ2 + k], x, y[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < NQ2; ++k) sA[e * NQP + pq * NQ2 + k] = y[k];
+                }
+                __syncthreads();
+            }
             // -------------------------------------------------------------- S2: q -> j      FP[p][k][j] -> sB
             for (int l = tid; l < E * NM * NQ2; l += T)
             {
@@ -355,7 +402,7 @@ __global__ void __launch_bounds__(256)
                     for (int q = 0; q < NM; ++q) x[q] = sCin[e * NMT + q * NM + p];
                     shp_fwd<NM, NQ1>(tab.b1t, x, y);
                 }
-                else if (IS_PRISM)
+                else if (IS_PRISM || IS_PYR)
                 {
                     double x[NM];
 #pragma unroll
@@ -539,6 +586,12 @@ __global__ void __launch_bounds__(256)
                             double t1 = fma(f[7], z, fma(f[4], y, f[1] * x));
                             const double t2 = fma(f[8], z, fma(f[5], y, f[2] * x));
                             if (IS_PRISM) t0 = fma(h0i, t2, t0) * sH1[s]; // IProductWRTDerivBase.h:1697-1733
+                            if (IS_PYR)
+                            {
+                                // IProductWRTDerivBase.h:2121-2164: both base directions collapse towards the apex
+                                t0 = fma(h0i, t2, t0) * sH1[s];
+                                t1 = fma(sH2[j], t2, t1) * sH1[s];
+                            }
                             if (IS_TET)
                             {
                                 // IProductWRTDerivBase.h:2551-2603
@@ -646,6 +699,21 @@ __global__ void __launch_bounds__(256)
                                 m11 = fma(f[7], f[7], fma(f[4], f[4], f[1] * f[1]));
                                 m22 = fma(f[8], f[8], fma(f[5], f[5], f[2] * f[2]));
                                 m12 = fma(f[7], f[8], fma(f[4], f[5], f[1] * f[2]));
+                            }
+                            else if (IS_PYR)
+                            {
+                                // Helmholtz.h:1842-1902
+                                const double a = sH1[s], h1j = sH2[j];
+                                const double t0 = a * fma(h0i, f[2], f[0]), t1 = a * fma(h0i, f[5], f[3]),
+                                             t2 = a * fma(h0i, f[8], f[6]);
+                                const double t3 = a * fma(h1j, f[2], f[1]), t4 = a * fma(h1j, f[5], f[4]),
+                                             t5 = a * fma(h1j, f[8], f[7]);
+                                m00 = fma(t2, t2, fma(t1, t1, t0 * t0));
+                                m11 = fma(t5, t5, fma(t4, t4, t3 * t3));
+                                m22 = fma(f[8], f[8], fma(f[5], f[5], f[2] * f[2]));
+                                m01 = fma(t2, t5, fma(t1, t4, t0 * t3));
+                                m02 = fma(f[8], t2, fma(f[5], t1, f[2] * t0));
+                                m12 = fma(f[8], t5, fma(f[5], t4, f[2] * t3));
                             }
                             else
                             {
@@ -769,7 +837,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
                 for (int q = 0; q < NM; ++q) sCin[e * NMT + q * NM + p] = y[q];
             }
-            else if (IS_PRISM)
+            else if (IS_PRISM || IS_PYR)
             {
                 double y[NM];
                 shp_tr<NQ1, NM>(tab.b1t, x, y);
@@ -887,6 +955,38 @@ __global__ void __launch_bounds__(256)
                     double s = 0.0;
 #pragma unroll
                     for (int k = 0; k < NQ2; ++k) s = fma(b2c[NQ2 + k], sA[e * NQP + (NM + q) * NQ2 + k], s);
+                    cout[1] += s;
+                }
+            }
+            __syncthreads();
+        }
+        if (IS_PYR)
+        {
+            for (int l = tid; l < E * NM * NM; l += T)
+            {
+                const int e = l / (NM * NM), pq = l - e * (NM * NM);
+                const int p = pq / NM, q = pq - p * NM;
+                const int m0 = sM0[pq], len = NM - (p > q ? p : q);
+                const double *row = b2c + m0 * NQ2;
+                double *cout = sCin + e * NMT + m0;
+                double x[NQ2];
+#pragma unroll
+                for (int k = 0; k < NQ2; ++k) x[k] = sA[e * NQP + pq * NQ2 + k];
+                for (int r = 0; r < len; ++r)
+                {
+                    double s = row[r * NQ2] * x[0];
+#pragma unroll
+                    for (int k = 1; k < NQ2; ++k) s = fma(row[r * NQ2 + k], x[k], s);
+                    cout[r] = s;
+                }
+                if (pq == 0)
+                {
+                    // top vertex (IProductKernels.hpp:552-596): mode 1 += sum_k b2[1][k] (fb[0][1][k] + fb[1][0][k] + fb[1][1][k])
+                    const double *fb = sA + e * NQP;
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NQ2; ++k)
+                        s = fma(b2c[NQ2 + k], fb[1 * NQ2 + k] + fb[NM * NQ2 + k] + fb[(NM + 1) * NQ2 + k], s);
                     cout[1] += s;
                 }
             }

@@ -916,6 +916,33 @@ def test_pyr_physderiv_shape_kernel(nm, deformed):
         assert max(rel_errs(g, w)) < 1e-12
 
 
+@pytest.mark.parametrize("deformed", [False, True])
+@pytest.mark.parametrize("nm", list(range(2, 10)))
+@pytest.mark.parametrize("base", [False, True])
+def test_pyr_shape_kernels(nm, deformed, base, monkeypatch):
+    """pyramids in the compile-time sized family (shape_kernels.cuh, nm = 2..9 with the default quadrature: mode lines of
+    length nm - max(p, q) from a first-mode table, two tensor contractions as for prisms, top-vertex term through the
+    entries (0,1), (1,0), (1,1); Laplacian metric / chain rule with both base directions collapsing towards the apex):
+    all five operators against the oracle, several batches plus a ragged last one.  base=True switches the tensor-core
+    kernels layered on top off (NEKMF_PYR_DMMA=0, NEKMF_DENSE=0) so that every operator runs this family at every order"""
+    if base:
+        monkeypatch.setenv("NEKMF_PYR_DMMA", "0")
+        monkeypatch.setenv("NEKMF_DENSE", "0")
+    else:
+        monkeypatch.delenv("NEKMF_PYR_DMMA", raising=False)
+        monkeypatch.delenv("NEKMF_DENSE", raising=False)
+    nk = nekmf()
+    coll = run_all_ops(nk, po.PYR, nm, nm + 1, 67, deformed, np.random.default_rng(41 * nm + deformed))
+    for op in (nk.eBwdTrans, nk.eIProductWRTBase, nk.ePhysDeriv, nk.eHelmholtz, nk.eIProductWRTDerivBase):
+        want = "shape_op_kernel<Pyr"
+        if not base:
+            if op in (nk.eBwdTrans, nk.eIProductWRTBase) and 3 <= nm <= 7:
+                want = "pyr_dmma_kernel"  # tensor-core tiles (prism_dmma.cu)
+            if op == nk.eHelmholtz and not deformed and nm <= 7:
+                want = "dense_helm_kernel"  # DMMA coefficient-space kernel (dense_helm.cu, instantiated up to nm = 7)
+        assert want in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
+
+
 @pytest.mark.parametrize("nm,nel", [(5, 1), (5, 37), (6, 8), (6, 1001), (7, 1), (7, 7), (7, 8), (7, 9), (7, 37), (7, 4099)])
 def test_tet_gemm_bwdtrans(nm, nel, monkeypatch):
     """BwdTrans on tetrahedra at nm = 5..7 as FP64 tensor-core GEMMs over eight elements (tet_gemm.cu: the two collapsed
