@@ -76,7 +76,8 @@ __global__ void assemble_kernel(const int *__restrict__ rowptr, const int *__res
 // the NCCL send buffer, and the last of them raises the neighbours' flags; the transfer then overlaps the rest of
 // the assemble.  The s.w terms of shared DOFs are left to the unpack kernel (their sums are not complete yet).
 template <bool EX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8) // 32 registers: all RED_BLOCKS = 8 x 148 blocks resident, one wave (40 registers
+                                           // left 6 per SM: a second, third-full wave)
     assemble_dot_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ sign,
                         const double *__restrict__ loc, double *__restrict__ glob, int nGlobal,
                         const double *__restrict__ w, const unsigned char *__restrict__ flags, int nDir,
@@ -102,16 +103,41 @@ __global__ void __launch_bounds__(256)
     }
     // (measured alternative: four rows per thread with interleaved rowptr -> col -> loc chains: 0.73 -> 1.25 ms on
     // 2^20 hex elements -- the four row windows thrash the L2 lines the neighbouring rows share)
+    // The row's chain rowptr -> col -> loc is three dependent DRAM latencies (ncu: 45 long-scoreboard stall cycles per
+    // issue at full occupancy, 65 % of the HBM peak), so the grid-stride loop is software-pipelined: this trip loads
+    // rowptr of the row two trips ahead, the first two column indices of the next row and the values of its own row,
+    // all independent of each other.  The sum keeps the order s = ((0 + t0) + t1) + ... of the plain loop.
+    auto val = [&](int i) { return sign ? sign[i] * __ldg(loc + i) : __ldg(loc + i); };
+    const int stride = gridDim.x * blockDim.x;
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int b0 = 0, e0 = 0, b1 = 0, e1 = 0, c00 = 0, c01 = 0;
+    if (g < nGlobal) { b0 = rowptr[g]; e0 = rowptr[g + 1]; }
+    if (g < nGlobal - stride) { b1 = rowptr[g + stride]; e1 = rowptr[g + stride + 1]; }
+    if (e0 > b0) c00 = col[b0];
+    if (e0 > b0 + 1) c01 = col[b0 + 1];
     double mu = 0.0;
-    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nGlobal; g += gridDim.x * blockDim.x)
+    for (; g < nGlobal; g += stride)
     {
-        const double s = row_sum(g);
-        glob[g] = s;
+        int b2 = 0, e2 = 0;
+        if (g < nGlobal - 2 * stride) { b2 = rowptr[g + 2 * stride]; e2 = rowptr[g + 2 * stride + 1]; }
+        double v0 = 0.0, v1 = 0.0, wg = 0.0;
+        if (e0 > b0) v0 = val(c00);
+        if (e0 > b0 + 1) v1 = val(c01);
+        unsigned char f = 0;
         if (g >= nDir)
         {
-            const unsigned char f = flags ? flags[g] : (unsigned char)1;
-            if ((f & 1) && !(f & 2)) mu = fma(s, w[g], mu);
+            f  = flags ? flags[g] : (unsigned char)1;
+            wg = w[g];
         }
+        int c10 = 0, c11 = 0;
+        if (e1 > b1) c10 = col[b1];
+        if (e1 > b1 + 1) c11 = col[b1 + 1];
+        double s = v0 + v1;
+        for (int k = b0 + 2; k < e0; ++k) s += val(col[k]);
+        glob[g] = s;
+        if ((f & 1) && !(f & 2)) mu = fma(s, wg, mu);
+        b0 = b1; e0 = e1; c00 = c10; c01 = c11;
+        b1 = b2; e1 = e2;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);

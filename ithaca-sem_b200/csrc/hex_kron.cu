@@ -51,6 +51,7 @@ struct KronArgs
     // sign[i] * in[map[i]] (AssemblyMapCG::v_GlobalToLocal fused into the operator's load)
     const int *map;
     const double *sign;
+    int gather_rows; // gather order: 1 = one (q, r) row of ALL the batch's elements per instruction, 0 = local index order
 };
 
 constexpr int kron_pad(int minimum, int residue) // smallest v >= minimum with v % 16 == residue
@@ -155,10 +156,27 @@ __global__ void __launch_bounds__(KronCfg<NM, GATHER, WSEL>::T, 1)
     // registers (completes at the next cp_async_wait_all).  Measured alternative: the values through registers
     // (__ldg early, st.shared after the exchanges) halves the shared-memory wavefronts but exposes the load latency
     // with 8 warps per SM: 0.75 -> 1.47 ms on 2^20 elements.
+    // Order: with consecutive elements of a batch adjacent in the mesh (structured numbering, or any element ordering
+    // with locality) the p-lines of one (q, r) row of ALL EPW elements are neighbours in the global vector, so one
+    // instruction whose lanes are (element, p) touches 2-3 cache lines instead of the 8-9 that 32 consecutive local
+    // indices of one element span -- the L1 tag stage handles one line per cycle and was the limiter of this kernel.
     auto gather = [&](int wb) {
-        const int n = batch_ne(wb) * NM3;
+        const int ne = batch_ne(wb);
+        if (args.gather_rows)
+        {
+            if (active && e < ne)
+            {
+                const int base = e * NM3 + s1;
+#pragma unroll 5
+                for (int qr = 0; qr < NM2; ++qr) cp_async8(sIn + base + qr * NM, args.in + sMap[base + qr * NM]);
+            }
+        }
+        else
+        {
+            const int n = ne * NM3;
 #pragma unroll 4
-        for (int i = lane; i < n; i += 32) cp_async8(sIn + i, args.in + sMap[i]);
+            for (int i = lane; i < n; i += 32) cp_async8(sIn + i, args.in + sMap[i]);
+        }
     };
     auto issue    = [&](int wb) { // lane 0; sIn and sGeo are free
         const int ne   = batch_ne(wb);
@@ -464,6 +482,8 @@ template <int NM, bool GATHER, int WSEL = 0> static int kron_launch_t(nekmf_op_s
     a.in = in; a.out = out; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
     a.map  = GATHER ? op->gather_map + (size_t)op->run_e0 * Cfg::NM3 : nullptr;
     a.sign = GATHER && op->gather_sign ? op->gather_sign + (size_t)op->run_e0 * Cfg::NM3 : nullptr;
+    static const int gather_rows = [] { const char *v = getenv("NEKMF_GATHER_ROWS"); return (v && v[0] == '0') ? 0 : 1; }(); // A/B knob
+    a.gather_rows = gather_rows;
     a.io_aligned = GATHER ? ((((uintptr_t)out) & 15) == 0) : ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
     const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
     int grid           = bps * NUM_SMS;
@@ -554,7 +574,7 @@ template <int NM> static int kron_rows_launch(nekmf_op_s *op, const double *cons
     }
     KronArgs a;
     a.in = in[0]; a.out = out[0]; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
-    a.map = nullptr; a.sign = nullptr;
+    a.map = nullptr; a.sign = nullptr; a.gather_rows = 0;
     a.io_aligned = ((((uintptr_t)in[0]) | ((uintptr_t)out[0])) & 15) == 0;
     const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
     int grid           = st->blocks_per_sm * NUM_SMS;
@@ -583,7 +603,7 @@ template <int NM> static int kron_lane_launch(nekmf_op_s *op, KronState *st, con
     }
     KronArgs a;
     a.in = in; a.out = out; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
-    a.map = nullptr; a.sign = nullptr;
+    a.map = nullptr; a.sign = nullptr; a.gather_rows = 0;
     a.io_aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
     const int nBatches = (op->run_ne + 32 * Cfg::WARPS - 1) / (32 * Cfg::WARPS);
     int grid           = st->blocks_per_sm_lane * NUM_SMS;
