@@ -590,9 +590,10 @@ void hex_dmma_maybe_wrap(nekmf_op_s *op)
     if (op->optype != NEKMF_BWDTRANS && op->optype != NEKMF_IPRODUCTWRTBASE) return;
     const bool all = v && v[0] == 'a';
     // measured A/B (profiles/r02_sweep_hex_dmma_{all,0}.jsonl): every nm = 7 cell (0.77-0.90 against 0.47-0.78 of the
-    // HBM peak) and regular IProductWRTBase at nm = 11 (0.39 against 0.36); the half-empty second row tile loses to
-    // the pencil kernels everywhere else
-    const bool faster = nm == 7 || (nm == 11 && op->optype == NEKMF_IPRODUCTWRTBASE && !op->deformed);
+    // HBM peak); the half-empty second row tile loses to the pencil kernels everywhere else (regular IProductWRTBase at
+    // nm = 11 was 0.39 against 0.36 until the pencil kernel went to one element per CTA: 0.56,
+    // profiles/r02_sweep_hex_nodmma_v2.jsonl)
+    const bool faster = nm == 7;
     if (!all && !faster) return;
     switch (nm)
     {

@@ -105,7 +105,11 @@ template <int OP, int NM, int NQ, bool DEF> struct HexCfg
     // E even when possible (keeps every full batch of odd-sized coefficient blocks 16-byte aligned)
     static constexpr int E_RAW = E_FIT < 1 ? 1 : (E_FIT > 8 ? 8 : E_FIT);
     static constexpr int E_THR = (1024 / NQ2) < 1 ? 1 : (1024 / NQ2);
-    static constexpr int E_MIN = E_RAW < E_THR ? E_RAW : E_THR;
+    // regular IProductWRTBase at nm = 11: two elements per CTA compile to 168 registers plus spills and ONE resident CTA of 9
+    // warps (0.46 ms, slower than the deformed variant that streams the Jacobian on top); one element per CTA is the deformed
+    // variant's shape (64 registers, four CTAs)
+    static constexpr bool E_ONE = OP == HEX_IPROD && !DEF && NM == 11;
+    static constexpr int E_MIN = E_ONE ? 1 : (E_RAW < E_THR ? E_RAW : E_THR);
     static constexpr int E     = (E_MIN >= 2 && (E_MIN % 2)) ? E_MIN - 1 : E_MIN;
     static constexpr int T     = round_up(E * NQ2, 32);
     static constexpr int CIN   = HASCIN ? round_up(E * NM3, 2) : 0;
@@ -115,7 +119,18 @@ template <int OP, int NM, int NQ, bool DEF> struct HexCfg
     // unrolls into >160 registers, which leaves ONE CTA per SM.  Bound the allocation so that two CTAs are
     // resident (measured: nm=5 1.25 -> 1.15 ms, nm=8 1.74 -> 1.18 ms, nm=11 2.42 -> 1.70 ms; the same bound
     // on IProductWRTDerivBase lost more than it won and is not applied).
-    static constexpr int MINB = (!DEF && OP == HEX_HELM && 2 * SMEM <= 220 * 1024) ? 2 : 0; // 0 = no bound
+    static constexpr int MINB_HELM = (!DEF && OP == HEX_HELM && 2 * SMEM <= 220 * 1024) ? 2 : 0; // 0 = no bound
+    // regular PhysDeriv / IProductWRTBase / IProductWRTDerivBase at nm >= 7: ptxas settles at 147-234 registers, which
+    // leaves ONE CTA of 5-9 warps per SM where shared memory has room for 2-4 (cuobjdump -res-usage of hex_nm*.o).
+    // Bound the allocation to the number of CTAs shared memory admits, as long as >= 80 registers per thread remain.
+    static constexpr int T_ALLOC = round_up(T, 128); // warps are allocated in fours
+    static constexpr int SM_FIT  = (int)((220 * 1024) / SMEM) > 4 ? 4 : (int)((220 * 1024) / SMEM);
+    static constexpr int minb_for(int m) { return m <= 1 ? 0 : ((65536 / (m * T_ALLOC) >= 80) ? m : minb_for(m - 1)); }
+    // A/B over nm = 7..11 (profiles/r02_sweep_hex_minb_{A,B}.jsonl): IProductWRTDerivBase 1.16 -> 0.91, 1.23 -> 0.86, 1.11 -> 0.82,
+    // 0.99 -> 0.90 ms at nm = 7, 9, 10, 11 and PhysDeriv 0.87 -> 0.68, 0.68 -> 0.61, 0.60 -> 0.53 ms at nm = 7, 10, 11; it LOSES at
+    // nm = 8 (three CTAs: 96 registers, spills) and for IProductWRTBase, which keep the compiler's choice
+    static constexpr bool MINB_ON = !DEF && NM >= 7 && NM != 8 && (OP == HEX_PD || OP == HEX_IPWDB);
+    static constexpr int MINB     = MINB_ON ? minb_for(SM_FIT) : MINB_HELM;
 };
 
 // y[b] = sum_a M[a*NOUT+b] x[a]          (forward: basis / derivative evaluation)
@@ -151,6 +166,13 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T, HexCfg<OP, NM, NQ,
     using Tr  = HexOpTraits<OP>;
     constexpr int E = Cfg::E, T = Cfg::T;
     constexpr int NM2 = NM * NM, NM3 = NM2 * NM, NQ2 = NQ * NQ, NQ3 = NQ2 * NQ;
+    // shared-memory pitches of the mode-indexed intermediates: lanes that own consecutive (k,j) / (r,q) lines read or
+    // write them NM doubles apart, which for even NM is a 2..8-way bank conflict (NM = 8: all of a half-warp on two
+    // banks; ncu-visible as the nm = 8 dip of every operator) -- an odd line pitch and a k-slab pitch that is not a
+    // multiple of 16 doubles remove it; both still fit the NQ^3 work buffers (NM < NQ)
+    constexpr int NMP = (NM % 2 == 0 && NM < NQ) ? NM + 1 : NM;
+    constexpr int K1P = (NM2 % 16 == 0 && NM2 + 8 <= NQ2) ? NM2 + 8 : NM2;
+    constexpr int COUT = NM2 * NMP; // element pitch of the staged result
     constexpr int NGEO = Cfg::NGEO, NQ3P = Cfg::NQ3P, GEOA = E * NQ3P; // GEOA: doubles per staged geometry array
     constexpr int INSZ = Tr::COEFF_IN ? NM3 : NQ3; // doubles per element of each input array
     constexpr int NIN  = OP == HEX_IPWDB ? 3 : 1;
@@ -267,7 +289,7 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T, HexCfg<OP, NM, NQ,
                 for (int r = 0; r < NM; ++r) x[r] = sCin[e * NM3 + r * NM2 + qp];
                 mat_fwd<NM, NQ>(tab.B, x, y);
 #pragma unroll
-                for (int k = 0; k < NQ; ++k) sA[e * NQ3 + k * NM2 + qp] = y[k];
+                for (int k = 0; k < NQ; ++k) sA[e * NQ3 + k * K1P + qp] = y[k];
             }
             __syncthreads();
             if (tid == 0 && bnext < nBatches) issue_inputs(bnext); // sCin is free again
@@ -278,10 +300,10 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T, HexCfg<OP, NM, NQ,
                 const int k = kp / NM, p = kp - k * NM;
                 double x[NM], y[NQ];
 #pragma unroll
-                for (int q = 0; q < NM; ++q) x[q] = sA[e * NQ3 + k * NM2 + q * NM + p];
+                for (int q = 0; q < NM; ++q) x[q] = sA[e * NQ3 + k * K1P + q * NM + p];
                 mat_fwd<NM, NQ>(tab.B, x, y);
 #pragma unroll
-                for (int j = 0; j < NQ; ++j) sB[e * NQ3 + k * (NQ * NM) + j * NM + p] = y[j];
+                for (int j = 0; j < NQ; ++j) sB[e * NQ3 + (k * NQ + j) * NMP + p] = y[j];
             }
             __syncthreads();
             // P3: p -> i.  pencils (k,j); u[k][j][i] -> sU, and (Helmholtz) du/dxi0 -> sA
@@ -289,7 +311,7 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T, HexCfg<OP, NM, NQ,
             {
                 double x[NM], y[NQ];
 #pragma unroll
-                for (int p = 0; p < NM; ++p) x[p] = sB[pe * NQ3 + pr * NM + p];
+                for (int p = 0; p < NM; ++p) x[p] = sB[pe * NQ3 + pr * NMP + p];
                 mat_fwd<NM, NQ>(tab.B, x, y);
 #pragma unroll
                 for (int i = 0; i < NQ; ++i) sU[pe * NQ3 + pr * NQ + i] = y[i];
@@ -560,12 +582,23 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T, HexCfg<OP, NM, NQ,
             for (int i = 0; i < NQ; ++i) x[i] = sB[e * NQ3 + rq * NQ + i];
             mat_tr<NQ, NM>(tab.B, x, y);
 #pragma unroll
-            for (int p = 0; p < NM; ++p) sC[e * NM3 + rq * NM + p] = y[p];
+            for (int p = 0; p < NM; ++p) sC[e * COUT + rq * NMP + p] = y[p];
         }
         __syncthreads();
         {
             double *dst = args.out0 + (size_t)e0 * NM3;
-            for (int i = tid; i < ne * NM3; i += T) dst[i] = sC[i];
+            if (NMP == NM)
+            {
+                for (int i = tid; i < ne * NM3; i += T) dst[i] = sC[i];
+            }
+            else
+            {
+                for (int i = tid; i < ne * NM3; i += T)
+                {
+                    const int rq = i / NM, p = i - rq * NM; // rq runs over (element, r, q): COUT = NM2 * NMP
+                    dst[i] = sC[rq * NMP + p];
+                }
+            }
         }
         // sC is next written in P7a/P9 of the following batch, several barriers away -- except for
         // IProductWRTDerivBase whose next inputs land in sA/sB/sC
