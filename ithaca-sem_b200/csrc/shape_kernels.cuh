@@ -156,7 +156,17 @@ __global__ void __launch_bounds__(256)
     constexpr bool HELM_BACK = OP == NEKMF_HELMHOLTZ || IPWDB;
     constexpr bool COEFF_OUT = OP == NEKMF_HELMHOLTZ || OP == NEKMF_IPRODUCTWRTBASE || IPWDB;
     constexpr int NDF = DIM * DIM;
-    constexpr int LN  = NQ1 * NQ2; // (j,k) lines, ln = k*NQ1 + j; FP layout [p][ln]
+    constexpr int LN  = NQ1 * NQ2; // (j,k) lines, ln = k*NQ1 + j
+    // shared-memory pitches of the two mode-indexed intermediates, odd so that lanes owning consecutive lines hit
+    // different banks: FP[p][k][j] is written / read by lanes (p, k) NQ1 doubles apart (NQ1 = 8 at nm = 7 for Quad / Prism /
+    // Pyr, at nm = 8 for Tri / Tet: a whole half-warp on two banks), FPQ[pair][k] by lanes (pair) NQ2 doubles apart.  Both
+    // padded layouts still fit the quadrature-sized buffers (asserted below).
+    // (only where the pitch is a multiple of four doubles, i.e. 4-way conflicts or worse: the 2-way cases -- pitches 6 and
+    // 10 -- measured equal or slower with the padded index arithmetic, profiles/r02_final_sweep_collapsed.jsonl history)
+    constexpr int J1  = (NQ1 % 4 == 0) ? NQ1 + 1 : NQ1, LNP = NQ2 * J1;
+    constexpr int K2  = (NQ2 % 4 == 0) ? NQ2 + 1 : NQ2;
+    static_assert(NM * LNP <= NQP, "padded FP layout does not fit the work buffer");
+    static_assert(DIM == 2 || (IS_TET ? NPAIR : NM * NM) * K2 <= NQP, "padded FPQ layout does not fit the work buffer");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sAux = reinterpret_cast<double *>(smem_raw);
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(256)
                         for (int k = 0; k < NQ2; ++k) y[k] = fma(row[r * NQ2 + k], x, y[k]);
                     }
 #pragma unroll
-                    for (int k = 0; k < NQ2; ++k) sA[e * NQP + c * NQ2 + k] = y[k];
+                    for (int k = 0; k < NQ2; ++k) sA[e * NQP + c * K2 + k] = y[k];
                 }
                 __syncthreads();
             }
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__(256)
                         for (int k = 0; k < NQ2; ++k) y[k] = fma(b2c[NQ2 + k], x, y[k]);
                     }
 #pragma unroll
-                    for (int k = 0; k < NQ2; ++k) sA[e * NQP + pq * NQ2 + k] = y[k];
+                    for (int k = 0; k < NQ2; ++k) sA[e * NQP + pq * K2 + k] = y[k];
                 }
                 __syncthreads();
             }
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(256)
                         for (int k = 0; k < NQ2; ++k) y[k] = fma(b2c[NQ2 + k], x, y[k]);
                     }
 #pragma unroll
-                    for (int k = 0; k < NQ2; ++k) sA[e * NQP + pq * NQ2 + k] = y[k];
+                    for (int k = 0; k < NQ2; ++k) sA[e * NQP + pq * K2 + k] = y[k];
                 }
                 __syncthreads();
             }
@@ -406,7 +416,7 @@ __global__ void __launch_bounds__(256)
                 {
                     double x[NM];
 #pragma unroll
-                    for (int q = 0; q < NM; ++q) x[q] = sA[e * NQP + (p * NM + q) * NQ2 + k];
+                    for (int q = 0; q < NM; ++q) x[q] = sA[e * NQP + (p * NM + q) * K2 + k];
                     shp_fwd<NM, NQ1>(tab.b1t, x, y);
                 }
                 else
@@ -418,7 +428,7 @@ __global__ void __launch_bounds__(256)
                     for (int j = 0; j < NQ1; ++j) y[j] = 0.0;
                     for (int q = 0; q < len; ++q)
                     {
-                        const double x = IS_TRI ? sCin[e * NMT + c0 + q] : sA[e * NQP + (c0 + q) * NQ2 + k];
+                        const double x = IS_TRI ? sCin[e * NMT + c0 + q] : sA[e * NQP + (c0 + q) * K2 + k];
 #pragma unroll
                         for (int j = 0; j < NQ1; ++j) y[j] = fma(row[q * NQ1 + j], x, y[j]);
                     }
@@ -448,16 +458,17 @@ __global__ void __launch_bounds__(256)
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < NQ1; ++j) sB[e * NQP + p * LN + k * NQ1 + j] = y[j];
+                for (int j = 0; j < NQ1; ++j) sB[e * NQP + p * LNP + k * J1 + j] = y[j];
             }
             __syncthreads();
             // -------------------------------------------------------------- S3: p -> i      u -> sU (Helmholtz: du/dxi0 -> sA)
             for (int l = tid; l < E * LN; l += T)
             {
                 const int e = l / LN, ln = l - e * LN;
+                const int lnp = ln + (ln / NQ1) * (J1 - NQ1); // (k, j) in the padded [p][k][J1] layout
                 double x[NM], y[NQ0];
 #pragma unroll
-                for (int p = 0; p < NM; ++p) x[p] = sB[e * NQP + p * LN + ln];
+                for (int p = 0; p < NM; ++p) x[p] = sB[e * NQP + p * LNP + lnp];
                 shp_fwd<NM, NQ0>(tab.b0, x, y);
 #pragma unroll
                 for (int i = 0; i < NQ0; ++i) sU[e * NQP + ln * P1 + i] = y[i];
@@ -818,7 +829,7 @@ __global__ void __launch_bounds__(256)
             }
             shp_tr<NQ0, NM>(tab.b0, v, f);
 #pragma unroll
-            for (int p = 0; p < NM; ++p) sB[e * NQP + p * LN + ln] = f[p];
+            for (int p = 0; p < NM; ++p) sB[e * NQP + p * LNP + ln + (ln / NQ1) * (J1 - NQ1)] = f[p];
         }
         __syncthreads();
         if (IP_PREF && b + (int)gridDim.x < nBatches) prefetch_phys(b + gridDim.x, sU);
@@ -829,7 +840,7 @@ __global__ void __launch_bounds__(256)
             const int p = pk / NQ2, k = pk - p * NQ2;
             double x[NQ1];
 #pragma unroll
-            for (int j = 0; j < NQ1; ++j) x[j] = sB[e * NQP + p * LN + k * NQ1 + j];
+            for (int j = 0; j < NQ1; ++j) x[j] = sB[e * NQP + p * LNP + k * J1 + j];
             if (IS_QUAD)
             {
                 double y[NM];
@@ -842,7 +853,7 @@ __global__ void __launch_bounds__(256)
                 double y[NM];
                 shp_tr<NQ1, NM>(tab.b1t, x, y);
 #pragma unroll
-                for (int q = 0; q < NM; ++q) sA[e * NQP + (p * NM + q) * NQ2 + k] = y[q];
+                for (int q = 0; q < NM; ++q) sA[e * NQP + (p * NM + q) * K2 + k] = y[q];
             }
             else
             {
@@ -854,7 +865,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
                     for (int j = 1; j < NQ1; ++j) s = fma(row[q * NQ1 + j], x[j], s);
                     if (IS_TRI) sCin[e * NMT + c0 + q] = s;
-                    else sA[e * NQP + (c0 + q) * NQ2 + k] = s;
+                    else sA[e * NQP + (c0 + q) * K2 + k] = s;
                 }
                 if (IS_TET && p < 2)
                 {
@@ -883,7 +894,7 @@ __global__ void __launch_bounds__(256)
             {
                 double s = 0.0;
 #pragma unroll
-                for (int j = 0; j < NQ1; ++j) s = fma(b1c[NQ1 + j], sB[e * NQP + 1 * LN + j], s);
+                for (int j = 0; j < NQ1; ++j) s = fma(b1c[NQ1 + j], sB[e * NQP + 1 * LNP + j], s);
                 sCin[e * NMT + 1] += s;
             }
             __syncthreads();
@@ -898,7 +909,7 @@ __global__ void __launch_bounds__(256)
                 const double *row = b2c + m0 * NQ2;
                 double x[NQ2];
 #pragma unroll
-                for (int k = 0; k < NQ2; ++k) x[k] = sA[e * NQP + c * NQ2 + k];
+                for (int k = 0; k < NQ2; ++k) x[k] = sA[e * NQP + c * K2 + k];
                 for (int r = 0; r < len; ++r)
                 {
                     double s = row[r * NQ2] * x[0];
@@ -941,7 +952,7 @@ __global__ void __launch_bounds__(256)
                 double *cout = sCin + e * NMT + NM * r0 + q * len;
                 double x[NQ2];
 #pragma unroll
-                for (int k = 0; k < NQ2; ++k) x[k] = sA[e * NQP + pq * NQ2 + k];
+                for (int k = 0; k < NQ2; ++k) x[k] = sA[e * NQP + pq * K2 + k];
                 for (int r = 0; r < len; ++r)
                 {
                     double s = row[r * NQ2] * x[0];
@@ -954,7 +965,7 @@ __global__ void __launch_bounds__(256)
                     // singular edge: mode (0,q,1) += sum_k b2[(0,1)][k] fb[1][q][k]
                     double s = 0.0;
 #pragma unroll
-                    for (int k = 0; k < NQ2; ++k) s = fma(b2c[NQ2 + k], sA[e * NQP + (NM + q) * NQ2 + k], s);
+                    for (int k = 0; k < NQ2; ++k) s = fma(b2c[NQ2 + k], sA[e * NQP + (NM + q) * K2 + k], s);
                     cout[1] += s;
                 }
             }
@@ -971,7 +982,7 @@ __global__ void __launch_bounds__(256)
                 double *cout = sCin + e * NMT + m0;
                 double x[NQ2];
 #pragma unroll
-                for (int k = 0; k < NQ2; ++k) x[k] = sA[e * NQP + pq * NQ2 + k];
+                for (int k = 0; k < NQ2; ++k) x[k] = sA[e * NQP + pq * K2 + k];
                 for (int r = 0; r < len; ++r)
                 {
                     double s = row[r * NQ2] * x[0];
@@ -986,7 +997,7 @@ __global__ void __launch_bounds__(256)
                     double s = 0.0;
 #pragma unroll
                     for (int k = 0; k < NQ2; ++k)
-                        s = fma(b2c[NQ2 + k], fb[1 * NQ2 + k] + fb[NM * NQ2 + k] + fb[(NM + 1) * NQ2 + k], s);
+                        s = fma(b2c[NQ2 + k], fb[1 * K2 + k] + fb[NM * K2 + k] + fb[(NM + 1) * K2 + k], s);
                     cout[1] += s;
                 }
             }
