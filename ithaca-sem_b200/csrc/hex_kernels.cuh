@@ -89,7 +89,16 @@ template <int OP, int NM, int NQ, bool DEF> struct HexCfg
 {
     static constexpr int NM3 = NM * NM * NM, NQ3 = NQ * NQ * NQ, NQ2 = NQ * NQ;
     static constexpr int NQ3P = round_up(NQ3, 2); // element pitch of the (internal) geometry arrays
-    static constexpr int NGEO = DEF ? HexOpTraits<OP>::NGEO : 0;
+    // deformed Helmholtz / PhysDeriv / IProductWRTDerivBase at high order: nine or ten staged factor arrays are 80-200 KB
+    // per element, i.e. ONE CTA of 4-5 warps per SM.  GEO_DIRECT reads the factors in the column pass straight from
+    // global memory instead (lanes = consecutive (j,i) points of a k-plane: fully coalesced), which frees the shared
+    // memory for more resident CTAs.
+    // Measured at nm = 9..11 (profiles/r02_sweep_hex_geodirect.jsonl against r02_final_sweep_hex.jsonl): faster for
+    // Helmholtz at nm = 9 (3.44 -> 2.91 ms) and PhysDeriv / IProductWRTDerivBase at nm = 10 (1.90 -> 1.78, 3.01 -> 2.27 ms),
+    // slower in the other six cells (the staged copy hides the latency better once two elements no longer fit) -- taken
+    // exactly where it won.
+    static constexpr bool GEO_DIRECT = DEF && ((OP == HEX_HELM && NM == 9) || ((OP == HEX_PD || OP == HEX_IPWDB) && NM == 10));
+    static constexpr int NGEO = (DEF && !GEO_DIRECT) ? HexOpTraits<OP>::NGEO : 0;
     // work buffers actually live at the same time (the others alias them, see the kernel):
     //   BwdTrans: P1 -> sA, P2 -> sB, P3 -> sU = sA           IProductWRTBase: sU, sA, sB, sC = sA
     static constexpr int NBUF    = OP == HEX_BWD ? 2 : (OP == HEX_IPROD ? 3 : 4);
@@ -389,6 +398,12 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T, HexCfg<OP, NM, NQ,
                 if (OP != HEX_PD) rjac = __ldg(args.jac + eg);
             }
             const double wij = sW[pa] * sW[pb];
+            // deformed factors of point gpt: staged copy, or (GEO_DIRECT) the internal [array][element][NQ3P] global layout
+            const size_t gdir = (size_t)b * GEOA;
+            auto gdf = [&](int n, int gpt) {
+                return Cfg::GEO_DIRECT ? (ev ? __ldg(args.df + (size_t)n * args.dfStride + gdir + gpt) : 0.0) : sGeo[n * GEOA + gpt];
+            };
+            auto gjac = [&](int gpt) { return Cfg::GEO_DIRECT ? (ev ? __ldg(args.jac + gdir + gpt) : 0.0) : sGeo[9 * GEOA + gpt]; };
 
             if (OP == HEX_HELM)
             {
@@ -415,8 +430,8 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T, HexCfg<OP, NM, NQ,
                     {
                         double f[9];
 #pragma unroll
-                        for (int n = 0; n < 9; ++n) f[n] = sGeo[n * GEOA + gpt];
-                        jw  = sGeo[9 * GEOA + gpt] * (wij * tab.w[k]);
+                        for (int n = 0; n < 9; ++n) f[n] = gdf(n, gpt);
+                        jw  = gjac(gpt) * (wij * tab.w[k]);
                         m00 = f[0] * f[0] + f[3] * f[3] + f[6] * f[6];
                         m01 = f[0] * f[1] + f[3] * f[4] + f[6] * f[7];
                         m02 = f[0] * f[2] + f[3] * f[5] + f[6] * f[8];
@@ -458,8 +473,8 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T, HexCfg<OP, NM, NQ,
                     if (DEF)
                     {
 #pragma unroll
-                        for (int n = 0; n < 9; ++n) f[n] = sGeo[n * GEOA + gpt];
-                        jw = sGeo[9 * GEOA + gpt] * (wij * tab.w[k]);
+                        for (int n = 0; n < 9; ++n) f[n] = gdf(n, gpt);
+                        jw = gjac(gpt) * (wij * tab.w[k]);
                     }
                     else
                     {
@@ -488,7 +503,7 @@ __global__ void __launch_bounds__(HexCfg<OP, NM, NQ, DEF>::T, HexCfg<OP, NM, NQ,
                     if (DEF)
                     {
 #pragma unroll
-                        for (int n = 0; n < 9; ++n) f[n] = sGeo[n * GEOA + gpt];
+                        for (int n = 0; n < 9; ++n) f[n] = gdf(n, gpt);
                     }
                     else
                     {
