@@ -408,8 +408,13 @@ def main():
     Ke = 3
     l0 = nk.launch_count()
     te = 0.0
+    zero_dev = torch.zeros(S["mesh"].nLocal, dtype=torch.float64, device=dev)
     for _ in range(Ke):
-        coef_host.zero_()  # the caller's initial guess / Dirichlet values: not part of the solve
+        # the caller's initial guess / Dirichlet values (zero): not part of the solve.  Reset by a DMA write, not by the
+        # CPU: 262 MB of lines the host has just written are read back by the next H2D at 42 instead of 55 GB/s
+        # (tools/e2e_breakdown.py: 17.0 against 12.9 ms for the pair of input arrays) -- an artefact of timing the call
+        # right after a host memset, not a property of the solve
+        coef_host.copy_(zero_dev)
         barrier()
         t0 = time.perf_counter()
         its_e, eps_e = hs.HelmSolve(f_host, coef_host, phys_host, tol=E2E_TOL)  # synchronous
@@ -422,7 +427,9 @@ def main():
            "launches": (nk.launch_count() - l0) // Ke, "device_ms": hs.last_ms(), "u_err": u_err,
            "h2d": (f_host.numel() + coef_host.numel()) * 8, "d2h": (coef_host.numel() + phys_host.numel()) * 8,
            "ndof_local": S["mesh"].nLocal}
-    del hs, S, f_host, coef_host, phys_host
+    e2e["phases_ms"] = dict(zip(("h2d", "iproduct_lift_assemble", "cg", "globaltolocal_bwdtrans", "d2h"),
+                                [round(v, 3) for v in hs.last_phases()]))
+    del hs, S, f_host, coef_host, phys_host, zero_dev
     torch.cuda.empty_cache()
 
     # ---- BASELINE configs[4]: 2^20 hex elements at P=4 split in z-slabs over the ranks (STRONG scaling),
@@ -471,7 +478,7 @@ def main():
         "e2e": {"value": world * e2e["ndof_local"] * e2e["applies"] / e2e["s"] / 1e9, "unit": "GDOF/s",
                 "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["s"] * 1e3,
                 "helmholtz_applies": e2e["applies"], "cg_iterations": e2e["iterations"], "tol": E2E_TOL,
-                "device_ms": e2e["device_ms"], "gpu_launches": e2e["launches"],
+                "device_ms": e2e["device_ms"], "phases_ms": e2e["phases_ms"], "gpu_launches": e2e["launches"],
                 "max_abs_error_vs_analytic_solution": e2e["u_err"],
                 "note": "Helmholtz-apply DOF/s delivered by one nekmf_helmsolve call (= ContField::HelmSolve + "
                         "BwdTrans) on pinned host arrays: H2D forcing+coefficients, IProductWRTBase, Dirichlet lift, "

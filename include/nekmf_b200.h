@@ -273,6 +273,9 @@ int nekmf_helmsolve(nekmf_helmsolve_t hs, const double *forcing, double *inout, 
                     int maxiter, int *iterations, double *final_eps);
 /* device time of the last call, copies included (CUDA events on the solver's stream); ms < 0 if none ran */
 int nekmf_helmsolve_last_ms(nekmf_helmsolve_t hs, float *ms);
+/* the same call split into its phases (profiling hook): ms[0] host -> device copies, ms[1] IProductWRTBase + Dirichlet
+ * lift + Assemble, ms[2] the CG solve, ms[3] GlobalToLocal + BwdTrans, ms[4] device -> host copies; all < 0 if none ran */
+int nekmf_helmsolve_last_phases(nekmf_helmsolve_t hs, float ms[5]);
 int nekmf_helmsolve_destroy(nekmf_helmsolve_t hs);
 
 #ifdef __cplusplus

@@ -81,9 +81,11 @@ __global__ void __launch_bounds__(256, 8) // 32 registers: all RED_BLOCKS = 8 x 
     assemble_dot_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ sign,
                         const double *__restrict__ loc, double *__restrict__ glob, int nGlobal,
                         const double *__restrict__ w, const unsigned char *__restrict__ flags, int nDir,
-                        double *__restrict__ part, const __grid_constant__ nekmf_exdev ex, int nIfBlocks)
+                        double *__restrict__ part, const __grid_constant__ nekmf_exdev ex, int nIfBlocks,
+                        const int *__restrict__ skip)
 {
     __shared__ double sh[8];
+    if (!EX && skip && *skip) return; // single-rank solves: an iteration enqueued after convergence
     auto row_sum = [&](int g) {
         const int b = rowptr[g], e = rowptr[g + 1];
         double s = 0.0;
@@ -247,20 +249,21 @@ int map_assemble_device(nekmf_map_s *m, const double *loc, double *glob, cudaStr
     return NEKMF_OK;
 }
 int map_assemble_dot_device(nekmf_map_s *m, const double *loc, double *glob, const double *w,
-                            const unsigned char *flags, int nDir, double *part, const nekmf_exdev *ex, cudaStream_t st)
+                            const unsigned char *flags, int nDir, double *part, const nekmf_exdev *ex, cudaStream_t st,
+                            const int *skip)
 {
     if (ex && ex->total > 0)
     {
         int nIf = (ex->total + 255) / 256;
         if (nIf > RED_BLOCKS) nIf = RED_BLOCKS;
         assemble_dot_kernel<true><<<RED_BLOCKS, 256, 0, st>>>(m->d_rowptr, m->d_col, m->d_sign, loc, glob, m->nGlobal, w,
-                                                              flags, nDir, part, *ex, nIf);
+                                                              flags, nDir, part, *ex, nIf, nullptr);
     }
     else
     {
         nekmf_exdev none;
         assemble_dot_kernel<false><<<RED_BLOCKS, 256, 0, st>>>(m->d_rowptr, m->d_col, m->d_sign, loc, glob, m->nGlobal,
-                                                               w, flags, nDir, part, none, 0);
+                                                               w, flags, nDir, part, none, 0, skip);
     }
     ++g_launches;
     NEKMF_CUDA(cudaGetLastError());

@@ -228,14 +228,20 @@ static int cg_matvec_device(nekmf_cg_s *cg, const double *w, double *s, double *
     op->run_e0     = 0;
     op->run_ne     = op->nElmt;
     op->run_stream = cg->stream;
+    // single-rank iteration (mu_part given): launches enqueued after the convergence flag went up return at once (the
+    // host reads the flag one graph behind the launches).  Sharded solves keep running them: peers wait on the deposits.
+    const bool single = !cg->ex && !(cg->comm && cg->comm->nranks > 1);
+    const int *skip   = (mu_part && single) ? &cg->d_scal->done : nullptr;
     if (op->gather_ok)
     {
         const double *in[3] = {w, w, w};
         op->gather_map      = cg->map->d_map;
         op->gather_sign     = cg->map->d_sign;
+        op->gather_skip     = skip;
         rc                  = op->launch(op, in, out);
         op->gather_map      = nullptr;
         op->gather_sign     = nullptr;
+        op->gather_skip     = nullptr;
     }
     else
     {
@@ -255,7 +261,7 @@ static int cg_matvec_device(nekmf_cg_s *cg, const double *w, double *s, double *
     }
     if (cg->nGlobal == 0) return NEKMF_OK;
     rc = map_assemble_dot_device(cg->map, cg->d_lout, s, w, cg->d_flags, cg->nDir, mu_part, ex ? &ex->dev : nullptr,
-                                 cg->stream);
+                                 cg->stream, skip);
     if (rc || !cg->ex) return rc;
     rc = exchange_transport_device(cg->ex, cg->stream);
     if (rc) return rc;

@@ -25,6 +25,7 @@ struct nekmf_helmsolve_s
     bool anyDir = true; // nDir summed over the ranks > 0
     double *d_phys = nullptr, *d_coef = nullptr, *d_wsp = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ph[4] = {nullptr, nullptr, nullptr, nullptr}; // phase boundaries between ev[0] and ev[1]
     bool timed        = false;
 };
 
@@ -97,6 +98,7 @@ int nekmf_helmsolve_create(nekmf_cg_t cg, nekmf_op_t iprod, nekmf_op_t bwd, nekm
     if (e == cudaSuccess) e = cudaMalloc(&hs->d_coef, ((size_t)hs->nLocal + 2) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&hs->d_wsp, ((size_t)hs->nLocal + 2) * 8);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&hs->ev[i]);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&hs->ph[i]);
     if (e != cudaSuccess)
     {
         set_error("nekmf_helmsolve_create: %s", cudaGetErrorString(e));
@@ -145,6 +147,7 @@ int nekmf_helmsolve(nekmf_helmsolve_t hs, const double *forcing, double *inout, 
         f    = hs->d_phys;
         coef = hs->d_coef;
     }
+    NEKMF_CUDA(cudaEventRecord(hs->ph[0], st));
     if (helm->nElmt > 0)
     {
         rc = op_launch_on(hs->iprod, f, hs->d_wsp, st);
@@ -162,12 +165,14 @@ int nekmf_helmsolve(nekmf_helmsolve_t hs, const double *forcing, double *inout, 
     if (!rc && cg->ex) rc = exchange_add_device(cg->ex, cg->d_rhs, st);
     if (rc) return rc;
     NEKMF_CUDA(cudaMemsetAsync(cg->d_x, 0, (size_t)cg->nGlobal * 8, st));
+    NEKMF_CUDA(cudaEventRecord(hs->ph[1], st));
     int its = 0;
     double eps = 0.0;
     const int src = nekmf_cg_solve(cg, cg->d_rhs, cg->d_x, NEKMF_DEVICE, tol, maxiter, &its, &eps);
     if (iterations) *iterations = its;
     if (final_eps) *final_eps = eps;
     if (src != NEKMF_OK && src != NEKMF_ERR_NOCONVERGE) return src;
+    NEKMF_CUDA(cudaEventRecord(hs->ph[2], st));
     if (nL > 0)
     {
         g2l_add_kernel<<<grid_for(nL), 256, 0, st>>>(cg->map->d_map, cg->map->d_sign, cg->d_x, coef, nL, hs->anyDir ? 1 : 0);
@@ -180,6 +185,7 @@ int nekmf_helmsolve(nekmf_helmsolve_t hs, const double *forcing, double *inout, 
         rc = op_launch_on(hs->bwd, coef, phys, st);
         if (rc) return rc;
     }
+    NEKMF_CUDA(cudaEventRecord(hs->ph[3], st));
     if (host)
     {
         NEKMF_CUDA(cudaMemcpyAsync(inout, hs->d_coef, nL * 8, cudaMemcpyDeviceToHost, st));
@@ -201,6 +207,17 @@ int nekmf_helmsolve_last_ms(nekmf_helmsolve_t hs, float *ms)
     return NEKMF_OK;
 }
 
+int nekmf_helmsolve_last_phases(nekmf_helmsolve_t hs, float ms[5])
+{
+    if (!hs || !ms) { set_error("nekmf_helmsolve_last_phases: null argument"); return NEKMF_ERR_ARG; }
+    for (int i = 0; i < 5; ++i) ms[i] = -1.0f;
+    if (!hs->timed) return NEKMF_OK;
+    NEKMF_CUDA(cudaEventSynchronize(hs->ev[1]));
+    cudaEvent_t seq[6] = {hs->ev[0], hs->ph[0], hs->ph[1], hs->ph[2], hs->ph[3], hs->ev[1]};
+    for (int i = 0; i < 5; ++i) NEKMF_CUDA(cudaEventElapsedTime(&ms[i], seq[i], seq[i + 1]));
+    return NEKMF_OK;
+}
+
 int nekmf_helmsolve_destroy(nekmf_helmsolve_t hs)
 {
     if (!hs) return NEKMF_OK;
@@ -210,6 +227,8 @@ int nekmf_helmsolve_destroy(nekmf_helmsolve_t hs)
     cudaFree(hs->d_wsp);
     for (int i = 0; i < 2; ++i)
         if (hs->ev[i]) cudaEventDestroy(hs->ev[i]);
+    for (int i = 0; i < 4; ++i)
+        if (hs->ph[i]) cudaEventDestroy(hs->ph[i]);
     delete hs;
     return NEKMF_OK;
 }

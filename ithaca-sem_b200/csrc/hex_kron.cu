@@ -51,6 +51,7 @@ struct KronArgs
     // sign[i] * in[map[i]] (AssemblyMapCG::v_GlobalToLocal fused into the operator's load)
     const int *map;
     const double *sign;
+    const int *skip; // GATHER: non-zero flag = nothing to do (the solver converged after this launch was enqueued)
     int gather_rows; // gather order: 1 = one (q, r) row of ALL the batch's elements per instruction, 0 = local index order
 };
 
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(KronCfg<NM, GATHER, WSEL>::T, 1)
     constexpr int NM2 = Cfg::NM2, NM3 = Cfg::NM3, EPW = Cfg::EPW, INB = Cfg::INB, PS = Cfg::PS, ES = Cfg::ES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (GATHER && args.skip && *args.skip) return;
     double *wbase = reinterpret_cast<double *>(smem_raw) + (size_t)warp * Cfg::PER_WARP;
     double *sIn   = wbase;                  // [INB]  input block of the current step
     double *sGeo  = wbase + INB;            // [GEO]  per-element scalars
@@ -484,6 +486,7 @@ template <int NM, bool GATHER, int WSEL = 0> static int kron_launch_t(nekmf_op_s
     a.sign = GATHER && op->gather_sign ? op->gather_sign + (size_t)op->run_e0 * Cfg::NM3 : nullptr;
     static const int gather_rows = [] { const char *v = getenv("NEKMF_GATHER_ROWS"); return (v && v[0] == '0') ? 0 : 1; }(); // A/B knob
     a.gather_rows = gather_rows;
+    a.skip        = GATHER ? op->gather_skip : nullptr;
     a.io_aligned = GATHER ? ((((uintptr_t)out) & 15) == 0) : ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
     const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
     int grid           = bps * NUM_SMS;
@@ -574,7 +577,7 @@ template <int NM> static int kron_rows_launch(nekmf_op_s *op, const double *cons
     }
     KronArgs a;
     a.in = in[0]; a.out = out[0]; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
-    a.map = nullptr; a.sign = nullptr; a.gather_rows = 0;
+    a.map = nullptr; a.sign = nullptr; a.gather_rows = 0; a.skip = nullptr;
     a.io_aligned = ((((uintptr_t)in[0]) | ((uintptr_t)out[0])) & 15) == 0;
     const int nBatches = (op->run_ne + Cfg::EPW * Cfg::WARPS - 1) / (Cfg::EPW * Cfg::WARPS);
     int grid           = st->blocks_per_sm * NUM_SMS;
@@ -603,7 +606,7 @@ template <int NM> static int kron_lane_launch(nekmf_op_s *op, KronState *st, con
     }
     KronArgs a;
     a.in = in; a.out = out; a.geo4 = st->d_geo4 + (size_t)op->run_e0 * 4; a.nElmt = op->run_ne; a.lambda = op->lambda;
-    a.map = nullptr; a.sign = nullptr; a.gather_rows = 0;
+    a.map = nullptr; a.sign = nullptr; a.gather_rows = 0; a.skip = nullptr;
     a.io_aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
     const int nBatches = (op->run_ne + 32 * Cfg::WARPS - 1) / (32 * Cfg::WARPS);
     int grid           = st->blocks_per_sm_lane * NUM_SMS;

@@ -89,7 +89,7 @@ int map_assemble_device(nekmf_map_s *m, const double *loc, double *glob, cudaStr
 // added after the exchange).  ex != null: the first blocks also deposit the interface values with the peers.
 int map_assemble_dot_device(nekmf_map_s *m, const double *loc, double *glob, const double *w,
                             const unsigned char *flags, int nDir, double *part, const nekmf_exdev *ex,
-                            cudaStream_t st);
+                            cudaStream_t st, const int *skip = nullptr); // skip: single-rank only (no peer waits on it)
 // glob[idx] += peers' glob[idx]; the building blocks are also used by the CG
 int exchange_add_device(nekmf_exchange_s *ex, double *glob, cudaStream_t st);
 int exchange_transport_device(nekmf_exchange_s *ex, cudaStream_t st); // NCCL send/recv of the staged values (no-op in peer-memory mode)

@@ -49,6 +49,9 @@ struct nekmf_op_s
     bool gather_ok           = false;
     const int *gather_map    = nullptr;
     const double *gather_sign = nullptr;
+    // with gather_map: device flag that turns the launch into a no-op when non-zero (iterations a solver enqueued
+    // before it knew it had converged)
+    const int *gather_skip = nullptr;
     int kron         = 0; // regular Helmholtz: coefficient-space kernel available (1 hex_kron.cu, 2 quad_kron.cu, 3 dense_helm.cu, 4 its prism variant)
     bool timing      = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

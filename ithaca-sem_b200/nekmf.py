@@ -56,6 +56,7 @@ EXPORTS = [
     "nekmf_comm_unique_id", "nekmf_comm_create", "nekmf_comm_transport", "nekmf_comm_destroy", "nekmf_exchange_create",
     "nekmf_exchange_add", "nekmf_exchange_destroy", "nekmf_cg_create", "nekmf_cg_solve", "nekmf_cg_matvec",
     "nekmf_cg_last_loop", "nekmf_cg_destroy", "nekmf_helmsolve_create", "nekmf_helmsolve", "nekmf_helmsolve_last_ms",
+    "nekmf_helmsolve_last_phases",
     "nekmf_helmsolve_destroy", "nekmf_op_diagonal", "nekmf_cg_set_jacobi",
 ]
 
@@ -115,6 +116,7 @@ def lib():
         L.nekmf_helmsolve_create.argtypes = [_vp, _vp, _vp, C.POINTER(_vp)]
         L.nekmf_helmsolve.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, _ip, _dp]
         L.nekmf_helmsolve_last_ms.argtypes = [_vp, C.POINTER(C.c_float)]
+        L.nekmf_helmsolve_last_phases.argtypes = [_vp, C.POINTER(C.c_float)]
         L.nekmf_helmsolve_destroy.argtypes = [_vp]
         L.nekmf_malloc_device.argtypes = [C.POINTER(_vp), C.c_size_t]
         L.nekmf_free_device.argtypes = [_vp]
@@ -596,6 +598,12 @@ class HelmSolver:
         ms = C.c_float(-1.0)
         check(lib().nekmf_helmsolve_last_ms(self.h, C.byref(ms)), "nekmf_helmsolve_last_ms")
         return ms.value
+
+    def last_phases(self):
+        """-> [h2d, IProductWRTBase + lift + Assemble, CG, GlobalToLocal + BwdTrans, d2h] in ms of the last call"""
+        ms = (C.c_float * 5)()
+        check(lib().nekmf_helmsolve_last_phases(self.h, ms), "nekmf_helmsolve_last_phases")
+        return [float(v) for v in ms]
 
     def __del__(self):
         try:
