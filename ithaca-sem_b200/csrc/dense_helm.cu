@@ -446,7 +446,9 @@ static bool dense_wanted(const nekmf_op_s *op)
     switch (op->shape)
     {
         case NEKMF_TET: return true;
-        case NEKMF_PYR: return true;
+        // pyramids: 3-40x over the runtime-sized kernel it was measured against; against the compile-time sized pencil
+        // kernel (round 2) it wins at nm 2..6 (0.40-1.41 against 1.24-1.65 ms) and loses at nm = 7 (2.30 against 1.61 ms)
+        case NEKMF_PYR: return op->nm[0] <= 6;
         case NEKMF_TRI: return op->nm[0] >= 3;
         default: return false;
     }

@@ -140,8 +140,13 @@ template <> struct ShpMetric<NEKMF_TRI>
     }
 };
 
+// Helmholtz at nm >= 7 compiles to 146-254 registers, i.e. ONE resident CTA of eight warps where shared memory admits two
+// (cuobjdump -res-usage): bounded to 128 registers there.  A/B (profiles/r02_sweep_shp_minb_B.jsonl against
+// r02_final_sweep_*.jsonl): deformed Quad 1.57 -> 1.43, 1.92 -> 1.57, 1.93 -> 1.55 ms at nm = 7, 8, 9; deformed Prism 3.74 -> 2.59,
+// 4.87 -> 2.81 ms and Pyr 4.22 -> 3.05, 5.27 -> 3.27 ms at nm = 8, 9; deformed Tet 6.84 -> 4.86 ms at nm = 9; nothing slower.
+// (0 = no bound; a minimum of ONE block makes ptxas spend up to 255 registers and costs up to 1.6x)
 template <int SHAPE, int OP, int NM, bool DEF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (OP == NEKMF_HELMHOLTZ && NM >= 7) ? 2 : 0)
     shape_op_kernel(const __grid_constant__ ShpTab<SHAPE, NM> tab, const __grid_constant__ ShpArgs args)
 {
     using Dm = ShpDims<SHAPE, NM>;

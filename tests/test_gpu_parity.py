@@ -938,8 +938,8 @@ def test_pyr_shape_kernels(nm, deformed, base, monkeypatch):
         if not base:
             if op in (nk.eBwdTrans, nk.eIProductWRTBase) and 3 <= nm <= 7:
                 want = "pyr_dmma_kernel"  # tensor-core tiles (prism_dmma.cu)
-            if op == nk.eHelmholtz and not deformed and nm <= 7:
-                want = "dense_helm_kernel"  # DMMA coefficient-space kernel (dense_helm.cu, instantiated up to nm = 7)
+            if op == nk.eHelmholtz and not deformed and nm <= 6:
+                want = "dense_helm_kernel"  # DMMA coefficient-space kernel (dense_helm.cu; the pencil kernel wins from nm = 7)
         assert want in coll.m_ops[op].kernel_name, coll.m_ops[op].kernel_name
 
 
