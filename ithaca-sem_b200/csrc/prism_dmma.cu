@@ -452,6 +452,13 @@ void pyr_dmma_maybe_wrap(nekmf_op_s *op)
     if (op->deformed && op->geo_pitch != op->nqTot) return;
     const char *v = getenv("NEKMF_PYR_DMMA");
     if (v && v[0] == '0') return;
+    // default = the cells where the tensor tiles beat the compile-time sized pencil kernels that pyramids got later in round 2
+    // (profiles/r02_final_sweep_collapsed.jsonl against r02_sweep_pyr_shape_1.jsonl): nm = 7 (0.36 / 0.55 / 0.67 against 0.54 /
+    // 0.59 / 0.79 ms), BwdTrans and deformed IProductWRTBase at nm = 5; the pencil kernels win at nm = 3, 4, 6 (0.37-0.45
+    // against 0.46-0.91 ms).  NEKMF_PYR_DMMA=1 takes the tiles at every instantiated order.
+    const bool forced = v && v[0] == '1';
+    const bool faster = nm == 7 || (nm == 5 && (op->optype == NEKMF_BWDTRANS || op->deformed));
+    if (!forced && !faster) return;
     switch (nm)
     {
         case 3: prism_dmma_wrap<true, 3>(op); break;

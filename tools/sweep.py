@@ -18,34 +18,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 from _util import nekmf  # noqa: E402
 import bench  # noqa: E402
+from flop_model import algorithmic_bytes, algorithmic_flops  # noqa: E402
 
 OPS = {"BwdTrans": 0, "Helmholtz": 1, "IProductWRTBase": 2, "IProductWRTDerivBase": 3, "PhysDeriv": 4}
-
-
-def algorithmic_bytes(op, dim, nmTot, nqTot, deformed):
-    """per element, SURVEY.md 8(a)/(d): every input and output array once, geometry once"""
-    g = nqTot if deformed else 1
-    ndf = dim * dim
-    return 8 * {"BwdTrans": nmTot + nqTot, "IProductWRTBase": nqTot + nmTot + g,
-                "PhysDeriv": nqTot + dim * nqTot + ndf * g, "Helmholtz": 2 * nmTot + (ndf + 1) * g,
-                "IProductWRTDerivBase": dim * nqTot + nmTot + (ndf + 1) * g}[op]
-
-
-def algorithmic_flops(op, shape, nm, nq):
-    """per element, hexahedra and quadrilaterals with nq = nm + 1, counted on the reference's algorithm
-    (SURVEY.md 8(a)/(d)): sum-factorised passes 2*(nq nm^d-1 ... ) flops, tensor derivatives 2*d*nq^(d+1),
-    pointwise metric work.  None for the collapsed shapes (their pass lengths depend on the mode index)."""
-    if shape == "Hex":
-        sf = 2 * (nq * nm ** 3 + nq ** 2 * nm ** 2 + nq ** 3 * nm)
-        der, pts = 2 * 3 * nq ** 4, nq ** 3
-        return {"BwdTrans": sf, "IProductWRTBase": sf + 3 * pts, "PhysDeriv": der + 15 * pts,
-                "Helmholtz": 5 * sf + der + 50 * pts, "IProductWRTDerivBase": 3 * sf + 24 * pts}[op]
-    if shape == "Quad":
-        sf = 2 * (nq * nm ** 2 + nq ** 2 * nm)
-        der, pts = 2 * 2 * nq ** 3, nq ** 2
-        return {"BwdTrans": sf, "IProductWRTBase": sf + 2 * pts, "PhysDeriv": der + 6 * pts,
-                "Helmholtz": 4 * sf + der + 20 * pts, "IProductWRTDerivBase": 2 * sf + 10 * pts}[op]
-    return None
 
 
 def iter_points(shapes_arg, lo, hi, geom_arg, ops, reps, words):
