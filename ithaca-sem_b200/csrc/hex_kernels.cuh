@@ -139,7 +139,9 @@ template <int OP, int NM, int NQ, bool DEF> struct HexCfg
     // 0.99 -> 0.90 ms at nm = 7, 9, 10, 11 and PhysDeriv 0.87 -> 0.68, 0.68 -> 0.61, 0.60 -> 0.53 ms at nm = 7, 10, 11; it LOSES at
     // nm = 8 (three CTAs: 96 registers, spills) and for IProductWRTBase, which keep the compiler's choice
     static constexpr bool MINB_ON = !DEF && NM >= 7 && NM != 8 && (OP == HEX_PD || OP == HEX_IPWDB);
-    static constexpr int MINB     = MINB_ON ? minb_for(SM_FIT) : MINB_HELM;
+    // deformed Helmholtz at nm = 9 with direct geometry: two CTAs (128 registers) 2.91 -> 2.61 ms; at nm = 7, 8 direct geometry
+    // loses to the staged copy (1.89 -> 3.05, 1.77 -> 2.19 ms)
+    static constexpr int MINB     = MINB_ON ? minb_for(SM_FIT) : ((GEO_DIRECT && OP == HEX_HELM) ? 2 : MINB_HELM);
 };
 
 // y[b] = sum_a M[a*NOUT+b] x[a]          (forward: basis / derivative evaluation)
