@@ -439,3 +439,40 @@ def test_interface_from_universal_map_world_size_2_gloo(tmp_path):
     # every interior DOF of the full mesh is owned exactly once
     full = load_pkg_module("mesh").StructuredHexMesh(2, 2, 4, 3)
     assert res[0][1] + res[1][1] == full.nGlobal - full.nDir
+
+
+def test_flop_model_counts_the_reference_loops():
+    """tools/flop_model.py (the FP64 fractions of the sweep tables): the closed-form pass lengths against a literal count of the
+    multiply-adds in the reference's BwdTrans loop nests (BwdTransKernels.hpp:78-484), every shape, nm = 2..9"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from flop_model import algorithmic_flops
+
+    def count(shape, nm):
+        nq = nm + 1
+        if shape == "Hex":
+            return 2 * (nq * nm ** 3 + nq ** 2 * nm ** 2 + nq ** 3 * nm)
+        if shape == "Quad":
+            return 2 * (nq * nm ** 2 + nq ** 2 * nm)
+        if shape == "Tri":
+            nq0, nq1 = nq, nm
+            n = sum(nm - p for p in range(nm)) * nq1          # q-contraction per (j, p)
+            return 2 * (n + nq1 * nq0 * nm)                      # p-contraction per (j, i)
+        nq0, nq1, nq2 = nq, (nm if shape == "Tet" else nq), nm
+        if shape == "Prism":
+            s1 = nq2 * sum(nm * (nm - p) for p in range(nm))
+            s2 = nq2 * nq1 * nm * nm
+        elif shape == "Pyr":
+            s1 = nq2 * sum(nm - max(p, q) for p in range(nm) for q in range(nm))
+            s2 = nq2 * nq1 * nm * nm
+        else:
+            s1 = nq2 * sum(nm - p - q for p in range(nm) for q in range(nm - p))
+            s2 = nq2 * nq1 * sum(nm - p for p in range(nm))
+        return 2 * (s1 + s2 + nq2 * nq1 * nq0 * nm)
+
+    for shape in ("Hex", "Quad", "Tri", "Prism", "Pyr", "Tet"):
+        for nm in range(2, 10):
+            assert algorithmic_flops("BwdTrans", shape, nm, nm + 1) == count(shape, nm), (shape, nm)
+            # the composite operators are built from the same pass count
+            sf = count(shape, nm)
+            assert algorithmic_flops("Helmholtz", shape, nm, nm + 1) > (5 if shape not in ("Quad", "Tri") else 4) * sf
