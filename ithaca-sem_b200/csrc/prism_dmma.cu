@@ -126,6 +126,13 @@ __global__ void __launch_bounds__(PrismDmmaCfg<PYR, OP, NM, DEF>::T, MINB)
     }
     // tile column g of pass 1 <-> second index (q resp. j) = g/2 for even g, 4 + g/2 for odd g
     const int col0 = (g & 1) ? 4 + (g >> 1) : (g >> 1);
+    // mode line (p, q): first coefficient, first row of the xi_2 table, length.  Prisms: closed forms (the lane-dependent
+    // lookups in the kernel-parameter tables that the pyramid needs cost the prism kernels 0.19 -> 0.28 ms at nm = 7 when
+    // both shapes went through them); pyramids: tables.
+    auto mpr     = [](int p) { return p * NM - p * (p - 1) / 2; }; // first row of the (p, .) block of the prism table
+    auto l_start = [&](int p, int q) { return PYR ? tab.start[p * NM + q] : NM * mpr(p) + q * (NM - p); };
+    auto l_len   = [&](int p, int q) { return PYR ? tab.len[p * NM + q] : NM - p; };
+    auto l_row   = [&](int p, int q) { return PYR ? tab.row[p * NM + q] : mpr(p); };
 
     uint32_t phase[2] = {0, 0};
     int slot          = 0;
@@ -170,8 +177,8 @@ __global__ void __launch_bounds__(PrismDmmaCfg<PYR, OP, NM, DEF>::T, MINB)
                 const int p0 = t, p1 = 4 + t;
                 const bool v0 = q < NM && p0 < NM, v1 = q < NM && p1 < NM;
                 double c0[NM], c1[NM > 4 ? NM - 4 : 1];
-                const int base0 = v0 ? tab.start[p0 * NM + q] : 0, len0 = v0 ? tab.len[p0 * NM + q] : 0;
-                const int base1 = v1 ? tab.start[p1 * NM + q] : 0, len1 = v1 ? tab.len[p1 * NM + q] : 0;
+                const int base0 = v0 ? l_start(p0, q) : 0, len0 = v0 ? l_len(p0, q) : 0;
+                const int base1 = v1 ? l_start(p1, q) : 0, len1 = v1 ? l_len(p1, q) : 0;
 #pragma unroll
                 for (int r = 0; r < NM; ++r)
                 {
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(PrismDmmaCfg<PYR, OP, NM, DEF>::T, MINB)
                 const bool cor  = v0 && (PYR ? ((p0 == 0 && q == 1) || (p0 == 1 && q <= 1)) : p0 == 1);
                 const double xc = U[cor ? (PYR ? 1 : q * NM + 1) : 0];
                 const double cc = cor ? xc : 0.0;
-                const int row0 = v0 ? tab.row[p0 * NM + q] : 0, row1 = v1 ? tab.row[p1 * NM + q] : 0;
+                const int row0 = v0 ? l_row(p0, q) : 0, row1 = v1 ? l_row(p1, q) : 0;
                 const int i0 = 2 * t;
                 double *o = args.out + el * NQT + g * NQ0 + i0;
 #pragma unroll
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(PrismDmmaCfg<PYR, OP, NM, DEF>::T, MINB)
                 // the lane owns (p, q) = (2t, g) and (2t + 1, g) of the result
                 const int p0 = 2 * t, p1 = 2 * t + 1;
                 const bool o0 = g < NM && p0 < NM, o1 = g < NM && p1 < NM;
-                const int row0 = o0 ? tab.row[p0 * NM + g] : 0, row1 = o1 ? tab.row[p1 * NM + g] : 0;
+                const int row0 = o0 ? l_row(p0, g) : 0, row1 = o1 ? l_row(p1, g) : 0;
                 // corrections: prism, singular edge: the (1, q) value also feeds mode (0, q, 1) through the row (0, 1);
                 // pyramid, top vertex: the (0,1), (1,0), (1,1) values feed mode (0,0,1) through the row 1 (lane (g,t) = (1,0)
                 // adds its share to the staged result afterwards)
@@ -286,16 +293,16 @@ __global__ void __launch_bounds__(PrismDmmaCfg<PYR, OP, NM, DEF>::T, MINB)
                 // the (p, q) owners write their mode lines: staged in shared memory, stored coalesced
                 if (o0)
                 {
-                    double *o    = sStg + tab.start[p0 * NM + g];
-                    const int ln = tab.len[p0 * NM + g];
+                    double *o    = sStg + l_start(p0, g);
+                    const int ln = l_len(p0, g);
 #pragma unroll
                     for (int r = 0; r < NM; ++r)
                         if (r < ln) o[r] = acc0[r];
                 }
                 if (o1)
                 {
-                    double *o    = sStg + tab.start[p1 * NM + g];
-                    const int ln = tab.len[p1 * NM + g];
+                    double *o    = sStg + l_start(p1, g);
+                    const int ln = l_len(p1, g);
 #pragma unroll
                     for (int r = 0; r < NM - 1; ++r)
                         if (r < ln) o[r] = acc1[r];
